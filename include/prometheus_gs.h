@@ -1,0 +1,200 @@
+/*
+ * prometheus_gs.h — C-ABI of the B200-native GS-decoder rendering hot path.
+ *
+ * This is the drop-in boundary: a plain C interface (device pointers, sizes, a
+ * CUDA stream) that a host binding — the ctypes loader in prometheus_b200/_lib.py,
+ * or the stub shown in INTEGRATION.md — calls in place of the kernels the reference
+ * reaches through `gsplat.rasterization(...)`
+ * (reference call site: prometheus/modules/renderers/gaussians_renderer.py:413-427)
+ * and through the ~40 ATen ops of `GaussianConverter.forward` (same file :210-287).
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer on the current CUDA device unless a
+ *     parameter is documented as "host". Tensors are row-major and contiguous.
+ *   - fp32 = float, ids = int32_t, sort keys = int64_t.
+ *   - The caller owns every buffer (torch's caching allocator in our binding).
+ *     Functions never allocate, never synchronise the device and never block the
+ *     host; they enqueue work on `stream` (a cudaStream_t passed as void*).
+ *   - Return value: PM_OK (0) or a negative PM_ERR_* code. Argument errors are
+ *     detected on the host before anything is enqueued.
+ *   - "P" below is the number of (camera, Gaussian) pairs, P = C * N, flattened
+ *     camera-major: pair index f = c * N + g  ("flatten id").
+ *
+ * There is no CPU fallback behind this interface: if the library was not built
+ * for sm_100a or no GPU is present, the calls fail with PM_ERR_CUDA.
+ */
+#ifndef PROMETHEUS_GS_H
+#define PROMETHEUS_GS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PM_ABI_VERSION 1
+
+typedef void *pm_stream_t; /* cudaStream_t */
+
+enum pm_status {
+  PM_OK = 0,
+  PM_ERR_BAD_ARG = -1,     /* null pointer, negative size, misaligned buffer      */
+  PM_ERR_UNSUPPORTED = -2, /* e.g. tile_size != 16, more than 4 colour channels   */
+  PM_ERR_WORKSPACE = -3,   /* workspace too small for the requested problem size  */
+  PM_ERR_CUDA = -4,        /* a CUDA runtime call / launch failed                 */
+  PM_ERR_RANGE = -5        /* size exceeds an implementation limit (2^30 isects)  */
+};
+
+/* GaussianConverter.gs_convert_mode (gaussians_renderer.py:175, :258-285) */
+enum pm_convert_mode {
+  PM_MODE_MVSPLAT = 0,
+  PM_MODE_GSLRM = 1,
+  PM_MODE_DIRECTOR3D = 2
+};
+
+int pm_abi_version(void);
+const char *pm_status_string(int status);
+/* Last CUDA error string recorded by a failing call on this host thread. */
+const char *pm_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------- *
+ * Stage 1 — unproject: per-pixel 14-channel decoder maps -> 3D Gaussians.
+ * Replaces GaussianConverter.forward (gaussians_renderer.py:210-287).
+ *
+ *   params   [V, 14, h, w]  channel-planar (rgb3, uv-offset2, depth1, opacity1,
+ *                           scale3, quat4), V = B*N views
+ *   cameras  [V, 18]        c2w 3x4 row-major (OpenGL) + fx, fy, cx, cy, H, W
+ *   muls     [14]           per-channel multipliers (`converter.muls` buffer)
+ * outputs, G = V*h*w Gaussians in (view, row, col) order:
+ *   xyz [G,3]  rgb [G,3]  opacity [G]  scales [G,3]  quats [G,4] (wxyz)
+ * ------------------------------------------------------------------------- */
+int pm_unproject_fwd(const float *params, const float *cameras, const float *muls,
+                     int mode, float z_near, float z_far, float s_min, float s_max,
+                     int n_views, int h, int w,
+                     float *xyz, float *rgb, float *opacity, float *scales, float *quats,
+                     pm_stream_t stream);
+
+/* VJP of pm_unproject_fwd w.r.t. params (cameras carry no gradient in the
+ * reference: gs_decoder_system.py:200 feeds dataset cameras). Any v_* input may
+ * be NULL (treated as zero). v_params [V,14,h,w] is fully overwritten. */
+int pm_unproject_bwd(const float *params, const float *cameras, const float *muls,
+                     int mode, float z_near, float z_far, float s_min, float s_max,
+                     int n_views, int h, int w,
+                     const float *v_xyz, const float *v_rgb, const float *v_opacity,
+                     const float *v_scales, const float *v_quats,
+                     float *v_params, pm_stream_t stream);
+
+/* Camera preparation on the device. Replaces the host round trip of
+ * convert_camera_parameters_into_viewpoint_cameras + MiniCam + the K build
+ * (gaussians_renderer.py:453-472, :139-169, :404-412): rescale intrinsics to the
+ * render size, flip OpenGL->OpenCV, invert c2w, centre the principal point.
+ *   cameras [n,18] -> viewmats [n,4,4] (world-to-camera), Ks [n,3,3] */
+int pm_camera_prep(const float *cameras, int n, int h, int w,
+                   float *viewmats, float *Ks, pm_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * Stage 2 — EWA projection (+ fused tile-count). Replaces gsplat 1.4.0
+ * fully_fused_projection fwd/bwd and pass 1 of isect_tiles.
+ *   means [N,3] quats [N,4] scales [N,3] viewmats [C,4,4] Ks [C,3,3]
+ * outputs (all [C,N,...]): radii i32, means2d [.,2], depths, conics [.,3],
+ *   tiles_per_gauss i32 (may be NULL to skip the count).
+ * Culled pairs get radius 0 and zeros in the other outputs.
+ * ------------------------------------------------------------------------- */
+int pm_project_fwd(const float *means, const float *quats, const float *scales,
+                   const float *viewmats, const float *Ks,
+                   int N, int C, int width, int height, int tile_size,
+                   float eps2d, float near_plane, float far_plane, float radius_clip,
+                   int32_t *radii, float *means2d, float *depths, float *conics,
+                   int32_t *tiles_per_gauss, pm_stream_t stream);
+
+/* VJP of the projection. v_means2d [C,N,2], v_depths [C,N], v_conics [C,N,3]
+ * (any may be NULL) -> v_means [N,3], v_quats [N,4], v_scales [N,3], summed over
+ * cameras, fully overwritten. viewmats/Ks carry no gradient on this path. */
+int pm_project_bwd(const float *means, const float *quats, const float *scales,
+                   const float *viewmats, const float *Ks,
+                   int N, int C, int width, int height, float eps2d,
+                   const int32_t *radii, const float *conics,
+                   const float *v_means2d, const float *v_depths, const float *v_conics,
+                   float *v_means, float *v_quats, float *v_scales, pm_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * Stage 3 — tile binning and depth sort. Replaces gsplat isect_tiles (cumsum +
+ * emit), cub::DeviceRadixSort::SortPairs and isect_offset_encode.
+ * ------------------------------------------------------------------------- */
+
+/* Inclusive prefix sum of tiles_per_gauss [P] -> cum [P] (int32); the total is
+ * also written to *n_isects_out (device int32). */
+size_t pm_scan_workspace_bytes(int64_t P);
+int pm_scan_tiles(const int32_t *tiles_per_gauss, int64_t P, int32_t *cum,
+                  int32_t *n_isects_out, void *workspace, size_t workspace_bytes,
+                  pm_stream_t stream);
+
+/* Emit one (key, value) per (pair, tile): key = cam << (32+tile_bits) |
+ * tile << 32 | depth_bits, value = flatten id. Output slot of pair f's k-th
+ * tile (row-major over its tile AABB) is cum[f-1] + k. */
+int pm_bin_emit(const float *means2d, const int32_t *radii, const float *depths,
+                const int32_t *cum, int N, int C, int tile_size,
+                int tile_width, int tile_height,
+                int64_t *isect_ids, int32_t *flatten_ids, int64_t capacity,
+                pm_stream_t stream);
+
+/* Stable LSD radix sort (hand-written onesweep, no CUB) of n (key,value) pairs
+ * on key bits [0, end_bit). Double-buffered: input is buffer 0; *result_buffer
+ * (host) receives 0 or 1 = which buffer holds the sorted output (decided on the
+ * host from the pass count, before launch). If d_n is non-NULL the element
+ * count is read on the device from *d_n (must be <= n) so no host sync is
+ * needed; n then only sizes the launch. */
+size_t pm_sort_workspace_bytes(int64_t n);
+int pm_sort_pairs(int64_t *keys0, int32_t *vals0, int64_t *keys1, int32_t *vals1,
+                  int64_t n, const int32_t *d_n, int end_bit,
+                  void *workspace, size_t workspace_bytes, int *result_buffer,
+                  pm_stream_t stream);
+
+/* Per-(camera,tile) start offsets into the sorted list: isect_offsets
+ * [C, tile_height, tile_width] int32 (lower bound of each tile id). */
+int pm_tile_offsets(const int64_t *sorted_isect_ids, int64_t n, const int32_t *d_n,
+                    int C, int tile_width, int tile_height,
+                    int32_t *isect_offsets, pm_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * Stage 4 — front-to-back alpha compositing, forward and backward. Replaces
+ * gsplat rasterize_to_pixels fwd/bwd (packed=False, tile_size 16).
+ *
+ *   means2d [C,N,2]  conics [C,N,3]
+ *   opacities [N]                      (shared by all cameras)
+ *   colors  [N,D] (colors_per_camera=0) or [C,N,D] (=1), 0 <= D <= 3 .. 4
+ *   depths  [C,N] or NULL: appended as one more channel (render_mode *+D/ED)
+ *           channels CD = D + (depths != NULL), 1 <= CD <= 4
+ *   backgrounds [C,D] or NULL (the depth channel's background is 0)
+ * outputs: render [C,H,W,CD], alphas [C,H,W], last_ids [C,H,W] int32 (index into
+ *   the sorted list of the last Gaussian composited into the pixel).
+ * ------------------------------------------------------------------------- */
+int pm_composite_fwd(const float *means2d, const float *conics, const float *opacities,
+                     const float *colors, int colors_per_camera, int D,
+                     const float *depths, const float *backgrounds,
+                     const int32_t *isect_offsets, const int32_t *flatten_ids,
+                     int64_t n_isects, const int32_t *d_n,
+                     int N, int C, int width, int height, int tile_size,
+                     float *render, float *alphas, int32_t *last_ids,
+                     pm_stream_t stream);
+
+/* Backward. v_render [C,H,W,CD], v_alphas [C,H,W] (either may be NULL).
+ * Gradients are ACCUMULATED (+=) into v_means2d [C,N,2], v_conics [C,N,3],
+ * v_colors ([N,D] or [C,N,D]), v_opacities [N], v_depths [C,N]: the caller
+ * zero-fills them. v_depths must be non-NULL iff depths is. */
+int pm_composite_bwd(const float *means2d, const float *conics, const float *opacities,
+                     const float *colors, int colors_per_camera, int D,
+                     const float *depths, const float *backgrounds,
+                     const int32_t *isect_offsets, const int32_t *flatten_ids,
+                     int64_t n_isects, const int32_t *d_n,
+                     int N, int C, int width, int height, int tile_size,
+                     const float *alphas, const int32_t *last_ids,
+                     const float *v_render, const float *v_alphas,
+                     float *v_means2d, float *v_conics, float *v_colors,
+                     float *v_opacities, float *v_depths, pm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROMETHEUS_GS_H */
