@@ -35,6 +35,12 @@ extern "C" {
 
 #define PM_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define PM_API __attribute__((visibility("default")))
+#else
+#define PM_API
+#endif
+
 typedef void *pm_stream_t; /* cudaStream_t */
 
 enum pm_status {
@@ -53,10 +59,10 @@ enum pm_convert_mode {
   PM_MODE_DIRECTOR3D = 2
 };
 
-int pm_abi_version(void);
-const char *pm_status_string(int status);
+PM_API int pm_abi_version(void);
+PM_API const char *pm_status_string(int status);
 /* Last CUDA error string recorded by a failing call on this host thread. */
-const char *pm_last_cuda_error(void);
+PM_API const char *pm_last_cuda_error(void);
 
 /* ------------------------------------------------------------------------- *
  * Stage 1 — unproject: per-pixel 14-channel decoder maps -> 3D Gaussians.
@@ -69,7 +75,7 @@ const char *pm_last_cuda_error(void);
  * outputs, G = V*h*w Gaussians in (view, row, col) order:
  *   xyz [G,3]  rgb [G,3]  opacity [G]  scales [G,3]  quats [G,4] (wxyz)
  * ------------------------------------------------------------------------- */
-int pm_unproject_fwd(const float *params, const float *cameras, const float *muls,
+PM_API int pm_unproject_fwd(const float *params, const float *cameras, const float *muls,
                      int mode, float z_near, float z_far, float s_min, float s_max,
                      int n_views, int h, int w,
                      float *xyz, float *rgb, float *opacity, float *scales, float *quats,
@@ -78,7 +84,7 @@ int pm_unproject_fwd(const float *params, const float *cameras, const float *mul
 /* VJP of pm_unproject_fwd w.r.t. params (cameras carry no gradient in the
  * reference: gs_decoder_system.py:200 feeds dataset cameras). Any v_* input may
  * be NULL (treated as zero). v_params [V,14,h,w] is fully overwritten. */
-int pm_unproject_bwd(const float *params, const float *cameras, const float *muls,
+PM_API int pm_unproject_bwd(const float *params, const float *cameras, const float *muls,
                      int mode, float z_near, float z_far, float s_min, float s_max,
                      int n_views, int h, int w,
                      const float *v_xyz, const float *v_rgb, const float *v_opacity,
@@ -90,7 +96,7 @@ int pm_unproject_bwd(const float *params, const float *cameras, const float *mul
  * (gaussians_renderer.py:453-472, :139-169, :404-412): rescale intrinsics to the
  * render size, flip OpenGL->OpenCV, invert c2w, centre the principal point.
  *   cameras [n,18] -> viewmats [n,4,4] (world-to-camera), Ks [n,3,3] */
-int pm_camera_prep(const float *cameras, int n, int h, int w,
+PM_API int pm_camera_prep(const float *cameras, int n, int h, int w,
                    float *viewmats, float *Ks, pm_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
@@ -101,7 +107,7 @@ int pm_camera_prep(const float *cameras, int n, int h, int w,
  *   tiles_per_gauss i32 (may be NULL to skip the count).
  * Culled pairs get radius 0 and zeros in the other outputs.
  * ------------------------------------------------------------------------- */
-int pm_project_fwd(const float *means, const float *quats, const float *scales,
+PM_API int pm_project_fwd(const float *means, const float *quats, const float *scales,
                    const float *viewmats, const float *Ks,
                    int N, int C, int width, int height, int tile_size,
                    float eps2d, float near_plane, float far_plane, float radius_clip,
@@ -111,7 +117,7 @@ int pm_project_fwd(const float *means, const float *quats, const float *scales,
 /* VJP of the projection. v_means2d [C,N,2], v_depths [C,N], v_conics [C,N,3]
  * (any may be NULL) -> v_means [N,3], v_quats [N,4], v_scales [N,3], summed over
  * cameras, fully overwritten. viewmats/Ks carry no gradient on this path. */
-int pm_project_bwd(const float *means, const float *quats, const float *scales,
+PM_API int pm_project_bwd(const float *means, const float *quats, const float *scales,
                    const float *viewmats, const float *Ks,
                    int N, int C, int width, int height, float eps2d,
                    const int32_t *radii, const float *conics,
@@ -125,15 +131,15 @@ int pm_project_bwd(const float *means, const float *quats, const float *scales,
 
 /* Inclusive prefix sum of tiles_per_gauss [P] -> cum [P] (int32); the total is
  * also written to *n_isects_out (device int32). */
-size_t pm_scan_workspace_bytes(int64_t P);
-int pm_scan_tiles(const int32_t *tiles_per_gauss, int64_t P, int32_t *cum,
+PM_API size_t pm_scan_workspace_bytes(int64_t P);
+PM_API int pm_scan_tiles(const int32_t *tiles_per_gauss, int64_t P, int32_t *cum,
                   int32_t *n_isects_out, void *workspace, size_t workspace_bytes,
                   pm_stream_t stream);
 
 /* Emit one (key, value) per (pair, tile): key = cam << (32+tile_bits) |
  * tile << 32 | depth_bits, value = flatten id. Output slot of pair f's k-th
  * tile (row-major over its tile AABB) is cum[f-1] + k. */
-int pm_bin_emit(const float *means2d, const int32_t *radii, const float *depths,
+PM_API int pm_bin_emit(const float *means2d, const int32_t *radii, const float *depths,
                 const int32_t *cum, int N, int C, int tile_size,
                 int tile_width, int tile_height,
                 int64_t *isect_ids, int32_t *flatten_ids, int64_t capacity,
@@ -145,15 +151,15 @@ int pm_bin_emit(const float *means2d, const int32_t *radii, const float *depths,
  * host from the pass count, before launch). If d_n is non-NULL the element
  * count is read on the device from *d_n (must be <= n) so no host sync is
  * needed; n then only sizes the launch. */
-size_t pm_sort_workspace_bytes(int64_t n);
-int pm_sort_pairs(int64_t *keys0, int32_t *vals0, int64_t *keys1, int32_t *vals1,
+PM_API size_t pm_sort_workspace_bytes(int64_t n);
+PM_API int pm_sort_pairs(int64_t *keys0, int32_t *vals0, int64_t *keys1, int32_t *vals1,
                   int64_t n, const int32_t *d_n, int end_bit,
                   void *workspace, size_t workspace_bytes, int *result_buffer,
                   pm_stream_t stream);
 
 /* Per-(camera,tile) start offsets into the sorted list: isect_offsets
  * [C, tile_height, tile_width] int32 (lower bound of each tile id). */
-int pm_tile_offsets(const int64_t *sorted_isect_ids, int64_t n, const int32_t *d_n,
+PM_API int pm_tile_offsets(const int64_t *sorted_isect_ids, int64_t n, const int32_t *d_n,
                     int C, int tile_width, int tile_height,
                     int32_t *isect_offsets, pm_stream_t stream);
 
@@ -170,7 +176,7 @@ int pm_tile_offsets(const int64_t *sorted_isect_ids, int64_t n, const int32_t *d
  * outputs: render [C,H,W,CD], alphas [C,H,W], last_ids [C,H,W] int32 (index into
  *   the sorted list of the last Gaussian composited into the pixel).
  * ------------------------------------------------------------------------- */
-int pm_composite_fwd(const float *means2d, const float *conics, const float *opacities,
+PM_API int pm_composite_fwd(const float *means2d, const float *conics, const float *opacities,
                      const float *colors, int colors_per_camera, int D,
                      const float *depths, const float *backgrounds,
                      const int32_t *isect_offsets, const int32_t *flatten_ids,
@@ -183,7 +189,7 @@ int pm_composite_fwd(const float *means2d, const float *conics, const float *opa
  * Gradients are ACCUMULATED (+=) into v_means2d [C,N,2], v_conics [C,N,3],
  * v_colors ([N,D] or [C,N,D]), v_opacities [N], v_depths [C,N]: the caller
  * zero-fills them. v_depths must be non-NULL iff depths is. */
-int pm_composite_bwd(const float *means2d, const float *conics, const float *opacities,
+PM_API int pm_composite_bwd(const float *means2d, const float *conics, const float *opacities,
                      const float *colors, int colors_per_camera, int D,
                      const float *depths, const float *backgrounds,
                      const int32_t *isect_offsets, const int32_t *flatten_ids,

@@ -1,0 +1,13 @@
+"""prometheus_b200 — B200-native (sm_100a) GS-decoder rendering hot path of
+houstonwhy/Prometheus: unproject -> EWA project -> tile bin + radix sort ->
+alpha composite (fwd + bwd), behind the reference's own operator interface.
+
+Public surface (mirrors the reference, see DESIGN.md / INTEGRATION.md):
+  rasterization(...)            gsplat.rasterization contract
+  GaussianConverter, GaussianRenderer   module-level mirrors
+  install_as_gsplat()           plug the operator under the unmodified reference
+"""
+from .rasterization import rasterization  # noqa: F401
+from .renderer import GaussianConverter, GaussianRenderer, install_as_gsplat  # noqa: F401
+
+__all__ = ["rasterization", "GaussianConverter", "GaussianRenderer", "install_as_gsplat"]

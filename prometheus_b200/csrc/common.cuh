@@ -1,0 +1,64 @@
+// common.cuh — shared helpers for the sm_100a kernels behind include/prometheus_gs.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/prometheus_gs.h"
+
+namespace pm {
+
+void set_last_cuda_error(cudaError_t e);
+
+inline int check_launch() {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_cuda_error(e);
+    return PM_ERR_CUDA;
+  }
+  return PM_OK;
+}
+
+inline cudaStream_t as_stream(pm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kTile = 16;  // the only tile size the reference ever uses (gsplat default)
+
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Effective element count: the device-side count (if given) clamped to the host capacity.
+__device__ __forceinline__ int64_t effective_n(int64_t n_host, const int32_t *d_n) {
+  if (d_n == nullptr) return n_host;
+  int64_t v = (int64_t)(*d_n);
+  if (v < 0) v = 0;
+  return v < n_host ? v : n_host;
+}
+
+// floor(log2(n)) + 1, the bit widths gsplat packs tile and camera ids with.
+__host__ __device__ inline int n_bits_for(int n) {
+  int b = 0;
+  while (n > 0) {
+    ++b;
+    n >>= 1;
+  }
+  return b;
+}
+
+// Tile AABB of a projected Gaussian. Written with _rn
+// intrinsics so no compiler flag can contract or reorder it: the result must be
+// bit-identical between the count (project) and the emit kernels and the oracle.
+__device__ __forceinline__ int clamp_tile(float v, int hi) {
+  if (!(v > 0.0f)) return 0;
+  if (v >= (float)hi) return hi;
+  return (int)v;
+}
+__device__ __forceinline__ void tile_aabb(float mx, float my, int radius, int tile_width, int tile_height,
+                                          int &x0, int &x1, int &y0, int &y1) {
+  const float ts = (float)kTile;
+  const float tr = __fdiv_rn((float)radius, ts);
+  const float tx = __fdiv_rn(mx, ts), ty = __fdiv_rn(my, ts);
+  x0 = clamp_tile(floorf(__fsub_rn(tx, tr)), tile_width);
+  x1 = clamp_tile(ceilf(__fadd_rn(tx, tr)), tile_width);
+  y0 = clamp_tile(floorf(__fsub_rn(ty, tr)), tile_height);
+  y1 = clamp_tile(ceilf(__fadd_rn(ty, tr)), tile_height);
+}
+
+}  // namespace pm

@@ -1,0 +1,402 @@
+// composite.cu — stage 4: front-to-back alpha compositing of the depth-sorted
+// per-tile Gaussian lists, forward and backward.
+//
+// Replaces gsplat 1.4.0 rasterize_to_pixels_{fwd,bwd} (packed=False, tile 16),
+// reached by the reference through gsplat.rasterization
+// (prometheus/modules/renderers/gaussians_renderer.py:413-427); semantics per
+// SURVEY.md §8c steps 10 and 12.
+//
+// Design (B200): one 256-thread CTA per 16x16 tile; each of its 8 warps owns an
+// 8x4-pixel footprint. The tile's sorted list is staged in shared memory in
+// batches of 256 Gaussians (each thread gathers one record: flatten id -> mean,
+// conic, opacity, colour, depth = 44 algorithmic bytes). Instead of letting all
+// 256 pixels evaluate all 256 Gaussians (upstream), every warp first CULLS the
+// batch against its footprint: 32 lanes test 32 Gaussians in parallel against
+// the exact alpha >= 1/255 extent of each Gaussian (an axis-aligned bound of the
+// ellipse sigma <= ln(255*opacity)), __ballot_sync turns the hits into a bitmask,
+// and only the set bits are evaluated, in order. The bound is conservative, so
+// the surviving evaluations — and therefore the result — are identical to the
+// un-culled loop. Early termination is tracked per warp (__all_sync) and per CTA
+// (__syncthreads_count), so batches past the last needed intersection are never
+// loaded. The backward pass replays the same culled lists back to front, reduces
+// each Gaussian's gradient across the warp with shuffles, accumulates the 8
+// warps in shared memory and issues ONE global atomic per Gaussian-tile and
+// component (upstream: one per warp) — no per-pixel global atomics.
+#include "common.cuh"
+
+namespace pm {
+
+constexpr int kBatch = 256;
+constexpr float kAlphaMin = 1.0f / 255.0f;
+constexpr float kTStop = 1e-4f;
+
+struct __align__(16) GaussA { float mx, my, hx, hy; };      // mean + half extents of the alpha>=1/255 box
+struct __align__(16) GaussB { float cx, cy, cz, opac; };    // conic + opacity
+struct __align__(16) GaussC { float c0, c1, c2, c3; };      // colour channels (+ depth), zero padded
+
+// Gather one Gaussian of the sorted list into the staging records.
+__device__ __forceinline__ void gather(int32_t f, int N, const float *__restrict__ means2d,
+                                       const float *__restrict__ conics, const float *__restrict__ opacities,
+                                       const float *__restrict__ colors, int colors_per_camera, int D,
+                                       const float *__restrict__ depths, GaussA &a, GaussB &b, GaussC &c) {
+  const int32_t g = f % N;
+  const float2 m = __ldg(reinterpret_cast<const float2 *>(means2d) + f);
+  const float q0 = __ldg(conics + (size_t)f * 3 + 0), q1 = __ldg(conics + (size_t)f * 3 + 1),
+              q2 = __ldg(conics + (size_t)f * 3 + 2);
+  const float o = __ldg(opacities + g);
+  // extent of {alpha >= 1/255} = {sigma <= tau}, tau = ln(255*o): half widths sqrt(2 tau Sigma_xx),
+  // sqrt(2 tau Sigma_yy) with Sigma = conic^-1. Inflated so fp rounding can only over-include.
+  float hx, hy;
+  // det(conic) with Kahan's fma compensation: anisotropic splats cancel badly in q0*q2 - q1*q1
+  const float w = q1 * q1;
+  const float det = fmaf(q0, q2, -w) + fmaf(-q1, q1, w);
+  if (!(o * 255.0f > 1.0f)) {
+    hx = hy = -1e30f;  // alpha < 1/255 everywhere: never evaluated (as upstream would skip it)
+  } else if (!(det > 0.0f) || !(q0 > 0.0f) || !(q2 > 0.0f)) {
+    hx = hy = 3e38f;   // degenerate conic: no culling
+  } else {
+    const float two_tau = 2.0f * __logf(o * 255.0f) * 1.001f + 1e-3f;
+    hx = sqrtf(two_tau * q2 / det) * 1.005f + 0.05f;
+    hy = sqrtf(two_tau * q0 / det) * 1.005f + 0.05f;
+    if (!(hx == hx) || !(hy == hy)) hx = hy = 3e38f;
+  }
+  a = GaussA{m.x, m.y, hx, hy};
+  b = GaussB{q0, q1, q2, o};
+  float ch[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  const float *col = colors + (size_t)(colors_per_camera ? f : g) * D;
+  for (int k = 0; k < D; ++k) ch[k] = __ldg(col + k);
+  if (depths) ch[D] = __ldg(depths + f);
+  c = GaussC{ch[0], ch[1], ch[2], ch[3]};
+}
+
+__global__ void __launch_bounds__(256)
+composite_fwd_kernel(const float *__restrict__ means2d, const float *__restrict__ conics,
+                     const float *__restrict__ opacities, const float *__restrict__ colors,
+                     int colors_per_camera, int D, const float *__restrict__ depths,
+                     const float *__restrict__ backgrounds, const int32_t *__restrict__ offsets,
+                     const int32_t *__restrict__ flatten_ids, int64_t n_host,
+                     const int32_t *__restrict__ d_n, int N, int width, int height, int tile_width,
+                     int tile_height, float *__restrict__ render, float *__restrict__ alphas,
+                     int32_t *__restrict__ last_ids) {
+  __shared__ GaussA sA[kBatch];
+  __shared__ GaussB sB[kBatch];
+  __shared__ GaussC sC[kBatch];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_tiles = tile_width * tile_height;
+  const int ct = blockIdx.x;  // (camera, tile) flattened
+  const int cam = ct / n_tiles, tile = ct % n_tiles;
+  const int tile_y = tile / tile_width, tile_x = tile % tile_width;
+  // warp footprint: 8 wide x 4 high
+  const int wx0 = tile_x * kTile + (warp & 1) * 8, wy0 = tile_y * kTile + (warp >> 1) * 4;
+  const int ix = wx0 + (lane & 7), iy = wy0 + (lane >> 3);
+  const float px = (float)ix + 0.5f, py = (float)iy + 0.5f;
+  const float wcx = (float)wx0 + 4.0f, wcy = (float)wy0 + 2.0f;  // footprint centre (pixel centres span +-3.5, +-1.5)
+  const bool inside = ix < width && iy < height;
+  const int CD = D + (depths ? 1 : 0);
+
+  const int64_t n_isects = effective_n(n_host, d_n);
+  const int range_start = offsets[ct];
+  const int range_end = (ct == (int)gridDim.x - 1) ? (int)n_isects : offsets[ct + 1];
+
+  float T = 1.0f;
+  float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f, o3 = 0.0f;
+  int last = 0;
+  bool done = !inside;
+
+  for (int batch_start = range_start; batch_start < range_end; batch_start += kBatch) {
+    if (__syncthreads_count(done) == kBatch) break;
+    const int idx = batch_start + tid;
+    if (idx < range_end) gather(flatten_ids[idx], N, means2d, conics, opacities, colors, colors_per_camera, D, depths, sA[tid], sB[tid], sC[tid]);
+    __syncthreads();
+    const int batch_size = min(kBatch, range_end - batch_start);
+    if (__all_sync(0xffffffffu, done)) continue;  // this warp is finished; keep hitting the barriers
+    for (int sub = 0; sub < batch_size; sub += 32) {
+      const int j = sub + lane;
+      bool hit = false;
+      if (j < batch_size) {
+        const GaussA a = sA[j];
+        hit = fabsf(a.mx - wcx) <= a.hx + 3.5f && fabsf(a.my - wcy) <= a.hy + 1.5f;
+      }
+      unsigned mask = __ballot_sync(0xffffffffu, hit);
+      while (mask) {
+        const int t = sub + __ffs(mask) - 1;
+        mask &= mask - 1;
+        if (done) continue;
+        const GaussA a = sA[t];
+        const GaussB b = sB[t];
+        const float dx = a.mx - px, dy = a.my - py;
+        const float sigma = 0.5f * (b.cx * dx * dx + b.cz * dy * dy) + b.cy * dx * dy;
+        const float alpha = fminf(0.999f, b.opac * __expf(-sigma));
+        if (sigma < 0.0f || alpha < kAlphaMin) continue;
+        const float next_T = T * (1.0f - alpha);
+        if (next_T <= kTStop) { done = true; continue; }
+        const GaussC c = sC[t];
+        const float vis = alpha * T;
+        o0 += c.c0 * vis; o1 += c.c1 * vis; o2 += c.c2 * vis; o3 += c.c3 * vis;
+        last = batch_start + t;
+        T = next_T;
+      }
+      if (__all_sync(0xffffffffu, done)) break;
+    }
+  }
+
+  if (inside) {
+    const size_t pix = ((size_t)cam * height + iy) * width + ix;
+    alphas[pix] = 1.0f - T;
+    last_ids[pix] = last;
+    float out[4] = {o0, o1, o2, o3};
+    if (backgrounds) {
+      for (int k = 0; k < D; ++k) out[k] += T * __ldg(backgrounds + cam * D + k);
+    }
+    if (CD == 4) {
+      reinterpret_cast<float4 *>(render)[pix] = make_float4(out[0], out[1], out[2], out[3]);
+    } else {
+      for (int k = 0; k < CD; ++k) render[pix * CD + k] = out[k];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Backward.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int kGradStride = 11;  // 10 gradient components per staged Gaussian (+1: bank spread)
+
+__global__ void __launch_bounds__(256)
+composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict__ conics,
+                     const float *__restrict__ opacities, const float *__restrict__ colors,
+                     int colors_per_camera, int D, const float *__restrict__ depths,
+                     const float *__restrict__ backgrounds, const int32_t *__restrict__ offsets,
+                     const int32_t *__restrict__ flatten_ids, int64_t n_host,
+                     const int32_t *__restrict__ d_n, int N, int width, int height, int tile_width,
+                     int tile_height, const float *__restrict__ alphas,
+                     const int32_t *__restrict__ last_ids, const float *__restrict__ v_render,
+                     const float *__restrict__ v_alphas, float *__restrict__ v_means2d,
+                     float *__restrict__ v_conics, float *__restrict__ v_colors,
+                     float *__restrict__ v_opacities, float *__restrict__ v_depths) {
+  __shared__ GaussA sA[kBatch];
+  __shared__ GaussB sB[kBatch];
+  __shared__ GaussC sC[kBatch];
+  __shared__ int32_t sF[kBatch];
+  __shared__ float sG[kBatch * kGradStride];
+  __shared__ int s_max_last;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_tiles = tile_width * tile_height;
+  const int ct = blockIdx.x;
+  const int cam = ct / n_tiles, tile = ct % n_tiles;
+  const int tile_y = tile / tile_width, tile_x = tile % tile_width;
+  const int wx0 = tile_x * kTile + (warp & 1) * 8, wy0 = tile_y * kTile + (warp >> 1) * 4;
+  const int ix = wx0 + (lane & 7), iy = wy0 + (lane >> 3);
+  const float px = (float)ix + 0.5f, py = (float)iy + 0.5f;
+  const float wcx = (float)wx0 + 4.0f, wcy = (float)wy0 + 2.0f;
+  const bool inside = ix < width && iy < height;
+  const int CD = D + (depths ? 1 : 0);
+
+  const int64_t n_isects = effective_n(n_host, d_n);
+  const int range_start = offsets[ct];
+  const int range_end = (ct == (int)gridDim.x - 1) ? (int)n_isects : offsets[ct + 1];
+  if (range_end <= range_start) return;
+
+  // per-pixel state
+  float T_final = 1.0f, vr[4] = {0.0f, 0.0f, 0.0f, 0.0f}, va = 0.0f;
+  int my_last = -1;  // nothing to replay for pixels outside the image
+  if (inside) {
+    const size_t pix = ((size_t)cam * height + iy) * width + ix;
+    T_final = 1.0f - alphas[pix];
+    my_last = last_ids[pix];
+    if (v_render) {
+      if (CD == 4) {
+        const float4 t = reinterpret_cast<const float4 *>(v_render)[pix];
+        vr[0] = t.x; vr[1] = t.y; vr[2] = t.z; vr[3] = t.w;
+      } else {
+        for (int k = 0; k < CD; ++k) vr[k] = v_render[pix * CD + k];
+      }
+    }
+    if (v_alphas) va = v_alphas[pix];
+  }
+  // -T_final * sum_k bg_k v_render_k, folded into the alpha-gradient seed
+  float bg_dot = 0.0f;
+  if (backgrounds)
+    for (int k = 0; k < D; ++k) bg_dot += __ldg(backgrounds + cam * D + k) * vr[k];
+  const float va_seed = T_final * (va - bg_dot);
+
+  if (tid == 0) s_max_last = -1;
+  __syncthreads();
+  {
+    int m = my_last;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) atomicMax(&s_max_last, m);
+  }
+  __syncthreads();
+  const int max_last = s_max_last;
+  if (max_last < range_start) return;  // (last_ids are 0 for untouched pixels; 0 >= range_start only in tile 0)
+
+  float T = T_final;
+  float buf0 = 0.0f, buf1 = 0.0f, buf2 = 0.0f, buf3 = 0.0f;
+  // batches are aligned to the forward pass's batches; walk them back to front
+  const int n_needed = max_last - range_start + 1;
+  const int first_batch = (n_needed - 1) / kBatch;
+  for (int bi = first_batch; bi >= 0; --bi) {
+    const int batch_start = range_start + bi * kBatch;
+    const int batch_size = min(kBatch, min(range_end, max_last + 1) - batch_start);
+    __syncthreads();  // previous batch fully flushed
+    if (tid < batch_size) {
+      const int32_t f = flatten_ids[batch_start + tid];
+      sF[tid] = f;
+      gather(f, N, means2d, conics, opacities, colors, colors_per_camera, D, depths, sA[tid], sB[tid], sC[tid]);
+    }
+    for (int i = tid; i < kBatch * kGradStride; i += 256) sG[i] = 0.0f;
+    __syncthreads();
+
+    for (int sub = ((batch_size - 1) / 32) * 32; sub >= 0; sub -= 32) {
+      const int j = sub + lane;
+      bool hit = false;
+      if (j < batch_size) {
+        const GaussA a = sA[j];
+        hit = fabsf(a.mx - wcx) <= a.hx + 3.5f && fabsf(a.my - wcy) <= a.hy + 1.5f;
+      }
+      unsigned mask = __ballot_sync(0xffffffffu, hit);
+      while (mask) {
+        const int bit = 31 - __clz(mask);
+        mask &= ~(1u << bit);
+        const int t = sub + bit;
+        const GaussA a = sA[t];
+        const GaussB b = sB[t];
+        const float dx = a.mx - px, dy = a.my - py;
+        const float sigma = 0.5f * (b.cx * dx * dx + b.cz * dy * dy) + b.cy * dx * dy;
+        const float vis = __expf(-sigma);
+        const float alpha = fminf(0.999f, b.opac * vis);
+        const bool valid = (batch_start + t <= my_last) && !(sigma < 0.0f || alpha < kAlphaMin);
+        if (!__any_sync(0xffffffffu, valid)) continue;
+        float g_c0 = 0.0f, g_c1 = 0.0f, g_c2 = 0.0f, g_c3 = 0.0f;
+        float g_q0 = 0.0f, g_q1 = 0.0f, g_q2 = 0.0f, g_mx = 0.0f, g_my = 0.0f, g_o = 0.0f;
+        if (valid) {
+          const GaussC c = sC[t];
+          const float ra = 1.0f / (1.0f - alpha);
+          T *= ra;
+          const float fac = alpha * T;
+          g_c0 = fac * vr[0]; g_c1 = fac * vr[1]; g_c2 = fac * vr[2]; g_c3 = fac * vr[3];
+          float v_alpha = (c.c0 * T - buf0 * ra) * vr[0] + (c.c1 * T - buf1 * ra) * vr[1] +
+                          (c.c2 * T - buf2 * ra) * vr[2] + (c.c3 * T - buf3 * ra) * vr[3];
+          v_alpha += va_seed * ra;
+          if (b.opac * vis <= 0.999f) {
+            const float v_sigma = -b.opac * vis * v_alpha;
+            g_q0 = 0.5f * v_sigma * dx * dx;
+            g_q1 = v_sigma * dx * dy;
+            g_q2 = 0.5f * v_sigma * dy * dy;
+            g_mx = v_sigma * (b.cx * dx + b.cy * dy);
+            g_my = v_sigma * (b.cy * dx + b.cz * dy);
+            g_o = vis * v_alpha;
+          }
+          buf0 += c.c0 * fac; buf1 += c.c1 * fac; buf2 += c.c2 * fac; buf3 += c.c3 * fac;
+        }
+        g_c0 = warp_sum(g_c0); g_c1 = warp_sum(g_c1); g_c2 = warp_sum(g_c2); g_c3 = warp_sum(g_c3);
+        g_q0 = warp_sum(g_q0); g_q1 = warp_sum(g_q1); g_q2 = warp_sum(g_q2);
+        g_mx = warp_sum(g_mx); g_my = warp_sum(g_my); g_o = warp_sum(g_o);
+        if (lane < 10) {
+          float v = g_c0;
+          v = lane == 1 ? g_c1 : v; v = lane == 2 ? g_c2 : v; v = lane == 3 ? g_c3 : v;
+          v = lane == 4 ? g_q0 : v; v = lane == 5 ? g_q1 : v; v = lane == 6 ? g_q2 : v;
+          v = lane == 7 ? g_mx : v; v = lane == 8 ? g_my : v; v = lane == 9 ? g_o : v;
+          atomicAdd(&sG[t * kGradStride + lane], v);
+        }
+      }
+    }
+    __syncthreads();
+    // flush: one global atomic per Gaussian-tile and component
+    if (tid < batch_size) {
+      const float *gr = &sG[tid * kGradStride];
+      const int32_t f = sF[tid];
+      const int32_t g = f % N;
+      float *vc = v_colors + (size_t)(colors_per_camera ? f : g) * D;
+      for (int k = 0; k < D; ++k)
+        if (gr[k] != 0.0f) atomicAdd(vc + k, gr[k]);
+      if (depths && gr[D] != 0.0f) atomicAdd(v_depths + f, gr[D]);
+      if (gr[4] != 0.0f) atomicAdd(v_conics + (size_t)f * 3 + 0, gr[4]);
+      if (gr[5] != 0.0f) atomicAdd(v_conics + (size_t)f * 3 + 1, gr[5]);
+      if (gr[6] != 0.0f) atomicAdd(v_conics + (size_t)f * 3 + 2, gr[6]);
+      if (gr[7] != 0.0f) atomicAdd(v_means2d + (size_t)f * 2 + 0, gr[7]);
+      if (gr[8] != 0.0f) atomicAdd(v_means2d + (size_t)f * 2 + 1, gr[8]);
+      if (gr[9] != 0.0f) atomicAdd(v_opacities + g, gr[9]);
+    }
+  }
+}
+
+static int check_common(const float *means2d, const float *conics, const float *opacities,
+                        const float *colors, int D, const float *depths, const int32_t *offsets,
+                        const int32_t *flatten_ids, int64_t n_isects, int N, int C, int width,
+                        int height, int tile_size) {
+  if (N < 0 || C < 0 || width <= 0 || height <= 0 || n_isects < 0 || D < 0) return PM_ERR_BAD_ARG;
+  if (tile_size != kTile) return PM_ERR_UNSUPPORTED;
+  const int CD = D + (depths ? 1 : 0);
+  if (CD < 1 || CD > 4) return PM_ERR_UNSUPPORTED;
+  if (!means2d || !conics || !opacities || !offsets) return PM_ERR_BAD_ARG;
+  if (D > 0 && !colors) return PM_ERR_BAD_ARG;
+  if (n_isects > 0 && !flatten_ids) return PM_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(means2d) & 7) != 0) return PM_ERR_BAD_ARG;
+  if (n_isects >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
+  return PM_OK;
+}
+
+}  // namespace pm
+
+extern "C" {
+
+int pm_composite_fwd(const float *means2d, const float *conics, const float *opacities,
+                     const float *colors, int colors_per_camera, int D, const float *depths,
+                     const float *backgrounds, const int32_t *isect_offsets,
+                     const int32_t *flatten_ids, int64_t n_isects, const int32_t *d_n, int N, int C,
+                     int width, int height, int tile_size, float *render, float *alphas,
+                     int32_t *last_ids, pm_stream_t stream) {
+  const int rc = pm::check_common(means2d, conics, opacities, colors, D, depths, isect_offsets, flatten_ids,
+                                  n_isects, N, C, width, height, tile_size);
+  if (rc != PM_OK) return rc;
+  if (!render || !alphas || !last_ids) return PM_ERR_BAD_ARG;
+  const int CD = D + (depths ? 1 : 0);
+  if (CD == 4 && (reinterpret_cast<uintptr_t>(render) & 15) != 0) return PM_ERR_BAD_ARG;
+  if (C == 0) return PM_OK;
+  const int tw = (width + pm::kTile - 1) / pm::kTile, th = (height + pm::kTile - 1) / pm::kTile;
+  const int64_t blocks = (int64_t)C * tw * th;
+  if (blocks >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
+  pm::composite_fwd_kernel<<<(unsigned)blocks, 256, 0, pm::as_stream(stream)>>>(
+      means2d, conics, opacities, colors, colors_per_camera, D, depths, backgrounds, isect_offsets,
+      flatten_ids, n_isects, d_n, N, width, height, tw, th, render, alphas, last_ids);
+  return pm::check_launch();
+}
+
+int pm_composite_bwd(const float *means2d, const float *conics, const float *opacities,
+                     const float *colors, int colors_per_camera, int D, const float *depths,
+                     const float *backgrounds, const int32_t *isect_offsets,
+                     const int32_t *flatten_ids, int64_t n_isects, const int32_t *d_n, int N, int C,
+                     int width, int height, int tile_size, const float *alphas,
+                     const int32_t *last_ids, const float *v_render, const float *v_alphas,
+                     float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
+                     float *v_depths, pm_stream_t stream) {
+  const int rc = pm::check_common(means2d, conics, opacities, colors, D, depths, isect_offsets, flatten_ids,
+                                  n_isects, N, C, width, height, tile_size);
+  if (rc != PM_OK) return rc;
+  if (!alphas || !last_ids || !v_means2d || !v_conics || !v_opacities) return PM_ERR_BAD_ARG;
+  if (D > 0 && !v_colors) return PM_ERR_BAD_ARG;
+  if ((depths != nullptr) != (v_depths != nullptr)) return PM_ERR_BAD_ARG;
+  const int CD = D + (depths ? 1 : 0);
+  if (CD == 4 && v_render && (reinterpret_cast<uintptr_t>(v_render) & 15) != 0) return PM_ERR_BAD_ARG;
+  if (C == 0 || n_isects == 0) return PM_OK;
+  const int tw = (width + pm::kTile - 1) / pm::kTile, th = (height + pm::kTile - 1) / pm::kTile;
+  const int64_t blocks = (int64_t)C * tw * th;
+  if (blocks >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
+  pm::composite_bwd_kernel<<<(unsigned)blocks, 256, 0, pm::as_stream(stream)>>>(
+      means2d, conics, opacities, colors, colors_per_camera, D, depths, backgrounds, isect_offsets,
+      flatten_ids, n_isects, d_n, N, width, height, tw, th, alphas, last_ids, v_render, v_alphas,
+      v_means2d, v_conics, v_colors, v_opacities, v_depths);
+  return pm::check_launch();
+}
+
+}  // extern "C"

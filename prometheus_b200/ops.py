@@ -1,0 +1,243 @@
+"""Stage-level ops: torch tensors in, torch tensors out, computed by the CUDA
+kernels behind the C-ABI (include/prometheus_gs.h). No autograd here — see
+rasterization.py / renderer.py for the differentiable wrappers.
+
+Every function requires CUDA tensors; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+TILE = 16
+MODES = {"mvsplat": 0, "gslrm": 1, "director3d": 2}
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (prometheus_b200 has no CPU path)")
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _opt(t, dtype, name):
+    return None if t is None else _req(t, dtype, name)
+
+
+def tile_grid(width: int, height: int) -> Tuple[int, int]:
+    return (width + TILE - 1) // TILE, (height + TILE - 1) // TILE
+
+
+def key_bits(tile_width: int, tile_height: int, C: int) -> Tuple[int, int]:
+    """floor(log2(n))+1 bit widths gsplat packs tile and camera ids with."""
+    return int(tile_width * tile_height).bit_length(), int(C).bit_length()
+
+
+# ------------------------------------------------------------------ stage 1
+def unproject_fwd(params, cameras, muls, mode, z_near, z_far, s_min, s_max, out=None):
+    """params [V,14,h,w], cameras [V,18] -> (xyz [G,3], rgb [G,3], opacity [G], scales [G,3], quats [G,4]).
+    `out` may hold five preallocated tensors (e.g. slots of an all-gather buffer)."""
+    L = _lib.load()
+    params = _req(params, torch.float32, "params")
+    cameras = _req(cameras, torch.float32, "cameras")
+    muls = _req(muls, torch.float32, "muls").reshape(-1)
+    V, Cc, h, w = params.shape
+    assert Cc == 14 and cameras.shape == (V, 18) and muls.numel() == 14
+    G = V * h * w
+    dev = params.device
+    if out is None:
+        out = (torch.empty(G, 3, device=dev), torch.empty(G, 3, device=dev), torch.empty(G, device=dev),
+               torch.empty(G, 3, device=dev), torch.empty(G, 4, device=dev))
+    xyz, rgb, opacity, scales, quats = out
+    for t, n in zip(out, (3 * G, 3 * G, G, 3 * G, 4 * G)):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n
+    _lib.check(L.pm_unproject_fwd(_ptr(params), _ptr(cameras), _ptr(muls), MODES[mode], z_near, z_far,
+                                  s_min, s_max, V, h, w, _ptr(xyz), _ptr(rgb), _ptr(opacity), _ptr(scales),
+                                  _ptr(quats), _stream()), "pm_unproject_fwd")
+    return xyz, rgb, opacity, scales, quats
+
+
+def unproject_bwd(params, cameras, muls, mode, z_near, z_far, s_min, s_max, v_xyz, v_rgb, v_opacity,
+                  v_scales, v_quats):
+    L = _lib.load()
+    params = _req(params, torch.float32, "params")
+    cameras = _req(cameras, torch.float32, "cameras")
+    muls = _req(muls, torch.float32, "muls").reshape(-1)
+    V, _, h, w = params.shape
+    vs = [_opt(t, torch.float32, "grad") for t in (v_xyz, v_rgb, v_opacity, v_scales, v_quats)]
+    v_params = torch.empty_like(params)
+    _lib.check(L.pm_unproject_bwd(_ptr(params), _ptr(cameras), _ptr(muls), MODES[mode], z_near, z_far,
+                                  s_min, s_max, V, h, w, *[_ptr(t) for t in vs], _ptr(v_params), _stream()),
+               "pm_unproject_bwd")
+    return v_params
+
+
+def camera_prep(cameras, h: int, w: int):
+    """cameras [n,18] -> viewmats [n,4,4], Ks [n,3,3], all on the device, no host sync."""
+    L = _lib.load()
+    cameras = _req(cameras, torch.float32, "cameras").reshape(-1, 18)
+    n = cameras.shape[0]
+    viewmats = torch.empty(n, 4, 4, device=cameras.device)
+    Ks = torch.empty(n, 3, 3, device=cameras.device)
+    _lib.check(L.pm_camera_prep(_ptr(cameras), n, h, w, _ptr(viewmats), _ptr(Ks), _stream()), "pm_camera_prep")
+    return viewmats, Ks
+
+
+# ------------------------------------------------------------------ stage 2
+def project_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d=0.3, near_plane=0.01,
+                far_plane=1e10, radius_clip=0.0, count_tiles=True):
+    L = _lib.load()
+    means, quats, scales = (_req(t, torch.float32, n) for t, n in ((means, "means"), (quats, "quats"), (scales, "scales")))
+    viewmats, Ks = _req(viewmats, torch.float32, "viewmats"), _req(Ks, torch.float32, "Ks")
+    N, C = means.shape[0], viewmats.shape[0]
+    dev = means.device
+    radii = torch.empty(C, N, dtype=torch.int32, device=dev)
+    means2d = torch.empty(C, N, 2, device=dev)
+    depths = torch.empty(C, N, device=dev)
+    conics = torch.empty(C, N, 3, device=dev)
+    tpg = torch.empty(C, N, dtype=torch.int32, device=dev) if count_tiles else None
+    _lib.check(L.pm_project_fwd(_ptr(means), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks), N, C, width,
+                                height, TILE, eps2d, near_plane, far_plane, radius_clip, _ptr(radii),
+                                _ptr(means2d), _ptr(depths), _ptr(conics), _ptr(tpg), _stream()), "pm_project_fwd")
+    return radii, means2d, depths, conics, tpg
+
+
+def project_bwd(means, quats, scales, viewmats, Ks, width, height, radii, conics, v_means2d, v_depths,
+                v_conics, eps2d=0.3):
+    L = _lib.load()
+    means, quats, scales = (_req(t, torch.float32, "in") for t in (means, quats, scales))
+    viewmats, Ks = _req(viewmats, torch.float32, "viewmats"), _req(Ks, torch.float32, "Ks")
+    N, C = means.shape[0], viewmats.shape[0]
+    v_means2d, v_depths, v_conics = (_opt(t, torch.float32, "grad") for t in (v_means2d, v_depths, v_conics))
+    v_means, v_quats, v_scales = torch.empty_like(means), torch.empty_like(quats), torch.empty_like(scales)
+    _lib.check(L.pm_project_bwd(_ptr(means), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks), N, C, width,
+                                height, eps2d, _ptr(radii), _ptr(conics), _ptr(v_means2d), _ptr(v_depths),
+                                _ptr(v_conics), _ptr(v_means), _ptr(v_quats), _ptr(v_scales), _stream()),
+               "pm_project_bwd")
+    return v_means, v_quats, v_scales
+
+
+# ------------------------------------------------------------------ stage 3
+def scan_tiles(tiles_per_gauss):
+    """Inclusive prefix sum -> (cum int32 [P], n_isects device int32 [1])."""
+    L = _lib.load()
+    tpg = _req(tiles_per_gauss, torch.int32, "tiles_per_gauss").reshape(-1)
+    P = tpg.numel()
+    dev = tpg.device
+    cum = torch.empty(P, dtype=torch.int32, device=dev)
+    n_out = torch.empty(1, dtype=torch.int32, device=dev)
+    ws_bytes = int(L.pm_scan_workspace_bytes(P))
+    ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=dev)
+    _lib.check(L.pm_scan_tiles(_ptr(tpg), P, _ptr(cum), _ptr(n_out), _ptr(ws), ws_bytes, _stream()), "pm_scan_tiles")
+    return cum, n_out
+
+
+def bin_emit(means2d, radii, depths, cum, width, height, capacity: int):
+    L = _lib.load()
+    C, N = radii.shape
+    tw, th = tile_grid(width, height)
+    dev = radii.device
+    ids = torch.empty(capacity, dtype=torch.int64, device=dev)
+    flat = torch.empty(capacity, dtype=torch.int32, device=dev)
+    _lib.check(L.pm_bin_emit(_ptr(means2d), _ptr(radii), _ptr(depths), _ptr(cum), N, C, TILE, tw, th,
+                             _ptr(ids), _ptr(flat), capacity, _stream()), "pm_bin_emit")
+    return ids, flat
+
+
+def sort_pairs(keys, vals, end_bit: int, d_n=None, return_workspace=False):
+    """Stable radix sort of (int64 key, int32 value) pairs on bits [0, end_bit).
+    `keys`/`vals` are clobbered (ping-pong buffer 0). Returns the sorted pair."""
+    L = _lib.load()
+    assert keys.dtype == torch.int64 and vals.dtype == torch.int32 and keys.is_cuda and vals.is_cuda
+    assert keys.is_contiguous() and vals.is_contiguous() and keys.numel() == vals.numel()
+    n = keys.numel()
+    keys1, vals1 = torch.empty_like(keys), torch.empty_like(vals)
+    ws_bytes = int(L.pm_sort_workspace_bytes(n))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
+    sel = ctypes.c_int(0)
+    _lib.check(L.pm_sort_pairs(_ptr(keys), _ptr(vals), _ptr(keys1), _ptr(vals1), n, _ptr(d_n), end_bit,
+                               _ptr(ws), ws_bytes, ctypes.byref(sel), _stream()), "pm_sort_pairs")
+    out = (keys1, vals1) if sel.value == 1 else (keys, vals)
+    if return_workspace:
+        return out + (ws,)
+    return out
+
+
+def sort_error_flag(ws: torch.Tensor) -> int:
+    """Look-back timeout flag of a finished sort (debug aid; synchronises)."""
+    words = ws.view(torch.int32)
+    return int(words[8 * 256 + 8].item())
+
+
+def tile_offsets(sorted_ids, C: int, width: int, height: int, d_n=None):
+    L = _lib.load()
+    tw, th = tile_grid(width, height)
+    off = torch.empty(C, th, tw, dtype=torch.int32, device=sorted_ids.device)
+    _lib.check(L.pm_tile_offsets(_ptr(sorted_ids), sorted_ids.numel(), _ptr(d_n), C, tw, th, _ptr(off), _stream()),
+               "pm_tile_offsets")
+    return off
+
+
+# ------------------------------------------------------------------ stage 4
+def _colors_layout(colors, C, N):
+    if colors is None:
+        return None, 0, 0
+    if colors.dim() == 3:
+        assert colors.shape[:2] == (C, N), f"colors {tuple(colors.shape)} vs C={C}, N={N}"
+        return colors, 1, colors.shape[-1]
+    assert colors.dim() == 2 and colors.shape[0] == N
+    return colors, 0, colors.shape[-1]
+
+
+def composite_fwd(means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width,
+                  height, d_n=None):
+    """-> render [C,H,W,CD], alphas [C,H,W], last_ids [C,H,W] (see pm_composite_fwd)."""
+    L = _lib.load()
+    C, N = means2d.shape[:2]
+    colors, per_cam, D = _colors_layout(colors, C, N)
+    CD = D + (0 if depths is None else 1)
+    dev = means2d.device
+    render = torch.empty(C, height, width, CD, device=dev)
+    alphas = torch.empty(C, height, width, device=dev)
+    last_ids = torch.empty(C, height, width, dtype=torch.int32, device=dev)
+    _lib.check(L.pm_composite_fwd(_ptr(means2d), _ptr(conics), _ptr(opacities), _ptr(colors), per_cam, D,
+                                  _ptr(depths), _ptr(backgrounds), _ptr(offsets), _ptr(flatten_ids),
+                                  flatten_ids.numel(), _ptr(d_n), N, C, width, height, TILE, _ptr(render),
+                                  _ptr(alphas), _ptr(last_ids), _stream()), "pm_composite_fwd")
+    return render, alphas, last_ids
+
+
+def composite_bwd(means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width,
+                  height, alphas, last_ids, v_render, v_alphas, d_n=None):
+    L = _lib.load()
+    C, N = means2d.shape[:2]
+    colors, per_cam, D = _colors_layout(colors, C, N)
+    v_render = _opt(v_render, torch.float32, "v_render")
+    v_alphas = _opt(v_alphas, torch.float32, "v_alphas")
+    v_means2d = torch.zeros_like(means2d)
+    v_conics = torch.zeros_like(conics)
+    v_colors = torch.zeros_like(colors) if colors is not None else None
+    v_opac = torch.zeros_like(opacities)
+    v_depths = torch.zeros_like(depths) if depths is not None else None
+    _lib.check(L.pm_composite_bwd(_ptr(means2d), _ptr(conics), _ptr(opacities), _ptr(colors), per_cam, D,
+                                  _ptr(depths), _ptr(backgrounds), _ptr(offsets), _ptr(flatten_ids),
+                                  flatten_ids.numel(), _ptr(d_n), N, C, width, height, TILE, _ptr(alphas),
+                                  _ptr(last_ids), _ptr(v_render), _ptr(v_alphas), _ptr(v_means2d),
+                                  _ptr(v_conics), _ptr(v_colors), _ptr(v_opac), _ptr(v_depths), _stream()),
+               "pm_composite_bwd")
+    return v_means2d, v_conics, v_colors, v_opac, v_depths

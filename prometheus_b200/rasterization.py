@@ -1,0 +1,200 @@
+"""`rasterization(...)` — the operator the reference binds to.
+
+Same signature, argument meaning, return tuple and error behaviour as
+`gsplat.rasterization` (gsplat 1.4.0) for the configuration Prometheus uses
+(reference call site prometheus/modules/renderers/gaussians_renderer.py:413-427:
+packed=False, sh_degree=None, pinhole, classic mode), computed by the sm_100a
+kernels behind include/prometheus_gs.h. `meta` exposes every intermediate
+upstream exposes (radii, means2d, depths, conics, opacities, tiles_per_gauss,
+isect_ids, flatten_ids, isect_offsets, tile_width, ...) — they are the bit-exact
+parity surface — and `meta["means2d"]` is a graph tensor that accepts
+`retain_grad()` (used at gaussians_renderer.py:428-435 and by the SDS refiner).
+
+Autograd is wired as two nodes like upstream (projection -> compositing), so
+gradients reach means/quats/scales/opacities/colors/backgrounds.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import ops
+
+_RENDER_MODES = ("RGB", "D", "ED", "RGB+D", "RGB+ED")
+
+
+class _Project(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
+                radius_clip):
+        radii, means2d, depths, conics, tpg = ops.project_fwd(
+            means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip)
+        ctx.save_for_backward(means, quats, scales, viewmats, Ks, radii, conics)
+        ctx.dims = (width, height, eps2d)
+        ctx.mark_non_differentiable(radii, tpg)
+        return means2d, depths, conics, radii, tpg
+
+    @staticmethod
+    def backward(ctx, v_means2d, v_depths, v_conics, _v_radii, _v_tpg):
+        means, quats, scales, viewmats, Ks, radii, conics = ctx.saved_tensors
+        width, height, eps2d = ctx.dims
+        v_means, v_quats, v_scales = ops.project_bwd(means, quats, scales, viewmats, Ks, width, height, radii,
+                                                     conics, v_means2d, v_depths, v_conics, eps2d)
+        return (v_means, v_quats, v_scales) + (None,) * 8
+
+
+class _Composite(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width,
+                height, d_n):
+        means2d, conics = means2d.contiguous(), conics.contiguous()
+        opacities = opacities.contiguous()
+        colors = None if colors is None else colors.contiguous()
+        depths = None if depths is None else depths.contiguous()
+        backgrounds = None if backgrounds is None else backgrounds.contiguous().float()
+        render, alphas, last_ids = ops.composite_fwd(means2d, conics, opacities, colors, depths, backgrounds,
+                                                     offsets, flatten_ids, width, height, d_n)
+        ctx.save_for_backward(means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids,
+                              alphas, last_ids, d_n)
+        ctx.dims = (width, height)
+        ctx.last_ids = last_ids
+        return render, alphas.unsqueeze(-1)
+
+    @staticmethod
+    def backward(ctx, v_render, v_alphas):
+        (means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, alphas, last_ids,
+         d_n) = ctx.saved_tensors
+        width, height = ctx.dims
+        v_alphas2 = None if v_alphas is None else v_alphas.squeeze(-1)
+        v_means2d, v_conics, v_colors, v_opac, v_depths = ops.composite_bwd(
+            means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width, height, alphas,
+            last_ids, v_render, v_alphas2, d_n)
+        v_bg = None
+        if backgrounds is not None and ctx.needs_input_grad[5] and v_render is not None:
+            D = backgrounds.shape[-1]
+            v_bg = (v_render[..., :D] * (1.0 - alphas).unsqueeze(-1)).sum(dim=(1, 2))
+        return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None, None
+
+
+def isect_tiles(means2d, radii, depths, tiles_per_gauss, width, height, C):
+    """Tile binning + depth sort (no gradient). Returns sorted isect_ids, flatten_ids and
+    isect_offsets. One host sync: n_isects sizes the output arrays, as upstream."""
+    cum, n_dev = ops.scan_tiles(tiles_per_gauss)
+    n_isects = int(n_dev.item())
+    tw, th = ops.tile_grid(width, height)
+    ids, flat = ops.bin_emit(means2d, radii, depths, cum, width, height, n_isects)
+    tb, cb = ops.key_bits(tw, th, C)
+    ids, flat = ops.sort_pairs(ids, flat, 32 + tb + cb)
+    offsets = ops.tile_offsets(ids, C, width, height)
+    return ids, flat, offsets
+
+
+def rasterization(
+    means: Tensor,  # [N, 3]
+    quats: Tensor,  # [N, 4]
+    scales: Tensor,  # [N, 3]
+    opacities: Tensor,  # [N]
+    colors: Tensor,  # [(C,) N, D]
+    viewmats: Tensor,  # [C, 4, 4]
+    Ks: Tensor,  # [C, 3, 3]
+    width: int,
+    height: int,
+    near_plane: float = 0.01,
+    far_plane: float = 1e10,
+    radius_clip: float = 0.0,
+    eps2d: float = 0.3,
+    sh_degree: Optional[int] = None,
+    packed: bool = True,
+    tile_size: int = 16,
+    backgrounds: Optional[Tensor] = None,
+    render_mode: str = "RGB",
+    sparse_grad: bool = False,
+    absgrad: bool = False,
+    rasterize_mode: str = "classic",
+    channel_chunk: int = 32,
+    distributed: bool = False,
+    camera_model: str = "pinhole",
+    covars: Optional[Tensor] = None,
+) -> Tuple[Tensor, Tensor, Dict]:
+    return _rasterize_core(means, quats, scales, opacities, colors, viewmats, Ks, width, height, near_plane,
+                           far_plane, radius_clip, eps2d, sh_degree, packed, tile_size, backgrounds, render_mode,
+                           sparse_grad, absgrad, rasterize_mode, channel_chunk, distributed, camera_model,
+                           covars, per_view_means2d=False)
+
+
+def _rasterize_core(means, quats, scales, opacities, colors, viewmats, Ks, width, height, near_plane=0.01,
+                    far_plane=1e10, radius_clip=0.0, eps2d=0.3, sh_degree=None, packed=True, tile_size=16,
+                    backgrounds=None, render_mode="RGB", sparse_grad=False, absgrad=False,
+                    rasterize_mode="classic", channel_chunk=32, distributed=False, camera_model="pinhole",
+                    covars=None, per_view_means2d=False):
+    """Body of `rasterization`. `per_view_means2d=True` (used by renderer.GaussianRenderer)
+    additionally returns meta["means2d_views"]: one [1,N,2] graph tensor per camera with
+    retain_grad() set, the batched equivalent of gaussians_renderer.py:428-445."""
+    N = means.shape[0]
+    C = viewmats.shape[0]
+    assert means.shape == (N, 3), means.shape
+    assert quats.shape == (N, 4), quats.shape
+    assert scales.shape == (N, 3), scales.shape
+    assert opacities.shape == (N,), opacities.shape
+    assert viewmats.shape == (C, 4, 4), viewmats.shape
+    assert Ks.shape == (C, 3, 3), Ks.shape
+    assert render_mode in _RENDER_MODES, render_mode
+    assert (colors.dim() == 2 and colors.shape[0] == N) or (colors.dim() == 3 and colors.shape[:2] == (C, N)), colors.shape
+    if backgrounds is not None:
+        assert backgrounds.shape == (C, colors.shape[-1]), backgrounds.shape
+    # what this drop-in covers is exactly the reference's configuration of the path
+    if packed:
+        raise NotImplementedError("prometheus_b200.rasterization: packed=True is not implemented "
+                                  "(the reference calls with packed=False, gaussians_renderer.py:425)")
+    for name, bad in (("sh_degree", sh_degree is not None), ("sparse_grad", sparse_grad), ("absgrad", absgrad),
+                      ("distributed", distributed), ("covars", covars is not None),
+                      ("rasterize_mode", rasterize_mode != "classic"), ("camera_model", camera_model != "pinhole"),
+                      ("tile_size", tile_size != 16)):
+        if bad:
+            raise NotImplementedError(f"prometheus_b200.rasterization: {name} is outside the reference's path")
+    if not means.is_cuda:
+        raise RuntimeError("prometheus_b200.rasterization needs CUDA tensors: there is no CPU fallback")
+
+    f32 = lambda t: t if t.dtype == torch.float32 else t.float()
+    means, quats, scales, opacities, colors = map(f32, (means, quats, scales, opacities, colors))
+    viewmats, Ks = f32(viewmats).contiguous(), f32(Ks).contiguous()
+
+    means2d, depths, conics, radii, tpg = _Project.apply(
+        means.contiguous(), quats.contiguous(), scales.contiguous(), viewmats, Ks, width, height, eps2d,
+        near_plane, far_plane, radius_clip)
+    isect_ids, flatten_ids, isect_offsets = isect_tiles(means2d.detach(), radii, depths.detach(), tpg, width,
+                                                        height, C)
+
+    means2d_views = None
+    means2d_in = means2d
+    if per_view_means2d:
+        means2d_views = [v.unsqueeze(0) for v in means2d.unbind(0)]
+        if means2d.requires_grad:
+            for v in means2d_views:
+                v.retain_grad()
+            means2d_in = torch.cat(means2d_views, dim=0)
+
+    with_depth = render_mode in ("D", "ED", "RGB+D", "RGB+ED")
+    only_depth = render_mode in ("D", "ED")
+    D = colors.shape[-1]
+    if (0 if only_depth else D) + (1 if with_depth else 0) > 4:
+        raise NotImplementedError("prometheus_b200.rasterization: at most 4 render channels (RGB + depth)")
+    render, alphas = _Composite.apply(
+        means2d_in, conics, opacities, None if only_depth else colors, depths if with_depth else None,
+        None if only_depth else backgrounds, isect_offsets, flatten_ids, width, height, None)
+    if render_mode in ("ED", "RGB+ED"):
+        render = torch.cat([render[..., :-1], render[..., -1:] / alphas.clamp(min=1e-10)], dim=-1)
+
+    tw, th = ops.tile_grid(width, height)
+    meta = {
+        "camera_ids": None, "gaussian_ids": None, "radii": radii, "means2d": means2d, "depths": depths,
+        "conics": conics, "opacities": opacities.unsqueeze(0).expand(C, N), "tile_width": tw, "tile_height": th,
+        "tiles_per_gauss": tpg, "isect_ids": isect_ids, "flatten_ids": flatten_ids,
+        "isect_offsets": isect_offsets, "width": width, "height": height, "tile_size": tile_size,
+        "n_cameras": C,
+    }
+    if means2d_views is not None:
+        meta["means2d_views"] = means2d_views
+    return render, alphas, meta

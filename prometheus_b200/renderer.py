@@ -1,0 +1,128 @@
+"""Module-level mirror of the reference's renderer module
+(prometheus/modules/renderers/gaussians_renderer.py): `GaussianConverter` and
+`GaussianRenderer` with the same constructor arguments, forward signatures,
+buffer names (`converter.muls`, `renderer.bg_color` — checkpoints are loaded with
+strict=True in paper/stage1_eval.py:167), return tuples and side attributes
+(`.radii`, `.viewspace_points`), computed B200-natively:
+
+  * GaussianConverter.forward = ONE fused unproject kernel (fwd) / ONE (bwd)
+    instead of ~40 ATen launches (gaussians_renderer.py:210-287);
+  * GaussianRenderer.forward renders all N views of a scene in one batched launch
+    set (C = N cameras), with the camera conversion done on the device — none of
+    the reference's per-view `.cpu()` round trips, numpy inverses, host-built K
+    uploads or the trailing torch.cuda.synchronize() (:453-472, :404-412, :510).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+from torch import nn
+
+from . import ops
+from .rasterization import _rasterize_core, rasterization
+
+
+class _Unproject(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, params, cameras, muls, mode, z_near, z_far, s_min, s_max):
+        params = params.float().contiguous()
+        cameras = cameras.float().contiguous()
+        out = ops.unproject_fwd(params, cameras, muls, mode, z_near, z_far, s_min, s_max)
+        ctx.save_for_backward(params, cameras, muls)
+        ctx.cfg = (mode, z_near, z_far, s_min, s_max)
+        return out
+
+    @staticmethod
+    def backward(ctx, v_xyz, v_rgb, v_opacity, v_scales, v_quats):
+        params, cameras, muls = ctx.saved_tensors
+        v_params = ops.unproject_bwd(params, cameras, muls, *ctx.cfg, v_xyz, v_rgb, v_opacity, v_scales, v_quats)
+        return v_params, None, None, None, None, None, None, None
+
+
+class GaussianConverter(nn.Module):
+    """Drop-in for the reference class of the same name (gaussians_renderer.py:173-287)."""
+
+    def __init__(self, gs_convert_mode: str = "mvsplat", z_near: float = 0.001, z_far: float = 100,
+                 s_min: float = 0.001, s_max: float = 1.0):
+        super().__init__()
+        if gs_convert_mode not in ops.MODES:
+            raise ValueError("unsupport decode type")
+        self.gs_convert_mode = gs_convert_mode
+        self.z_near, self.z_far = z_near, z_far
+        self.s_min, self.s_max = s_min, s_max
+        self.gaussian_channels = [3, 2, 1, 1, 3, 4]
+        if gs_convert_mode == "director3d":
+            muls = torch.Tensor([0.01] * 3 + [0.01] * 2 + [0.05] * 1 + [0.05] * 1 + [0.005] * 3 + [0.005] * 4).reshape(1, -1)
+            self.register_buffer("muls", muls)
+            self.muls = self.muls / self.muls.max()
+        else:
+            self.register_buffer("muls", torch.ones(1, 14))
+
+    def forward(self, local_gaussian_params, cameras):
+        B, N, C, h, w = local_gaussian_params.shape
+        assert C == sum(self.gaussian_channels)
+        xyz, rgb, opacity, scales, quats = _Unproject.apply(
+            local_gaussian_params.reshape(B * N, C, h, w), cameras.reshape(B * N, 18), self.muls,
+            self.gs_convert_mode, float(self.z_near), float(self.z_far), float(self.s_min), float(self.s_max))
+        return (xyz.reshape(B, -1, 3), rgb.reshape(B, -1, 1, 3), opacity.reshape(B, -1, 1),
+                scales.reshape(B, -1, 3), quats.reshape(B, -1, 4))
+
+
+class GaussianRenderer(nn.Module):
+    """Drop-in for the reference class of the same name (gaussians_renderer.py:289-512)."""
+
+    def __init__(self, sh_degree=0, background=[1, 1, 1]):
+        super().__init__()
+        self.sh_degree = sh_degree
+        self.register_buffer("bg_color", torch.tensor(background).float())
+        self.radii: List[torch.Tensor] = []
+        self.viewspace_points: List[torch.Tensor] = []
+
+    def _backgrounds(self, bg_color, n_views: int, device) -> torch.Tensor:
+        # reference :381-386 — 'random' draws a fresh colour per rendered view
+        if isinstance(bg_color, str) and bg_color == "random":
+            return torch.rand(n_views, 3, device=device)
+        if bg_color is None:
+            return self.bg_color.to(device).expand(n_views, 3).contiguous()
+        return torch.as_tensor(bg_color, dtype=torch.float32, device=device).reshape(1, 3).expand(n_views, 3).contiguous()
+
+    def forward(self, cameras, gaussians, scaling_modifier=1.0, bg_color=None, h=256, w=256):
+        B, N = cameras.shape[:2]
+        xyz, features, opacity, scales, rotations = gaussians
+        device = xyz.device
+        self.radii = []
+        self.viewspace_points = []
+        viewmats, Ks = ops.camera_prep(cameras.reshape(B * N, 18), h, w)
+        viewmats, Ks = viewmats.reshape(B, N, 4, 4), Ks.reshape(B, N, 3, 3)
+        images, depths, masks = [], [], []
+        for i in range(B):
+            bgs = self._backgrounds(bg_color, N, device)
+            sc = scales[i] if scaling_modifier == 1.0 else scales[i] * scaling_modifier
+            render, alphas, info = _rasterize_core(
+                means=xyz[i], quats=rotations[i], scales=sc, opacities=opacity[i].squeeze(-1),
+                colors=features[i][:, 0], viewmats=viewmats[i], Ks=Ks[i], backgrounds=bgs, width=int(w),
+                height=int(h), render_mode="RGB+ED", packed=False, per_view_means2d=True)
+            images.append(render[..., :3].permute(0, 3, 1, 2))
+            depths.append(render[..., 3:].permute(0, 3, 1, 2))
+            masks.append(alphas.permute(0, 3, 1, 2).clamp(0, 1))
+            for j in range(N):
+                self.radii.append(info["radii"][j])
+                self.viewspace_points.append(info["means2d_views"][j])
+        images = torch.stack(images, dim=0) * 2 - 1
+        depths = torch.stack(depths, dim=0)
+        masks = torch.stack(masks, dim=0)
+        return images, depths, masks, None, None
+
+
+def install_as_gsplat() -> None:
+    """Make `from gsplat import rasterization` (gaussians_renderer.py:11) resolve to
+    this package. Call before `prometheus.modules` is imported."""
+    import sys
+    import types
+
+    mod = types.ModuleType("gsplat")
+    mod.rasterization = rasterization
+    mod.__version__ = "1.4.0+prometheus_b200"
+    mod.__doc__ = "prometheus_b200 drop-in for the gsplat.rasterization operator"
+    sys.modules["gsplat"] = mod

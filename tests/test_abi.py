@@ -1,0 +1,79 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds, loads and exports
+every symbol include/prometheus_gs.h declares; argument validation happens on the
+host before anything is enqueued (so it is testable without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from prometheus_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "prometheus_gs.h")).read()
+    return sorted(set(re.findall(r"PM_API[^;(]*?\b(pm_\w+)\s*\(", hdr)))
+
+
+def test_header_declares_expected_surface():
+    syms = declared_symbols()
+    for s in ("pm_unproject_fwd", "pm_unproject_bwd", "pm_camera_prep", "pm_project_fwd", "pm_project_bwd",
+              "pm_scan_tiles", "pm_bin_emit", "pm_sort_pairs", "pm_tile_offsets", "pm_composite_fwd",
+              "pm_composite_bwd", "pm_abi_version"):
+        assert s in syms
+    assert set(syms) == set(_lib.SIGNATURES)  # the ctypes binding mirrors the header one to one
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    assert os.path.exists(_lib.library_path())
+    for s in declared_symbols():
+        assert hasattr(lib, s), s
+    assert lib.pm_abi_version() == 1
+    assert lib.pm_status_string(0) == b"ok"
+    assert b"workspace" in lib.pm_status_string(-3)
+
+
+def test_no_torch_or_oracle_in_the_abi():
+    """The boundary is plain C: the shared library must not link torch or the oracle."""
+    import subprocess
+
+    out = subprocess.run(["ldd", _lib.library_path()], capture_output=True, text=True).stdout
+    assert "torch" not in out and "oracle" not in out and "c10" not in out
+
+
+def test_argument_errors_are_reported_before_launch():
+    lib = _lib.load()
+    null = ctypes.c_void_p(None)
+    one = ctypes.c_void_p(16)  # never dereferenced: validation fails first
+    assert lib.pm_unproject_fwd(null, null, null, 0, 0.01, 100.0, 0.001, 1.0, 1, 4, 4, null, null, null, null, null, null) == -1
+    assert lib.pm_unproject_fwd(one, one, one, 7, 0.01, 100.0, 0.001, 1.0, 1, 4, 4, one, one, one, one, one, null) == -2
+    assert lib.pm_project_fwd(one, one, one, one, one, 4, 1, 32, 32, 8, 0.3, 0.01, 1e10, 0.0, one, one, one, one, null, null) == -2  # tile_size 8
+    assert lib.pm_project_fwd(one, one, one, one, one, -1, 1, 32, 32, 16, 0.3, 0.01, 1e10, 0.0, one, one, one, one, null, null) == -1
+    sel = ctypes.c_int(-1)
+    assert lib.pm_sort_pairs(one, one, one, one, 100, null, 40, one, 8, ctypes.byref(sel), null) == -3  # workspace too small
+    assert lib.pm_sort_pairs(one, one, one, one, 1 << 31, null, 40, one, 1 << 40, ctypes.byref(sel), null) == -5
+    assert lib.pm_sort_pairs(null, null, null, null, 0, null, 44, null, 0, ctypes.byref(sel), null) == 0 and sel.value == 0
+    assert lib.pm_composite_fwd(one, one, one, one, 0, 5, null, null, one, one, 10, null, 4, 1, 32, 32, 16, one, one, one, null) == -2
+    assert lib.pm_sort_workspace_bytes(1 << 20) >= (1 << 20) // 4096 * 1024 * 4
+    assert lib.pm_scan_workspace_bytes(1 << 20) >= (1 << 20) // 2048 * 4
+
+
+def test_ops_refuse_cpu_tensors():
+    """No CPU fallback: handing the product CPU tensors is an error, not a slow path."""
+    import torch
+
+    import prometheus_b200 as pb
+
+    N = 8
+    with pytest.raises(RuntimeError, match="no CPU"):
+        pb.rasterization(torch.zeros(N, 3), torch.ones(N, 4), torch.ones(N, 3), torch.ones(N), torch.ones(N, 3),
+                         torch.eye(4)[None], torch.eye(3)[None], 32, 32, packed=False)
+    with pytest.raises(NotImplementedError):
+        pb.rasterization(torch.zeros(N, 3), torch.ones(N, 4), torch.ones(N, 3), torch.ones(N), torch.ones(N, 3),
+                         torch.eye(4)[None], torch.eye(3)[None], 32, 32)  # packed=True default upstream
+    with pytest.raises(AssertionError):
+        pb.rasterization(torch.zeros(N, 2), torch.ones(N, 4), torch.ones(N, 3), torch.ones(N), torch.ones(N, 3),
+                         torch.eye(4)[None], torch.eye(3)[None], 32, 32, packed=False)
