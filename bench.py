@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the GS-decoder rendering hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (our CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...  (CPU reference arm)
+
+Workload (BASELINE.json configs[1], "C2"): 8 input views x 512^2 RGB-D maps ->
+2,097,152 pixel-aligned Gaussians (unproject) -> 8 target views at 512^2 (project,
+tile-bin, radix sort, alpha composite). One STEP = one such decode+render batch of
+synthetic input. At N>1 every rank renders its own scene (scene sharding, no
+data-path collective) => weak scaling; value = all ranks' pixels / max-over-ranks time.
+
+metric: rendered Mpix/s, forward. Extra keys: Gaussians/s, fwd+bwd numbers, the
+per-stage breakdown with algorithmic bytes, `roofline` for the dominant kernel,
+`cpu_baseline` (the C oracle on all host cores, bounded sample) and `e2e`
+(host buffers in, host buffers out, copies inside the timed region).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "rendered Mpix/s (fwd: unproject+project+bin/sort+composite)"
+UNIT = "Mpix/s"
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = "/tmp/pm_clocks_%d_%d.csv" % (os.getpid(), gpu_index)
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        self.f.close()
+        sm, smax, reasons = [], [], set()
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_reference_step(O, scene, gauss, n_views):
+    """One bounded sample of the workload on the CPU oracle: unproject all input views, then
+    render `n_views` of the target views (project + bin + sort + composite)."""
+    import numpy as np
+
+    from prometheus_b200 import scenes
+
+    t0 = time.perf_counter()
+    if gauss is None:
+        gauss = O.unproject(scene.params.numpy(), scene.cameras_in.numpy(), mode="mvsplat", z_near=scenes.Z_NEAR,
+                            z_far=scenes.Z_FAR, s_min=scenes.S_MIN, s_max=scenes.S_MAX)
+    t_unproj = time.perf_counter() - t0
+    S = scene.size_out
+    t0 = time.perf_counter()
+    vm, K = O.camera_prep(scene.cameras_out[0, :n_views].numpy(), S, S)
+    O.forward_pipeline(gauss["xyz"][0], gauss["rotations"][0], gauss["scales"][0], gauss["opacity"][0, :, 0],
+                       gauss["features"][0, :, 0], vm, K, S, S, backgrounds=np.ones((n_views, 3), np.float32),
+                       with_depth=True, want_fragile=False)
+    t_render = time.perf_counter() - t0
+    return gauss, t_unproj, t_render
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path. The reference is pure
+    Python whose kernels live in the un-vendored gsplat wheel (not installable here), so this arm
+    times the oracle port (oracle/gs_oracle.c, OpenMP, all host threads)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import gs_oracle as O
+    from prometheus_b200 import scenes
+
+    O.build()
+    cores = O.num_threads()
+    scene = scenes.make_scene(args.config)
+    S, V = scene.size_out, scene.cameras_out.shape[1]
+    k = args.ref_views  # bounded sample: k of the V target views per step (+ the full unproject)
+    times = []
+    for it in range(args.warmup + args.steps):
+        _, t_u, t_r = cpu_reference_step(O, scene, None, k)
+        if it >= args.warmup:
+            times.append(t_u * k / V + t_r)  # unproject cost attributed pro rata to the rendered views
+    t = sum(times) / len(times)
+    value = k * S * S / t / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, scene), "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "per step: unproject of all input views (pro-rated) + %d of %d target views "
+                                   "rendered by oracle/gs_oracle.c (OpenMP)" % (k, V)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gaussians_per_s": k * scene.n_gaussians / t,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(cfg, scene):
+    B, Vi = scene.params.shape[:2]
+    s = scene.params.shape[-1]
+    return "%s: %d scene x %d views x %d^2 RGB-D -> %d Gaussians, %d target views %d^2" % (
+        cfg, B, Vi, s, scene.n_gaussians, scene.cameras_out.shape[1], scene.size_out)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--ref-views", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bwd", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from prometheus_b200 import GaussianConverter, GaussianRenderer, ops, scenes
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert torch.cuda.is_available(), "bench.py (ours) needs a GPU: there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # every rank owns one scene of the named config (scene sharding; seeds differ per rank)
+    scene = scenes.make_scene(args.config, seed=1234 + 1000 * rank)
+    S = scene.size_out
+    B, V_out = scene.cameras_out.shape[:2]
+    pixels = B * V_out * S * S
+    conv = GaussianConverter("mvsplat", z_near=scenes.Z_NEAR, z_far=scenes.Z_FAR, s_min=scenes.S_MIN, s_max=scenes.S_MAX).to(dev)
+    rend = GaussianRenderer(background=[1, 1, 1]).to(dev)
+    params_h = scene.params.pin_memory()
+    cams_in_h = scene.cameras_in.pin_memory()
+    cams_out_h = scene.cameras_out.pin_memory()
+    params_d, cams_in_d, cams_out_d = params_h.to(dev), cams_in_h.to(dev), cams_out_h.to(dev)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_fwd(params, cin, cout):
+        with torch.no_grad():
+            g = conv(params, cin)
+            return rend(cout, g, bg_color=None, h=S, w=S)
+
+    def step_fwdbwd(params, cin, cout, target):
+        p = params.detach().requires_grad_(True)
+        g = conv(p, cin)
+        images, depths, masks, _, _ = rend(cout, g, bg_color=None, h=S, w=S)
+        loss = scenes.render_loss(images, depths, masks, target)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ops.PROFILE = [] if profile else None
+        n0 = ops.LAUNCHES
+        evs = []
+        for _ in range(steps):
+            flush_buf.fill_(1)  # L2 flush, outside the timed events
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        launches = ops.LAUNCHES - n0
+        prof, ops.PROFILE = ops.PROFILE, None
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms, launches, prof
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    total_ms, launches, prof = timed(lambda: step_fwd(params_d, cams_in_d, cams_out_d), args.steps, args.warmup, profile=True)
+    clocks = sampler.stop()
+    ms_per_step = total_ms / args.steps
+    value = world * pixels / (ms_per_step * 1e-3) / 1e6
+
+    # ---- per-stage breakdown (CUDA events on the launching stream, inside the timed region)
+    stage_ms = {}
+    for name, e0, e1 in prof:
+        stage_ms.setdefault(name, []).append(e0.elapsed_time(e1))
+    stage_avg = {k: sum(v) / args.steps for k, v in stage_ms.items()}  # per step (a stage may run B times)
+
+    # ---- algorithmic bytes from one instrumented forward
+    with torch.no_grad():
+        g = conv(params_d, cams_in_d)
+        vm, K = ops.camera_prep(cams_out_d[0], S, S)
+        from prometheus_b200.rasterization import _rasterize_core
+
+        r, a, meta = _rasterize_core(g[0][0], g[4][0], g[3][0], g[2][0, :, 0], g[1][0, :, 0], vm, K, S, S,
+                                     backgrounds=torch.ones(V_out, 3, device=dev), render_mode="RGB+ED", packed=False)
+        I = int(meta["isect_ids"].numel())
+        G = scene.n_gaussians
+        P = V_out * G
+        X = V_out * S * S
+        off = meta["isect_offsets"].flatten().long()
+        last = meta_last_ids(r, meta, ops, g, vm, K, S, V_out, dev)
+        tw = meta["tile_width"]
+        tiles_last = last.reshape(V_out, S // 16, 16, S // 16, 16).amax(dim=(2, 4)).flatten().long()
+        nxt = torch.cat([off[1:], torch.tensor([I], device=dev)])
+        nonempty = nxt > off
+        I_need = int(((tiles_last - off + 1).clamp(min=0) * nonempty).sum().item())
+    tb, cb = ops.key_bits(S // 16, S // 16, V_out)
+    passes = (32 + tb + cb + 7) // 8
+    bytes_alg = {
+        "unproject_fwd": 112 * G * B,
+        "project_fwd": (40 * G + 32 * P) * B,
+        "scan_tiles": 12 * P * B,
+        "bin_emit": (20 * P + 12 * I) * B,
+        "sort_pairs": (passes * 24 + 8) * I * B,
+        "tile_offsets": 8 * I * B,
+        "composite_fwd": (44 * I_need + 24 * X) * B,
+    }
+    peak, peak_src = read_peaks()
+    stages = {}
+    for k, ms in stage_avg.items():
+        if k in bytes_alg and ms > 0:
+            gbs = bytes_alg[k] / (ms * 1e-3) / 1e9
+            stages[k] = {"ms": round(ms, 4), "alg_bytes": bytes_alg[k], "GBps": round(gbs, 1), "frac_hbm": round(gbs / peak, 4)}
+        else:
+            stages[k] = {"ms": round(ms, 4)}
+    # dominant kernel: the single kernel with the largest share of the step. sort_pairs is a
+    # sequence of `passes`+2 kernels, so compare composite_fwd with one sort pass.
+    comp_ms = stage_avg.get("composite_fwd", 0.0)
+    sort_pass_ms = stage_avg.get("sort_pairs", 0.0) / max(passes, 1)
+    if comp_ms >= sort_pass_ms:
+        dom, dom_ms, dom_bytes = "composite_fwd_kernel", comp_ms / B, bytes_alg["composite_fwd"] / B
+    else:
+        dom, dom_ms, dom_bytes = "rs_onesweep_kernel", sort_pass_ms / B, 24 * I
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": round(dom_ms, 4),
+                "alg_bytes_per_launch": int(dom_bytes),
+                "note": "composite is FP32/MUFU-issue bound, not HBM bound (see DESIGN.md); I_need=%d of I=%d" % (I_need, I)}
+
+    # ---- e2e: host buffers in, host buffers out, copies inside the timed region
+    out_h = [torch.empty(B, V_out, c, S, S).pin_memory() for c in (3, 1, 1)]
+
+    def step_e2e():
+        p = params_h.to(dev, non_blocking=True)
+        ci = cams_in_h.to(dev, non_blocking=True)
+        co = cams_out_h.to(dev, non_blocking=True)
+        outs = step_fwd(p, ci, co)
+        for dst, src in zip(out_h, outs[:3]):
+            dst.copy_(src, non_blocking=True)
+
+    e2e_ms, _, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+    e2e_ms /= args.steps
+    h2d = params_h.numel() * 4 + cams_in_h.numel() * 4 + cams_out_h.numel() * 4
+    d2h = sum(t.numel() * 4 for t in out_h)
+    e2e = {"value": world * pixels / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 4)}
+
+    # ---- fwd+bwd (training-style step with the synthetic render loss)
+    extra = {}
+    if not args.no_bwd:
+        target = (torch.rand(B, V_out, 3, S, S, device=dev) * 2 - 1)
+        bsteps = max(3, args.steps // 2)
+        bwd_ms, bl, bprof = timed(lambda: step_fwdbwd(params_d, cams_in_d, cams_out_d, target), bsteps, 3, profile=True)
+        bwd_ms /= bsteps
+        bst = {}
+        for name, e0, e1 in bprof:
+            bst[name] = bst.get(name, 0.0) + e0.elapsed_time(e1) / bsteps
+        extra["fwd_bwd"] = {"value": world * pixels / (bwd_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": round(bwd_ms, 4),
+                            "gaussians_per_s": world * B * V_out * G / (bwd_ms * 1e-3),
+                            "stages_ms": {k: round(v, 4) for k, v in bst.items()}}
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle port on all host cores, bounded sample
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import gs_oracle as O
+
+        O.build()
+        k = 1
+        gauss, t_u, t_r = cpu_reference_step(O, scene, None, k)       # warm-up + measure view 0
+        gauss, _, t_r2 = cpu_reference_step(O, scene, gauss, k)
+        t_r = min(t_r, t_r2)
+        t = t_u * k / V_out + t_r
+        cpu_baseline = {"value": k * S * S / t / 1e6, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
+                        "sample": "oracle/gs_oracle.c (OpenMP): full unproject %.2fs (pro-rated) + 1 of %d target "
+                                  "views rendered in %.2fs" % (t_u, V_out, t_r)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args.config, scene), "parallelism": "scene-sharded x%d" % world,
+                       "l2": "256 MiB buffer written between timed steps (L2 flush, outside the events)"},
+            "gaussians_per_s": world * B * V_out * G / (ms_per_step * 1e-3),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "stages": stages,
+            "n_isects": I, "n_isects_needed": I_need,
+        }
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def meta_last_ids(r, meta, ops, g, vm, K, S, V_out, dev):
+    """last_ids of the forward (needed for I_need): re-run the composite stage alone."""
+    import torch
+
+    _, _, last = ops.composite_fwd(meta["means2d"].contiguous(), meta["conics"].contiguous(), g[2][0, :, 0].contiguous(),
+                                   g[1][0, :, 0].contiguous(), meta["depths"].contiguous(),
+                                   torch.ones(V_out, 3, device=dev), meta["isect_offsets"], meta["flatten_ids"], S, S)
+    return last
+
+
+if __name__ == "__main__":
+    main()

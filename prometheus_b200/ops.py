@@ -16,6 +16,39 @@ from . import _lib
 TILE = 16
 MODES = {"mvsplat": 0, "gslrm": 1, "director3d": 2}
 
+# ---- instrumentation (used by bench.py): how many of OUR kernels were launched, and, when
+# `PROFILE` is a list, a (name, start_event, end_event) record per C-ABI call, taken with CUDA
+# events on the launching stream.
+LAUNCHES = 0
+PROFILE = None
+
+
+def _instrument(name, n_launches):
+    def deco(fn):
+        import functools
+
+        @functools.wraps(fn)
+        def wrapper(*a, **k):
+            global LAUNCHES
+            n = n_launches(*a, **k) if callable(n_launches) else n_launches
+            LAUNCHES += n
+            if PROFILE is None:
+                return fn(*a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **k)
+            e1.record()
+            PROFILE.append((name, e0, e1))
+            return out
+
+        return wrapper
+
+    return deco
+
+
+def _sort_launches(keys, vals, end_bit, *a, **k):
+    return 2 + (end_bit + 7) // 8 if keys.numel() > 0 else 0
+
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -49,6 +82,7 @@ def key_bits(tile_width: int, tile_height: int, C: int) -> Tuple[int, int]:
 
 
 # ------------------------------------------------------------------ stage 1
+@_instrument("unproject_fwd", 1)
 def unproject_fwd(params, cameras, muls, mode, z_near, z_far, s_min, s_max, out=None):
     """params [V,14,h,w], cameras [V,18] -> (xyz [G,3], rgb [G,3], opacity [G], scales [G,3], quats [G,4]).
     `out` may hold five preallocated tensors (e.g. slots of an all-gather buffer)."""
@@ -72,6 +106,7 @@ def unproject_fwd(params, cameras, muls, mode, z_near, z_far, s_min, s_max, out=
     return xyz, rgb, opacity, scales, quats
 
 
+@_instrument("unproject_bwd", 1)
 def unproject_bwd(params, cameras, muls, mode, z_near, z_far, s_min, s_max, v_xyz, v_rgb, v_opacity,
                   v_scales, v_quats):
     L = _lib.load()
@@ -87,6 +122,7 @@ def unproject_bwd(params, cameras, muls, mode, z_near, z_far, s_min, s_max, v_xy
     return v_params
 
 
+@_instrument("camera_prep", 1)
 def camera_prep(cameras, h: int, w: int):
     """cameras [n,18] -> viewmats [n,4,4], Ks [n,3,3], all on the device, no host sync."""
     L = _lib.load()
@@ -99,6 +135,7 @@ def camera_prep(cameras, h: int, w: int):
 
 
 # ------------------------------------------------------------------ stage 2
+@_instrument("project_fwd", 1)
 def project_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d=0.3, near_plane=0.01,
                 far_plane=1e10, radius_clip=0.0, count_tiles=True):
     L = _lib.load()
@@ -117,6 +154,7 @@ def project_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d=0.3, ne
     return radii, means2d, depths, conics, tpg
 
 
+@_instrument("project_bwd", 1)
 def project_bwd(means, quats, scales, viewmats, Ks, width, height, radii, conics, v_means2d, v_depths,
                 v_conics, eps2d=0.3):
     L = _lib.load()
@@ -133,6 +171,7 @@ def project_bwd(means, quats, scales, viewmats, Ks, width, height, radii, conics
 
 
 # ------------------------------------------------------------------ stage 3
+@_instrument("scan_tiles", 3)
 def scan_tiles(tiles_per_gauss):
     """Inclusive prefix sum -> (cum int32 [P], n_isects device int32 [1])."""
     L = _lib.load()
@@ -147,6 +186,7 @@ def scan_tiles(tiles_per_gauss):
     return cum, n_out
 
 
+@_instrument("bin_emit", 1)
 def bin_emit(means2d, radii, depths, cum, width, height, capacity: int):
     L = _lib.load()
     C, N = radii.shape
@@ -159,6 +199,7 @@ def bin_emit(means2d, radii, depths, cum, width, height, capacity: int):
     return ids, flat
 
 
+@_instrument("sort_pairs", _sort_launches)
 def sort_pairs(keys, vals, end_bit: int, d_n=None, return_workspace=False):
     """Stable radix sort of (int64 key, int32 value) pairs on bits [0, end_bit).
     `keys`/`vals` are clobbered (ping-pong buffer 0). Returns the sorted pair."""
@@ -184,6 +225,7 @@ def sort_error_flag(ws: torch.Tensor) -> int:
     return int(words[8 * 256 + 8].item())
 
 
+@_instrument("tile_offsets", 1)
 def tile_offsets(sorted_ids, C: int, width: int, height: int, d_n=None):
     L = _lib.load()
     tw, th = tile_grid(width, height)
@@ -204,6 +246,7 @@ def _colors_layout(colors, C, N):
     return colors, 0, colors.shape[-1]
 
 
+@_instrument("composite_fwd", 1)
 def composite_fwd(means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width,
                   height, d_n=None):
     """-> render [C,H,W,CD], alphas [C,H,W], last_ids [C,H,W] (see pm_composite_fwd)."""
@@ -222,6 +265,7 @@ def composite_fwd(means2d, conics, opacities, colors, depths, backgrounds, offse
     return render, alphas, last_ids
 
 
+@_instrument("composite_bwd", 1)
 def composite_bwd(means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width,
                   height, alphas, last_ids, v_render, v_alphas, d_n=None):
     L = _lib.load()
