@@ -1,0 +1,69 @@
+"""Multi-GPU sharding of the hot path. One process per GPU,
+`torch.distributed` (NCCL over NVLink on the B200 box; gloo in the CPU tests).
+
+The path shards without any data-path collective along scenes and along target
+views. The one real exchange step: when ONE scene's input views are decoded on
+different ranks (config C5), every rank needs all Gaussians before it can render
+its slice of the target cameras -> a single all-gather of the packed per-rank
+Gaussian block (14 floats = 56 B per Gaussian). Each rank's unproject kernel
+writes straight into its slot of the gather buffer, so there is no staging copy
+on the send side.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+# floats per Gaussian in the packed block, in slot order
+FIELDS = (("xyz", 3), ("rgb", 3), ("opacity", 1), ("scales", 3), ("quats", 4))
+FLOATS_PER_GAUSSIAN = sum(n for _, n in FIELDS)  # 14
+
+
+def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced split of n items: the first n % world ranks get one extra."""
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def slot_views(slot: torch.Tensor, n_gauss: int):
+    """Carve one rank's flat slot [14 * n_gauss] into the five field tensors (views, no copy)."""
+    out, o = [], 0
+    for _, k in FIELDS:
+        t = slot[o:o + k * n_gauss]
+        out.append(t.view(n_gauss, k) if k > 1 else t.view(n_gauss))
+        o += k * n_gauss
+    return tuple(out)
+
+
+def gather_gaussians(unproject_into: Callable[[Sequence[torch.Tensor]], None], n_local: int,
+                     device, group: Optional[dist.ProcessGroup] = None):
+    """All ranks hold `n_local` Gaussians of one scene (equal counts). `unproject_into(slots)` must
+    fill the five field tensors of this rank's slot (on the GPU: `ops.unproject_fwd(..., out=slots)`).
+    Returns the full scene (xyz [G,3], rgb [G,3], opacity [G], scales [G,3], quats [G,4]) on every
+    rank, ordered by rank then local index — i.e. the same order a single-GPU unproject of all views
+    produces when views are sharded contiguously."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    buf = torch.empty(world, FLOATS_PER_GAUSSIAN * n_local, dtype=torch.float32, device=device)
+    unproject_into(slot_views(buf[rank], n_local))
+    if world > 1:
+        dist.all_gather_into_tensor(buf.view(-1), buf[rank].clone() if buf.device.type == "cpu" else buf[rank], group=group)
+    full, o = [], 0
+    for _, k in FIELDS:
+        t = buf[:, o:o + k * n_local]
+        full.append(t.reshape(world * n_local, k) if k > 1 else t.reshape(world * n_local))
+        o += k * n_local
+    return tuple(full)
+
+
+def render_sharded_views(render_fn: Callable[[torch.Tensor], Tuple[torch.Tensor, ...]], cameras: torch.Tensor,
+                         group: Optional[dist.ProcessGroup] = None):
+    """Target-view sharding: this rank renders cameras[shard_range(...)] with `render_fn`; no collective
+    (each rank keeps / consumes its own frames, e.g. its part of a trajectory video)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    s, e = shard_range(cameras.shape[0], world, rank)
+    return (s, e), render_fn(cameras[s:e])
