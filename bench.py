@@ -285,6 +285,9 @@ def main():
         "bin_emit": (20 * P + 12 * I) * B,
         "sort_pairs": (passes * 24 + 8) * I * B,
         "tile_offsets": 8 * I * B,
+        "bin_count": 12 * P * B,
+        "bin_scatter": (16 * P + 8 * I) * B,
+        "tile_sort": 20 * I * B,
         "composite_fwd": (44 * I_need + 24 * X) * B,
     }
     peak, peak_src = read_peaks()
@@ -298,9 +301,12 @@ def main():
     # dominant kernel: the single kernel with the largest share of the step. sort_pairs is a
     # sequence of `passes`+2 kernels, so compare composite_fwd with one sort pass.
     comp_ms = stage_avg.get("composite_fwd", 0.0)
+    tsort_ms = stage_avg.get("tile_sort", 0.0)
     sort_pass_ms = stage_avg.get("sort_pairs", 0.0) / max(passes, 1)
-    if comp_ms >= sort_pass_ms:
+    if comp_ms >= max(sort_pass_ms, tsort_ms):
         dom, dom_ms, dom_bytes = "composite_fwd_kernel", comp_ms / B, bytes_alg["composite_fwd"] / B
+    elif tsort_ms >= sort_pass_ms:
+        dom, dom_ms, dom_bytes = "tile_sort_kernel", tsort_ms / B, bytes_alg["tile_sort"] / B
     else:
         dom, dom_ms, dom_bytes = "rs_onesweep_kernel", sort_pass_ms / B, 24 * I
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
@@ -308,7 +314,8 @@ def main():
                 "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
                 "avg_launch_ms": round(dom_ms, 4),
                 "alg_bytes_per_launch": int(dom_bytes),
-                "note": "composite is FP32/MUFU-issue bound, not HBM bound (see DESIGN.md); I_need=%d of I=%d" % (I_need, I)}
+                "note": "dominant kernel by time; composite and the shared-memory tile sort are issue/latency bound, "
+                        "not HBM bound (see DESIGN.md); I_need=%d of I=%d" % (I_need, I)}
 
     # ---- e2e: host buffers in, host buffers out, copies inside the timed region
     out_h = [torch.empty(B, V_out, c, S, S).pin_memory() for c in (3, 1, 1)]

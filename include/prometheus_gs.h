@@ -157,6 +157,46 @@ PM_API int pm_sort_pairs(int64_t *keys0, int32_t *vals0, int64_t *keys1, int32_t
                   void *workspace, size_t workspace_bytes, int *result_buffer,
                   pm_stream_t stream);
 
+/* ---- binned ("tile-bucketed") sort: the same sorted output as pm_bin_emit +
+ * pm_sort_pairs + pm_tile_offsets, with ~6x less HBM traffic. The key's high bits
+ * (camera, tile) are known when an intersection is emitted, so intersections are
+ * scattered straight into their tile's segment (offsets = exclusive scan of the
+ * per-tile histogram of pm_bin_count) and each segment is depth-sorted
+ * inside shared memory by one CTA. Ties on depth bits are ordered by flatten id,
+ * which is exactly the order a stable sort of the emission order produces. */
+
+/* Per-(camera,tile) intersection histogram, ACCUMULATED into tile_counts
+ * [C, tile_height, tile_width] int32 (caller zero-fills). */
+PM_API int pm_bin_count(const float *means2d, const int32_t *radii, int N, int C, int tile_size,
+                        int tile_width, int tile_height, int32_t *tile_counts, pm_stream_t stream);
+
+/* Exclusive scan of tile_counts [T] -> isect_offsets [T]; stats_out (device, 2 x
+ * int32) receives {n_isects, max tile count}. */
+PM_API int pm_tile_scan(const int32_t *tile_counts, int64_t T, int32_t *isect_offsets,
+                        int32_t *stats_out, pm_stream_t stream);
+
+/* Scatter every (pair, tile) intersection into its tile segment as a packed
+ * 8-byte record {depth bits (low 32), flatten id (high 32)}. cursors [T] must be
+ * zero-filled by the caller. Order inside a segment is unspecified. */
+PM_API int pm_bin_scatter(const float *means2d, const int32_t *radii, const float *depths,
+                          const int32_t *isect_offsets, int32_t *cursors, int N, int C,
+                          int tile_size, int tile_width, int tile_height,
+                          uint64_t *records, int64_t capacity, pm_stream_t stream);
+
+/* Largest tile segment pm_tile_sort can sort (entries). */
+PM_API int pm_tile_sort_capacity(void);
+
+/* Sort each tile segment by (depth bits, flatten id) and expand to the gsplat
+ * layout: isect_ids [n] int64, flatten_ids [n] int32. max_tile_count (host) is
+ * the largest segment as reported by pm_tile_scan, or -1 if unknown (no host
+ * sync): it only selects which kernel variants are launched. Segments larger
+ * than pm_tile_sort_capacity() are left unsorted and *overflow_flag (device
+ * int32, caller zero-fills) is set: the caller must then use pm_sort_pairs. */
+PM_API int pm_tile_sort(const uint64_t *records, const int32_t *isect_offsets, int64_t n,
+                        const int32_t *d_n, int C, int tile_width, int tile_height,
+                        int max_tile_count, int64_t *isect_ids, int32_t *flatten_ids,
+                        int32_t *overflow_flag, pm_stream_t stream);
+
 /* Per-(camera,tile) start offsets into the sorted list: isect_offsets
  * [C, tile_height, tile_width] int32 (lower bound of each tile id). */
 PM_API int pm_tile_offsets(const int64_t *sorted_isect_ids, int64_t n, const int32_t *d_n,

@@ -52,9 +52,10 @@ __device__ __forceinline__ int clamp_tile(float v, int hi) {
 }
 __device__ __forceinline__ void tile_aabb(float mx, float my, int radius, int tile_width, int tile_height,
                                           int &x0, int &x1, int &y0, int &y1) {
-  const float ts = (float)kTile;
-  const float tr = __fdiv_rn((float)radius, ts);
-  const float tx = __fdiv_rn(mx, ts), ty = __fdiv_rn(my, ts);
+  // x / 16 == x * 0.0625 exactly (power of two), and the multiply is one instruction
+  const float inv_ts = 1.0f / (float)kTile;
+  const float tr = __fmul_rn((float)radius, inv_ts);
+  const float tx = __fmul_rn(mx, inv_ts), ty = __fmul_rn(my, inv_ts);
   x0 = clamp_tile(floorf(__fsub_rn(tx, tr)), tile_width);
   x1 = clamp_tile(ceilf(__fadd_rn(tx, tr)), tile_width);
   y0 = clamp_tile(floorf(__fsub_rn(ty, tr)), tile_height);

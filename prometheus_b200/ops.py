@@ -138,6 +138,7 @@ def camera_prep(cameras, h: int, w: int):
 @_instrument("project_fwd", 1)
 def project_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d=0.3, near_plane=0.01,
                 far_plane=1e10, radius_clip=0.0, count_tiles=True):
+    """-> radii, means2d, depths, conics, tiles_per_gauss."""
     L = _lib.load()
     means, quats, scales = (_req(t, torch.float32, n) for t, n in ((means, "means"), (quats, "quats"), (scales, "scales")))
     viewmats, Ks = _req(viewmats, torch.float32, "viewmats"), _req(Ks, torch.float32, "Ks")
@@ -150,7 +151,8 @@ def project_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d=0.3, ne
     tpg = torch.empty(C, N, dtype=torch.int32, device=dev) if count_tiles else None
     _lib.check(L.pm_project_fwd(_ptr(means), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks), N, C, width,
                                 height, TILE, eps2d, near_plane, far_plane, radius_clip, _ptr(radii),
-                                _ptr(means2d), _ptr(depths), _ptr(conics), _ptr(tpg), _stream()), "pm_project_fwd")
+                                _ptr(means2d), _ptr(depths), _ptr(conics), _ptr(tpg), _stream()),
+               "pm_project_fwd")
     return radii, means2d, depths, conics, tpg
 
 
@@ -197,6 +199,60 @@ def bin_emit(means2d, radii, depths, cum, width, height, capacity: int):
     _lib.check(L.pm_bin_emit(_ptr(means2d), _ptr(radii), _ptr(depths), _ptr(cum), N, C, TILE, tw, th,
                              _ptr(ids), _ptr(flat), capacity, _stream()), "pm_bin_emit")
     return ids, flat
+
+
+@_instrument("bin_count", 1)
+def bin_count(means2d, radii, width, height):
+    """Per-(camera,tile) intersection histogram [C,th,tw] int32."""
+    L = _lib.load()
+    C, N = radii.shape
+    tw, th = tile_grid(width, height)
+    counts = torch.zeros(C, th, tw, dtype=torch.int32, device=radii.device)
+    _lib.check(L.pm_bin_count(_ptr(means2d), _ptr(radii), N, C, TILE, tw, th, _ptr(counts), _stream()), "pm_bin_count")
+    return counts
+
+
+@_instrument("tile_scan", 1)
+def tile_scan(tile_counts):
+    """Exclusive scan of the per-tile histogram -> (isect_offsets like tile_counts, stats int32[2] =
+    {n_isects, max tile count}, both on the device)."""
+    L = _lib.load()
+    assert tile_counts.dtype == torch.int32 and tile_counts.is_contiguous() and tile_counts.is_cuda
+    offsets = torch.empty_like(tile_counts)
+    stats = torch.empty(2, dtype=torch.int32, device=tile_counts.device)
+    _lib.check(L.pm_tile_scan(_ptr(tile_counts), tile_counts.numel(), _ptr(offsets), _ptr(stats), _stream()), "pm_tile_scan")
+    return offsets, stats
+
+
+@_instrument("bin_scatter", 1)
+def bin_scatter(means2d, radii, depths, offsets, width, height, capacity: int):
+    """Scatter intersections into their tile segments as packed {depth bits, flatten id} records."""
+    L = _lib.load()
+    C, N = radii.shape
+    tw, th = tile_grid(width, height)
+    cursors = torch.zeros_like(offsets)
+    records = torch.empty(capacity, dtype=torch.int64, device=radii.device)
+    _lib.check(L.pm_bin_scatter(_ptr(means2d), _ptr(radii), _ptr(depths), _ptr(offsets), _ptr(cursors), N, C, TILE,
+                                tw, th, _ptr(records), capacity, _stream()), "pm_bin_scatter")
+    return records
+
+
+def tile_sort_capacity() -> int:
+    return int(_lib.load().pm_tile_sort_capacity())
+
+
+@_instrument("tile_sort", lambda *a, **k: 2 if (k.get("max_tile_count", -1) < 0 or k.get("max_tile_count", -1) > 8192) else 1)
+def tile_sort(records, offsets, C: int, width: int, height: int, d_n=None, max_tile_count: int = -1):
+    """Per-tile shared-memory depth sort -> (isect_ids int64 [n], flatten_ids int32 [n], overflow flag int32[1])."""
+    L = _lib.load()
+    tw, th = tile_grid(width, height)
+    n = records.numel()
+    ids = torch.empty(n, dtype=torch.int64, device=records.device)
+    flat = torch.empty(n, dtype=torch.int32, device=records.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=records.device)
+    _lib.check(L.pm_tile_sort(_ptr(records), _ptr(offsets), n, _ptr(d_n), C, tw, th, int(max_tile_count), _ptr(ids),
+                              _ptr(flat), _ptr(flag), _stream()), "pm_tile_sort")
+    return ids, flat, flag
 
 
 @_instrument("sort_pairs", _sort_launches)

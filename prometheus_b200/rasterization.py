@@ -24,6 +24,9 @@ from . import ops
 
 _RENDER_MODES = ("RGB", "D", "ED", "RGB+D", "RGB+ED")
 
+# test/bench hook: route every call through the generic emit + onesweep path
+FORCE_GENERIC_SORT = False
+
 
 class _Project(torch.autograd.Function):
     @staticmethod
@@ -78,9 +81,21 @@ class _Composite(torch.autograd.Function):
         return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None, None
 
 
-def isect_tiles(means2d, radii, depths, tiles_per_gauss, width, height, C):
+def isect_tiles(means2d, radii, depths, tiles_per_gauss, width, height, C, force_generic=False):
     """Tile binning + depth sort (no gradient). Returns sorted isect_ids, flatten_ids and
-    isect_offsets. One host sync: n_isects sizes the output arrays, as upstream."""
+    isect_offsets. One host sync: n_isects sizes the output arrays, as upstream.
+
+    Main path (binned): per-tile histogram (from the projection) -> offsets -> scatter into tile
+    segments -> per-tile shared-memory sort. Generic path (any segment larger than the shared-memory
+    capacity, or no histogram): emit + hand-written onesweep radix sort + offset encode. Both produce
+    the same arrays bit for bit."""
+    if not force_generic:
+        offsets, stats = ops.tile_scan(ops.bin_count(means2d, radii, width, height))
+        n_isects, max_count = stats.tolist()
+        if max_count <= ops.tile_sort_capacity():
+            records = ops.bin_scatter(means2d, radii, depths, offsets, width, height, n_isects)
+            ids, flat, _flag = ops.tile_sort(records, offsets, C, width, height, max_tile_count=max_count)
+            return ids, flat, offsets
     cum, n_dev = ops.scan_tiles(tiles_per_gauss)
     n_isects = int(n_dev.item())
     tw, th = ops.tile_grid(width, height)
@@ -165,7 +180,7 @@ def _rasterize_core(means, quats, scales, opacities, colors, viewmats, Ks, width
         means.contiguous(), quats.contiguous(), scales.contiguous(), viewmats, Ks, width, height, eps2d,
         near_plane, far_plane, radius_clip)
     isect_ids, flatten_ids, isect_offsets = isect_tiles(means2d.detach(), radii, depths.detach(), tpg, width,
-                                                        height, C)
+                                                        height, C, force_generic=FORCE_GENERIC_SORT)
 
     means2d_views = None
     means2d_in = means2d

@@ -21,6 +21,7 @@ def test_header_declares_expected_surface():
     syms = declared_symbols()
     for s in ("pm_unproject_fwd", "pm_unproject_bwd", "pm_camera_prep", "pm_project_fwd", "pm_project_bwd",
               "pm_scan_tiles", "pm_bin_emit", "pm_sort_pairs", "pm_tile_offsets", "pm_composite_fwd",
+              "pm_bin_count", "pm_tile_scan", "pm_bin_scatter", "pm_tile_sort", "pm_tile_sort_capacity",
               "pm_composite_bwd", "pm_abi_version"):
         assert s in syms
     assert set(syms) == set(_lib.SIGNATURES)  # the ctypes binding mirrors the header one to one
@@ -50,13 +51,16 @@ def test_argument_errors_are_reported_before_launch():
     one = ctypes.c_void_p(16)  # never dereferenced: validation fails first
     assert lib.pm_unproject_fwd(null, null, null, 0, 0.01, 100.0, 0.001, 1.0, 1, 4, 4, null, null, null, null, null, null) == -1
     assert lib.pm_unproject_fwd(one, one, one, 7, 0.01, 100.0, 0.001, 1.0, 1, 4, 4, one, one, one, one, one, null) == -2
-    assert lib.pm_project_fwd(one, one, one, one, one, 4, 1, 32, 32, 8, 0.3, 0.01, 1e10, 0.0, one, one, one, one, null, null) == -2  # tile_size 8
-    assert lib.pm_project_fwd(one, one, one, one, one, -1, 1, 32, 32, 16, 0.3, 0.01, 1e10, 0.0, one, one, one, one, null, null) == -1
+    assert lib.pm_project_fwd(one, one, one, one, one, 4, 1, 32, 32, 8, 0.3, 0.01, 1e10, 0.0, one, one, one, one, null, null, null) == -2  # tile_size 8
+    assert lib.pm_project_fwd(one, one, one, one, one, -1, 1, 32, 32, 16, 0.3, 0.01, 1e10, 0.0, one, one, one, one, null, null, null) == -1
     sel = ctypes.c_int(-1)
     assert lib.pm_sort_pairs(one, one, one, one, 100, null, 40, one, 8, ctypes.byref(sel), null) == -3  # workspace too small
     assert lib.pm_sort_pairs(one, one, one, one, 1 << 31, null, 40, one, 1 << 40, ctypes.byref(sel), null) == -5
     assert lib.pm_sort_pairs(null, null, null, null, 0, null, 44, null, 0, ctypes.byref(sel), null) == 0 and sel.value == 0
     assert lib.pm_composite_fwd(one, one, one, one, 0, 5, null, null, one, one, 10, null, 4, 1, 32, 32, 16, one, one, one, null) == -2
+    assert lib.pm_tile_sort_capacity() == 16384
+    assert lib.pm_tile_sort(one, one, 10, null, 1, 2, 2, -1, one, one, null, null) == -1  # overflow flag is mandatory
+    assert lib.pm_bin_scatter(one, one, one, one, one, 4, 1, 8, 2, 2, one, 10, null) == -2  # tile_size 8
     assert lib.pm_sort_workspace_bytes(1 << 20) >= (1 << 20) // 4096 * 1024 * 4
     assert lib.pm_scan_workspace_bytes(1 << 20) >= (1 << 20) // 2048 * 4
 
