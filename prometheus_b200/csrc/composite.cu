@@ -160,10 +160,47 @@ composite_fwd_kernel(const float *__restrict__ means2d, const float *__restrict_
 // ---------------------------------------------------------------------------
 // Backward.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float warp_sum(float v) {
+// Warp reduction of 10 gradient components with a halving butterfly: instead of reducing each
+// component over all 32 lanes (10 x 5 = 50 shuffles), every step pairs lanes and SPLITS the
+// component set between the two partners (10 -> 5 -> 3 -> 2 -> 1 -> 1), so 5+3+2+1+1 = 12 shuffles
+// leave the full sum of component `comp_of_lane()` on the even lanes that own one.
+__device__ __forceinline__ int comp_of_lane(int lane) {
+  if (lane & 1) return -1;                      // the odd partner holds a copy
+  const int b8 = (lane >> 3) & 1, b4 = (lane >> 2) & 1, b2 = (lane >> 1) & 1;
+  int sub;
+  if (!b8) sub = b4 ? (b2 ? -1 : 2) : b2;       // {0,1,2}
+  else sub = b4 ? -1 : 3 + b2;                  // {3,4}
+  return sub < 0 ? -1 : sub + ((lane & 16) ? 5 : 0);
+}
+
+__device__ __forceinline__ float butterfly_reduce10(const float (&v)[10], int lane) {
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+  float a[5], b[3], c[2];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+  for (int i = 0; i < 5; ++i) {
+    const float send = h16 ? v[i] : v[i + 5];
+    const float keep = h16 ? v[i + 5] : v[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float hi = i < 2 ? a[i + 3] : 0.0f;
+    const float send = h8 ? a[i] : hi;
+    const float keep = h8 ? hi : a[i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float hi = i < 1 ? b[2] : 0.0f;
+    const float send = h4 ? b[i] : hi;
+    const float keep = h4 ? hi : b[i];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float send = h2 ? c[0] : c[1];
+  const float keep = h2 ? c[1] : c[0];
+  float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  return d;
 }
 
 constexpr int kGradStride = 11;  // 10 gradient components per staged Gaussian (+1: bank spread)
@@ -216,16 +253,22 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
         const float4 t = reinterpret_cast<const float4 *>(v_render)[pix];
         vr[0] = t.x; vr[1] = t.y; vr[2] = t.z; vr[3] = t.w;
       } else {
-        for (int k = 0; k < CD; ++k) vr[k] = v_render[pix * CD + k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < CD) vr[k] = v_render[pix * CD + k];
       }
     }
     if (v_alphas) va = v_alphas[pix];
   }
   // -T_final * sum_k bg_k v_render_k, folded into the alpha-gradient seed
   float bg_dot = 0.0f;
-  if (backgrounds)
-    for (int k = 0; k < D; ++k) bg_dot += __ldg(backgrounds + cam * D + k) * vr[k];
+  if (backgrounds) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < D) bg_dot += __ldg(backgrounds + cam * D + k) * vr[k];
+  }
   const float va_seed = T_final * (va - bg_dot);
+  const int my_comp = comp_of_lane(lane);
 
   if (tid == 0) s_max_last = -1;
   __syncthreads();
@@ -276,38 +319,29 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
         const float alpha = fminf(0.999f, b.opac * vis);
         const bool valid = (batch_start + t <= my_last) && !(sigma < 0.0f || alpha < kAlphaMin);
         if (!__any_sync(0xffffffffu, valid)) continue;
-        float g_c0 = 0.0f, g_c1 = 0.0f, g_c2 = 0.0f, g_c3 = 0.0f;
-        float g_q0 = 0.0f, g_q1 = 0.0f, g_q2 = 0.0f, g_mx = 0.0f, g_my = 0.0f, g_o = 0.0f;
+        float gv[10] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};  // c0..c3, q0..q2, mx, my, o
         if (valid) {
           const GaussC c = sC[t];
           const float ra = 1.0f / (1.0f - alpha);
           T *= ra;
           const float fac = alpha * T;
-          g_c0 = fac * vr[0]; g_c1 = fac * vr[1]; g_c2 = fac * vr[2]; g_c3 = fac * vr[3];
+          gv[0] = fac * vr[0]; gv[1] = fac * vr[1]; gv[2] = fac * vr[2]; gv[3] = fac * vr[3];
           float v_alpha = (c.c0 * T - buf0 * ra) * vr[0] + (c.c1 * T - buf1 * ra) * vr[1] +
                           (c.c2 * T - buf2 * ra) * vr[2] + (c.c3 * T - buf3 * ra) * vr[3];
           v_alpha += va_seed * ra;
           if (b.opac * vis <= 0.999f) {
             const float v_sigma = -b.opac * vis * v_alpha;
-            g_q0 = 0.5f * v_sigma * dx * dx;
-            g_q1 = v_sigma * dx * dy;
-            g_q2 = 0.5f * v_sigma * dy * dy;
-            g_mx = v_sigma * (b.cx * dx + b.cy * dy);
-            g_my = v_sigma * (b.cy * dx + b.cz * dy);
-            g_o = vis * v_alpha;
+            gv[4] = 0.5f * v_sigma * dx * dx;
+            gv[5] = v_sigma * dx * dy;
+            gv[6] = 0.5f * v_sigma * dy * dy;
+            gv[7] = v_sigma * (b.cx * dx + b.cy * dy);
+            gv[8] = v_sigma * (b.cy * dx + b.cz * dy);
+            gv[9] = vis * v_alpha;
           }
           buf0 += c.c0 * fac; buf1 += c.c1 * fac; buf2 += c.c2 * fac; buf3 += c.c3 * fac;
         }
-        g_c0 = warp_sum(g_c0); g_c1 = warp_sum(g_c1); g_c2 = warp_sum(g_c2); g_c3 = warp_sum(g_c3);
-        g_q0 = warp_sum(g_q0); g_q1 = warp_sum(g_q1); g_q2 = warp_sum(g_q2);
-        g_mx = warp_sum(g_mx); g_my = warp_sum(g_my); g_o = warp_sum(g_o);
-        if (lane < 10) {
-          float v = g_c0;
-          v = lane == 1 ? g_c1 : v; v = lane == 2 ? g_c2 : v; v = lane == 3 ? g_c3 : v;
-          v = lane == 4 ? g_q0 : v; v = lane == 5 ? g_q1 : v; v = lane == 6 ? g_q2 : v;
-          v = lane == 7 ? g_mx : v; v = lane == 8 ? g_my : v; v = lane == 9 ? g_o : v;
-          atomicAdd(&sG[t * kGradStride + lane], v);
-        }
+        const float total = butterfly_reduce10(gv, lane);
+        if (my_comp >= 0) atomicAdd(&sG[t * kGradStride + my_comp], total);
       }
     }
     __syncthreads();
