@@ -6,8 +6,10 @@ Public surface (mirrors the reference, see DESIGN.md / INTEGRATION.md):
   rasterization(...)            gsplat.rasterization contract
   GaussianConverter, GaussianRenderer   module-level mirrors
   install_as_gsplat()           plug the operator under the unmodified reference
+  DecodeRenderPipeline          streaming host->device->host decode+render (copies overlap compute)
 """
 from .rasterization import rasterization  # noqa: F401
 from .renderer import GaussianConverter, GaussianRenderer, install_as_gsplat  # noqa: F401
+from .pipeline import DecodeRenderPipeline  # noqa: F401
 
-__all__ = ["rasterization", "GaussianConverter", "GaussianRenderer", "install_as_gsplat"]
+__all__ = ["rasterization", "GaussianConverter", "GaussianRenderer", "install_as_gsplat", "DecodeRenderPipeline"]

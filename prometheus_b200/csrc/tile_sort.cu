@@ -174,14 +174,13 @@ constexpr int kTsRadix = 256;
 constexpr int kTsCapSmall = 8192;
 constexpr int kTsCapLarge = 16384;
 
-// 9-bit label match (8 digit bits + "invalid" bit) with ballots: lanes with equal labels.
-__device__ __forceinline__ unsigned match_label9(uint32_t label) {
+// 8-bit digit match with ballots: mask of the lanes holding the same digit.
+__device__ __forceinline__ unsigned match_digit8(uint32_t d) {
   unsigned peers = 0xffffffffu;
 #pragma unroll
-  for (int b = 0; b < 9; ++b) {
-    const bool bit = (label >> b) & 1u;
-    const unsigned m = __ballot_sync(0xffffffffu, bit);
-    peers &= bit ? m : ~m;
+  for (int b = 0; b < 8; ++b) {
+    const unsigned m = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+    peers &= ((d >> b) & 1u) ? m : ~m;
   }
   return peers;
 }
@@ -254,6 +253,10 @@ tile_sort_kernel(const uint64_t *__restrict__ records, const int32_t *__restrict
     kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
   }
   const uint32_t range = kmax - kmin;  // only the bits of (key - min) that vary need sorting
+  // Work on tile-relative keys. Empty slots become all-ones: digit 255 in every pass, and since they
+  // start behind every real element a stable sort keeps them there — no validity test in the ranking.
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) dk[k] = (chunk0 + k * 32 + lane < cnt) ? dk[k] - kmin : 0xffffffffu;
 
   for (int shift = 0; shift < 32 && (range >> shift) != 0; shift += 8) {
     for (int i = tid; i < kTsWarps * kTsRadix / 2; i += kTsThreads) reinterpret_cast<uint32_t *>(warp_hist)[i] = 0;
@@ -261,13 +264,11 @@ tile_sort_kernel(const uint64_t *__restrict__ records, const int32_t *__restrict
     // rank inside the warp's chunk (stable: item order is (k, lane))
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
-      const int slot = chunk0 + k * 32 + lane;
-      const bool valid = slot < cnt;
-      const uint32_t d = valid ? (((dk[k] - kmin) >> shift) & 0xffu) : 256u;
-      const unsigned peers = HW_MATCH ? __match_any_sync(0xffffffffu, d) : match_label9(d);
+      const uint32_t d = (dk[k] >> shift) & 0xffu;
+      const unsigned peers = HW_MATCH ? __match_any_sync(0xffffffffu, d) : match_digit8(d);
       const unsigned lower = peers & ((1u << lane) - 1);
       uint32_t base = 0;
-      if (valid && lower == 0) {
+      if (lower == 0) {
         base = warp_hist[warp][d];
         warp_hist[warp][d] = (uint16_t)(base + __popc(peers));
       }
@@ -304,21 +305,15 @@ tile_sort_kernel(const uint64_t *__restrict__ records, const int32_t *__restrict
     // scatter to the sorted slot, then read back in chunk order
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
-      const int slot = chunk0 + k * 32 + lane;
-      if (slot < cnt) {
-        const uint32_t d = ((dk[k] - kmin) >> shift) & 0xffu;
-        buf[digit_start[d] + warp_hist[warp][d] + (pk[k] >> 16)] = make_uint2(dk[k], pk[k] & 0xffffu);
-      }
+      const uint32_t d = (dk[k] >> shift) & 0xffu;
+      buf[digit_start[d] + warp_hist[warp][d] + (pk[k] >> 16)] = make_uint2(dk[k], pk[k] & 0xffffu);
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
-      const int slot = chunk0 + k * 32 + lane;
-      if (slot < cnt) {
-        const uint2 v = buf[slot];
-        dk[k] = v.x;
-        pk[k] = v.y;
-      }
+      const uint2 v = buf[chunk0 + k * 32 + lane];
+      dk[k] = v.x;
+      pk[k] = v.y;
     }
     __syncthreads();
   }
@@ -329,7 +324,7 @@ tile_sort_kernel(const uint64_t *__restrict__ records, const int32_t *__restrict
     const int slot = chunk0 + k * 32 + lane;
     if (slot < cnt) {
       const uint32_t fid = (uint32_t)(__ldg(reinterpret_cast<const unsigned long long *>(records) + (size_t)start + (pk[k] & 0xffffu)) >> 32);
-      buf[slot] = make_uint2(dk[k], fid);
+      buf[slot] = make_uint2(dk[k] + kmin, fid);
     }
   }
   __syncthreads();
@@ -431,8 +426,8 @@ int pm_tile_sort(const uint64_t *records, const int32_t *isect_offsets, int64_t 
   static bool attr_set = false;
   static int small_variant = 0;
   if (!attr_set) {
-    const char *e = getenv("PM_TILE_SORT_VARIANT");  // dev knob: 0 = 1024x8 (default), 1 = 512x16
-    small_variant = e ? atoi(e) : 0;
+    const char *e = getenv("PM_TILE_SORT_VARIANT");  // dev knob: 1 = 512 thr x 16 (default, 2 CTAs/SM), 0 = 1024x8, 2 = 1024x8 + match.any
+    small_variant = e ? atoi(e) : 1;
     if (cudaFuncSetAttribute(pm::tile_sort_kernel<1024, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)pm::ts_smem_bytes<1024, 8>()) != cudaSuccess ||
         cudaFuncSetAttribute(pm::tile_sort_kernel<1024, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
