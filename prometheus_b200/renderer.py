@@ -72,6 +72,10 @@ class GaussianConverter(nn.Module):
 class GaussianRenderer(nn.Module):
     """Drop-in for the reference class of the same name (gaussians_renderer.py:289-512)."""
 
+    # cameras rendered per batched launch set: bounds the per-pair / per-intersection buffers
+    # (32 B per (camera, Gaussian) pair) when a long trajectory is rendered from a big scene
+    view_chunk = 8
+
     def __init__(self, sh_degree=0, background=[1, 1, 1]):
         super().__init__()
         self.sh_degree = sh_degree
@@ -99,16 +103,22 @@ class GaussianRenderer(nn.Module):
         for i in range(B):
             bgs = self._backgrounds(bg_color, N, device)
             sc = scales[i] if scaling_modifier == 1.0 else scales[i] * scaling_modifier
-            render, alphas, info = _rasterize_core(
-                means=xyz[i], quats=rotations[i], scales=sc, opacities=opacity[i].squeeze(-1),
-                colors=features[i][:, 0], viewmats=viewmats[i], Ks=Ks[i], backgrounds=bgs, width=int(w),
-                height=int(h), render_mode="RGB+ED", packed=False, per_view_means2d=True)
-            images.append(render[..., :3].permute(0, 3, 1, 2))
-            depths.append(render[..., 3:].permute(0, 3, 1, 2))
-            masks.append(alphas.permute(0, 3, 1, 2).clamp(0, 1))
-            for j in range(N):
-                self.radii.append(info["radii"][j])
-                self.viewspace_points.append(info["means2d_views"][j])
+            im_i, de_i, ma_i = [], [], []
+            for c0 in range(0, N, self.view_chunk):
+                c1 = min(N, c0 + self.view_chunk)
+                render, alphas, info = _rasterize_core(
+                    means=xyz[i], quats=rotations[i], scales=sc, opacities=opacity[i].squeeze(-1),
+                    colors=features[i][:, 0], viewmats=viewmats[i, c0:c1], Ks=Ks[i, c0:c1], backgrounds=bgs[c0:c1],
+                    width=int(w), height=int(h), render_mode="RGB+ED", packed=False, per_view_means2d=True)
+                im_i.append(render[..., :3].permute(0, 3, 1, 2))
+                de_i.append(render[..., 3:].permute(0, 3, 1, 2))
+                ma_i.append(alphas.permute(0, 3, 1, 2).clamp(0, 1))
+                for j in range(c1 - c0):
+                    self.radii.append(info["radii"][j])
+                    self.viewspace_points.append(info["means2d_views"][j])
+            images.append(im_i[0] if len(im_i) == 1 else torch.cat(im_i, 0))
+            depths.append(de_i[0] if len(de_i) == 1 else torch.cat(de_i, 0))
+            masks.append(ma_i[0] if len(ma_i) == 1 else torch.cat(ma_i, 0))
         images = torch.stack(images, dim=0) * 2 - 1
         depths = torch.stack(depths, dim=0)
         masks = torch.stack(masks, dim=0)

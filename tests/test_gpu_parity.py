@@ -483,3 +483,20 @@ def test_full_size_properties_c2():
     r3, _, _ = rasterization(xyz[0], rot[0], scl[0], op[0, :, 0], feat[0, :, 0] * 0.5, vm, K, 512, 512,
                              backgrounds=bg * 0.5, render_mode="RGB", packed=False)
     assert allclose(r3.cpu().numpy(), 0.5 * r[..., :3].cpu().numpy(), atol=1e-6, rtol=1e-5)
+
+
+def test_gather_gaussians_single_rank_matches_plain_unproject():
+    """world_size 1: the gather path (unproject writes into the rank's slot of the packed buffer) returns the
+    same Gaussians, in the same order, as the plain converter."""
+    from prometheus_b200 import GaussianConverter, ops, parallel, scenes
+
+    sc = scenes.make_scene("C1", seed=21, views_in=3, size_in=24)
+    conv = GaussianConverter("mvsplat", z_near=0.01, z_far=100.0, s_min=0.001, s_max=1.0).to(DEV)
+    ref = conv(sc.params.to(DEV), sc.cameras_in.to(DEV))
+    muls = torch.ones(14, device=DEV)
+    n_local = sc.n_gaussians
+    full = parallel.gather_gaussians(
+        lambda slots: ops.unproject_fwd(sc.params[0].to(DEV), sc.cameras_in[0].to(DEV), muls, "mvsplat", 0.01, 100.0,
+                                        0.001, 1.0, out=slots), n_local, torch.device(DEV))
+    for got, want in zip(full, (ref[0][0], ref[1][0, :, 0], ref[2][0, :, 0], ref[3][0], ref[4][0])):
+        assert torch.equal(got, want)
