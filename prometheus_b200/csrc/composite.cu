@@ -31,8 +31,34 @@ constexpr float kAlphaMin = 1.0f / 255.0f;
 constexpr float kTStop = 1e-4f;
 
 struct __align__(16) GaussA { float mx, my, hx, hy; };      // mean + half extents of the alpha>=1/255 box
-struct __align__(16) GaussB { float cx, cy, cz, opac; };    // conic + opacity
+struct __align__(16) GaussB { float cx, cy, cz, opac; };    // conic pre-scaled to base-2 exponent units + opacity
 struct __align__(16) GaussC { float c0, c1, c2, c3; };      // colour channels (+ depth), zero padded
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+// Shared-memory accesses of the hot loops go through explicit 32-bit shared addresses: with plain
+// array indexing nvcc re-derived the shared window base (S2R SR_CgaCtaId + LEA) on every iteration.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// -sigma * log2(e) from the pre-scaled conic; written with explicit roundings so the forward and the
+// backward kernel evaluate bit-identical alphas (their skip / stop decisions must agree).
+__device__ __forceinline__ float power2(float Q0, float Q1, float Q2, float dx, float dy) {
+  return __fmaf_rn(Q0, __fmul_rn(dx, dx), __fmaf_rn(Q2, __fmul_rn(dy, dy), __fmul_rn(Q1, __fmul_rn(dx, dy))));
+}
 
 // Gather one Gaussian of the sorted list into the staging records.
 __device__ __forceinline__ void gather(int32_t f, int N, const float *__restrict__ means2d,
@@ -61,7 +87,8 @@ __device__ __forceinline__ void gather(int32_t f, int N, const float *__restrict
     if (!(hx == hx) || !(hy == hy)) hx = hy = 3e38f;
   }
   a = GaussA{m.x, m.y, hx, hy};
-  b = GaussB{q0, q1, q2, o};
+  // exp(-sigma) = 2^(Q0 dx^2 + Q1 dx dy + Q2 dy^2) with Q0 = -q0/2 * log2e, Q1 = -q1 * log2e, Q2 = -q2/2 * log2e
+  b = GaussB{q0 * (-0.5f * kLog2e), q1 * (-kLog2e), q2 * (-0.5f * kLog2e), o};
   float ch[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   const float *col = colors + (size_t)(colors_per_camera ? f : g) * D;
   for (int k = 0; k < D; ++k) ch[k] = __ldg(col + k);
@@ -103,6 +130,7 @@ composite_fwd_kernel(const float *__restrict__ means2d, const float *__restrict_
   float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f, o3 = 0.0f;
   int last = 0;
   bool done = !inside;
+  const uint32_t aA = smem_u32(sA), aB = smem_u32(sB), aC = smem_u32(sC);
 
   for (int batch_start = range_start; batch_start < range_end; batch_start += kBatch) {
     if (__syncthreads_count(done) == kBatch) break;
@@ -115,27 +143,28 @@ composite_fwd_kernel(const float *__restrict__ means2d, const float *__restrict_
       const int j = sub + lane;
       bool hit = false;
       if (j < batch_size) {
-        const GaussA a = sA[j];
-        hit = fabsf(a.mx - wcx) <= a.hx + 3.5f && fabsf(a.my - wcy) <= a.hy + 1.5f;
+        const float4 a = lds128(aA + j * 16);
+        hit = fabsf(a.x - wcx) <= a.z + 3.5f && fabsf(a.y - wcy) <= a.w + 1.5f;
       }
       unsigned mask = __ballot_sync(0xffffffffu, hit);
-      while (mask) {
+      while (mask) {  // branch-free body: every lane evaluates, selects decide what sticks
         const int t = sub + __ffs(mask) - 1;
         mask &= mask - 1;
-        if (done) continue;
-        const GaussA a = sA[t];
-        const GaussB b = sB[t];
-        const float dx = a.mx - px, dy = a.my - py;
-        const float sigma = 0.5f * (b.cx * dx * dx + b.cz * dy * dy) + b.cy * dx * dy;
-        const float alpha = fminf(0.999f, b.opac * __expf(-sigma));
-        if (sigma < 0.0f || alpha < kAlphaMin) continue;
+        const float2 m = lds64(aA + t * 16);
+        const float4 b = lds128(aB + t * 16);
+        const float4 c = lds128(aC + t * 16);
+        const float dx = m.x - px, dy = m.y - py;
+        const float p = power2(b.x, b.y, b.z, dx, dy);  // = -sigma * log2e
+        const float alpha = fminf(0.999f, b.w * ex2_approx(p));
         const float next_T = T * (1.0f - alpha);
-        if (next_T <= kTStop) { done = true; continue; }
-        const GaussC c = sC[t];
-        const float vis = alpha * T;
-        o0 += c.c0 * vis; o1 += c.c1 * vis; o2 += c.c2 * vis; o3 += c.c3 * vis;
-        last = batch_start + t;
-        T = next_T;
+        const bool contrib = !done && !(p > 0.0f) && alpha >= kAlphaMin;  // p > 0 <=> sigma < 0
+        const bool stop = contrib && next_T <= kTStop;
+        const bool add = contrib && !stop;
+        done = done || stop;
+        const float w = add ? alpha * T : 0.0f;
+        o0 = fmaf(c.x, w, o0); o1 = fmaf(c.y, w, o1); o2 = fmaf(c.z, w, o2); o3 = fmaf(c.w, w, o3);
+        T = add ? next_T : T;
+        last = add ? batch_start + t : last;
       }
       if (__all_sync(0xffffffffu, done)) break;
     }
@@ -269,6 +298,7 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
   }
   const float va_seed = T_final * (va - bg_dot);
   const int my_comp = comp_of_lane(lane);
+  const uint32_t aA = smem_u32(sA), aB = smem_u32(sB), aC = smem_u32(sC);
 
   if (tid == 0) s_max_last = -1;
   __syncthreads();
@@ -303,42 +333,44 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
       const int j = sub + lane;
       bool hit = false;
       if (j < batch_size) {
-        const GaussA a = sA[j];
-        hit = fabsf(a.mx - wcx) <= a.hx + 3.5f && fabsf(a.my - wcy) <= a.hy + 1.5f;
+        const float4 a = lds128(aA + j * 16);
+        hit = fabsf(a.x - wcx) <= a.z + 3.5f && fabsf(a.y - wcy) <= a.w + 1.5f;
       }
       unsigned mask = __ballot_sync(0xffffffffu, hit);
       while (mask) {
         const int bit = 31 - __clz(mask);
         mask &= ~(1u << bit);
         const int t = sub + bit;
-        const GaussA a = sA[t];
-        const GaussB b = sB[t];
-        const float dx = a.mx - px, dy = a.my - py;
-        const float sigma = 0.5f * (b.cx * dx * dx + b.cz * dy * dy) + b.cy * dx * dy;
-        const float vis = __expf(-sigma);
-        const float alpha = fminf(0.999f, b.opac * vis);
-        const bool valid = (batch_start + t <= my_last) && !(sigma < 0.0f || alpha < kAlphaMin);
+        const float2 m = lds64(aA + t * 16);
+        const float4 b = lds128(aB + t * 16);  // pre-scaled conic (see gather) + opacity
+        const float dx = m.x - px, dy = m.y - py;
+        const float p = power2(b.x, b.y, b.z, dx, dy);  // same expression as the forward: identical alpha bits
+        const float vis = ex2_approx(p);
+        const float alpha = fminf(0.999f, b.w * vis);
+        const bool valid = (batch_start + t <= my_last) && !(p > 0.0f) && alpha >= kAlphaMin;
         if (!__any_sync(0xffffffffu, valid)) continue;
         float gv[10] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};  // c0..c3, q0..q2, mx, my, o
         if (valid) {
-          const GaussC c = sC[t];
+          const float4 c = lds128(aC + t * 16);
           const float ra = 1.0f / (1.0f - alpha);
           T *= ra;
           const float fac = alpha * T;
           gv[0] = fac * vr[0]; gv[1] = fac * vr[1]; gv[2] = fac * vr[2]; gv[3] = fac * vr[3];
-          float v_alpha = (c.c0 * T - buf0 * ra) * vr[0] + (c.c1 * T - buf1 * ra) * vr[1] +
-                          (c.c2 * T - buf2 * ra) * vr[2] + (c.c3 * T - buf3 * ra) * vr[3];
+          float v_alpha = (c.x * T - buf0 * ra) * vr[0] + (c.y * T - buf1 * ra) * vr[1] +
+                          (c.z * T - buf2 * ra) * vr[2] + (c.w * T - buf3 * ra) * vr[3];
           v_alpha += va_seed * ra;
-          if (b.opac * vis <= 0.999f) {
-            const float v_sigma = -b.opac * vis * v_alpha;
+          if (b.w * vis <= 0.999f) {
+            const float v_sigma = -b.w * vis * v_alpha;
             gv[4] = 0.5f * v_sigma * dx * dx;
             gv[5] = v_sigma * dx * dy;
             gv[6] = 0.5f * v_sigma * dy * dy;
-            gv[7] = v_sigma * (b.cx * dx + b.cy * dy);
-            gv[8] = v_sigma * (b.cy * dx + b.cz * dy);
+            // conic.x dx + conic.y dy etc. from the pre-scaled values: conic.x = -2/log2e * b.x, conic.y = -1/log2e * b.y
+            const float s2 = v_sigma * (-1.0f / kLog2e);
+            gv[7] = s2 * (2.0f * b.x * dx + b.y * dy);
+            gv[8] = s2 * (b.y * dx + 2.0f * b.z * dy);
             gv[9] = vis * v_alpha;
           }
-          buf0 += c.c0 * fac; buf1 += c.c1 * fac; buf2 += c.c2 * fac; buf3 += c.c3 * fac;
+          buf0 += c.x * fac; buf1 += c.y * fac; buf2 += c.z * fac; buf3 += c.w * fac;
         }
         const float total = butterfly_reduce10(gv, lane);
         if (my_comp >= 0) atomicAdd(&sG[t * kGradStride + my_comp], total);
