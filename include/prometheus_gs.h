@@ -183,17 +183,21 @@ PM_API int pm_bin_scatter(const float *means2d, const int32_t *radii, const floa
                           int tile_size, int tile_width, int tile_height,
                           uint64_t *records, int64_t capacity, pm_stream_t stream);
 
-/* Largest tile segment pm_tile_sort can sort (entries). */
+/* Segment size pm_tile_sort sorts in one shared-memory pass (entries). Larger
+ * segments are first split by depth through `scratch` (see pm_tile_sort). */
 PM_API int pm_tile_sort_capacity(void);
 
 /* Sort each tile segment by (depth bits, flatten id) and expand to the gsplat
  * layout: isect_ids [n] int64, flatten_ids [n] int32. max_tile_count (host) is
  * the largest segment as reported by pm_tile_scan, or -1 if unknown (no host
- * sync): it only selects which kernel variants are launched. Segments larger
- * than pm_tile_sort_capacity() are left unsorted and *overflow_flag (device
- * int32, caller zero-fills) is set: the caller must then use pm_sort_pairs. */
-PM_API int pm_tile_sort(const uint64_t *records, const int32_t *isect_offsets, int64_t n,
-                        const int32_t *d_n, int C, int tile_width, int tile_height,
+ * sync). Segments above pm_tile_sort_capacity() need `scratch` (n x 8 bytes,
+ * may be NULL otherwise): they are split into depth-ordered sub-buckets that
+ * are sorted group by group. Only a sub-bucket that is itself larger than the
+ * capacity (thousands of near-identical depths in one tile) cannot be handled:
+ * *overflow_flag (device int32, caller zero-fills) is then set and the caller
+ * must use pm_sort_pairs instead. */
+PM_API int pm_tile_sort(const uint64_t *records, uint64_t *scratch, const int32_t *isect_offsets,
+                        int64_t n, const int32_t *d_n, int C, int tile_width, int tile_height,
                         int max_tile_count, int64_t *isect_ids, int32_t *flatten_ids,
                         int32_t *overflow_flag, pm_stream_t stream);
 

@@ -34,7 +34,7 @@ SIGNATURES = {
     "pm_tile_scan": (c_int, [_P, _L, _P, _P, _P]),
     "pm_bin_scatter": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _L, _P]),
     "pm_tile_sort_capacity": (c_int, []),
-    "pm_tile_sort": (c_int, [_P, _P, _L, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "pm_tile_sort": (c_int, [_P, _P, _P, _L, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "pm_project_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pm_scan_workspace_bytes": (c_size_t, [_L]),
     "pm_scan_tiles": (c_int, [_P, _L, _P, _P, _P, _S, _P]),

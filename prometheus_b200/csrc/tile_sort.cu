@@ -171,8 +171,27 @@ tile_scan_kernel(const int32_t *__restrict__ counts, int64_t T, int32_t *__restr
 
 // ---- per-tile shared-memory sort ----
 constexpr int kTsRadix = 256;
-constexpr int kTsCapSmall = 8192;
-constexpr int kTsCapLarge = 16384;
+constexpr int kTsThreads = 512;
+constexpr int kTsItems = 16;
+constexpr int kTsWarps = kTsThreads / 32;
+constexpr int kTsCap = kTsThreads * kTsItems;  // 8192 entries sorted in one go
+constexpr size_t kTsSmemBytes = sizeof(uint2) * kTsCap + sizeof(uint16_t) * kTsWarps * kTsRadix +
+                                sizeof(uint32_t) * (kTsRadix + 64);
+
+struct TsSmem {
+  uint2 *buf;                         // [kTsCap] {key, local index | flatten id}
+  uint16_t (*warp_hist)[kTsRadix];    // [warps][256]
+  uint32_t *digit_start;              // [256]
+  uint32_t *red;                      // [64]
+};
+__device__ __forceinline__ TsSmem carve_ts_smem(unsigned char *base) {
+  TsSmem m;
+  m.buf = reinterpret_cast<uint2 *>(base);
+  m.warp_hist = reinterpret_cast<uint16_t(*)[kTsRadix]>(m.buf + kTsCap);
+  m.digit_start = reinterpret_cast<uint32_t *>(m.warp_hist + kTsWarps);
+  m.red = m.digit_start + kTsRadix;
+  return m;
+}
 
 // 8-bit digit match with ballots: mask of the lanes holding the same digit.
 __device__ __forceinline__ unsigned match_digit8(uint32_t d) {
@@ -185,43 +204,15 @@ __device__ __forceinline__ unsigned match_digit8(uint32_t d) {
   return peers;
 }
 
-template <int THREADS, int ITEMS>
-constexpr size_t ts_smem_bytes() {
-  return sizeof(uint2) * THREADS * ITEMS + sizeof(uint16_t) * (THREADS / 32) * kTsRadix + sizeof(uint32_t) * (kTsRadix + 64);
-}
-
-// Sorts segments with min_cnt < cnt <= kTsThreads*ITEMS; other segments are left to the other variant.
-// Registers hold, per item, the depth key and a packed (rank | local index); the flatten id stays in
-// global memory (L2-resident: the segment was just read) and is fetched once at the end.
-template <int THREADS, int ITEMS, bool HW_MATCH = false>
-__global__ void __launch_bounds__(THREADS, (THREADS * ITEMS <= 8192 && THREADS <= 512 ? 2 : 1))
-tile_sort_kernel(const uint64_t *__restrict__ records, const int32_t *__restrict__ offsets,
-                 int64_t n_host, const int32_t *__restrict__ d_n, int64_t total_tiles, int n_tiles,
-                 int tile_n_bits, int min_cnt, int64_t *__restrict__ isect_ids,
-                 int32_t *__restrict__ flatten_ids, int32_t *__restrict__ overflow_flag) {
-  constexpr int CAP = THREADS * ITEMS;
-  constexpr int kTsThreads = THREADS;
-  constexpr int kTsWarps = THREADS / 32;
-  extern __shared__ __align__(16) unsigned char ts_smem[];
-  uint2 *buf = reinterpret_cast<uint2 *>(ts_smem);                                    // [CAP] {key, local index}
-  uint16_t(*warp_hist)[kTsRadix] = reinterpret_cast<uint16_t(*)[kTsRadix]>(buf + CAP);  // [warps][256]
-  uint32_t *digit_start = reinterpret_cast<uint32_t *>(warp_hist + kTsWarps);         // [256]
-  uint32_t *red = digit_start + kTsRadix;                                             // [64]
-
+// Sort one segment of cnt <= kTsCap {depth bits, flatten id} records by (depth bits, flatten id) in
+// shared memory and write it out in the gsplat layout. Called by all kTsThreads threads of the CTA.
+// Registers hold, per item, the tile-relative depth key and a packed (rank | local index); the flatten
+// id stays in global memory (L2-resident: the segment was just read) and is fetched once at the end.
+__device__ __forceinline__ void sort_segment(const uint64_t *src, int cnt, int64_t key_hi, const TsSmem &sm,
+                                             int64_t *__restrict__ out_ids, int32_t *__restrict__ out_flat) {
+  constexpr int ITEMS = kTsItems;
+  uint2 *buf = sm.buf;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t ct = blockIdx.x;
-  const int64_t n_isects = effective_n(n_host, d_n);
-  const int start = offsets[ct];
-  const int end = (ct == total_tiles - 1) ? (int)n_isects : offsets[ct + 1];
-  const int cnt = end - start;
-  if (cnt <= min_cnt) return;
-  if (cnt > CAP) {
-    if (CAP >= kTsCapLarge && tid == 0) atomicExch(overflow_flag, 1);
-    return;
-  }
-  const int64_t cam = ct / n_tiles, tile = ct % n_tiles;
-  const int64_t key_hi = (cam << (32 + tile_n_bits)) | (tile << 32);
-
   // load, warp-striped inside a per-warp contiguous chunk: slot(w, k, l) = w*ITEMS*32 + k*32 + l
   uint32_t dk[ITEMS], pk[ITEMS];  // pk: low 16 bits = local index in the unsorted segment, high 16 = rank scratch
   const int chunk0 = warp * (ITEMS * 32);
@@ -230,7 +221,7 @@ tile_sort_kernel(const uint64_t *__restrict__ records, const int32_t *__restrict
   for (int k = 0; k < ITEMS; ++k) {
     const int slot = chunk0 + k * 32 + lane;
     if (slot < cnt) {
-      dk[k] = (uint32_t)__ldg(reinterpret_cast<const unsigned long long *>(records) + (size_t)start + slot);
+      dk[k] = (uint32_t)src[slot];
       kmin = min(kmin, dk[k]);
       kmax = max(kmax, dk[k]);
     } else {
@@ -243,10 +234,11 @@ tile_sort_kernel(const uint64_t *__restrict__ records, const int32_t *__restrict
     kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
     kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
   }
-  if (lane == 0) { red[warp] = kmin; red[32 + warp] = kmax; }
+  __syncthreads();  // previous use of the shared buffers (a previous group) is over
+  if (lane == 0) { sm.red[warp] = kmin; sm.red[32 + warp] = kmax; }
   __syncthreads();
-  kmin = lane < kTsWarps ? red[lane] : 0xffffffffu;
-  kmax = lane < kTsWarps ? red[32 + lane] : 0u;
+  kmin = lane < kTsWarps ? sm.red[lane] : 0xffffffffu;
+  kmax = lane < kTsWarps ? sm.red[32 + lane] : 0u;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
@@ -259,18 +251,18 @@ tile_sort_kernel(const uint64_t *__restrict__ records, const int32_t *__restrict
   for (int k = 0; k < ITEMS; ++k) dk[k] = (chunk0 + k * 32 + lane < cnt) ? dk[k] - kmin : 0xffffffffu;
 
   for (int shift = 0; shift < 32 && (range >> shift) != 0; shift += 8) {
-    for (int i = tid; i < kTsWarps * kTsRadix / 2; i += kTsThreads) reinterpret_cast<uint32_t *>(warp_hist)[i] = 0;
+    for (int i = tid; i < kTsWarps * kTsRadix / 2; i += kTsThreads) reinterpret_cast<uint32_t *>(sm.warp_hist)[i] = 0;
     __syncthreads();
     // rank inside the warp's chunk (stable: item order is (k, lane))
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
       const uint32_t d = (dk[k] >> shift) & 0xffu;
-      const unsigned peers = HW_MATCH ? __match_any_sync(0xffffffffu, d) : match_digit8(d);
+      const unsigned peers = match_digit8(d);
       const unsigned lower = peers & ((1u << lane) - 1);
       uint32_t base = 0;
       if (lower == 0) {
-        base = warp_hist[warp][d];
-        warp_hist[warp][d] = (uint16_t)(base + __popc(peers));
+        base = sm.warp_hist[warp][d];
+        sm.warp_hist[warp][d] = (uint16_t)(base + __popc(peers));
       }
       base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
       pk[k] = (pk[k] & 0xffffu) | ((base + __popc(lower)) << 16);
@@ -282,8 +274,8 @@ tile_sort_kernel(const uint64_t *__restrict__ records, const int32_t *__restrict
     if (tid < kTsRadix) {
 #pragma unroll
       for (int w = 0; w < kTsWarps; ++w) {
-        const uint32_t c = warp_hist[w][tid];
-        warp_hist[w][tid] = (uint16_t)count;
+        const uint32_t c = sm.warp_hist[w][tid];
+        sm.warp_hist[w][tid] = (uint16_t)count;
         count += c;
       }
       uint32_t inc = count;
@@ -292,21 +284,21 @@ tile_sort_kernel(const uint64_t *__restrict__ records, const int32_t *__restrict
         const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += t;
       }
-      if (lane == 31) red[warp] = inc;
-      digit_start[tid] = inc - count;
+      if (lane == 31) sm.red[warp] = inc;
+      sm.digit_start[tid] = inc - count;
     }
     __syncthreads();
     if (tid < kTsRadix) {
       uint32_t wbase = 0;
-      for (int w = 0; w < warp; ++w) wbase += red[w];
-      digit_start[tid] += wbase;
+      for (int w = 0; w < warp; ++w) wbase += sm.red[w];
+      sm.digit_start[tid] += wbase;
     }
     __syncthreads();
     // scatter to the sorted slot, then read back in chunk order
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
       const uint32_t d = (dk[k] >> shift) & 0xffu;
-      buf[digit_start[d] + warp_hist[warp][d] + (pk[k] >> 16)] = make_uint2(dk[k], pk[k] & 0xffffu);
+      buf[sm.digit_start[d] + sm.warp_hist[warp][d] + (pk[k] >> 16)] = make_uint2(dk[k], pk[k] & 0xffffu);
     }
     __syncthreads();
 #pragma unroll
@@ -322,10 +314,7 @@ tile_sort_kernel(const uint64_t *__restrict__ records, const int32_t *__restrict
 #pragma unroll
   for (int k = 0; k < ITEMS; ++k) {
     const int slot = chunk0 + k * 32 + lane;
-    if (slot < cnt) {
-      const uint32_t fid = (uint32_t)(__ldg(reinterpret_cast<const unsigned long long *>(records) + (size_t)start + (pk[k] & 0xffffu)) >> 32);
-      buf[slot] = make_uint2(dk[k] + kmin, fid);
-    }
+    if (slot < cnt) buf[slot] = make_uint2(dk[k] + kmin, (uint32_t)(src[pk[k] & 0xffffu] >> 32));
   }
   __syncthreads();
   // ties on the depth bits: order each run by flatten id (runs are rare and short; the thread that
@@ -351,8 +340,103 @@ tile_sort_kernel(const uint64_t *__restrict__ records, const int32_t *__restrict
   __syncthreads();
   for (int i = tid; i < cnt; i += kTsThreads) {
     const uint2 v = buf[i];
-    isect_ids[(size_t)start + i] = key_hi | (int64_t)v.x;
-    flatten_ids[(size_t)start + i] = (int32_t)v.y;
+    out_ids[i] = key_hi | (int64_t)v.x;
+    out_flat[i] = (int32_t)v.y;
+  }
+}
+
+// Segments of up to kTsCap entries: one sort. (Larger ones are left to tile_sort_big_kernel.)
+__global__ void __launch_bounds__(kTsThreads, 2)
+tile_sort_kernel(const uint64_t *__restrict__ records, const int32_t *__restrict__ offsets,
+                 int64_t n_host, const int32_t *__restrict__ d_n, int64_t total_tiles, int n_tiles,
+                 int tile_n_bits, int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids) {
+  extern __shared__ __align__(16) unsigned char ts_smem[];
+  const int64_t ct = blockIdx.x;
+  const int64_t n_isects = effective_n(n_host, d_n);
+  const int start = offsets[ct];
+  const int end = (ct == total_tiles - 1) ? (int)n_isects : offsets[ct + 1];
+  const int cnt = end - start;
+  if (cnt <= 0 || cnt > kTsCap) return;
+  const int64_t cam = ct / n_tiles, tile = ct % n_tiles;
+  const int64_t key_hi = (cam << (32 + tile_n_bits)) | (tile << 32);
+  sort_segment(records + start, cnt, key_hi, carve_ts_smem(ts_smem), isect_ids + start, flatten_ids + start);
+}
+
+// Segments larger than kTsCap: the CTA first splits the segment by the top 8 varying bits of the depth
+// key (a counting sort through the global `scratch` buffer), which leaves up to 256 depth-ordered
+// sub-buckets; consecutive sub-buckets are then grouped up to kTsCap entries and each group is sorted in
+// shared memory as above. Concatenating the groups gives the sorted segment. Only a single sub-bucket
+// larger than kTsCap (thousands of splats with near-identical depth in one tile) defeats it: the
+// overflow flag is raised and the caller falls back to the onesweep path.
+__global__ void __launch_bounds__(kTsThreads, 2)
+tile_sort_big_kernel(const uint64_t *__restrict__ records, uint64_t *__restrict__ scratch,
+                     const int32_t *__restrict__ offsets, int64_t n_host, const int32_t *__restrict__ d_n,
+                     int64_t total_tiles, int n_tiles, int tile_n_bits, int64_t *__restrict__ isect_ids,
+                     int32_t *__restrict__ flatten_ids, int32_t *__restrict__ overflow_flag) {
+  extern __shared__ __align__(16) unsigned char ts_smem[];
+  __shared__ int s_hist[kTsRadix + 1];
+  __shared__ int s_cursor[kTsRadix];
+  __shared__ uint32_t s_mm[2];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t ct = blockIdx.x;
+  const int64_t n_isects = effective_n(n_host, d_n);
+  const int start = offsets[ct];
+  const int end = (ct == total_tiles - 1) ? (int)n_isects : offsets[ct + 1];
+  const int cnt = end - start;
+  if (cnt <= kTsCap) return;
+  const int64_t cam = ct / n_tiles, tile = ct % n_tiles;
+  const int64_t key_hi = (cam << (32 + tile_n_bits)) | (tile << 32);
+  const uint64_t *src = records + start;
+  uint64_t *tmp = scratch + start;
+
+  if (tid == 0) { s_mm[0] = 0xffffffffu; s_mm[1] = 0u; }
+  for (int i = tid; i <= kTsRadix; i += kTsThreads) s_hist[i] = 0;
+  __syncthreads();
+  uint32_t kmin = 0xffffffffu, kmax = 0u;
+  for (int i = tid; i < cnt; i += kTsThreads) {
+    const uint32_t k = (uint32_t)src[i];
+    kmin = min(kmin, k);
+    kmax = max(kmax, k);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+  }
+  if (lane == 0) { atomicMin(&s_mm[0], kmin); atomicMax(&s_mm[1], kmax); }
+  __syncthreads();
+  kmin = s_mm[0];
+  const uint32_t range = s_mm[1] - kmin;
+  const int bits = 32 - __clz(range | 1u);
+  const int shift = bits > 8 ? bits - 8 : 0;
+  for (int i = tid; i < cnt; i += kTsThreads) atomicAdd(&s_hist[(((uint32_t)src[i] - kmin) >> shift) + 1], 1);
+  __syncthreads();
+  if (tid == 0) {
+    for (int d = 0; d < kTsRadix; ++d) s_hist[d + 1] += s_hist[d];  // s_hist[d] = start of sub-bucket d
+  }
+  __syncthreads();
+  for (int i = tid; i < kTsRadix; i += kTsThreads) s_cursor[i] = s_hist[i];
+  __syncthreads();
+  for (int i = tid; i < cnt; i += kTsThreads) {
+    const uint64_t r = src[i];
+    const int pos = atomicAdd(&s_cursor[((uint32_t)r - kmin) >> shift], 1);
+    tmp[pos] = r;
+  }
+  __threadfence_block();
+  __syncthreads();
+  const TsSmem sm = carve_ts_smem(ts_smem);
+  int g0 = 0;
+  while (g0 < kTsRadix) {
+    int g1 = g0 + 1;
+    while (g1 < kTsRadix && s_hist[g1 + 1] - s_hist[g0] <= kTsCap) ++g1;
+    const int gs = s_hist[g0], ge = s_hist[g1];
+    if (ge - gs > kTsCap) {  // a single sub-bucket that does not fit
+      if (tid == 0) atomicExch(overflow_flag, 1);
+      return;
+    }
+    if (ge > gs)
+      sort_segment(tmp + gs, ge - gs, key_hi, sm, isect_ids + start + gs, flatten_ids + start + gs);
+    g0 = g1;
   }
 }
 
@@ -409,14 +493,16 @@ int pm_bin_scatter(const float *means2d, const int32_t *radii, const float *dept
   return pm::check_launch();
 }
 
-int pm_tile_sort_capacity(void) { return pm::kTsCapLarge; }
+int pm_tile_sort_capacity(void) { return pm::kTsCap; }
 
-int pm_tile_sort(const uint64_t *records, const int32_t *isect_offsets, int64_t n, const int32_t *d_n,
-                 int C, int tile_width, int tile_height, int max_tile_count, int64_t *isect_ids,
-                 int32_t *flatten_ids, int32_t *overflow_flag, pm_stream_t stream) {
+int pm_tile_sort(const uint64_t *records, uint64_t *scratch, const int32_t *isect_offsets, int64_t n,
+                 const int32_t *d_n, int C, int tile_width, int tile_height, int max_tile_count,
+                 int64_t *isect_ids, int32_t *flatten_ids, int32_t *overflow_flag, pm_stream_t stream) {
   if (n < 0 || C < 0 || tile_width <= 0 || tile_height <= 0 || !overflow_flag) return PM_ERR_BAD_ARG;
   if (n == 0 || C == 0) return PM_OK;
   if (!records || !isect_offsets || !isect_ids || !flatten_ids) return PM_ERR_BAD_ARG;
+  const bool need_big = max_tile_count < 0 || max_tile_count > pm::kTsCap;
+  if (need_big && !scratch) return PM_ERR_BAD_ARG;
   if (n >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
   const int n_tiles = tile_width * tile_height;
   const int64_t total = (int64_t)C * n_tiles;
@@ -424,39 +510,22 @@ int pm_tile_sort(const uint64_t *records, const int32_t *isect_offsets, int64_t 
   const int tile_n_bits = pm::n_bits_for(n_tiles);
   if (tile_n_bits + pm::n_bits_for(C) > 32) return PM_ERR_RANGE;
   static bool attr_set = false;
-  static int small_variant = 0;
   if (!attr_set) {
-    const char *e = getenv("PM_TILE_SORT_VARIANT");  // dev knob: 1 = 512 thr x 16 (default, 2 CTAs/SM), 0 = 1024x8, 2 = 1024x8 + match.any
-    small_variant = e ? atoi(e) : 1;
-    if (cudaFuncSetAttribute(pm::tile_sort_kernel<1024, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)pm::ts_smem_bytes<1024, 8>()) != cudaSuccess ||
-        cudaFuncSetAttribute(pm::tile_sort_kernel<1024, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)pm::ts_smem_bytes<1024, 8>()) != cudaSuccess ||
-        cudaFuncSetAttribute(pm::tile_sort_kernel<512, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)pm::ts_smem_bytes<512, 16>()) != cudaSuccess ||
-        cudaFuncSetAttribute(pm::tile_sort_kernel<512, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)pm::ts_smem_bytes<512, 32>()) != cudaSuccess) {
+    if (cudaFuncSetAttribute(pm::tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)pm::kTsSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(pm::tile_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)pm::kTsSmemBytes) != cudaSuccess) {
       pm::set_last_cuda_error(cudaGetLastError());
       return PM_ERR_CUDA;
     }
     attr_set = true;
   }
   cudaStream_t s = pm::as_stream(stream);
-  // segments of up to 8192 entries go to the small variant; the (rare) larger ones, up to 16384, to a
-  // second launch. max_tile_count < 0 means "unknown" (no host sync): launch both.
-  if (small_variant == 1)
-    pm::tile_sort_kernel<512, 16><<<(unsigned)total, 512, pm::ts_smem_bytes<512, 16>(), s>>>(
-        records, isect_offsets, n, d_n, total, n_tiles, tile_n_bits, 0, isect_ids, flatten_ids, overflow_flag);
-  else if (small_variant == 2)
-    pm::tile_sort_kernel<1024, 8, true><<<(unsigned)total, 1024, pm::ts_smem_bytes<1024, 8>(), s>>>(
-        records, isect_offsets, n, d_n, total, n_tiles, tile_n_bits, 0, isect_ids, flatten_ids, overflow_flag);
-  else
-    pm::tile_sort_kernel<1024, 8><<<(unsigned)total, 1024, pm::ts_smem_bytes<1024, 8>(), s>>>(
-        records, isect_offsets, n, d_n, total, n_tiles, tile_n_bits, 0, isect_ids, flatten_ids, overflow_flag);
-  if (max_tile_count < 0 || max_tile_count > pm::kTsCapSmall)
-    pm::tile_sort_kernel<512, 32><<<(unsigned)total, 512, pm::ts_smem_bytes<512, 32>(), s>>>(
-        records, isect_offsets, n, d_n, total, n_tiles, tile_n_bits, pm::kTsCapSmall, isect_ids, flatten_ids,
-        overflow_flag);
+  pm::tile_sort_kernel<<<(unsigned)total, pm::kTsThreads, pm::kTsSmemBytes, s>>>(
+      records, isect_offsets, n, d_n, total, n_tiles, tile_n_bits, isect_ids, flatten_ids);
+  if (need_big)  // max_tile_count < 0 means "unknown" (no host sync): always launch it
+    pm::tile_sort_big_kernel<<<(unsigned)total, pm::kTsThreads, pm::kTsSmemBytes, s>>>(
+        records, scratch, isect_offsets, n, d_n, total, n_tiles, tile_n_bits, isect_ids, flatten_ids, overflow_flag);
   return pm::check_launch();
 }
 

@@ -243,15 +243,18 @@ def tile_sort_capacity() -> int:
 
 @_instrument("tile_sort", lambda *a, **k: 2 if (k.get("max_tile_count", -1) < 0 or k.get("max_tile_count", -1) > 8192) else 1)
 def tile_sort(records, offsets, C: int, width: int, height: int, d_n=None, max_tile_count: int = -1):
-    """Per-tile shared-memory depth sort -> (isect_ids int64 [n], flatten_ids int32 [n], overflow flag int32[1])."""
+    """Per-tile shared-memory depth sort -> (isect_ids int64 [n], flatten_ids int32 [n], overflow flag int32[1]).
+    Tiles above the one-pass capacity are split by depth through a scratch buffer first."""
     L = _lib.load()
     tw, th = tile_grid(width, height)
     n = records.numel()
     ids = torch.empty(n, dtype=torch.int64, device=records.device)
     flat = torch.empty(n, dtype=torch.int32, device=records.device)
     flag = torch.zeros(1, dtype=torch.int32, device=records.device)
-    _lib.check(L.pm_tile_sort(_ptr(records), _ptr(offsets), n, _ptr(d_n), C, tw, th, int(max_tile_count), _ptr(ids),
-                              _ptr(flat), _ptr(flag), _stream()), "pm_tile_sort")
+    need_big = max_tile_count < 0 or max_tile_count > tile_sort_capacity()
+    scratch = torch.empty_like(records) if need_big else None
+    _lib.check(L.pm_tile_sort(_ptr(records), _ptr(scratch), _ptr(offsets), n, _ptr(d_n), C, tw, th, int(max_tile_count),
+                              _ptr(ids), _ptr(flat), _ptr(flag), _stream()), "pm_tile_sort")
     return ids, flat, flag
 
 

@@ -92,9 +92,10 @@ def isect_tiles(means2d, radii, depths, tiles_per_gauss, width, height, C, force
     if not force_generic:
         offsets, stats = ops.tile_scan(ops.bin_count(means2d, radii, width, height))
         n_isects, max_count = stats.tolist()
-        if max_count <= ops.tile_sort_capacity():
-            records = ops.bin_scatter(means2d, radii, depths, offsets, width, height, n_isects)
-            ids, flat, _flag = ops.tile_sort(records, offsets, C, width, height, max_tile_count=max_count)
+        records = ops.bin_scatter(means2d, radii, depths, offsets, width, height, n_isects)
+        ids, flat, flag = ops.tile_sort(records, offsets, C, width, height, max_tile_count=max_count)
+        # only tiles above the one-pass capacity can overflow (a depth sub-bucket that does not fit)
+        if max_count <= ops.tile_sort_capacity() or int(flag.item()) == 0:
             return ids, flat, offsets
     cum, n_dev = ops.scan_tiles(tiles_per_gauss)
     n_isects = int(n_dev.item())

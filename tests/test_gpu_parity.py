@@ -192,7 +192,7 @@ def _binned(ops, st, s, C):
     offsets, stats = ops.tile_scan(tile_counts)
     n, max_count = stats.tolist()
     records = ops.bin_scatter(means2d, radii, depths, offsets, s["width"], s["height"], n)
-    ids, flat, flag = ops.tile_sort(records, offsets, C, s["width"], s["height"])
+    ids, flat, flag = ops.tile_sort(records, offsets, C, s["width"], s["height"], max_tile_count=max_count)
     return tile_counts, offsets, n, max_count, ids, flat, flag
 
 
@@ -231,19 +231,30 @@ def test_binned_sort_depth_ties_and_overflow_fallback(oracle):
     assert int(flag.item()) == 0
     assert np.array_equal(ids.cpu().numpy(), st["isect_ids"]) and np.array_equal(flat.cpu().numpy(), st["flatten_ids"])
 
-    # (b) 17000 small splats on one pixel -> one tile segment of 17000 > 16384
-    n_big = 17000
-    g = torch.Generator().manual_seed(2)
-    means = np.zeros((n_big, 3), np.float32)
-    means[:, 2] = 2.0 + torch.rand(n_big, generator=g).numpy()
-    big = dict(means=means, quats=np.tile(np.array([[1, 0, 0, 0]], np.float32), (n_big, 1)),
-               scales=np.full((n_big, 3), 0.01, np.float32), opacities=np.full(n_big, 0.01, np.float32),
-               colors=torch.rand(n_big, 3, generator=g).numpy(), viewmats=np.eye(4, dtype=np.float32)[None],
-               Ks=np.array([[[100.0, 0, 24.0], [0, 100.0, 24.0], [0, 0, 1]]], np.float32), width=64, height=64)
+    # (b) one tile far above the one-pass shared-memory capacity (8192 entries)
+    def stack_on_one_pixel(n_big, same_depth):
+        g = torch.Generator().manual_seed(2)
+        means = np.zeros((n_big, 3), np.float32)
+        means[:, 2] = 2.5 if same_depth else 2.0 + torch.rand(n_big, generator=g).numpy()
+        return dict(means=means, quats=np.tile(np.array([[1, 0, 0, 0]], np.float32), (n_big, 1)),
+                    scales=np.full((n_big, 3), 0.01, np.float32), opacities=np.full(n_big, 0.01, np.float32),
+                    colors=torch.rand(n_big, 3, generator=g).numpy(), viewmats=np.eye(4, dtype=np.float32)[None],
+                    Ks=np.array([[[100.0, 0, 24.0], [0, 100.0, 24.0], [0, 0, 1]]], np.float32), width=64, height=64)
+
+    # (b1) 17000 splats with distinct depths: split by depth through the scratch buffer, then sorted group by group
+    big = stack_on_one_pixel(17000, same_depth=False)
+    st = oracle.forward_pipeline(big["means"], big["quats"], big["scales"], big["opacities"], big["colors"], big["viewmats"],
+                                 big["Ks"], 64, 64, backgrounds=None)
+    _, _, _, max_count, ids, flat, flag = _binned(ops, st, big, 1)
+    assert max_count == 17000 > ops.tile_sort_capacity() and int(flag.item()) == 0
+    assert np.array_equal(ids.cpu().numpy(), st["isect_ids"]) and np.array_equal(flat.cpu().numpy(), st["flatten_ids"])
+    # (b2) 9000 splats with IDENTICAL depth bits: one depth sub-bucket larger than the capacity -> overflow flag,
+    # and the operator falls back to the generic onesweep path
+    big = stack_on_one_pixel(9000, same_depth=True)
     st = oracle.forward_pipeline(big["means"], big["quats"], big["scales"], big["opacities"], big["colors"], big["viewmats"],
                                  big["Ks"], 64, 64, backgrounds=None)
     _, _, _, max_count, _, _, flag = _binned(ops, st, big, 1)
-    assert max_count == n_big > ops.tile_sort_capacity() and int(flag.item()) == 1
+    assert max_count == 9000 and int(flag.item()) == 1
     r, a, m = pb.rasterization(*[dev(big[k]) for k in ("means", "quats", "scales", "opacities", "colors")], dev(big["viewmats"]),
                                dev(big["Ks"]), 64, 64, packed=False)
     assert np.array_equal(m["isect_ids"].cpu().numpy(), st["isect_ids"]) and np.array_equal(m["flatten_ids"].cpu().numpy(), st["flatten_ids"])

@@ -32,7 +32,6 @@ print("tile_scan %.3f ms" % t(lambda: ops.tile_scan(tc)))
 print("bin_scatter %.3f ms" % t(lambda: ops.bin_scatter(means2d, radii, depths, offsets, 512, 512, n)))
 rec = ops.bin_scatter(means2d, radii, depths, offsets, 512, 512, n)
 print("tile_sort %.3f ms" % t(lambda: ops.tile_sort(rec, offsets, 8, 512, 512, max_tile_count=mx)))
-print("tile_sort small only %.3f ms" % t(lambda: ops.tile_sort(rec, offsets, 8, 512, 512, max_tile_count=100)))
 ids, flat, flag = ops.tile_sort(rec, offsets, 8, 512, 512, max_tile_count=mx)
 print("overflow flag", int(flag.item()))
 q = torch.quantile(tc.float().flatten(), torch.tensor([0.5, 0.9, 0.99, 1.0], device=dev))
