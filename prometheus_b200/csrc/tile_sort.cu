@@ -23,8 +23,9 @@
 //
 // Atomics: neighbouring Gaussians hit the same few tiles at the same time, and
 // same-address global atomics from many CTAs serialise in L2 (measured: +2 ms for
-// 47.6M plain REDs). So count and scatter privatise per CTA: a 512-slot shared-memory
-// hash table keyed by tile id aggregates the CTA's ~770 intersections into ~40 global
+// 47.6M plain REDs). So count and scatter privatise per CTA in shared memory (a dense
+// window of tiles around the CTA's bounding box, or a 512-slot hash table when the
+// input is scattered), which aggregates the CTA's ~770 intersections into ~40 global
 // atomics (one per distinct tile), and CTAs are visited in a strided order so that
 // concurrently resident CTAs work on far-apart Gaussians.
 #include <stdlib.h>
@@ -63,7 +64,15 @@ __device__ __forceinline__ int hash_find(const TileHash &h, int t) {
   return -1;
 }
 
+constexpr int kWinCells = 2048;  // dense per-CTA window of tiles (covers e.g. 64 x 32 tiles)
+
 // SCATTER=false: histogram only. SCATTER=true: reserve ranges through `global` (= cursors) and write records.
+//
+// Per-CTA privatisation in two flavours, chosen per CTA (block-uniform):
+//   dense  — the tiles touched by the CTA's 256 Gaussians fit a window of kWinCells tiles around their
+//            bounding box (always true for pixel-aligned input: half an image row lands on ~50 tiles):
+//            one native shared-memory integer atomic per intersection, no probing;
+//   hashed — otherwise (scattered input on a large image): the 512-slot hash table.
 template <bool SCATTER>
 __global__ void __launch_bounds__(256)
 bin_kernel(const float *__restrict__ means2d, const int32_t *__restrict__ radii,
@@ -71,7 +80,10 @@ bin_kernel(const float *__restrict__ means2d, const int32_t *__restrict__ radii,
            int32_t *__restrict__ global, int N, int tile_width, int tile_height, int chunk_stride,
            uint64_t *__restrict__ records, int64_t capacity) {
   __shared__ TileHash h;
-  for (int i = threadIdx.x; i < kHashSlots; i += blockDim.x) { h.key[i] = -1; h.cnt[i] = 0; }
+  __shared__ int win[kWinCells];
+  __shared__ int win_base[SCATTER ? kWinCells : 1];
+  __shared__ int box[4];  // min x, min y, max x, max y over the CTA's tile AABBs
+  if (threadIdx.x == 0) { box[0] = 0x7fffffff; box[1] = 0x7fffffff; box[2] = 0; box[3] = 0; }
   __syncthreads();
   // strided CTA order: consecutive (= concurrently resident) CTAs touch far-apart chunks
   const int chunk = (int)(((int64_t)blockIdx.x * chunk_stride) % gridDim.x);
@@ -88,8 +100,54 @@ bin_kernel(const float *__restrict__ means2d, const int32_t *__restrict__ radii,
       if (SCATTER) rec = ((uint64_t)(uint32_t)f << 32) | (uint64_t)__float_as_uint(depths[f]);
     }
   }
+  const bool nonempty = x1 > x0 && y1 > y0;
+  {
+    const int bx0 = __reduce_min_sync(0xffffffffu, nonempty ? x0 : 0x7fffffff);
+    const int by0 = __reduce_min_sync(0xffffffffu, nonempty ? y0 : 0x7fffffff);
+    const int bx1 = __reduce_max_sync(0xffffffffu, nonempty ? x1 : 0);
+    const int by1 = __reduce_max_sync(0xffffffffu, nonempty ? y1 : 0);
+    if ((threadIdx.x & 31) == 0 && bx1 > 0) {
+      atomicMin(&box[0], bx0); atomicMin(&box[1], by0); atomicMax(&box[2], bx1); atomicMax(&box[3], by1);
+    }
+  }
+  __syncthreads();
+  const int wx0 = box[0], wy0 = box[1];
+  const int ww = box[2] - wx0, wh = box[3] - wy0;
+  if (box[2] == 0 || ww <= 0 || wh <= 0) return;  // nothing visible in this CTA
   const int n_tiles = tile_width * tile_height;
   int32_t *gl = global + (size_t)cid * n_tiles;
+  const int32_t *off = offsets + (size_t)cid * n_tiles;
+  const bool dense = ww * wh <= kWinCells;
+
+  if (dense) {
+    const int cells = ww * wh;
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) win[i] = 0;
+    __syncthreads();
+    for (int y = y0; y < y1; ++y)
+      for (int x = x0; x < x1; ++x) atomicAdd(&win[(y - wy0) * ww + (x - wx0)], 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+      const int c = win[i];
+      if (c > 0) {
+        const int t = (wy0 + i / ww) * tile_width + wx0 + i % ww;
+        const int b = atomicAdd(gl + t, c);
+        if (SCATTER) { win_base[i] = b; win[i] = 0; }
+      }
+    }
+    if (!SCATTER) return;
+    __syncthreads();
+    for (int y = y0; y < y1; ++y)
+      for (int x = x0; x < x1; ++x) {
+        const int cell = (y - wy0) * ww + (x - wx0);
+        const int pos = win_base[cell] + atomicAdd(&win[cell], 1);
+        const int64_t slot = (int64_t)off[y * tile_width + x] + pos;
+        if (slot < capacity) records[slot] = rec;
+      }
+    return;
+  }
+
+  for (int i = threadIdx.x; i < kHashSlots; i += blockDim.x) { h.key[i] = -1; h.cnt[i] = 0; }
+  __syncthreads();
   // phase 1: count per distinct tile in shared memory
   for (int y = y0; y < y1; ++y)
     for (int x = x0; x < x1; ++x) {
@@ -111,7 +169,6 @@ bin_kernel(const float *__restrict__ means2d, const int32_t *__restrict__ radii,
   if (!SCATTER) return;
   __syncthreads();
   // phase 3: place the records (rank inside the CTA's reservation from a second shared counter)
-  const int32_t *off = offsets + (size_t)cid * n_tiles;
   for (int y = y0; y < y1; ++y)
     for (int x = x0; x < x1; ++x) {
       const int t = y * tile_width + x;

@@ -261,6 +261,27 @@ def test_binned_sort_depth_ties_and_overflow_fallback(oracle):
     assert np.array_equal(m["isect_offsets"].cpu().numpy(), st["isect_offsets"])
 
 
+def test_binned_sort_hashed_privatisation_on_a_large_image(oracle):
+    """Scattered splats on a 1024x800 image: a CTA's tiles no longer fit the dense shared-memory window
+    (64x50 tiles > 2048 cells), so bin_count / bin_scatter take the hash-table path."""
+    from prometheus_b200 import ops
+
+    g = torch.Generator().manual_seed(12)
+    n = 6000
+    means = torch.rand(n, 3, generator=g) * torch.tensor([5.0, 4.0, 2.0]) + torch.tensor([-2.5, -2.0, 2.0])
+    s = dict(means=means.numpy(), quats=torch.randn(n, 4, generator=g).numpy(),
+             scales=(torch.rand(n, 3, generator=g) * 0.05 + 0.005).numpy(), opacities=torch.rand(n, generator=g).numpy(),
+             colors=torch.rand(n, 3, generator=g).numpy(), viewmats=np.eye(4, dtype=np.float32)[None],
+             Ks=np.array([[[400.0, 0, 512.0], [0, 400.0, 400.0], [0, 0, 1]]], np.float32), width=1024, height=800)
+    st = oracle.forward_pipeline(s["means"], s["quats"], s["scales"], s["opacities"], s["colors"], s["viewmats"], s["Ks"],
+                                 1024, 800, backgrounds=None, want_fragile=False)
+    assert len(st["isect_ids"]) > 10000
+    tile_counts, offsets, n_is, max_count, ids, flat, flag = _binned(ops, st, s, 1)
+    assert n_is == len(st["isect_ids"]) and int(flag.item()) == 0
+    assert np.array_equal(offsets.cpu().numpy(), st["isect_offsets"])
+    assert np.array_equal(ids.cpu().numpy(), st["isect_ids"]) and np.array_equal(flat.cpu().numpy(), st["flatten_ids"])
+
+
 def test_generic_and_binned_paths_agree_through_the_operator(cases):
     import importlib
 
