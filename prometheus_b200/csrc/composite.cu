@@ -49,6 +49,11 @@ __device__ __forceinline__ float2 lds64(uint32_t a) {
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
   return v;
 }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -352,7 +357,7 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
         float gv[10] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};  // c0..c3, q0..q2, mx, my, o
         if (valid) {
           const float4 c = lds128(aC + t * 16);
-          const float ra = 1.0f / (1.0f - alpha);
+          const float ra = rcp_approx(1.0f - alpha);  // 1 - alpha >= 1e-3: MUFU.RCP (1 ulp) instead of the IEEE divide sequence
           T *= ra;
           const float fac = alpha * T;
           gv[0] = fac * vr[0]; gv[1] = fac * vr[1]; gv[2] = fac * vr[2]; gv[3] = fac * vr[3];
