@@ -152,6 +152,30 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def torch_cpu_baseline(O):
+    """Pure-PyTorch CPU restatement (oracle/torch_ref.py) on 1 target view of config C1
+    (4 x 256^2 -> 262,144 Gaussians, one 256^2 view), all host cores."""
+    import torch
+
+    from oracle import torch_ref
+    from prometheus_b200 import scenes
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    sc = scenes.make_scene("C1")
+    g = O.unproject(sc.params.numpy(), sc.cameras_in.numpy(), mode="mvsplat", z_near=scenes.Z_NEAR, z_far=scenes.Z_FAR,
+                    s_min=scenes.S_MIN, s_max=scenes.S_MAX)
+    vm, K = O.camera_prep(sc.cameras_out[0, :1].numpy(), 256, 256)
+    args = [torch.from_numpy(g[k][0]) for k in ("xyz", "rotations", "scales")]
+    args += [torch.from_numpy(g["opacity"][0, :, 0]), torch.from_numpy(g["features"][0, :, 0])]
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        torch_ref.rasterization(*args, torch.from_numpy(vm), torch.from_numpy(K), 256, 256,
+                                backgrounds=torch.ones(1, 3), render_mode="RGB+ED")
+    dt = time.perf_counter() - t0
+    return {"value": 256 * 256 / dt / 1e6, "unit": UNIT, "cores": os.cpu_count(),
+            "sample": "oracle/torch_ref.py, 1 target view of C1 (262144 Gaussians -> 256^2) in %.2fs" % dt}
+
+
 def workload_name(cfg, scene):
     B, Vi = scene.params.shape[:2]
     s = scene.params.shape[-1]
@@ -398,6 +422,12 @@ def main():
         cpu_baseline = {"value": k * S * S / t / 1e6, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
                         "sample": "oracle/gs_oracle.c (OpenMP): full unproject %.2fs (pro-rated) + 1 of %d target "
                                   "views rendered in %.2fs" % (t_u, V_out, t_r)}
+        # BASELINE.json also names the pure-PyTorch rasterisation path (gsplat's _torch_impl analogue):
+        # oracle/torch_ref.py on all host cores, bounded sample = 1 target view of config C1.
+        try:
+            cpu_baseline["torch_restatement"] = torch_cpu_baseline(O)
+        except Exception as e:  # noqa: BLE001
+            cpu_baseline["torch_restatement"] = {"error": str(e)[:200]}
 
     if rank == 0:
         line = {
