@@ -340,8 +340,13 @@ def main():
     else:
         dom, dom_ms, dom_bytes = "rs_onesweep_kernel", sort_pass_ms / B, 24 * I
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    traffic = None  # DRAM bytes per launch of that kernel from the committed ncu capture (profiles/traffic.json)
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom) if args.config == "C2" else None
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "avg_launch_ms": round(dom_ms, 4),
                 "alg_bytes_per_launch": int(dom_bytes),
                 "note": "dominant kernel by time; composite and the shared-memory tile sort are issue/latency bound, "
