@@ -318,6 +318,8 @@ def main():
         "bin_count": 12 * P * B,
         "bin_scatter": (16 * P + 8 * I) * B,
         "tile_sort": 20 * I * B,
+        # fused sort-as-you-go: one pass over the tile's records at minimum + composite traffic
+        "tile_render_fwd": (8 * I + 4 * I_need + 44 * I_need + 24 * X) * B,
         "composite_fwd": (44 * I_need + 24 * X) * B,
     }
     peak, peak_src = read_peaks()
@@ -333,7 +335,10 @@ def main():
     comp_ms = stage_avg.get("composite_fwd", 0.0)
     tsort_ms = stage_avg.get("tile_sort", 0.0)
     sort_pass_ms = stage_avg.get("sort_pairs", 0.0) / max(passes, 1)
-    if comp_ms >= max(sort_pass_ms, tsort_ms):
+    fused_ms = stage_avg.get("tile_render_fwd", 0.0)
+    if fused_ms >= max(comp_ms, sort_pass_ms, tsort_ms) and fused_ms > 0:
+        dom, dom_ms, dom_bytes = "tile_render_fwd_kernel", fused_ms / B, bytes_alg["tile_render_fwd"] / B
+    elif comp_ms >= max(sort_pass_ms, tsort_ms):
         dom, dom_ms, dom_bytes = "composite_fwd_kernel", comp_ms / B, bytes_alg["composite_fwd"] / B
     elif tsort_ms >= sort_pass_ms:
         dom, dom_ms, dom_bytes = "tile_sort_kernel", tsort_ms / B, bytes_alg["tile_sort"] / B

@@ -229,6 +229,24 @@ PM_API int pm_composite_fwd(const float *means2d, const float *conics, const flo
                      float *render, float *alphas, int32_t *last_ids,
                      pm_stream_t stream);
 
+/* Fused "sort-as-you-go" forward (fast path of the module-level renderer): takes
+ * the UNSORTED per-tile records of pm_bin_scatter and, per tile, sorts only as
+ * many depth-ordered groups as the compositor consumes before every pixel of
+ * the tile is saturated. render / alphas / last_ids are bit-identical to
+ * pm_tile_sort + pm_composite_fwd; flatten_ids [n] is filled for the first
+ * sorted_counts[c,ty,tx] entries of each tile only (all that pm_composite_bwd
+ * reads). *overflow_flag (device int32, caller zero-fills) is set if a depth
+ * sub-bucket of some tile exceeds the 2048-record group capacity: the caller
+ * must then redo the call with pm_tile_sort + pm_composite_fwd. */
+PM_API int pm_tile_render_fwd(const uint64_t *records, const int32_t *isect_offsets, int64_t n_isects,
+                              const int32_t *d_n, const float *means2d, const float *conics,
+                              const float *opacities, const float *colors, int colors_per_camera, int D,
+                              const float *depths, const float *backgrounds, int N, int C,
+                              int width, int height, int tile_size,
+                              float *render, float *alphas, int32_t *last_ids,
+                              int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
+                              pm_stream_t stream);
+
 /* Backward. v_render [C,H,W,CD], v_alphas [C,H,W] (either may be NULL).
  * Gradients are ACCUMULATED (+=) into v_means2d [C,N,2], v_conics [C,N,3],
  * v_colors ([N,D] or [C,N,D]), v_opacities [N], v_depths [C,N]: the caller

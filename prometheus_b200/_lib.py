@@ -43,6 +43,7 @@ SIGNATURES = {
     "pm_sort_pairs": (c_int, [_P, _P, _P, _P, _L, _P, _I, _P, _S, POINTER(c_int), _P]),
     "pm_tile_offsets": (c_int, [_P, _L, _P, _I, _I, _I, _P, _P]),
     "pm_composite_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "pm_tile_render_fwd": (c_int, [_P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "pm_composite_bwd": (c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I,
                                  _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }

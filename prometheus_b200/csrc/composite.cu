@@ -22,84 +22,9 @@
 // each Gaussian's gradient across the warp with shuffles, accumulates the 8
 // warps in shared memory and issues ONE global atomic per Gaussian-tile and
 // component (upstream: one per warp) — no per-pixel global atomics.
-#include "common.cuh"
+#include "composite_common.cuh"
 
 namespace pm {
-
-constexpr int kBatch = 256;
-constexpr float kAlphaMin = 1.0f / 255.0f;
-constexpr float kTStop = 1e-4f;
-
-struct __align__(16) GaussA { float mx, my, hx, hy; };      // mean + half extents of the alpha>=1/255 box
-struct __align__(16) GaussB { float cx, cy, cz, opac; };    // conic pre-scaled to base-2 exponent units + opacity
-struct __align__(16) GaussC { float c0, c1, c2, c3; };      // colour channels (+ depth), zero padded
-
-constexpr float kLog2e = 1.4426950408889634f;
-
-// Shared-memory accesses of the hot loops go through explicit 32-bit shared addresses: with plain
-// array indexing nvcc re-derived the shared window base (S2R SR_CgaCtaId + LEA) on every iteration.
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ float4 lds128(uint32_t a) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ float2 lds64(uint32_t a) {
-  float2 v;
-  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// -sigma * log2(e) from the pre-scaled conic; written with explicit roundings so the forward and the
-// backward kernel evaluate bit-identical alphas (their skip / stop decisions must agree).
-__device__ __forceinline__ float power2(float Q0, float Q1, float Q2, float dx, float dy) {
-  return __fmaf_rn(Q0, __fmul_rn(dx, dx), __fmaf_rn(Q2, __fmul_rn(dy, dy), __fmul_rn(Q1, __fmul_rn(dx, dy))));
-}
-
-// Gather one Gaussian of the sorted list into the staging records.
-__device__ __forceinline__ void gather(int32_t f, int N, const float *__restrict__ means2d,
-                                       const float *__restrict__ conics, const float *__restrict__ opacities,
-                                       const float *__restrict__ colors, int colors_per_camera, int D,
-                                       const float *__restrict__ depths, GaussA &a, GaussB &b, GaussC &c) {
-  const int32_t g = f % N;
-  const float2 m = __ldg(reinterpret_cast<const float2 *>(means2d) + f);
-  const float q0 = __ldg(conics + (size_t)f * 3 + 0), q1 = __ldg(conics + (size_t)f * 3 + 1),
-              q2 = __ldg(conics + (size_t)f * 3 + 2);
-  const float o = __ldg(opacities + g);
-  // extent of {alpha >= 1/255} = {sigma <= tau}, tau = ln(255*o): half widths sqrt(2 tau Sigma_xx),
-  // sqrt(2 tau Sigma_yy) with Sigma = conic^-1. Inflated so fp rounding can only over-include.
-  float hx, hy;
-  // det(conic) with Kahan's fma compensation: anisotropic splats cancel badly in q0*q2 - q1*q1
-  const float w = q1 * q1;
-  const float det = fmaf(q0, q2, -w) + fmaf(-q1, q1, w);
-  if (!(o * 255.0f > 1.0f)) {
-    hx = hy = -1e30f;  // alpha < 1/255 everywhere: never evaluated (as upstream would skip it)
-  } else if (!(det > 0.0f) || !(q0 > 0.0f) || !(q2 > 0.0f)) {
-    hx = hy = 3e38f;   // degenerate conic: no culling
-  } else {
-    const float two_tau = 2.0f * __logf(o * 255.0f) * 1.001f + 1e-3f;
-    hx = sqrtf(two_tau * q2 / det) * 1.005f + 0.05f;
-    hy = sqrtf(two_tau * q0 / det) * 1.005f + 0.05f;
-    if (!(hx == hx) || !(hy == hy)) hx = hy = 3e38f;
-  }
-  a = GaussA{m.x, m.y, hx, hy};
-  // exp(-sigma) = 2^(Q0 dx^2 + Q1 dx dy + Q2 dy^2) with Q0 = -q0/2 * log2e, Q1 = -q1 * log2e, Q2 = -q2/2 * log2e
-  b = GaussB{q0 * (-0.5f * kLog2e), q1 * (-kLog2e), q2 * (-0.5f * kLog2e), o};
-  float ch[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-  const float *col = colors + (size_t)(colors_per_camera ? f : g) * D;
-  for (int k = 0; k < D; ++k) ch[k] = __ldg(col + k);
-  if (depths) ch[D] = __ldg(depths + f);
-  c = GaussC{ch[0], ch[1], ch[2], ch[3]};
-}
 
 __global__ void __launch_bounds__(256)
 composite_fwd_kernel(const float *__restrict__ means2d, const float *__restrict__ conics,
@@ -131,64 +56,21 @@ composite_fwd_kernel(const float *__restrict__ means2d, const float *__restrict_
   const int range_start = offsets[ct];
   const int range_end = (ct == (int)gridDim.x - 1) ? (int)n_isects : offsets[ct + 1];
 
-  float T = 1.0f;
-  float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f, o3 = 0.0f;
-  int last = 0;
-  bool done = !inside;
+  PixelState st{1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0, !inside};
+  const WarpFootprint fp{px, py, wcx, wcy};
   const uint32_t aA = smem_u32(sA), aB = smem_u32(sB), aC = smem_u32(sC);
 
   for (int batch_start = range_start; batch_start < range_end; batch_start += kBatch) {
-    if (__syncthreads_count(done) == kBatch) break;
+    if (__syncthreads_count(st.done) == kBatch) break;
     const int idx = batch_start + tid;
     if (idx < range_end) gather(flatten_ids[idx], N, means2d, conics, opacities, colors, colors_per_camera, D, depths, sA[tid], sB[tid], sC[tid]);
     __syncthreads();
     const int batch_size = min(kBatch, range_end - batch_start);
-    if (__all_sync(0xffffffffu, done)) continue;  // this warp is finished; keep hitting the barriers
-    for (int sub = 0; sub < batch_size; sub += 32) {
-      const int j = sub + lane;
-      bool hit = false;
-      if (j < batch_size) {
-        const float4 a = lds128(aA + j * 16);
-        hit = fabsf(a.x - wcx) <= a.z + 3.5f && fabsf(a.y - wcy) <= a.w + 1.5f;
-      }
-      unsigned mask = __ballot_sync(0xffffffffu, hit);
-      while (mask) {  // branch-free body: every lane evaluates, selects decide what sticks
-        const int t = sub + __ffs(mask) - 1;
-        mask &= mask - 1;
-        const float2 m = lds64(aA + t * 16);
-        const float4 b = lds128(aB + t * 16);
-        const float4 c = lds128(aC + t * 16);
-        const float dx = m.x - px, dy = m.y - py;
-        const float p = power2(b.x, b.y, b.z, dx, dy);  // = -sigma * log2e
-        const float alpha = fminf(0.999f, b.w * ex2_approx(p));
-        const float next_T = T * (1.0f - alpha);
-        const bool contrib = !done && !(p > 0.0f) && alpha >= kAlphaMin;  // p > 0 <=> sigma < 0
-        const bool stop = contrib && next_T <= kTStop;
-        const bool add = contrib && !stop;
-        done = done || stop;
-        const float w = add ? alpha * T : 0.0f;
-        o0 = fmaf(c.x, w, o0); o1 = fmaf(c.y, w, o1); o2 = fmaf(c.z, w, o2); o3 = fmaf(c.w, w, o3);
-        T = add ? next_T : T;
-        last = add ? batch_start + t : last;
-      }
-      if (__all_sync(0xffffffffu, done)) break;
-    }
+    if (__all_sync(0xffffffffu, st.done)) continue;  // this warp is finished; keep hitting the barriers
+    composite_batch_fwd(aA, aB, aC, batch_size, batch_start, fp, st);
   }
 
-  if (inside) {
-    const size_t pix = ((size_t)cam * height + iy) * width + ix;
-    alphas[pix] = 1.0f - T;
-    last_ids[pix] = last;
-    float out[4] = {o0, o1, o2, o3};
-    if (backgrounds) {
-      for (int k = 0; k < D; ++k) out[k] += T * __ldg(backgrounds + cam * D + k);
-    }
-    if (CD == 4) {
-      reinterpret_cast<float4 *>(render)[pix] = make_float4(out[0], out[1], out[2], out[3]);
-    } else {
-      for (int k = 0; k < CD; ++k) render[pix * CD + k] = out[k];
-    }
-  }
+  if (inside) store_pixel(st, ((size_t)cam * height + iy) * width + ix, cam, D, CD, backgrounds, render, alphas, last_ids);
 }
 
 // ---------------------------------------------------------------------------

@@ -1,0 +1,315 @@
+// tile_render.cu — fused "sort-as-you-go" tile renderer (forward), the fast path behind
+// prometheus_b200.GaussianRenderer.
+//
+// Front-to-back compositing stops as soon as every pixel of a tile is saturated; on the
+// pixel-aligned scenes of this workload that happens after ~19 % of the tile's depth-sorted list
+// (I_need / I, bench.py). The separate-stage pipeline (tile_sort.cu + composite.cu — what
+// gsplat.rasterization needs, because it exposes the fully sorted arrays) still sorts 100 % of every
+// tile. This kernel sorts only what the compositor consumes: one CTA per (camera, tile)
+//   1. reads the tile's unsorted {depth bits, flatten id} records (written by bin_scatter),
+//      finds the depth range and histograms the records into 256 depth-ordered sub-buckets;
+//   2. walks the sub-buckets front to back in groups of <= 2048 records: collect the group into
+//      shared memory, radix-sort it there by (depth bits, flatten id), write the sorted flatten ids
+//      to their final positions (the backward pass replays them), composite the group with exactly
+//      the code of composite_fwd_kernel (composite_common.cuh);
+//   3. stops at the first group boundary where all 256 pixels are done.
+// Because sub-buckets partition the keys by value and ties are ordered by flatten id, position k of
+// the tile's list holds the same Gaussian as after a full stable sort, so images, alphas and
+// last_ids are BIT-IDENTICAL to the separate-stage path (tests/test_gpu_parity.py) — only the tail of
+// flatten_ids that nobody reads is left unsorted.
+// Reference semantics: gsplat 1.4.0 isect_tiles + rasterize_to_pixels_fwd (call site
+// prometheus/modules/renderers/gaussians_renderer.py:413-427), SURVEY.md §8c steps 6-10.
+#include "composite_common.cuh"
+
+namespace pm {
+
+constexpr int kTrThreads = 256;
+constexpr int kTrWarps = kTrThreads / 32;
+constexpr int kTrItems = 8;
+constexpr int kTrCap = kTrThreads * kTrItems;  // 2048 records per group
+constexpr int kTrRadix = 256;
+
+__device__ __forceinline__ unsigned tr_match_digit8(uint32_t d) {
+  unsigned peers = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const unsigned m = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+    peers &= ((d >> b) & 1u) ? m : ~m;
+  }
+  return peers;
+}
+
+struct TrShared {
+  uint2 gbuf[kTrCap];                      // group being sorted: {depth bits, flatten id}
+  uint16_t warp_hist[kTrWarps][kTrRadix];
+  uint32_t digit_start[kTrRadix];
+  uint32_t red[64];
+  int bucket[kTrRadix + 1];                // start of each depth sub-bucket inside the tile's list
+  GaussA sA[kBatch];
+  GaussB sB[kBatch];
+  GaussC sC[kBatch];
+  int cnt;
+  uint32_t kmin, kmax;
+};
+
+// Sort sh.gbuf[0..m) by (key, flatten id); gmin/gmax = key range of the group. All threads call it.
+__device__ __forceinline__ void sort_group(TrShared &sh, int m, uint32_t gmin, uint32_t gmax) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int chunk0 = warp * (kTrItems * 32);
+  uint32_t dk[kTrItems], fid[kTrItems], rk[kTrItems];
+#pragma unroll
+  for (int k = 0; k < kTrItems; ++k) {
+    const int slot = chunk0 + k * 32 + lane;
+    if (slot < m) {
+      const uint2 v = sh.gbuf[slot];
+      dk[k] = v.x - gmin;
+      fid[k] = v.y;
+    } else {  // empty slots: all-ones, sorted like real records and therefore kept at the end
+      dk[k] = 0xffffffffu;
+      fid[k] = 0xffffffffu;
+    }
+  }
+  const uint32_t range = gmax - gmin;
+  for (int shift = 0; shift < 32 && (range >> shift) != 0; shift += 8) {
+    __syncthreads();
+    for (int i = tid; i < kTrWarps * kTrRadix / 2; i += kTrThreads) reinterpret_cast<uint32_t *>(sh.warp_hist)[i] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kTrItems; ++k) {
+      const uint32_t d = (dk[k] >> shift) & 0xffu;
+      const unsigned peers = tr_match_digit8(d);
+      const unsigned lower = peers & ((1u << lane) - 1);
+      uint32_t base = 0;
+      if (lower == 0) {
+        base = sh.warp_hist[warp][d];
+        sh.warp_hist[warp][d] = (uint16_t)(base + __popc(peers));
+      }
+      base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
+      rk[k] = base + __popc(lower);
+      __syncwarp();
+    }
+    __syncthreads();
+    {  // digit d (thread d): exclusive offsets across warps, then exclusive scan over the 256 digits
+      uint32_t count = 0;
+#pragma unroll
+      for (int w = 0; w < kTrWarps; ++w) {
+        const uint32_t c = sh.warp_hist[w][tid];
+        sh.warp_hist[w][tid] = (uint16_t)count;
+        count += c;
+      }
+      uint32_t inc = count;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (lane == 31) sh.red[warp] = inc;
+      sh.digit_start[tid] = inc - count;
+    }
+    __syncthreads();
+    {
+      uint32_t wbase = 0;
+      for (int w = 0; w < warp; ++w) wbase += sh.red[w];
+      sh.digit_start[tid] += wbase;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kTrItems; ++k) {
+      const uint32_t d = (dk[k] >> shift) & 0xffu;
+      sh.gbuf[sh.digit_start[d] + sh.warp_hist[warp][d] + rk[k]] = make_uint2(dk[k], fid[k]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kTrItems; ++k) {
+      const uint2 v = sh.gbuf[chunk0 + k * 32 + lane];
+      dk[k] = v.x;
+      fid[k] = v.y;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kTrItems; ++k) {
+    const int slot = chunk0 + k * 32 + lane;
+    if (slot < m) sh.gbuf[slot] = make_uint2(dk[k] + gmin, fid[k]);
+  }
+  __syncthreads();
+  // ties on the depth bits: order each run by flatten id
+#pragma unroll
+  for (int k = 0; k < kTrItems; ++k) {
+    const int slot = chunk0 + k * 32 + lane;
+    if (slot < m - 1) {
+      const uint32_t key = sh.gbuf[slot].x;
+      const bool run_start = (slot == 0 || sh.gbuf[slot - 1].x != key) && sh.gbuf[slot + 1].x == key;
+      if (run_start) {
+        int e = slot + 1;
+        while (e < m && sh.gbuf[e].x == key) ++e;
+        for (int i = slot + 1; i < e; ++i) {
+          const uint32_t v = sh.gbuf[i].y;
+          int j = i - 1;
+          while (j >= slot && sh.gbuf[j].y > v) { sh.gbuf[j + 1].y = sh.gbuf[j].y; --j; }
+          sh.gbuf[j + 1].y = v;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kTrThreads, 4)
+tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__restrict__ offsets,
+                       int64_t n_host, const int32_t *__restrict__ d_n, const float *__restrict__ means2d,
+                       const float *__restrict__ conics, const float *__restrict__ opacities,
+                       const float *__restrict__ colors, int colors_per_camera, int D,
+                       const float *__restrict__ depths, const float *__restrict__ backgrounds, int N,
+                       int width, int height, int tile_width, int tile_height, float *__restrict__ render,
+                       float *__restrict__ alphas, int32_t *__restrict__ last_ids,
+                       int32_t *__restrict__ flatten_ids, int32_t *__restrict__ sorted_counts,
+                       int32_t *__restrict__ overflow_flag) {
+  __shared__ TrShared sh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_tiles = tile_width * tile_height;
+  const int ct = blockIdx.x;
+  const int cam = ct / n_tiles, tile = ct % n_tiles;
+  const int tile_y = tile / tile_width, tile_x = tile % tile_width;
+  const int wx0 = tile_x * kTile + (warp & 1) * 8, wy0 = tile_y * kTile + (warp >> 1) * 4;
+  const int ix = wx0 + (lane & 7), iy = wy0 + (lane >> 3);
+  const bool inside = ix < width && iy < height;
+  const int CD = D + (depths ? 1 : 0);
+  const WarpFootprint fp{(float)ix + 0.5f, (float)iy + 0.5f, (float)wx0 + 4.0f, (float)wy0 + 2.0f};
+  PixelState st{1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0, !inside};
+  const uint32_t aA = smem_u32(sh.sA), aB = smem_u32(sh.sB), aC = smem_u32(sh.sC);
+
+  const int64_t n_isects = effective_n(n_host, d_n);
+  const int start = offsets[ct];
+  const int end = (ct == (int)gridDim.x - 1) ? (int)n_isects : offsets[ct + 1];
+  const int cnt = end - start;
+  const uint64_t *src = records + start;
+  int sorted = 0;
+
+  if (cnt > 0) {
+    // ---- 1. depth range of the tile and histogram over 256 depth-ordered sub-buckets
+    if (tid == 0) { sh.kmin = 0xffffffffu; sh.kmax = 0u; }
+    for (int i = tid; i <= kTrRadix; i += kTrThreads) sh.bucket[i] = 0;
+    __syncthreads();
+    uint32_t kmin = 0xffffffffu, kmax = 0u;
+    for (int i = tid; i < cnt; i += kTrThreads) {
+      const uint32_t k = (uint32_t)__ldg(reinterpret_cast<const unsigned long long *>(src) + i);
+      kmin = min(kmin, k);
+      kmax = max(kmax, k);
+    }
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    if (lane == 0) { atomicMin(&sh.kmin, kmin); atomicMax(&sh.kmax, kmax); }
+    __syncthreads();
+    kmin = sh.kmin;
+    const uint32_t range = sh.kmax - kmin;
+    const int bits = 32 - __clz(range | 1u);
+    const int shift = bits > 8 ? bits - 8 : 0;
+    for (int i = tid; i < cnt; i += kTrThreads) {
+      const uint32_t k = (uint32_t)__ldg(reinterpret_cast<const unsigned long long *>(src) + i);
+      atomicAdd(&sh.bucket[((k - kmin) >> shift) + 1], 1);
+    }
+    __syncthreads();
+    {  // exclusive scan: bucket[d] = start of sub-bucket d, bucket[256] = cnt
+      const int v = sh.bucket[tid + 1];
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (lane == 31) sh.red[warp] = (uint32_t)inc;
+      __syncthreads();
+      int wbase = 0;
+      for (int w = 0; w < warp; ++w) wbase += (int)sh.red[w];
+      sh.bucket[tid + 1] = wbase + inc;
+      __syncthreads();
+    }
+
+    // ---- 2. groups of sub-buckets, front to back, until every pixel is done
+    int g0 = 0;
+    while (g0 < kTrRadix) {
+      if (__syncthreads_count(st.done) == kTrThreads) break;
+      int g1 = g0 + 1;
+      while (g1 < kTrRadix && sh.bucket[g1 + 1] - sh.bucket[g0] <= kTrCap) ++g1;
+      const int gs = sh.bucket[g0], ge = sh.bucket[g1];
+      const int m = ge - gs;
+      if (m > kTrCap) {  // one depth sub-bucket does not fit: the caller re-renders with the separate stages
+        if (tid == 0) atomicExch(overflow_flag, 1);
+        break;
+      }
+      if (m > 0) {
+        // collect the group (order does not matter: the sort below keys on (depth bits, flatten id))
+        if (tid == 0) { sh.cnt = 0; sh.kmin = 0xffffffffu; sh.kmax = 0u; }
+        __syncthreads();
+        uint32_t gmin = 0xffffffffu, gmax = 0u;
+        for (int i = tid; i < cnt; i += kTrThreads) {
+          const uint64_t r = __ldg(reinterpret_cast<const unsigned long long *>(src) + i);
+          const uint32_t k = (uint32_t)r;
+          const int b = (int)((k - kmin) >> shift);
+          if (b >= g0 && b < g1) {
+            sh.gbuf[atomicAdd(&sh.cnt, 1)] = make_uint2(k, (uint32_t)(r >> 32));
+            gmin = min(gmin, k);
+            gmax = max(gmax, k);
+          }
+        }
+        gmin = __reduce_min_sync(0xffffffffu, gmin);
+        gmax = __reduce_max_sync(0xffffffffu, gmax);
+        if (lane == 0) { atomicMin(&sh.kmin, gmin); atomicMax(&sh.kmax, gmax); }
+        __syncthreads();
+        sort_group(sh, m, sh.kmin, sh.kmax);
+        // sorted flatten ids go to their final positions (read again by the backward pass)
+        for (int i = tid; i < m; i += kTrThreads) flatten_ids[(size_t)start + gs + i] = (int32_t)sh.gbuf[i].y;
+        sorted = ge;
+        // composite the group, batch by batch — same code as composite_fwd_kernel
+        for (int b0 = 0; b0 < m; b0 += kBatch) {
+          if (b0 > 0 && __syncthreads_count(st.done) == kTrThreads) break;
+          if (b0 + tid < m)
+            gather((int32_t)sh.gbuf[b0 + tid].y, N, means2d, conics, opacities, colors, colors_per_camera, D, depths,
+                   sh.sA[tid], sh.sB[tid], sh.sC[tid]);
+          __syncthreads();
+          if (!__all_sync(0xffffffffu, st.done))
+            composite_batch_fwd(aA, aB, aC, min(kBatch, m - b0), start + gs + b0, fp, st);
+        }
+      }
+      g0 = g1;
+    }
+  }
+  if (tid == 0) sorted_counts[ct] = sorted;
+  if (inside) store_pixel(st, ((size_t)cam * height + iy) * width + ix, cam, D, CD, backgrounds, render, alphas, last_ids);
+}
+
+}  // namespace pm
+
+extern "C" {
+
+int pm_tile_render_fwd(const uint64_t *records, const int32_t *isect_offsets, int64_t n_isects,
+                       const int32_t *d_n, const float *means2d, const float *conics,
+                       const float *opacities, const float *colors, int colors_per_camera, int D,
+                       const float *depths, const float *backgrounds, int N, int C, int width, int height,
+                       int tile_size, float *render, float *alphas, int32_t *last_ids,
+                       int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
+                       pm_stream_t stream) {
+  if (N < 0 || C < 0 || width <= 0 || height <= 0 || n_isects < 0 || D < 0) return PM_ERR_BAD_ARG;
+  if (tile_size != pm::kTile) return PM_ERR_UNSUPPORTED;
+  const int CD = D + (depths ? 1 : 0);
+  if (CD < 1 || CD > 4) return PM_ERR_UNSUPPORTED;
+  if (!means2d || !conics || !opacities || !isect_offsets || !render || !alphas || !last_ids || !sorted_counts ||
+      !overflow_flag)
+    return PM_ERR_BAD_ARG;
+  if (D > 0 && !colors) return PM_ERR_BAD_ARG;
+  if (n_isects > 0 && (!records || !flatten_ids)) return PM_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(means2d) & 7) != 0) return PM_ERR_BAD_ARG;
+  if (CD == 4 && (reinterpret_cast<uintptr_t>(render) & 15) != 0) return PM_ERR_BAD_ARG;
+  if (n_isects >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
+  if (C == 0) return PM_OK;
+  const int tw = (width + pm::kTile - 1) / pm::kTile, th = (height + pm::kTile - 1) / pm::kTile;
+  const int64_t blocks = (int64_t)C * tw * th;
+  if (blocks >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
+  pm::tile_render_fwd_kernel<<<(unsigned)blocks, pm::kTrThreads, 0, pm::as_stream(stream)>>>(
+      records, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera, D, depths,
+      backgrounds, N, width, height, tw, th, render, alphas, last_ids, flatten_ids, sorted_counts, overflow_flag);
+  return pm::check_launch();
+}
+
+}  // extern "C"

@@ -324,6 +324,29 @@ def composite_fwd(means2d, conics, opacities, colors, depths, backgrounds, offse
     return render, alphas, last_ids
 
 
+@_instrument("tile_render_fwd", 1)
+def tile_render_fwd(records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height, d_n=None):
+    """Fused sort-as-you-go forward -> render, alphas, last_ids, flatten_ids (sorted prefix per tile),
+    sorted_counts [C,th,tw], overflow flag int32[1]."""
+    L = _lib.load()
+    C, N = means2d.shape[:2]
+    colors, per_cam, D = _colors_layout(colors, C, N)
+    CD = D + (0 if depths is None else 1)
+    dev = means2d.device
+    n = records.numel()
+    render = torch.empty(C, height, width, CD, device=dev)
+    alphas = torch.empty(C, height, width, device=dev)
+    last_ids = torch.empty(C, height, width, dtype=torch.int32, device=dev)
+    flat = torch.empty(n, dtype=torch.int32, device=dev)
+    sorted_counts = torch.empty_like(offsets)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(L.pm_tile_render_fwd(_ptr(records), _ptr(offsets), n, _ptr(d_n), _ptr(means2d), _ptr(conics),
+                                    _ptr(opacities), _ptr(colors), per_cam, D, _ptr(depths), _ptr(backgrounds), N, C,
+                                    width, height, TILE, _ptr(render), _ptr(alphas), _ptr(last_ids), _ptr(flat),
+                                    _ptr(sorted_counts), _ptr(flag), _stream()), "pm_tile_render_fwd")
+    return render, alphas, last_ids, flat, sorted_counts, flag
+
+
 @_instrument("composite_bwd", 1)
 def composite_bwd(means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width,
                   height, alphas, last_ids, v_render, v_alphas, d_n=None):

@@ -81,6 +81,42 @@ class _Composite(torch.autograd.Function):
         return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None, None
 
 
+class _TileRender(torch.autograd.Function):
+    """Fused sort-as-you-go forward (ops.tile_render_fwd) + the ordinary compositing backward."""
+
+    @staticmethod
+    def forward(ctx, means2d, conics, opacities, colors, depths, backgrounds, records, offsets, width, height):
+        means2d, conics = means2d.contiguous(), conics.contiguous()
+        opacities = opacities.contiguous()
+        colors = None if colors is None else colors.contiguous()
+        depths = None if depths is None else depths.contiguous()
+        backgrounds = None if backgrounds is None else backgrounds.contiguous().float()
+        render, alphas, last_ids, flat, sorted_counts, flag = ops.tile_render_fwd(
+            records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height)
+        ctx.save_for_backward(means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, alphas, last_ids)
+        ctx.dims = (width, height)
+        ctx.mark_non_differentiable(flag, flat, sorted_counts)
+        return render, alphas.unsqueeze(-1), flag, flat, sorted_counts
+
+    @staticmethod
+    def backward(ctx, v_render, v_alphas, _vf, _vflat, _vsc):
+        means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, alphas, last_ids = ctx.saved_tensors
+        width, height = ctx.dims
+        v_alphas2 = None if v_alphas is None else v_alphas.squeeze(-1)
+        v_means2d, v_conics, v_colors, v_opac, v_depths = ops.composite_bwd(
+            means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, width, height, alphas, last_ids,
+            v_render, v_alphas2, None)
+        v_bg = None
+        if backgrounds is not None and ctx.needs_input_grad[5] and v_render is not None:
+            D = backgrounds.shape[-1]
+            v_bg = (v_render[..., :D] * (1.0 - alphas).unsqueeze(-1)).sum(dim=(1, 2))
+        return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None
+
+
+# Largest per-tile group the fused kernel sorts at once (tile_render.cu: kTrCap)
+FUSED_GROUP_CAP = 2048
+
+
 def isect_tiles(means2d, radii, depths, tiles_per_gauss, width, height, C, force_generic=False):
     """Tile binning + depth sort (no gradient). Returns sorted isect_ids, flatten_ids and
     isect_offsets. One host sync: n_isects sizes the output arrays, as upstream.
@@ -144,10 +180,13 @@ def _rasterize_core(means, quats, scales, opacities, colors, viewmats, Ks, width
                     far_plane=1e10, radius_clip=0.0, eps2d=0.3, sh_degree=None, packed=True, tile_size=16,
                     backgrounds=None, render_mode="RGB", sparse_grad=False, absgrad=False,
                     rasterize_mode="classic", channel_chunk=32, distributed=False, camera_model="pinhole",
-                    covars=None, per_view_means2d=False):
+                    covars=None, per_view_means2d=False, fused=False):
     """Body of `rasterization`. `per_view_means2d=True` (used by renderer.GaussianRenderer)
     additionally returns meta["means2d_views"]: one [1,N,2] graph tensor per camera with
-    retain_grad() set, the batched equivalent of gaussians_renderer.py:428-445."""
+    retain_grad() set, the batched equivalent of gaussians_renderer.py:428-445.
+    `fused=True` (module-level fast path) renders with the sort-as-you-go kernel: images are
+    bit-identical, but meta["isect_ids"] is None and meta["flatten_ids"] is sorted only up to
+    meta["sorted_counts"] entries per tile."""
     N = means.shape[0]
     C = viewmats.shape[0]
     assert means.shape == (N, 3), means.shape
@@ -180,8 +219,11 @@ def _rasterize_core(means, quats, scales, opacities, colors, viewmats, Ks, width
     means2d, depths, conics, radii, tpg = _Project.apply(
         means.contiguous(), quats.contiguous(), scales.contiguous(), viewmats, Ks, width, height, eps2d,
         near_plane, far_plane, radius_clip)
-    isect_ids, flatten_ids, isect_offsets = isect_tiles(means2d.detach(), radii, depths.detach(), tpg, width,
-                                                        height, C, force_generic=FORCE_GENERIC_SORT)
+    with_depth = render_mode in ("D", "ED", "RGB+D", "RGB+ED")
+    only_depth = render_mode in ("D", "ED")
+    D = colors.shape[-1]
+    if (0 if only_depth else D) + (1 if with_depth else 0) > 4:
+        raise NotImplementedError("prometheus_b200.rasterization: at most 4 render channels (RGB + depth)")
 
     means2d_views = None
     means2d_in = means2d
@@ -191,15 +233,26 @@ def _rasterize_core(means, quats, scales, opacities, colors, viewmats, Ks, width
             for v in means2d_views:
                 v.retain_grad()
             means2d_in = torch.cat(means2d_views, dim=0)
+    comp_args = (means2d_in, conics, opacities, None if only_depth else colors, depths if with_depth else None,
+                 None if only_depth else backgrounds)
 
-    with_depth = render_mode in ("D", "ED", "RGB+D", "RGB+ED")
-    only_depth = render_mode in ("D", "ED")
-    D = colors.shape[-1]
-    if (0 if only_depth else D) + (1 if with_depth else 0) > 4:
-        raise NotImplementedError("prometheus_b200.rasterization: at most 4 render channels (RGB + depth)")
-    render, alphas = _Composite.apply(
-        means2d_in, conics, opacities, None if only_depth else colors, depths if with_depth else None,
-        None if only_depth else backgrounds, isect_offsets, flatten_ids, width, height, None)
+    render = None
+    sorted_counts = None
+    if fused and not FORCE_GENERIC_SORT:
+        m2d, dep = means2d.detach(), depths.detach()
+        isect_offsets, stats = ops.tile_scan(ops.bin_count(m2d, radii, width, height))
+        n_isects, max_count = stats.tolist()
+        records = ops.bin_scatter(m2d, radii, dep, isect_offsets, width, height, n_isects)
+        render, alphas, flag, flatten_ids, sorted_counts = _TileRender.apply(*comp_args, records, isect_offsets, width, height)
+        isect_ids = None
+        # a depth sub-bucket larger than the group capacity can only exist if some tile is larger than it
+        if max_count > FUSED_GROUP_CAP and int(flag.item()) != 0:
+            render = None
+    if render is None:
+        isect_ids, flatten_ids, isect_offsets = isect_tiles(means2d.detach(), radii, depths.detach(), tpg, width,
+                                                            height, C, force_generic=FORCE_GENERIC_SORT)
+        sorted_counts = None
+        render, alphas = _Composite.apply(*comp_args, isect_offsets, flatten_ids, width, height, None)
     if render_mode in ("ED", "RGB+ED"):
         render = torch.cat([render[..., :-1], render[..., -1:] / alphas.clamp(min=1e-10)], dim=-1)
 
@@ -213,4 +266,6 @@ def _rasterize_core(means, quats, scales, opacities, colors, viewmats, Ks, width
     }
     if means2d_views is not None:
         meta["means2d_views"] = means2d_views
+    if sorted_counts is not None:
+        meta["sorted_counts"] = sorted_counts
     return render, alphas, meta

@@ -75,6 +75,9 @@ class GaussianRenderer(nn.Module):
     # cameras rendered per batched launch set: bounds the per-pair / per-intersection buffers
     # (32 B per (camera, Gaussian) pair) when a long trajectory is rendered from a big scene
     view_chunk = 8
+    # render with the fused sort-as-you-go kernel (tile_render.cu): bit-identical images, but only the
+    # part of each tile's list that the compositor consumes gets sorted
+    fused = True
 
     def __init__(self, sh_degree=0, background=[1, 1, 1]):
         super().__init__()
@@ -109,7 +112,7 @@ class GaussianRenderer(nn.Module):
                 render, alphas, info = _rasterize_core(
                     means=xyz[i], quats=rotations[i], scales=sc, opacities=opacity[i].squeeze(-1),
                     colors=features[i][:, 0], viewmats=viewmats[i, c0:c1], Ks=Ks[i, c0:c1], backgrounds=bgs[c0:c1],
-                    width=int(w), height=int(h), render_mode="RGB+ED", packed=False, per_view_means2d=True)
+                    width=int(w), height=int(h), render_mode="RGB+ED", packed=False, per_view_means2d=True, fused=self.fused)
                 im_i.append(render[..., :3].permute(0, 3, 1, 2))
                 de_i.append(render[..., 3:].permute(0, 3, 1, 2))
                 ma_i.append(alphas.permute(0, 3, 1, 2).clamp(0, 1))

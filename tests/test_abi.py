@@ -21,7 +21,7 @@ def test_header_declares_expected_surface():
     syms = declared_symbols()
     for s in ("pm_unproject_fwd", "pm_unproject_bwd", "pm_camera_prep", "pm_project_fwd", "pm_project_bwd",
               "pm_scan_tiles", "pm_bin_emit", "pm_sort_pairs", "pm_tile_offsets", "pm_composite_fwd",
-              "pm_bin_count", "pm_tile_scan", "pm_bin_scatter", "pm_tile_sort", "pm_tile_sort_capacity",
+              "pm_tile_render_fwd", "pm_bin_count", "pm_tile_scan", "pm_bin_scatter", "pm_tile_sort", "pm_tile_sort_capacity",
               "pm_composite_bwd", "pm_abi_version"):
         assert s in syms
     assert set(syms) == set(_lib.SIGNATURES)  # the ctypes binding mirrors the header one to one
