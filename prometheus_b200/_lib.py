@@ -13,7 +13,8 @@ import subprocess
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_PKG, "libprometheus_gs.so")
+# PM_GS_LIB: developer knob for A/B-timing an alternative build of the same C-ABI (tools/stage_bench.py)
+_SO = os.environ.get("PM_GS_LIB") or os.path.join(_PKG, "libprometheus_gs.so")
 _CSRC = os.path.join(_PKG, "csrc")
 _lib = None
 
@@ -80,7 +81,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if _stale():
+    if not os.environ.get("PM_GS_LIB") and _stale():
         try:
             build()
         except Exception as e:  # noqa: BLE001

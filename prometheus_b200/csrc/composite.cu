@@ -35,9 +35,9 @@ composite_fwd_kernel(const float *__restrict__ means2d, const float *__restrict_
                      const int32_t *__restrict__ d_n, int N, int width, int height, int tile_width,
                      int tile_height, float *__restrict__ render, float *__restrict__ alphas,
                      int32_t *__restrict__ last_ids) {
-  __shared__ GaussA sA[kBatch];
-  __shared__ GaussB sB[kBatch];
-  __shared__ GaussC sC[kBatch];
+  __shared__ Staged<kBatch> stg;
+  __shared__ uint32_t queue[8][kQueueWords];
+  staged_init_null(stg);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_tiles = tile_width * tile_height;
@@ -56,18 +56,18 @@ composite_fwd_kernel(const float *__restrict__ means2d, const float *__restrict_
   const int range_start = offsets[ct];
   const int range_end = (ct == (int)gridDim.x - 1) ? (int)n_isects : offsets[ct + 1];
 
-  PixelState st{1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0, !inside};
+  PixelState st{inside ? 1.0f : -1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0};
   const WarpFootprint fp{px, py, wcx, wcy};
-  const uint32_t aA = smem_u32(sA), aB = smem_u32(sB), aC = smem_u32(sC);
+  const uint32_t aS = smem_u32(&stg), aQ = smem_u32(queue[warp]);
 
   for (int batch_start = range_start; batch_start < range_end; batch_start += kBatch) {
-    if (__syncthreads_count(st.done) == kBatch) break;
+    if (__syncthreads_count(pixel_done(st)) == kBatch) break;
     const int idx = batch_start + tid;
-    if (idx < range_end) gather(flatten_ids[idx], N, means2d, conics, opacities, colors, colors_per_camera, D, depths, sA[tid], sB[tid], sC[tid]);
+    if (idx < range_end) { const int32_t f = flatten_ids[idx]; gather(f, f - cam * N, means2d, conics, opacities, colors, colors_per_camera, D, depths, stg.sA[tid], stg.sB[tid], stg.sC[tid]); }
     __syncthreads();
     const int batch_size = min(kBatch, range_end - batch_start);
-    if (__all_sync(0xffffffffu, st.done)) continue;  // this warp is finished; keep hitting the barriers
-    composite_batch_fwd(aA, aB, aC, batch_size, batch_start, fp, st);
+    if (__all_sync(0xffffffffu, pixel_done(st))) continue;  // this warp is finished; keep hitting the barriers
+    composite_batch_fwd<kBatch>(aS, aQ, batch_size, batch_start, fp, st);
   }
 
   if (inside) store_pixel(st, ((size_t)cam * height + iy) * width + ix, cam, D, CD, backgrounds, render, alphas, last_ids);
@@ -211,7 +211,7 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
     if (tid < batch_size) {
       const int32_t f = flatten_ids[batch_start + tid];
       sF[tid] = f;
-      gather(f, N, means2d, conics, opacities, colors, colors_per_camera, D, depths, sA[tid], sB[tid], sC[tid]);
+      gather(f, f - cam * N, means2d, conics, opacities, colors, colors_per_camera, D, depths, sA[tid], sB[tid], sC[tid]);
     }
     for (int i = tid; i < kBatch * kGradStride; i += 256) sG[i] = 0.0f;
     __syncthreads();
@@ -268,7 +268,7 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
     if (tid < batch_size) {
       const float *gr = &sG[tid * kGradStride];
       const int32_t f = sF[tid];
-      const int32_t g = f % N;
+      const int32_t g = f - cam * N;
       float *vc = v_colors + (size_t)(colors_per_camera ? f : g) * D;
       for (int k = 0; k < D; ++k)
         if (gr[k] != 0.0f) atomicAdd(vc + k, gr[k]);

@@ -46,16 +46,39 @@ __device__ __forceinline__ float power2(float Q0, float Q1, float Q2, float dx, 
   return __fmaf_rn(Q0, __fmul_rn(dx, dx), __fmaf_rn(Q2, __fmul_rn(dy, dy), __fmul_rn(Q1, __fmul_rn(dx, dy))));
 }
 
-// Gather one Gaussian of the sorted list into the staging records.
-__device__ __forceinline__ void gather(int32_t f, int N, const float *__restrict__ means2d,
-                                       const float *__restrict__ conics, const float *__restrict__ opacities,
-                                       const float *__restrict__ colors, int colors_per_camera, int D,
-                                       const float *__restrict__ depths, GaussA &a, GaussB &b, GaussC &c) {
-  const int32_t g = f % N;
-  const float2 m = __ldg(reinterpret_cast<const float2 *>(means2d) + f);
-  const float q0 = __ldg(conics + (size_t)f * 3 + 0), q1 = __ldg(conics + (size_t)f * 3 + 1),
-              q2 = __ldg(conics + (size_t)f * 3 + 2);
-  const float o = __ldg(opacities + g);
+// Gather one Gaussian of the sorted list into the staging records, in two halves so that callers can
+// put the global loads of several Gaussians in flight before the first use (gather_load) and do the
+// arithmetic afterwards (gather_finish). f = flatten id (camera * N + g), g = Gaussian id.
+struct GaussRaw {
+  float2 m;
+  float q0, q1, q2, o;
+  float ch[4];
+};
+__device__ __forceinline__ GaussRaw gather_load(int32_t f, int32_t g, const float *__restrict__ means2d,
+                                                const float *__restrict__ conics, const float *__restrict__ opacities,
+                                                const float *__restrict__ colors, int colors_per_camera, int D,
+                                                const float *__restrict__ depths) {
+  GaussRaw r;
+  r.m = __ldg(reinterpret_cast<const float2 *>(means2d) + f);
+  r.q0 = __ldg(conics + (size_t)f * 3 + 0);
+  r.q1 = __ldg(conics + (size_t)f * 3 + 1);
+  r.q2 = __ldg(conics + (size_t)f * 3 + 2);
+  r.o = __ldg(opacities + g);
+  r.ch[0] = r.ch[1] = r.ch[2] = r.ch[3] = 0.0f;
+  const float *col = colors + (size_t)(colors_per_camera ? f : g) * D;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < D) r.ch[k] = __ldg(col + k);
+  if (depths) {
+    const float d = __ldg(depths + f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k == D) r.ch[k] = d;
+  }
+  return r;
+}
+__device__ __forceinline__ void gather_finish(const GaussRaw &r, GaussA &a, GaussB &b, GaussC &c) {
+  const float q0 = r.q0, q1 = r.q1, q2 = r.q2, o = r.o;
   // extent of {alpha >= 1/255} = {sigma <= tau}, tau = ln(255*o): half widths sqrt(2 tau Sigma_xx),
   // sqrt(2 tau Sigma_yy) with Sigma = conic^-1. Inflated so fp rounding can only over-include.
   float hx, hy;
@@ -72,23 +95,27 @@ __device__ __forceinline__ void gather(int32_t f, int N, const float *__restrict
     hy = sqrtf(two_tau * q0 / det) * 1.005f + 0.05f;
     if (!(hx == hx) || !(hy == hy)) hx = hy = 3e38f;
   }
-  a = GaussA{m.x, m.y, hx, hy};
+  a = GaussA{r.m.x, r.m.y, hx, hy};
   // exp(-sigma) = 2^(Q0 dx^2 + Q1 dx dy + Q2 dy^2) with Q0 = -q0/2 * log2e, Q1 = -q1 * log2e, Q2 = -q2/2 * log2e
   b = GaussB{q0 * (-0.5f * kLog2e), q1 * (-kLog2e), q2 * (-0.5f * kLog2e), o};
-  float ch[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-  const float *col = colors + (size_t)(colors_per_camera ? f : g) * D;
-  for (int k = 0; k < D; ++k) ch[k] = __ldg(col + k);
-  if (depths) ch[D] = __ldg(depths + f);
-  c = GaussC{ch[0], ch[1], ch[2], ch[3]};
+  c = GaussC{r.ch[0], r.ch[1], r.ch[2], r.ch[3]};
+}
+__device__ __forceinline__ void gather(int32_t f, int32_t g, const float *__restrict__ means2d,
+                                       const float *__restrict__ conics, const float *__restrict__ opacities,
+                                       const float *__restrict__ colors, int colors_per_camera, int D,
+                                       const float *__restrict__ depths, GaussA &a, GaussB &b, GaussC &c) {
+  gather_finish(gather_load(f, g, means2d, conics, opacities, colors, colors_per_camera, D, depths), a, b, c);
 }
 
-
-// Per-pixel forward state of one lane.
+// Per-pixel forward state of one lane. The sign of T carries the "done" flag: T > 0 while the pixel
+// is live (the stop rule keeps a live T above 1e-4), T < 0 once it stopped or if it lies outside the
+// image; |T| is the transmittance the epilogue writes. A done pixel can never add again because
+// next_T = T (1 - alpha) stays negative, so no separate flag has to be tested in the hot loop.
 struct PixelState {
   float T, o0, o1, o2, o3;
   int last;
-  bool done;
 };
+__device__ __forceinline__ bool pixel_done(const PixelState &st) { return st.T < 0.0f; }
 
 // Footprint of one warp: 8 x 4 pixels of the 16 x 16 tile.
 struct WarpFootprint {
@@ -96,54 +123,114 @@ struct WarpFootprint {
   float wcx, wcy;  // footprint centre (pixel centres span +-3.5, +-1.5 around it)
 };
 
-// Composite one staged batch (records in shared memory at aA/aB/aC, `batch_size` valid entries whose
-// position in the tile's sorted list starts at `list_pos`) into the lane's pixel. Warp-level culling via
-// ballot, branch-free body. Returns with st.done updated; callers handle the CTA-level early exit.
-__device__ __forceinline__ void composite_batch_fwd(uint32_t aA, uint32_t aB, uint32_t aC, int batch_size,
-                                                    int list_pos, const WarpFootprint &fp, PixelState &st) {
+// Staged Gaussians of one batch / group, structure of arrays with compile-time strides so that the hot
+// loop addresses all three records of a Gaussian from ONE register (+ immediates).
+template <int CAP>
+struct Staged {
+  GaussA sA[CAP + 1];  // slot CAP is a null Gaussian (opacity 0): pads odd hit counts in the pairwise loop
+  GaussB sB[CAP + 1];
+  GaussC sC[CAP + 1];
+};
+constexpr int kQueueWords = 34;  // per-warp hit queue: up to 32 hits + pad, as shared-memory addresses
+
+template <int CAP>
+__device__ __forceinline__ void staged_init_null(Staged<CAP> &s) {
+  if (threadIdx.x == 0) {
+    s.sA[CAP] = GaussA{0.0f, 0.0f, -1e30f, -1e30f};
+    s.sB[CAP] = GaussB{0.0f, 0.0f, 0.0f, 0.0f};
+    s.sC[CAP] = GaussC{0.0f, 0.0f, 0.0f, 0.0f};
+  }
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint2 lds64u(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+  return v;
+}
+
+// alpha of the staged Gaussian whose A record sits at shared address `ga`, at the lane's pixel, and
+// whether it may contribute (sigma >= 0, alpha >= 1/255)
+template <int CAP>
+__device__ __forceinline__ void eval_alpha(uint32_t ga, const WarpFootprint &fp, float &alpha, bool &contrib) {
+  const float2 m = lds64(ga);
+  const float4 b = lds128(ga + (CAP + 1) * 16);
+  const float dx = m.x - fp.px, dy = m.y - fp.py;
+  const float p = power2(b.x, b.y, b.z, dx, dy);  // = -sigma * log2e
+  alpha = fminf(0.999f, b.w * ex2_approx(p));
+  contrib = !(p > 0.0f) && alpha >= kAlphaMin;  // p > 0 <=> sigma < 0
+}
+
+// fold one evaluated Gaussian into the pixel (branch-free: selects decide what sticks)
+__device__ __forceinline__ void blend(const float4 &c, float alpha, bool contrib, uint32_t ga, uint32_t &last_ga,
+                                      PixelState &st) {
+  const float next_T = st.T * (1.0f - alpha);
+  const bool stop = contrib && next_T <= kTStop;  // also true for a done pixel (next_T < 0): harmless
+  const bool add = contrib && !stop;
+  const float w = add ? alpha * st.T : 0.0f;
+  st.o0 = fmaf(c.x, w, st.o0); st.o1 = fmaf(c.y, w, st.o1); st.o2 = fmaf(c.z, w, st.o2); st.o3 = fmaf(c.w, w, st.o3);
+  st.T = add ? next_T : st.T;
+  st.T = stop ? -fabsf(st.T) : st.T;
+  last_ga = add ? ga : last_ga;
+}
+
+// Composite one staged run (`batch_size` valid entries of the Staged<CAP> block at shared address aS,
+// whose position in the tile's sorted list starts at `list_pos`) into the lane's pixel.
+//   * warp-level culling: 32 lanes test 32 Gaussians against the warp's 8x4 footprint, ballot;
+//   * the hits' shared-memory addresses are compacted into the warp's queue (aQ, kQueueWords words), so
+//     the evaluation loop walks a dense list — one LDS.64 per two hits instead of a bit scan, shift,
+//     mask update and address computation per hit (10 of 38 instructions per hit, profiles/r1f_*);
+//   * hits are evaluated two at a time (their alphas are independent, only the transmittance chain is
+//     serial), which hides the LDS -> FMA -> MUFU latency with fewer resident warps. An odd count is
+//     padded with the null Gaussian.
+// Returns when the run is exhausted or every pixel of the warp is done; callers handle CTA-level exits.
+template <int CAP>
+__device__ __forceinline__ void composite_batch_fwd(uint32_t aS, uint32_t aQ, int batch_size, int list_pos,
+                                                    const WarpFootprint &fp, PixelState &st) {
   const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  uint32_t last_ga = 0;
   for (int sub = 0; sub < batch_size; sub += 32) {
     const int j = sub + lane;
     bool hit = false;
     if (j < batch_size) {
-      const float4 a = lds128(aA + j * 16);
+      const float4 a = lds128(aS + j * 16);
       hit = fabsf(a.x - fp.wcx) <= a.z + 3.5f && fabsf(a.y - fp.wcy) <= a.w + 1.5f;
     }
-    unsigned mask = __ballot_sync(0xffffffffu, hit);
-    while (mask) {  // branch-free body: every lane evaluates, selects decide what sticks
-      const int t = sub + __ffs(mask) - 1;
-      mask &= mask - 1;
-      const float2 m = lds64(aA + t * 16);
-      const float4 b = lds128(aB + t * 16);
-      const float4 c = lds128(aC + t * 16);
-      const float dx = m.x - fp.px, dy = m.y - fp.py;
-      const float p = power2(b.x, b.y, b.z, dx, dy);  // = -sigma * log2e
-      const float alpha = fminf(0.999f, b.w * ex2_approx(p));
-      const float next_T = st.T * (1.0f - alpha);
-      const bool contrib = !st.done && !(p > 0.0f) && alpha >= kAlphaMin;  // p > 0 <=> sigma < 0
-      const bool stop = contrib && next_T <= kTStop;
-      const bool add = contrib && !stop;
-      st.done = st.done || stop;
-      const float w = add ? alpha * st.T : 0.0f;
-      st.o0 = fmaf(c.x, w, st.o0); st.o1 = fmaf(c.y, w, st.o1); st.o2 = fmaf(c.z, w, st.o2); st.o3 = fmaf(c.w, w, st.o3);
-      st.T = add ? next_T : st.T;
-      st.last = add ? list_pos + t : st.last;
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if (bal == 0u) continue;
+    const int n = __popc(bal);
+    if (hit) sts32(aQ + __popc(bal & lt) * 4, aS + j * 16);
+    if (lane == 0) sts32(aQ + n * 4, aS + CAP * 16);
+    __syncwarp();
+    for (int i = 0; i < n; i += 2) {
+      const uint2 ga = lds64u(aQ + i * 4);
+      float alpha0, alpha1;
+      bool c0, c1;
+      eval_alpha<CAP>(ga.x, fp, alpha0, c0);
+      eval_alpha<CAP>(ga.y, fp, alpha1, c1);
+      const float4 col0 = lds128(ga.x + 2 * (CAP + 1) * 16);
+      const float4 col1 = lds128(ga.y + 2 * (CAP + 1) * 16);
+      blend(col0, alpha0, c0, ga.x, last_ga, st);
+      blend(col1, alpha1, c1, ga.y, last_ga, st);
     }
-    if (__all_sync(0xffffffffu, st.done)) break;
+    __syncwarp();
+    if (__all_sync(0xffffffffu, pixel_done(st))) break;
   }
+  if (last_ga != 0u) st.last = list_pos + (int)((last_ga - aS) >> 4);
 }
 
 // Write one pixel's results (shared epilogue).
 __device__ __forceinline__ void store_pixel(const PixelState &st, size_t pix, int cam, int D, int CD,
                                             const float *__restrict__ backgrounds, float *__restrict__ render,
                                             float *__restrict__ alphas, int32_t *__restrict__ last_ids) {
-  alphas[pix] = 1.0f - st.T;
+  const float T = fabsf(st.T);
+  alphas[pix] = 1.0f - T;
   last_ids[pix] = st.last;
   float out[4] = {st.o0, st.o1, st.o2, st.o3};
   if (backgrounds) {
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      if (k < D) out[k] += st.T * __ldg(backgrounds + cam * D + k);
+      if (k < D) out[k] += T * __ldg(backgrounds + cam * D + k);
   }
   if (CD == 4) {
     reinterpret_cast<float4 *>(render)[pix] = make_float4(out[0], out[1], out[2], out[3]);

@@ -8,10 +8,13 @@
 // tile. This kernel sorts only what the compositor consumes: one CTA per (camera, tile)
 //   1. reads the tile's unsorted {depth bits, flatten id} records (written by bin_scatter),
 //      finds the depth range and histograms the records into 256 depth-ordered sub-buckets;
-//   2. walks the sub-buckets front to back in groups of <= 2048 records: collect the group into
+//   2. walks the sub-buckets front to back in groups of <= 1024 records: collect the group into
 //      shared memory, radix-sort it there by (depth bits, flatten id), write the sorted flatten ids
-//      to their final positions (the backward pass replays them), composite the group with exactly
-//      the code of composite_fwd_kernel (composite_common.cuh);
+//      to their final positions (the backward pass replays them), stage the WHOLE group's Gaussian
+//      records (mean/extent, conic/opacity, colour: 48 B each, over the sort buffers) and let the 8
+//      warps composite it with no CTA barrier in between — each warp runs at its own pace through
+//      the staged group and drops out when its 32 pixels are done (the per-256 barrier of the
+//      separate-stage kernel was 30 % of this kernel's stall samples, profiles/r1e_*);
 //   3. stops at the first group boundary where all 256 pixels are done.
 // Because sub-buckets partition the keys by value and ties are ordered by flatten id, position k of
 // the tile's list holds the same Gaussian as after a full stable sort, so images, alphas and
@@ -25,9 +28,22 @@ namespace pm {
 
 constexpr int kTrThreads = 256;
 constexpr int kTrWarps = kTrThreads / 32;
-constexpr int kTrItems = 8;
-constexpr int kTrCap = kTrThreads * kTrItems;  // 2048 records per group
+constexpr int kTrItems = 4;
+constexpr int kTrCap = kTrThreads * kTrItems;  // 1024 records per group
 constexpr int kTrRadix = 256;
+#ifndef PM_TR_MLP
+#define PM_TR_MLP 4
+#endif
+#ifndef PM_TR_GATHER2
+#define PM_TR_GATHER2 0
+#endif
+constexpr int kTrMlp = PM_TR_MLP;
+constexpr int kTrRankMax = 128;  // longest bucket run ordered by all-pairs ranking (longer: radix sort of the group)
+
+// depth sub-bucket of a key: monotone in the key for any kmin / shift
+__device__ __forceinline__ int tr_bucket(uint32_t k, uint32_t kmin, int shift) {
+  return k <= kmin ? 0 : (int)min((k - kmin) >> shift, 255u);
+}  // record loads in flight per thread in the passes over a tile's segment
 
 __device__ __forceinline__ unsigned tr_match_digit8(uint32_t d) {
   unsigned peers = 0xffffffffu;
@@ -40,17 +56,21 @@ __device__ __forceinline__ unsigned tr_match_digit8(uint32_t d) {
 }
 
 struct TrShared {
-  uint2 gbuf[kTrCap];                      // group being sorted: {depth bits, flatten id}
-  uint16_t warp_hist[kTrWarps][kTrRadix];
-  uint32_t digit_start[kTrRadix];
+  union {                                    // a group is first sorted, then staged over the same bytes
+    struct {
+      uint2 gbuf[kTrCap];                    // group being sorted: {depth bits, flatten id}
+      uint16_t warp_hist[kTrWarps][kTrRadix];
+      uint32_t digit_start[kTrRadix];
+    };
+    Staged<kTrCap> stg;                      // (its null slot lies beyond the sort buffers)
+  };
+  uint32_t queue[kTrWarps][kQueueWords];     // per-warp hit queues of composite_batch_fwd
   uint32_t red[64];
-  int bucket[kTrRadix + 1];                // start of each depth sub-bucket inside the tile's list
-  GaussA sA[kBatch];
-  GaussB sB[kBatch];
-  GaussC sC[kBatch];
+  int bucket[kTrRadix + 1];                  // start of each depth sub-bucket inside the tile's list
   int cnt;
   uint32_t kmin, kmax;
 };
+constexpr size_t kTrSmemBytes = sizeof(TrShared);
 
 // Sort sh.gbuf[0..m) by (key, flatten id); gmin/gmax = key range of the group. All threads call it.
 __device__ __forceinline__ void sort_group(TrShared &sh, int m, uint32_t gmin, uint32_t gmax) {
@@ -165,7 +185,8 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
                        float *__restrict__ alphas, int32_t *__restrict__ last_ids,
                        int32_t *__restrict__ flatten_ids, int32_t *__restrict__ sorted_counts,
                        int32_t *__restrict__ overflow_flag) {
-  __shared__ TrShared sh;
+  extern __shared__ __align__(16) unsigned char tr_smem[];
+  TrShared &sh = *reinterpret_cast<TrShared *>(tr_smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_tiles = tile_width * tile_height;
   const int ct = blockIdx.x;
@@ -175,27 +196,41 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
   const int ix = wx0 + (lane & 7), iy = wy0 + (lane >> 3);
   const bool inside = ix < width && iy < height;
   const int CD = D + (depths ? 1 : 0);
+  const int cam_base = cam * N;
   const WarpFootprint fp{(float)ix + 0.5f, (float)iy + 0.5f, (float)wx0 + 4.0f, (float)wy0 + 2.0f};
-  PixelState st{1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0, !inside};
-  const uint32_t aA = smem_u32(sh.sA), aB = smem_u32(sh.sB), aC = smem_u32(sh.sC);
+  PixelState st{inside ? 1.0f : -1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0};
+  const uint32_t aS = smem_u32(&sh.stg), aQ = smem_u32(sh.queue[warp]);
+  staged_init_null(sh.stg);
 
   const int64_t n_isects = effective_n(n_host, d_n);
   const int start = offsets[ct];
   const int end = (ct == (int)gridDim.x - 1) ? (int)n_isects : offsets[ct + 1];
   const int cnt = end - start;
-  const uint64_t *src = records + start;
+  const unsigned long long *src = reinterpret_cast<const unsigned long long *>(records) + start;
   int sorted = 0;
 
   if (cnt > 0) {
-    // ---- 1. depth range of the tile and histogram over 256 depth-ordered sub-buckets
+    // ---- 1. histogram of the tile's records over 256 depth-ordered sub-buckets. The bucket of a key is a
+    // monotone function of it — clamp((key - kmin) >> shift, 0, 255) — so ANY kmin / shift partition the
+    // keys by value; they only steer the bucket sizes. kmin / kmax therefore come from a strided sample
+    // of <= 1024 records (one round of 4 independent loads per thread, exact when the tile has <= 1024
+    // records) instead of a full pass; the few keys outside the sampled range land in buckets 0 / 255.
     if (tid == 0) { sh.kmin = 0xffffffffu; sh.kmax = 0u; }
     for (int i = tid; i <= kTrRadix; i += kTrThreads) sh.bucket[i] = 0;
     __syncthreads();
     uint32_t kmin = 0xffffffffu, kmax = 0u;
-    for (int i = tid; i < cnt; i += kTrThreads) {
-      const uint32_t k = (uint32_t)__ldg(reinterpret_cast<const unsigned long long *>(src) + i);
-      kmin = min(kmin, k);
-      kmax = max(kmax, k);
+    {
+      const int nsamp = min(cnt, 4 * kTrThreads);
+      const int stride = cnt / nsamp;
+      uint32_t k[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int sidx = u * kTrThreads + tid;
+        k[u] = sidx < nsamp ? (uint32_t)__ldg(src + (size_t)sidx * stride) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (u * kTrThreads + tid < nsamp) { kmin = min(kmin, k[u]); kmax = max(kmax, k[u]); }
     }
     kmin = __reduce_min_sync(0xffffffffu, kmin);
     kmax = __reduce_max_sync(0xffffffffu, kmax);
@@ -205,9 +240,17 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
     const uint32_t range = sh.kmax - kmin;
     const int bits = 32 - __clz(range | 1u);
     const int shift = bits > 8 ? bits - 8 : 0;
-    for (int i = tid; i < cnt; i += kTrThreads) {
-      const uint32_t k = (uint32_t)__ldg(reinterpret_cast<const unsigned long long *>(src) + i);
-      atomicAdd(&sh.bucket[((k - kmin) >> shift) + 1], 1);
+    // (every pass over the tile's records keeps kTrMlp loads per thread in flight)
+    for (int i0 = 0; i0 < cnt; i0 += kTrMlp * kTrThreads) {
+      uint32_t k[kTrMlp];
+#pragma unroll
+      for (int u = 0; u < kTrMlp; ++u) {
+        const int i = i0 + u * kTrThreads + tid;
+        k[u] = i < cnt ? (uint32_t)__ldg(src + i) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < kTrMlp; ++u)
+        if (i0 + u * kTrThreads + tid < cnt) atomicAdd(&sh.bucket[tr_bucket(k[u], kmin, shift) + 1], 1);
     }
     __syncthreads();
     {  // exclusive scan: bucket[d] = start of sub-bucket d, bucket[256] = cnt
@@ -229,48 +272,120 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
     // ---- 2. groups of sub-buckets, front to back, until every pixel is done
     int g0 = 0;
     while (g0 < kTrRadix) {
-      if (__syncthreads_count(st.done) == kTrThreads) break;
-      int g1 = g0 + 1;
-      while (g1 < kTrRadix && sh.bucket[g1 + 1] - sh.bucket[g0] <= kTrCap) ++g1;
-      const int gs = sh.bucket[g0], ge = sh.bucket[g1];
+      // group boundary barrier: the staged group of the previous round is dead after it
+      if (__syncthreads_count(pixel_done(st)) == kTrThreads) break;
+      // largest g1 with bucket[g1] - bucket[g0] <= capacity (binary search; bucket[] is monotone)
+      const int gs = sh.bucket[g0];
+      int g1 = g0 + 1, hi = kTrRadix;
+      while (g1 < hi) {
+        const int mid = (g1 + hi + 1) >> 1;
+        if (sh.bucket[mid] - gs <= kTrCap) g1 = mid; else hi = mid - 1;
+      }
+      const int ge = sh.bucket[g1];
       const int m = ge - gs;
       if (m > kTrCap) {  // one depth sub-bucket does not fit: the caller re-renders with the separate stages
         if (tid == 0) atomicExch(overflow_flag, 1);
         break;
       }
       if (m > 0) {
-        // collect the group (order does not matter: the sort below keys on (depth bits, flatten id))
-        if (tid == 0) { sh.cnt = 0; sh.kmin = 0xffffffffu; sh.kmax = 0u; }
+        // collect the group straight into bucket order (a counting-sort placement: the position of a
+        // record is its bucket's start + a per-bucket cursor), so that only the short runs of equal
+        // bucket remain to be ordered
+        uint32_t *cur = sh.digit_start;
+        for (int bb = g0 + tid; bb < g1; bb += kTrThreads) cur[bb] = 0u;
+        if (tid == 0) { sh.kmin = 0xffffffffu; sh.kmax = 0u; }
         __syncthreads();
         uint32_t gmin = 0xffffffffu, gmax = 0u;
-        for (int i = tid; i < cnt; i += kTrThreads) {
-          const uint64_t r = __ldg(reinterpret_cast<const unsigned long long *>(src) + i);
-          const uint32_t k = (uint32_t)r;
-          const int b = (int)((k - kmin) >> shift);
-          if (b >= g0 && b < g1) {
-            sh.gbuf[atomicAdd(&sh.cnt, 1)] = make_uint2(k, (uint32_t)(r >> 32));
-            gmin = min(gmin, k);
-            gmax = max(gmax, k);
+        for (int i0 = 0; i0 < cnt; i0 += kTrMlp * kTrThreads) {
+          unsigned long long r[kTrMlp];
+#pragma unroll
+          for (int u = 0; u < kTrMlp; ++u) {
+            const int i = i0 + u * kTrThreads + tid;
+            r[u] = i < cnt ? __ldg(src + i) : 0ull;
+          }
+#pragma unroll
+          for (int u = 0; u < kTrMlp; ++u) {
+            const uint32_t k = (uint32_t)r[u];
+            const int bb = tr_bucket(k, kmin, shift);
+            if (i0 + u * kTrThreads + tid < cnt && bb >= g0 && bb < g1) {
+              const int pos = sh.bucket[bb] - gs + (int)atomicAdd(&cur[bb], 1u);
+              sh.gbuf[pos] = make_uint2(k, (uint32_t)(r[u] >> 32));
+              gmin = min(gmin, k);
+              gmax = max(gmax, k);
+            }
           }
         }
+        bool fat = false;  // a run too long for the all-pairs ranking below
+        for (int bb = g0 + tid; bb < g1; bb += kTrThreads) fat |= sh.bucket[bb + 1] - sh.bucket[bb] > kTrRankMax;
         gmin = __reduce_min_sync(0xffffffffu, gmin);
         gmax = __reduce_max_sync(0xffffffffu, gmax);
         if (lane == 0) { atomicMin(&sh.kmin, gmin); atomicMax(&sh.kmax, gmax); }
-        __syncthreads();
-        sort_group(sh, m, sh.kmin, sh.kmax);
-        // sorted flatten ids go to their final positions (read again by the backward pass)
-        for (int i = tid; i < m; i += kTrThreads) flatten_ids[(size_t)start + gs + i] = (int32_t)sh.gbuf[i].y;
-        sorted = ge;
-        // composite the group, batch by batch — same code as composite_fwd_kernel
-        for (int b0 = 0; b0 < m; b0 += kBatch) {
-          if (b0 > 0 && __syncthreads_count(st.done) == kTrThreads) break;
-          if (b0 + tid < m)
-            gather((int32_t)sh.gbuf[b0 + tid].y, N, means2d, conics, opacities, colors, colors_per_camera, D, depths,
-                   sh.sA[tid], sh.sB[tid], sh.sC[tid]);
+        fat = __syncthreads_or(fat);
+        int32_t ids[kTrItems];
+        if (fat) {
+          sort_group(sh, m, sh.kmin, sh.kmax);  // LSD radix sort of the whole group
+#pragma unroll
+          for (int k = 0; k < kTrItems; ++k) {
+            const int slot = k * kTrThreads + tid;
+            ids[k] = slot < m ? (int32_t)sh.gbuf[slot].y : -1;
+          }
+        } else {
+          // rank every record inside its bucket's run by (depth bits, flatten id): runs are ~cnt/256 long,
+          // a warp's 32 consecutive records share one or two runs (broadcast reads), no barrier needed
+          uint32_t *sorted_ids = reinterpret_cast<uint32_t *>(sh.warp_hist);
+#pragma unroll
+          for (int k = 0; k < kTrItems; ++k) {
+            const int e = k * kTrThreads + tid;
+            if (e < m) {
+              const uint2 me = sh.gbuf[e];
+              const int bb = tr_bucket(me.x, kmin, shift);
+              const int rs = sh.bucket[bb] - gs, re = sh.bucket[bb + 1] - gs;
+              const unsigned long long mine = ((unsigned long long)me.x << 32) | me.y;
+              int rank = rs;
+              for (int j = rs; j < re; ++j) {
+                const uint2 o = sh.gbuf[j];
+                rank += (((unsigned long long)o.x << 32) | o.y) < mine;
+              }
+              sorted_ids[rank] = me.y;
+            }
+          }
           __syncthreads();
-          if (!__all_sync(0xffffffffu, st.done))
-            composite_batch_fwd(aA, aB, aC, min(kBatch, m - b0), start + gs + b0, fp, st);
+#pragma unroll
+          for (int k = 0; k < kTrItems; ++k) {
+            const int slot = k * kTrThreads + tid;
+            ids[k] = slot < m ? (int32_t)sorted_ids[slot] : -1;
+          }
         }
+        // sorted flatten ids go to their final positions (read again by the backward pass)
+#pragma unroll
+        for (int k = 0; k < kTrItems; ++k) {
+          const int slot = k * kTrThreads + tid;
+          if (slot < m) flatten_ids[(size_t)start + gs + slot] = ids[k];
+        }
+        sorted = ge;
+        __syncthreads();  // everyone holds its ids: the sort buffers may be overwritten by the staged records
+#if PM_TR_GATHER2
+#pragma unroll
+        for (int k = 0; k < kTrItems; k += 2) {  // two Gaussians' loads in flight per thread
+          const int s0 = k * kTrThreads + tid, s1 = s0 + kTrThreads;
+          GaussRaw r0, r1;
+          if (s0 < m) r0 = gather_load(ids[k], ids[k] - cam_base, means2d, conics, opacities, colors, colors_per_camera, D, depths);
+          if (s1 < m) r1 = gather_load(ids[k + 1], ids[k + 1] - cam_base, means2d, conics, opacities, colors, colors_per_camera, D, depths);
+          if (s0 < m) gather_finish(r0, sh.stg.sA[s0], sh.stg.sB[s0], sh.stg.sC[s0]);
+          if (s1 < m) gather_finish(r1, sh.stg.sA[s1], sh.stg.sB[s1], sh.stg.sC[s1]);
+        }
+#else
+#pragma unroll
+        for (int k = 0; k < kTrItems; ++k) {
+          const int slot = k * kTrThreads + tid;
+          if (slot < m)
+            gather(ids[k], ids[k] - cam_base, means2d, conics, opacities, colors, colors_per_camera, D, depths, sh.stg.sA[slot],
+                   sh.stg.sB[slot], sh.stg.sC[slot]);
+        }
+#endif
+        __syncthreads();
+        // composite the whole group; warps do not wait for each other — same arithmetic as composite_fwd_kernel
+        if (!__all_sync(0xffffffffu, pixel_done(st))) composite_batch_fwd<kTrCap>(aS, aQ, m, start + gs, fp, st);
       }
       g0 = g1;
     }
@@ -306,7 +421,16 @@ int pm_tile_render_fwd(const uint64_t *records, const int32_t *isect_offsets, in
   const int tw = (width + pm::kTile - 1) / pm::kTile, th = (height + pm::kTile - 1) / pm::kTile;
   const int64_t blocks = (int64_t)C * tw * th;
   if (blocks >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
-  pm::tile_render_fwd_kernel<<<(unsigned)blocks, pm::kTrThreads, 0, pm::as_stream(stream)>>>(
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(pm::tile_render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)pm::kTrSmemBytes) != cudaSuccess) {
+      pm::set_last_cuda_error(cudaGetLastError());
+      return PM_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  pm::tile_render_fwd_kernel<<<(unsigned)blocks, pm::kTrThreads, pm::kTrSmemBytes, pm::as_stream(stream)>>>(
       records, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera, D, depths,
       backgrounds, N, width, height, tw, th, render, alphas, last_ids, flatten_ids, sorted_counts, overflow_flag);
   return pm::check_launch();

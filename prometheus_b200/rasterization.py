@@ -114,7 +114,7 @@ class _TileRender(torch.autograd.Function):
 
 
 # Largest per-tile group the fused kernel sorts at once (tile_render.cu: kTrCap)
-FUSED_GROUP_CAP = 2048
+FUSED_GROUP_CAP = 1024
 
 
 def isect_tiles(means2d, radii, depths, tiles_per_gauss, width, height, C, force_generic=False):

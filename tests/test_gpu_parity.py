@@ -584,7 +584,7 @@ def test_fused_module_path_matches_unfused_including_gradients():
 
 
 def test_fused_overflow_falls_back():
-    """3000 splats with identical depth on one tile: one depth sub-bucket exceeds the fused group capacity (2048),
+    """3000 splats with identical depth on one tile: one depth sub-bucket exceeds the fused group capacity (1024),
     the overflow flag is raised and the module falls back to the separate stages — same image either way."""
     import importlib
 
@@ -602,3 +602,35 @@ def test_fused_overflow_falls_back():
     r2, a2, m2 = rz._rasterize_core(*args, packed=False, fused=False)
     assert m1["isect_ids"] is not None  # fell back to the separate-stage path
     assert torch.equal(r1, r2) and torch.equal(a1, a2)
+
+
+@pytest.mark.parametrize("n_same", [90, 400, 1000])
+def test_fused_equal_depth_runs(n_same):
+    """Runs of identical depth inside one tile (ties ordered by flatten id): short runs go through the fused
+    kernel's all-pairs ranking, runs above its limit (128) through the in-kernel radix sort, and neither may
+    raise the overflow flag while the run still fits one group (1024). Mixed with 700 splats at spread depths."""
+    import importlib
+
+    rz = importlib.import_module("prometheus_b200.rasterization")
+    g = torch.Generator().manual_seed(9)
+    n_far = 700
+    n = n_same + n_far
+    means = torch.zeros(n, 3)
+    means[:, :2] = (torch.rand(n, 2, generator=g) - 0.5) * 0.08
+    means[:n_same, 2] = 2.5
+    means[n_same:, 2] = 2.0 + torch.rand(n_far, generator=g) * 2.0
+    perm = torch.randperm(n, generator=g)
+    means = means[perm]
+    args = [means.to(DEV), torch.tensor([[1.0, 0, 0, 0]]).repeat(n, 1).to(DEV), torch.full((n, 3), 0.01).to(DEV),
+            torch.full((n,), 0.01).to(DEV), torch.rand(n, 3, generator=g).to(DEV), torch.eye(4)[None].to(DEV),
+            torch.tensor([[[100.0, 0, 24.0], [0, 100.0, 24.0], [0, 0, 1]]]).to(DEV), 64, 64]
+    r1, a1, m1 = rz._rasterize_core(*args, packed=False, fused=True)
+    r2, a2, m2 = rz._rasterize_core(*args, packed=False, fused=False)
+    assert m1["isect_ids"] is None  # stayed on the fused path
+    assert torch.equal(r1, r2) and torch.equal(a1, a2)
+    off = m2["isect_offsets"].reshape(-1).cpu().numpy()
+    sc = m1["sorted_counts"].reshape(-1).cpu().numpy()
+    f1, f2 = m1["flatten_ids"].cpu().numpy(), m2["flatten_ids"].cpu().numpy()
+    assert sc.max() > n_same  # low opacity: the whole list is consumed, including the equal-depth run
+    for t in np.nonzero(sc)[0]:
+        assert np.array_equal(f1[off[t]:off[t] + sc[t]], f2[off[t]:off[t] + sc[t]])
