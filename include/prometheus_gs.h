@@ -114,6 +114,16 @@ PM_API int pm_project_fwd(const float *means, const float *quats, const float *s
                    int32_t *radii, float *means2d, float *depths, float *conics,
                    int32_t *tiles_per_gauss, pm_stream_t stream);
 
+/* pm_project_fwd + pm_bin_count in one pass: additionally ACCUMULATES the per-(camera, tile)
+ * intersection histogram into tile_counts [C, tile_height, tile_width] int32 (caller zero-fills)
+ * while each pair's tile AABB is still in registers. Same outputs, bit for bit, as the two calls. */
+PM_API int pm_project_count_fwd(const float *means, const float *quats, const float *scales,
+                   const float *viewmats, const float *Ks,
+                   int N, int C, int width, int height, int tile_size,
+                   float eps2d, float near_plane, float far_plane, float radius_clip,
+                   int32_t *radii, float *means2d, float *depths, float *conics,
+                   int32_t *tiles_per_gauss, int32_t *tile_counts, pm_stream_t stream);
+
 /* VJP of the projection. v_means2d [C,N,2], v_depths [C,N], v_conics [C,N,3]
  * (any may be NULL) -> v_means [N,3], v_quats [N,4], v_scales [N,3], summed over
  * cameras, fully overwritten. viewmats/Ks carry no gradient on this path. */

@@ -31,6 +31,7 @@ SIGNATURES = {
     "pm_unproject_bwd": (c_int, [_P, _P, _P, _I, _F, _F, _F, _F, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "pm_camera_prep": (c_int, [_P, _I, _I, _I, _P, _P, _P]),
     "pm_project_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P]),
+    "pm_project_count_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
     "pm_bin_count": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "pm_tile_scan": (c_int, [_P, _L, _P, _P, _P]),
     "pm_bin_scatter": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _L, _P]),

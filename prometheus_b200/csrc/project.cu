@@ -12,7 +12,7 @@
 // are (a+b)+c; nvcc's default -prec-div/-prec-sqrt give correctly rounded / and
 // sqrt, and denormals are kept). The kernel is HBM-bound (40 B/Gaussian read,
 // 32 B/pair written for ~250 flops), so giving up FMA contraction costs nothing.
-#include "common.cuh"
+#include "binning_common.cuh"
 
 namespace pm {
 
@@ -64,34 +64,48 @@ __device__ __forceinline__ void quat_to_rotmat(float w, float x, float y, float 
   R[6] = 2.0f * (xz - wy);        R[7] = 2.0f * (yz + wx);        R[8] = 1.0f - 2.0f * (x2 + y2);
 }
 
+// One camera's constants, staged in shared memory once per CTA.
+struct ProjCamS {
+  ProjCam c;
+  ProjLims lims;
+};
+constexpr int kProjCamChunk = 32;  // cameras per launch (shared-memory table); more cameras = more launches
+
+// One thread per Gaussian, looping over the cameras of the launch: the Gaussian is read from HBM once and
+// its world covariance is computed once (the per-camera grid of the first version re-read 40 B/Gaussian
+// and redid the quaternion -> covariance arithmetic for every camera: 662 MB of DRAM reads for 84 MB of
+// input on C2, profiles/r1e_*). COUNT additionally accumulates the per-(camera, tile) intersection
+// histogram (what pm_bin_count computes from the stored radii / means2d) while the tile AABB is still in
+// registers, through the per-CTA privatised histogram of binning_common.cuh.
+template <bool COUNT>
 __global__ void __launch_bounds__(256)
 project_fwd_kernel(const float *__restrict__ means, const float *__restrict__ quats,
                    const float *__restrict__ scales, const float *__restrict__ viewmats,
-                   const float *__restrict__ Ks, int N, int width, int height,
+                   const float *__restrict__ Ks, int N, int cam0, int n_cams, int chunk_stride, int width, int height,
                    int tile_width, int tile_height, float eps2d, float near_plane, float far_plane,
                    float radius_clip, int32_t *__restrict__ radii, float *__restrict__ means2d,
                    float *__restrict__ depths, float *__restrict__ conics,
-                   int32_t *__restrict__ tiles_per_gauss) {
-  __shared__ ProjLims s_lims;
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  const int cid = blockIdx.y;
-  const ProjCam c = load_proj_cam(viewmats + (size_t)cid * 16, Ks + (size_t)cid * 9);
-  if (threadIdx.x == 0) s_lims = proj_lims(c, width, height);  // 6 IEEE divisions, once per block
+                   int32_t *__restrict__ tiles_per_gauss, int32_t *__restrict__ tile_counts) {
+  __shared__ ProjCamS s_cam[kProjCamChunk];
+  __shared__ TileCountSmem s_cnt[1];  // (unused and optimised away when !COUNT)
+  for (int i = threadIdx.x; i < n_cams; i += blockDim.x) {
+    ProjCamS pc;
+    pc.c = load_proj_cam(viewmats + (size_t)(cam0 + i) * 16, Ks + (size_t)(cam0 + i) * 9);
+    pc.lims = proj_lims(pc.c, width, height);
+    s_cam[i] = pc;
+  }
   __syncthreads();
+  // strided CTA order (see binning_common.cuh): concurrently resident CTAs touch far-apart tiles
+  const int chunk = (int)(((int64_t)blockIdx.x * chunk_stride) % gridDim.x);
+  const int g = chunk * blockDim.x + threadIdx.x;
   const bool in_range = g < N;
-  const size_t f = (size_t)cid * N + (in_range ? g : 0);
-  const float *R = c.R;
 
-  int radius_i = 0;
-  float m2x = 0.0f, m2y = 0.0f, depth = 0.0f, q0 = 0.0f, q1 = 0.0f, q2 = 0.0f;
-  do {
-    if (!in_range) break;
-    const float mx = means[(size_t)g * 3 + 0], my = means[(size_t)g * 3 + 1], mz = means[(size_t)g * 3 + 2];
-    const float px = sum3(R[0] * mx, R[1] * my, R[2] * mz) + c.t[0];
-    const float py = sum3(R[3] * mx, R[4] * my, R[5] * mz) + c.t[1];
-    const float pz = sum3(R[6] * mx, R[7] * my, R[8] * mz) + c.t[2];
-    if (pz < near_plane || pz > far_plane) break;
-
+  float mx = 0.0f, my = 0.0f, mz = 0.0f;
+  float S[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) S[i] = 0.0f;
+  if (in_range) {
+    mx = means[(size_t)g * 3 + 0]; my = means[(size_t)g * 3 + 1]; mz = means[(size_t)g * 3 + 2];
     const float4 q = reinterpret_cast<const float4 *>(quats)[g];
     const float s0 = scales[(size_t)g * 3 + 0], s1 = scales[(size_t)g * 3 + 1], s2 = scales[(size_t)g * 3 + 2];
     float Rq[9], M[9];
@@ -102,7 +116,6 @@ project_fwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
       M[r * 3 + 1] = Rq[r * 3 + 1] * s1;
       M[r * 3 + 2] = Rq[r * 3 + 2] * s2;
     }
-    float S[9];
     S[0] = sum3(M[0] * M[0], M[1] * M[1], M[2] * M[2]);
     S[1] = sum3(M[0] * M[3], M[1] * M[4], M[2] * M[5]);
     S[2] = sum3(M[0] * M[6], M[1] * M[7], M[2] * M[8]);
@@ -110,64 +123,80 @@ project_fwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
     S[5] = sum3(M[3] * M[6], M[4] * M[7], M[5] * M[8]);
     S[8] = sum3(M[6] * M[6], M[7] * M[7], M[8] * M[8]);
     S[3] = S[1]; S[6] = S[2]; S[7] = S[5];
-    float T[9];
+  }
+
+  for (int ci = 0; ci < n_cams; ++ci) {
+    const ProjCam &c = s_cam[ci].c;
+    const float *R = c.R;
+    const size_t f = (size_t)(cam0 + ci) * N + (in_range ? g : 0);
+    int radius_i = 0;
+    float m2x = 0.0f, m2y = 0.0f, depth = 0.0f, q0 = 0.0f, q1 = 0.0f, q2 = 0.0f;
+    do {
+      if (!in_range) break;
+      const float px = sum3(R[0] * mx, R[1] * my, R[2] * mz) + c.t[0];
+      const float py = sum3(R[3] * mx, R[4] * my, R[5] * mz) + c.t[1];
+      const float pz = sum3(R[6] * mx, R[7] * my, R[8] * mz) + c.t[2];
+      if (pz < near_plane || pz > far_plane) break;
+      float T[9];
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+      for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int k = 0; k < 3; ++k)
-        T[r * 3 + k] = sum3(R[r * 3 + 0] * S[0 * 3 + k], R[r * 3 + 1] * S[1 * 3 + k], R[r * 3 + 2] * S[2 * 3 + k]);
-    const float c00 = sum3(T[0] * R[0], T[1] * R[1], T[2] * R[2]);
-    const float c01 = sum3(T[0] * R[3], T[1] * R[4], T[2] * R[5]);
-    const float c02 = sum3(T[0] * R[6], T[1] * R[7], T[2] * R[8]);
-    const float c11 = sum3(T[3] * R[3], T[4] * R[4], T[5] * R[5]);
-    const float c12 = sum3(T[3] * R[6], T[4] * R[7], T[5] * R[8]);
-    const float c22 = sum3(T[6] * R[6], T[7] * R[7], T[8] * R[8]);
+        for (int k = 0; k < 3; ++k)
+          T[r * 3 + k] = sum3(R[r * 3 + 0] * S[0 * 3 + k], R[r * 3 + 1] * S[1 * 3 + k], R[r * 3 + 2] * S[2 * 3 + k]);
+      const float c00 = sum3(T[0] * R[0], T[1] * R[1], T[2] * R[2]);
+      const float c01 = sum3(T[0] * R[3], T[1] * R[4], T[2] * R[5]);
+      const float c02 = sum3(T[0] * R[6], T[1] * R[7], T[2] * R[8]);
+      const float c11 = sum3(T[3] * R[3], T[4] * R[4], T[5] * R[5]);
+      const float c12 = sum3(T[3] * R[6], T[4] * R[7], T[5] * R[8]);
+      const float c22 = sum3(T[6] * R[6], T[7] * R[7], T[8] * R[8]);
 
-    const float fx = c.fx, fy = c.fy, cx = c.cx, cy = c.cy;
-    const float lim_x_pos = s_lims.x_pos, lim_x_neg = s_lims.x_neg;
-    const float lim_y_pos = s_lims.y_pos, lim_y_neg = s_lims.y_neg;
-    const float rz = 1.0f / pz;
-    const float rz2 = rz * rz;
-    const float tx = pz * fminf(lim_x_pos, fmaxf(-lim_x_neg, px * rz));
-    const float ty = pz * fminf(lim_y_pos, fmaxf(-lim_y_neg, py * rz));
-    const float J00 = fx * rz, J02 = -((fx * tx) * rz2);
-    const float J11 = fy * rz, J12 = -((fy * ty) * rz2);
-    const float A00 = J00 * c00 + J02 * c02;
-    const float A01 = J00 * c01 + J02 * c12;
-    const float A02 = J00 * c02 + J02 * c22;
-    const float A11 = J11 * c11 + J12 * c12;
-    const float A12 = J11 * c12 + J12 * c22;
-    float v00 = A00 * J00 + A02 * J02;
-    const float v01 = A01 * J11 + A02 * J12;
-    float v11 = A11 * J11 + A12 * J12;
-    const float ux = (fx * px) * rz + cx;
-    const float uy = (fy * py) * rz + cy;
+      const float fx = c.fx, fy = c.fy, cx = c.cx, cy = c.cy;
+      const ProjLims &l = s_cam[ci].lims;
+      const float rz = 1.0f / pz;
+      const float rz2 = rz * rz;
+      const float tx = pz * fminf(l.x_pos, fmaxf(-l.x_neg, px * rz));
+      const float ty = pz * fminf(l.y_pos, fmaxf(-l.y_neg, py * rz));
+      const float J00 = fx * rz, J02 = -((fx * tx) * rz2);
+      const float J11 = fy * rz, J12 = -((fy * ty) * rz2);
+      const float A00 = J00 * c00 + J02 * c02;
+      const float A01 = J00 * c01 + J02 * c12;
+      const float A02 = J00 * c02 + J02 * c22;
+      const float A11 = J11 * c11 + J12 * c12;
+      const float A12 = J11 * c12 + J12 * c22;
+      float v00 = A00 * J00 + A02 * J02;
+      const float v01 = A01 * J11 + A02 * J12;
+      float v11 = A11 * J11 + A12 * J12;
+      const float ux = (fx * px) * rz + cx;
+      const float uy = (fy * py) * rz + cy;
 
-    v00 += eps2d;
-    v11 += eps2d;
-    const float det = v00 * v11 - v01 * v01;
-    if (!(det > 0.0f)) break;
-    const float inv_det = 1.0f / det;
-    const float b = 0.5f * (v00 + v11);
-    const float v1 = b + sqrtf(fmaxf(0.01f, b * b - det));
-    const float radius = ceilf(3.0f * sqrtf(v1));
-    if (radius <= radius_clip) break;
-    if (ux + radius <= 0.0f || ux - radius >= (float)width || uy + radius <= 0.0f ||
-        uy - radius >= (float)height)
-      break;
-    radius_i = radius > 2147483520.0f ? 2147483520 : (int)radius;
-    m2x = ux; m2y = uy; depth = pz;
-    q0 = v11 * inv_det; q1 = -v01 * inv_det; q2 = v00 * inv_det;
-  } while (false);
+      v00 += eps2d;
+      v11 += eps2d;
+      const float det = v00 * v11 - v01 * v01;
+      if (!(det > 0.0f)) break;
+      const float inv_det = 1.0f / det;
+      const float b = 0.5f * (v00 + v11);
+      const float v1 = b + sqrtf(fmaxf(0.01f, b * b - det));
+      const float radius = ceilf(3.0f * sqrtf(v1));
+      if (radius <= radius_clip) break;
+      if (ux + radius <= 0.0f || ux - radius >= (float)width || uy + radius <= 0.0f ||
+          uy - radius >= (float)height)
+        break;
+      radius_i = radius > 2147483520.0f ? 2147483520 : (int)radius;
+      m2x = ux; m2y = uy; depth = pz;
+      q0 = v11 * inv_det; q1 = -v01 * inv_det; q2 = v00 * inv_det;
+    } while (false);
 
-  int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
-  if (radius_i > 0) tile_aabb(m2x, m2y, radius_i, tile_width, tile_height, x0, x1, y0, y1);
-  if (in_range) {
-    radii[f] = radius_i;
-    reinterpret_cast<float2 *>(means2d)[f] = make_float2(m2x, m2y);
-    depths[f] = depth;
-    conics[f * 3 + 0] = q0; conics[f * 3 + 1] = q1; conics[f * 3 + 2] = q2;
-    if (tiles_per_gauss != nullptr) tiles_per_gauss[f] = (x1 - x0) * (y1 - y0);
+    int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+    if (radius_i > 0) tile_aabb(m2x, m2y, radius_i, tile_width, tile_height, x0, x1, y0, y1);
+    if (in_range) {
+      radii[f] = radius_i;
+      reinterpret_cast<float2 *>(means2d)[f] = make_float2(m2x, m2y);
+      depths[f] = depth;
+      conics[f * 3 + 0] = q0; conics[f * 3 + 1] = q1; conics[f * 3 + 2] = q2;
+      if (tiles_per_gauss != nullptr) tiles_per_gauss[f] = (x1 - x0) * (y1 - y0);
+    }
+    if (COUNT)
+      cta_tile_count(s_cnt[0], x0, x1, y0, y1, tile_counts + (size_t)(cam0 + ci) * tile_width * tile_height, tile_width);
   }
 }
 
@@ -175,10 +204,11 @@ project_fwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
 
 extern "C" {
 
-int pm_project_fwd(const float *means, const float *quats, const float *scales, const float *viewmats,
-                   const float *Ks, int N, int C, int width, int height, int tile_size, float eps2d,
-                   float near_plane, float far_plane, float radius_clip, int32_t *radii, float *means2d,
-                   float *depths, float *conics, int32_t *tiles_per_gauss, pm_stream_t stream) {
+static int project_fwd_launch(const float *means, const float *quats, const float *scales, const float *viewmats,
+                              const float *Ks, int N, int C, int width, int height, int tile_size, float eps2d,
+                              float near_plane, float far_plane, float radius_clip, int32_t *radii, float *means2d,
+                              float *depths, float *conics, int32_t *tiles_per_gauss, int32_t *tile_counts,
+                              pm_stream_t stream) {
   if (!means || !quats || !scales || !viewmats || !Ks || !radii || !means2d || !depths || !conics)
     return PM_ERR_BAD_ARG;
   if (N < 0 || C < 0 || width <= 0 || height <= 0) return PM_ERR_BAD_ARG;
@@ -188,11 +218,39 @@ int pm_project_fwd(const float *means, const float *quats, const float *scales, 
   if (C > 65535 || (int64_t)N * C >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
   if (N == 0 || C == 0) return PM_OK;
   const int tw = (width + pm::kTile - 1) / pm::kTile, th = (height + pm::kTile - 1) / pm::kTile;
-  dim3 grid((N + 255) / 256, C);
-  pm::project_fwd_kernel<<<grid, 256, 0, pm::as_stream(stream)>>>(
-      means, quats, scales, viewmats, Ks, N, width, height, tw, th, eps2d, near_plane, far_plane,
-      radius_clip, radii, means2d, depths, conics, tiles_per_gauss);
+  const int nb = (N + 255) / 256;
+  const int stride = pm::coprime_stride(nb);
+  for (int cam0 = 0; cam0 < C; cam0 += pm::kProjCamChunk) {
+    const int n_cams = C - cam0 < pm::kProjCamChunk ? C - cam0 : pm::kProjCamChunk;
+    if (tile_counts)
+      pm::project_fwd_kernel<true><<<nb, 256, 0, pm::as_stream(stream)>>>(
+          means, quats, scales, viewmats, Ks, N, cam0, n_cams, stride, width, height, tw, th, eps2d, near_plane,
+          far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, tile_counts);
+    else
+      pm::project_fwd_kernel<false><<<nb, 256, 0, pm::as_stream(stream)>>>(
+          means, quats, scales, viewmats, Ks, N, cam0, n_cams, stride, width, height, tw, th, eps2d, near_plane,
+          far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, nullptr);
+  }
   return pm::check_launch();
+}
+
+int pm_project_fwd(const float *means, const float *quats, const float *scales, const float *viewmats,
+                   const float *Ks, int N, int C, int width, int height, int tile_size, float eps2d,
+                   float near_plane, float far_plane, float radius_clip, int32_t *radii, float *means2d,
+                   float *depths, float *conics, int32_t *tiles_per_gauss, pm_stream_t stream) {
+  return project_fwd_launch(means, quats, scales, viewmats, Ks, N, C, width, height, tile_size, eps2d, near_plane,
+                            far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, nullptr, stream);
+}
+
+int pm_project_count_fwd(const float *means, const float *quats, const float *scales, const float *viewmats,
+                         const float *Ks, int N, int C, int width, int height, int tile_size, float eps2d,
+                         float near_plane, float far_plane, float radius_clip, int32_t *radii, float *means2d,
+                         float *depths, float *conics, int32_t *tiles_per_gauss, int32_t *tile_counts,
+                         pm_stream_t stream) {
+  if (!tile_counts) return PM_ERR_BAD_ARG;
+  return project_fwd_launch(means, quats, scales, viewmats, Ks, N, C, width, height, tile_size, eps2d, near_plane,
+                            far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, tile_counts,
+                            stream);
 }
 
 }  // extern "C"

@@ -30,41 +30,10 @@
 // concurrently resident CTAs work on far-apart Gaussians.
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "binning_common.cuh"
 
 namespace pm {
 
-constexpr int kHashSlots = 512;
-constexpr int kHashProbes = 16;
-
-struct TileHash {
-  int key[kHashSlots];
-  int cnt[kHashSlots];
-  int base[kHashSlots];
-};
-
-__device__ __forceinline__ unsigned hash_tile(int t) { return ((unsigned)t * 2654435761u) >> (32 - 9); }
-
-// returns the slot of tile t, inserting it if needed; -1 if the probe window is full
-__device__ __forceinline__ int hash_insert(TileHash &h, int t) {
-  unsigned s = hash_tile(t);
-  for (int p = 0; p < kHashProbes; ++p, s = (s + 1) & (kHashSlots - 1)) {
-    const int prev = atomicCAS(&h.key[s], -1, t);
-    if (prev == -1 || prev == t) return (int)s;
-  }
-  return -1;
-}
-__device__ __forceinline__ int hash_find(const TileHash &h, int t) {
-  unsigned s = hash_tile(t);
-  for (int p = 0; p < kHashProbes; ++p, s = (s + 1) & (kHashSlots - 1)) {
-    const int k = h.key[s];
-    if (k == t) return (int)s;
-    if (k == -1) return -1;
-  }
-  return -1;
-}
-
-constexpr int kWinCells = 2048;  // dense per-CTA window of tiles (covers e.g. 64 x 32 tiles)
 
 // SCATTER=false: histogram only. SCATTER=true: reserve ranges through `global` (= cursors) and write records.
 //
@@ -497,13 +466,6 @@ tile_sort_big_kernel(const uint64_t *__restrict__ records, uint64_t *__restrict_
   }
 }
 
-static int coprime_stride(int n) {
-  if (n <= 2) return 1;
-  int s = (int)(n * 0.6180339887) | 1;
-  auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
-  while (gcd(s, n) != 1) s += 2;
-  return s % n == 0 ? 1 : s;
-}
 
 }  // namespace pm
 

@@ -135,10 +135,11 @@ def camera_prep(cameras, h: int, w: int):
 
 
 # ------------------------------------------------------------------ stage 2
-@_instrument("project_fwd", 1)
+@_instrument("project_fwd", lambda means, quats, scales, viewmats, *a, **k: (viewmats.shape[0] + 31) // 32)
 def project_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d=0.3, near_plane=0.01,
-                far_plane=1e10, radius_clip=0.0, count_tiles=True):
-    """-> radii, means2d, depths, conics, tiles_per_gauss."""
+                far_plane=1e10, radius_clip=0.0, count_tiles=True, tile_histogram=False):
+    """-> radii, means2d, depths, conics, tiles_per_gauss (None unless count_tiles)
+    [, tile_counts [C,th,tw] int32 when tile_histogram: the fused pm_bin_count]."""
     L = _lib.load()
     means, quats, scales = (_req(t, torch.float32, n) for t, n in ((means, "means"), (quats, "quats"), (scales, "scales")))
     viewmats, Ks = _req(viewmats, torch.float32, "viewmats"), _req(Ks, torch.float32, "Ks")
@@ -149,6 +150,14 @@ def project_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d=0.3, ne
     depths = torch.empty(C, N, device=dev)
     conics = torch.empty(C, N, 3, device=dev)
     tpg = torch.empty(C, N, dtype=torch.int32, device=dev) if count_tiles else None
+    if tile_histogram:
+        tw, th = tile_grid(width, height)
+        counts = torch.zeros(C, th, tw, dtype=torch.int32, device=dev)
+        _lib.check(L.pm_project_count_fwd(_ptr(means), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks), N, C, width,
+                                          height, TILE, eps2d, near_plane, far_plane, radius_clip, _ptr(radii),
+                                          _ptr(means2d), _ptr(depths), _ptr(conics), _ptr(tpg), _ptr(counts), _stream()),
+                   "pm_project_count_fwd")
+        return radii, means2d, depths, conics, tpg, counts
     _lib.check(L.pm_project_fwd(_ptr(means), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks), N, C, width,
                                 height, TILE, eps2d, near_plane, far_plane, radius_clip, _ptr(radii),
                                 _ptr(means2d), _ptr(depths), _ptr(conics), _ptr(tpg), _stream()),

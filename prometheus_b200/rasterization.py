@@ -31,21 +31,24 @@ FORCE_GENERIC_SORT = False
 class _Project(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
-                radius_clip):
-        radii, means2d, depths, conics, tpg = ops.project_fwd(
-            means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip)
+                radius_clip, fused_count=False):
+        """fused_count (module fast path): skip tiles_per_gauss, return the per-tile histogram instead."""
+        out = ops.project_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
+                              radius_clip, count_tiles=not fused_count, tile_histogram=fused_count)
+        radii, means2d, depths, conics, tpg = out[:5]
+        aux = out[5] if fused_count else tpg
         ctx.save_for_backward(means, quats, scales, viewmats, Ks, radii, conics)
         ctx.dims = (width, height, eps2d)
-        ctx.mark_non_differentiable(radii, tpg)
-        return means2d, depths, conics, radii, tpg
+        ctx.mark_non_differentiable(radii, aux)
+        return means2d, depths, conics, radii, aux
 
     @staticmethod
-    def backward(ctx, v_means2d, v_depths, v_conics, _v_radii, _v_tpg):
+    def backward(ctx, v_means2d, v_depths, v_conics, _v_radii, _v_aux):
         means, quats, scales, viewmats, Ks, radii, conics = ctx.saved_tensors
         width, height, eps2d = ctx.dims
         v_means, v_quats, v_scales = ops.project_bwd(means, quats, scales, viewmats, Ks, width, height, radii,
                                                      conics, v_means2d, v_depths, v_conics, eps2d)
-        return (v_means, v_quats, v_scales) + (None,) * 8
+        return (v_means, v_quats, v_scales) + (None,) * 9
 
 
 class _Composite(torch.autograd.Function):
@@ -216,9 +219,11 @@ def _rasterize_core(means, quats, scales, opacities, colors, viewmats, Ks, width
     means, quats, scales, opacities, colors = map(f32, (means, quats, scales, opacities, colors))
     viewmats, Ks = f32(viewmats).contiguous(), f32(Ks).contiguous()
 
-    means2d, depths, conics, radii, tpg = _Project.apply(
+    use_fused = fused and not FORCE_GENERIC_SORT
+    means2d, depths, conics, radii, aux = _Project.apply(
         means.contiguous(), quats.contiguous(), scales.contiguous(), viewmats, Ks, width, height, eps2d,
-        near_plane, far_plane, radius_clip)
+        near_plane, far_plane, radius_clip, use_fused)
+    tpg = None if use_fused else aux
     with_depth = render_mode in ("D", "ED", "RGB+D", "RGB+ED")
     only_depth = render_mode in ("D", "ED")
     D = colors.shape[-1]
@@ -238,9 +243,9 @@ def _rasterize_core(means, quats, scales, opacities, colors, viewmats, Ks, width
 
     render = None
     sorted_counts = None
-    if fused and not FORCE_GENERIC_SORT:
+    if use_fused:
         m2d, dep = means2d.detach(), depths.detach()
-        isect_offsets, stats = ops.tile_scan(ops.bin_count(m2d, radii, width, height))
+        isect_offsets, stats = ops.tile_scan(aux)  # aux = per-tile histogram, counted inside the projection
         n_isects, max_count = stats.tolist()
         records = ops.bin_scatter(m2d, radii, dep, isect_offsets, width, height, n_isects)
         render, alphas, flag, flatten_ids, sorted_counts = _TileRender.apply(*comp_args, records, isect_offsets, width, height)

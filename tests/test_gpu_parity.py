@@ -634,3 +634,44 @@ def test_fused_equal_depth_runs(n_same):
     assert sc.max() > n_same  # low opacity: the whole list is consumed, including the equal-depth run
     for t in np.nonzero(sc)[0]:
         assert np.array_equal(f1[off[t]:off[t] + sc[t]], f2[off[t]:off[t] + sc[t]])
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_project_with_fused_tile_histogram(cases, name):
+    """pm_project_count_fwd = pm_project_fwd + pm_bin_count in one pass: identical projection outputs and
+    exactly the per-tile histogram the oracle's offsets imply."""
+    from prometheus_b200 import ops
+
+    s, _, st = cases[name]
+    proj_args = [dev(s[k]) for k in ("means", "quats", "scales", "viewmats", "Ks")] + [s["width"], s["height"]]
+    a = ops.project_fwd(*proj_args)
+    b = ops.project_fwd(*proj_args, count_tiles=False, tile_histogram=True)
+    for x, y in zip(a[:4], b[:4]):
+        assert torch.equal(x, y)
+    assert b[4] is None
+    off = st["isect_offsets"].reshape(-1)
+    want = np.diff(np.append(off, len(st["flatten_ids"])))
+    assert np.array_equal(b[5].cpu().numpy().reshape(-1), want)
+    assert torch.equal(b[5], ops.bin_count(a[1], a[0], s["width"], s["height"]))
+
+
+def test_project_fused_histogram_scattered_large_image():
+    """Hash-table path of the fused histogram (window of touched tiles > 2048 cells) and > 32 cameras
+    (two launches of the camera-looping kernel)."""
+    from prometheus_b200 import ops
+
+    g = torch.Generator().manual_seed(21)
+    n, C, W, H = 3000, 35, 1024, 800
+    means = torch.cat([(torch.rand(n, 2, generator=g) - 0.5) * 3.0, 2.0 + torch.rand(n, 1, generator=g)], 1)
+    quats = torch.randn(n, 4, generator=g)
+    scales = 0.005 + 0.05 * torch.rand(n, 3, generator=g)
+    viewmats = torch.eye(4).repeat(C, 1, 1)
+    viewmats[:, 0, 3] = torch.linspace(-0.3, 0.3, C)
+    Ks = torch.tensor([[600.0, 0, W / 2], [0, 600.0, H / 2], [0, 0, 1]]).repeat(C, 1, 1)
+    args = [dev(means), dev(quats), dev(scales), dev(viewmats), dev(Ks), W, H]
+    a = ops.project_fwd(*args)
+    b = ops.project_fwd(*args, count_tiles=True, tile_histogram=True)
+    for x, y in zip(a[:5], b[:5]):
+        assert torch.equal(x, y)
+    assert torch.equal(b[5], ops.bin_count(a[1], a[0], W, H))
+    assert int(b[5].sum()) == int(a[4].sum()) > 0
