@@ -246,7 +246,7 @@ PM_API int pm_composite_fwd(const float *means2d, const float *conics, const flo
  * pm_tile_sort + pm_composite_fwd; flatten_ids [n] is filled for the first
  * sorted_counts[c,ty,tx] entries of each tile only (all that pm_composite_bwd
  * reads). *overflow_flag (device int32, caller zero-fills) is set if a depth
- * sub-bucket of some tile exceeds the 2048-record group capacity: the caller
+ * sub-bucket of some tile exceeds the 1024-record group capacity: the caller
  * must then redo the call with pm_tile_sort + pm_composite_fwd. */
 PM_API int pm_tile_render_fwd(const uint64_t *records, const int32_t *isect_offsets, int64_t n_isects,
                               const int32_t *d_n, const float *means2d, const float *conics,
@@ -254,6 +254,22 @@ PM_API int pm_tile_render_fwd(const uint64_t *records, const int32_t *isect_offs
                               const float *depths, const float *backgrounds, int N, int C,
                               int width, int height, int tile_size,
                               float *render, float *alphas, int32_t *last_ids,
+                              int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
+                              pm_stream_t stream);
+
+/* The same kernel with the module-level epilogue fused in (RGB + expected depth, D = 3): writes
+ * what GaussianRenderer.forward returns (gaussians_renderer.py:437-440, :507-509) —
+ * images [C,3,H,W] = 2 rgb - 1, depth_out [C,1,H,W] = accumulated depth / max(alpha, 1e-10),
+ * masks [C,1,H,W] = alpha in [0,1] — instead of the interleaved render / alphas tensors.
+ * n_isects may be a speculative CAPACITY of records / flatten_ids with the true count in *d_n:
+ * nothing is accessed beyond min(n_isects, *d_n); if *d_n > n_isects the outputs are invalid and
+ * the caller must retry with a larger capacity. */
+PM_API int pm_tile_render_packed_fwd(const uint64_t *records, const int32_t *isect_offsets, int64_t n_isects,
+                              const int32_t *d_n, const float *means2d, const float *conics,
+                              const float *opacities, const float *colors, int colors_per_camera,
+                              const float *depths, const float *backgrounds, int N, int C,
+                              int width, int height, int tile_size,
+                              float *images, float *depth_out, float *masks, int32_t *last_ids,
                               int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
                               pm_stream_t stream);
 
@@ -271,6 +287,18 @@ PM_API int pm_composite_bwd(const float *means2d, const float *conics, const flo
                      const float *v_render, const float *v_alphas,
                      float *v_means2d, float *v_conics, float *v_colors,
                      float *v_opacities, float *v_depths, pm_stream_t stream);
+
+/* Backward of pm_tile_render_packed_fwd: cotangents of the packed outputs (any may be NULL) in,
+ * the same accumulated per-Gaussian gradients out. masks / depth_out are the forward's outputs. */
+PM_API int pm_composite_bwd_packed(const float *means2d, const float *conics, const float *opacities,
+                     const float *colors, int colors_per_camera, const float *depths,
+                     const float *backgrounds, const int32_t *isect_offsets,
+                     const int32_t *flatten_ids, int64_t n_isects, const int32_t *d_n,
+                     int N, int C, int width, int height, int tile_size,
+                     const float *masks, const float *depth_out, const int32_t *last_ids,
+                     const float *v_images, const float *v_depth_out, const float *v_masks,
+                     float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
+                     float *v_depths, pm_stream_t stream);
 
 #ifdef __cplusplus
 }

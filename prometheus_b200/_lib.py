@@ -46,6 +46,9 @@ SIGNATURES = {
     "pm_tile_offsets": (c_int, [_P, _L, _P, _I, _I, _I, _P, _P]),
     "pm_composite_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "pm_tile_render_fwd": (c_int, [_P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "pm_tile_render_packed_fwd": (c_int, [_P, _P, _L, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pm_composite_bwd_packed": (c_int, [_P, _P, _P, _P, _I, _P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I,
+                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pm_composite_bwd": (c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I,
                                  _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }

@@ -132,7 +132,9 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
                      const int32_t *__restrict__ last_ids, const float *__restrict__ v_render,
                      const float *__restrict__ v_alphas, float *__restrict__ v_means2d,
                      float *__restrict__ v_conics, float *__restrict__ v_colors,
-                     float *__restrict__ v_opacities, float *__restrict__ v_depths) {
+                     float *__restrict__ v_opacities, float *__restrict__ v_depths,
+                     const float *__restrict__ v_images, const float *__restrict__ v_depth_out,
+                     const float *__restrict__ v_masks, const float *__restrict__ depth_out, int packed) {
   __shared__ GaussA sA[kBatch];
   __shared__ GaussB sB[kBatch];
   __shared__ GaussC sC[kBatch];
@@ -160,7 +162,26 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
   // per-pixel state
   float T_final = 1.0f, vr[4] = {0.0f, 0.0f, 0.0f, 0.0f}, va = 0.0f;
   int my_last = -1;  // nothing to replay for pixels outside the image
-  if (inside) {
+  if (inside && packed) {
+    // cotangents of the packed module outputs (store_pixel_packed): images = 2 rgb - 1, depth_out =
+    // acc_depth / max(alpha, 1e-10), masks = clamp(alpha, 0, 1); `alphas` is the masks tensor
+    const size_t plane = (size_t)height * width, in_plane = (size_t)iy * width + ix;
+    const size_t pix = (size_t)cam * plane + in_plane;
+    const float alpha = alphas[pix];
+    T_final = 1.0f - alpha;
+    my_last = last_ids[pix];
+    if (v_images) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) vr[k] = 2.0f * v_images[((size_t)cam * 3 + k) * plane + in_plane];
+    }
+    if (v_masks) va = v_masks[pix];
+    if (v_depth_out) {
+      const float vd = v_depth_out[pix];
+      const float ac = fmaxf(alpha, 1e-10f);
+      vr[3] = vd / ac;
+      if (alpha >= 1e-10f) va -= depth_out[pix] * vd / ac;  // d(acc / alpha) / d alpha = -depth_out / alpha
+    }
+  } else if (inside) {
     const size_t pix = ((size_t)cam * height + iy) * width + ix;
     T_final = 1.0f - alphas[pix];
     my_last = last_ids[pix];
@@ -348,7 +369,31 @@ int pm_composite_bwd(const float *means2d, const float *conics, const float *opa
   pm::composite_bwd_kernel<<<(unsigned)blocks, 256, 0, pm::as_stream(stream)>>>(
       means2d, conics, opacities, colors, colors_per_camera, D, depths, backgrounds, isect_offsets,
       flatten_ids, n_isects, d_n, N, width, height, tw, th, alphas, last_ids, v_render, v_alphas,
-      v_means2d, v_conics, v_colors, v_opacities, v_depths);
+      v_means2d, v_conics, v_colors, v_opacities, v_depths, nullptr, nullptr, nullptr, nullptr, 0);
+  return pm::check_launch();
+}
+
+int pm_composite_bwd_packed(const float *means2d, const float *conics, const float *opacities,
+                            const float *colors, int colors_per_camera, const float *depths,
+                            const float *backgrounds, const int32_t *isect_offsets,
+                            const int32_t *flatten_ids, int64_t n_isects, const int32_t *d_n, int N, int C,
+                            int width, int height, int tile_size, const float *masks, const float *depth_out,
+                            const int32_t *last_ids, const float *v_images, const float *v_depth_out,
+                            const float *v_masks, float *v_means2d, float *v_conics, float *v_colors,
+                            float *v_opacities, float *v_depths, pm_stream_t stream) {
+  const int rc = pm::check_common(means2d, conics, opacities, colors, 3, depths, isect_offsets, flatten_ids,
+                                  n_isects, N, C, width, height, tile_size);
+  if (rc != PM_OK) return rc;
+  if (!depths || !masks || !depth_out || !last_ids || !v_means2d || !v_conics || !v_opacities || !v_colors || !v_depths)
+    return PM_ERR_BAD_ARG;
+  if (C == 0 || n_isects == 0) return PM_OK;
+  const int tw = (width + pm::kTile - 1) / pm::kTile, th = (height + pm::kTile - 1) / pm::kTile;
+  const int64_t blocks = (int64_t)C * tw * th;
+  if (blocks >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
+  pm::composite_bwd_kernel<<<(unsigned)blocks, 256, 0, pm::as_stream(stream)>>>(
+      means2d, conics, opacities, colors, colors_per_camera, 3, depths, backgrounds, isect_offsets,
+      flatten_ids, n_isects, d_n, N, width, height, tw, th, masks, last_ids, nullptr, nullptr,
+      v_means2d, v_conics, v_colors, v_opacities, v_depths, v_images, v_depth_out, v_masks, depth_out, 1);
   return pm::check_launch();
 }
 

@@ -241,4 +241,31 @@ __device__ __forceinline__ void store_pixel(const PixelState &st, size_t pix, in
   }
 }
 
+// Packed epilogue of the module fast path (RGB + expected depth, D = 3): writes what
+// GaussianRenderer.forward returns (gaussians_renderer.py:437-440, :507-509) straight from the
+// compositor's registers — images [C,3,H,W] = 2 rgb - 1, depths [C,1,H,W] = sum(depth alpha T) /
+// max(alpha, 1e-10) (gsplat's "ED" normalisation), masks [C,1,H,W] = alpha clamped to [0,1] — instead of
+// an interleaved render tensor that six elementwise / copy kernels then slice, divide, permute and rescale.
+// Same roundings as those ATen kernels, so the images are bit-identical to the unpacked path.
+__device__ __forceinline__ void store_pixel_packed(const PixelState &st, int cam, int iy, int ix, int width, int height,
+                                                   const float *__restrict__ backgrounds, float *__restrict__ images,
+                                                   float *__restrict__ depth_out, float *__restrict__ masks,
+                                                   int32_t *__restrict__ last_ids) {
+  const float T = fabsf(st.T);
+  const float alpha = 1.0f - T;
+  const size_t plane = (size_t)height * width;
+  const size_t in_plane = (size_t)iy * width + ix;
+  const size_t pix = (size_t)cam * plane + in_plane;
+  float out[3] = {st.o0, st.o1, st.o2};
+  if (backgrounds) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out[k] += T * __ldg(backgrounds + cam * 3 + k);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) images[((size_t)cam * 3 + k) * plane + in_plane] = __fmaf_rn(2.0f, out[k], -1.0f);
+  depth_out[pix] = __fdiv_rn(st.o3, fmaxf(alpha, 1e-10f));
+  masks[pix] = fminf(fmaxf(alpha, 0.0f), 1.0f);
+  last_ids[pix] = st.last;
+}
+
 }  // namespace pm

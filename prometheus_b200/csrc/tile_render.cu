@@ -184,7 +184,8 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
                        int width, int height, int tile_width, int tile_height, float *__restrict__ render,
                        float *__restrict__ alphas, int32_t *__restrict__ last_ids,
                        int32_t *__restrict__ flatten_ids, int32_t *__restrict__ sorted_counts,
-                       int32_t *__restrict__ overflow_flag) {
+                       int32_t *__restrict__ overflow_flag, float *__restrict__ images,
+                       float *__restrict__ depth_out, float *__restrict__ masks) {
   extern __shared__ __align__(16) unsigned char tr_smem[];
   TrShared &sh = *reinterpret_cast<TrShared *>(tr_smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -203,8 +204,10 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
   staged_init_null(sh.stg);
 
   const int64_t n_isects = effective_n(n_host, d_n);
-  const int start = offsets[ct];
-  const int end = (ct == (int)gridDim.x - 1) ? (int)n_isects : offsets[ct + 1];
+  // (clamped: with a speculative record capacity smaller than the device-side count the result is
+  //  discarded by the caller, but nothing may be read or written out of bounds)
+  const int start = min(offsets[ct], (int)n_isects);
+  const int end = (ct == (int)gridDim.x - 1) ? (int)n_isects : min(offsets[ct + 1], (int)n_isects);
   const int cnt = end - start;
   const unsigned long long *src = reinterpret_cast<const unsigned long long *>(records) + start;
   int sorted = 0;
@@ -391,31 +394,41 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
     }
   }
   if (tid == 0) sorted_counts[ct] = sorted;
-  if (inside) store_pixel(st, ((size_t)cam * height + iy) * width + ix, cam, D, CD, backgrounds, render, alphas, last_ids);
+  if (inside) {
+    if (images != nullptr)  // packed module outputs (pm_tile_render_packed_fwd)
+      store_pixel_packed(st, cam, iy, ix, width, height, backgrounds, images, depth_out, masks, last_ids);
+    else
+      store_pixel(st, ((size_t)cam * height + iy) * width + ix, cam, D, CD, backgrounds, render, alphas, last_ids);
+  }
 }
 
 }  // namespace pm
 
 extern "C" {
 
-int pm_tile_render_fwd(const uint64_t *records, const int32_t *isect_offsets, int64_t n_isects,
-                       const int32_t *d_n, const float *means2d, const float *conics,
-                       const float *opacities, const float *colors, int colors_per_camera, int D,
-                       const float *depths, const float *backgrounds, int N, int C, int width, int height,
-                       int tile_size, float *render, float *alphas, int32_t *last_ids,
-                       int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
-                       pm_stream_t stream) {
+static int tile_render_launch(const uint64_t *records, const int32_t *isect_offsets, int64_t n_isects,
+                              const int32_t *d_n, const float *means2d, const float *conics, const float *opacities,
+                              const float *colors, int colors_per_camera, int D, const float *depths,
+                              const float *backgrounds, int N, int C, int width, int height, int tile_size,
+                              float *render, float *alphas, int32_t *last_ids, int32_t *flatten_ids,
+                              int32_t *sorted_counts, int32_t *overflow_flag, float *images, float *depth_out,
+                              float *masks, pm_stream_t stream) {
   if (N < 0 || C < 0 || width <= 0 || height <= 0 || n_isects < 0 || D < 0) return PM_ERR_BAD_ARG;
   if (tile_size != pm::kTile) return PM_ERR_UNSUPPORTED;
   const int CD = D + (depths ? 1 : 0);
   if (CD < 1 || CD > 4) return PM_ERR_UNSUPPORTED;
-  if (!means2d || !conics || !opacities || !isect_offsets || !render || !alphas || !last_ids || !sorted_counts ||
-      !overflow_flag)
+  if (!means2d || !conics || !opacities || !isect_offsets || !last_ids || !sorted_counts || !overflow_flag)
     return PM_ERR_BAD_ARG;
+  if (images) {  // packed outputs: RGB + expected depth only
+    if (D != 3 || !depths) return PM_ERR_UNSUPPORTED;
+    if (!depth_out || !masks) return PM_ERR_BAD_ARG;
+  } else {
+    if (!render || !alphas) return PM_ERR_BAD_ARG;
+    if (CD == 4 && (reinterpret_cast<uintptr_t>(render) & 15) != 0) return PM_ERR_BAD_ARG;
+  }
   if (D > 0 && !colors) return PM_ERR_BAD_ARG;
   if (n_isects > 0 && (!records || !flatten_ids)) return PM_ERR_BAD_ARG;
   if ((reinterpret_cast<uintptr_t>(means2d) & 7) != 0) return PM_ERR_BAD_ARG;
-  if (CD == 4 && (reinterpret_cast<uintptr_t>(render) & 15) != 0) return PM_ERR_BAD_ARG;
   if (n_isects >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
   if (C == 0) return PM_OK;
   const int tw = (width + pm::kTile - 1) / pm::kTile, th = (height + pm::kTile - 1) / pm::kTile;
@@ -432,8 +445,34 @@ int pm_tile_render_fwd(const uint64_t *records, const int32_t *isect_offsets, in
   }
   pm::tile_render_fwd_kernel<<<(unsigned)blocks, pm::kTrThreads, pm::kTrSmemBytes, pm::as_stream(stream)>>>(
       records, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera, D, depths,
-      backgrounds, N, width, height, tw, th, render, alphas, last_ids, flatten_ids, sorted_counts, overflow_flag);
+      backgrounds, N, width, height, tw, th, render, alphas, last_ids, flatten_ids, sorted_counts, overflow_flag,
+      images, depth_out, masks);
   return pm::check_launch();
+}
+
+int pm_tile_render_fwd(const uint64_t *records, const int32_t *isect_offsets, int64_t n_isects,
+                       const int32_t *d_n, const float *means2d, const float *conics,
+                       const float *opacities, const float *colors, int colors_per_camera, int D,
+                       const float *depths, const float *backgrounds, int N, int C, int width, int height,
+                       int tile_size, float *render, float *alphas, int32_t *last_ids,
+                       int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
+                       pm_stream_t stream) {
+  return tile_render_launch(records, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera,
+                            D, depths, backgrounds, N, C, width, height, tile_size, render, alphas, last_ids,
+                            flatten_ids, sorted_counts, overflow_flag, nullptr, nullptr, nullptr, stream);
+}
+
+int pm_tile_render_packed_fwd(const uint64_t *records, const int32_t *isect_offsets, int64_t n_isects,
+                              const int32_t *d_n, const float *means2d, const float *conics,
+                              const float *opacities, const float *colors, int colors_per_camera,
+                              const float *depths, const float *backgrounds, int N, int C, int width, int height,
+                              int tile_size, float *images, float *depth_out, float *masks, int32_t *last_ids,
+                              int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
+                              pm_stream_t stream) {
+  if (!images) return PM_ERR_BAD_ARG;
+  return tile_render_launch(records, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera,
+                            3, depths, backgrounds, N, C, width, height, tile_size, nullptr, nullptr, last_ids,
+                            flatten_ids, sorted_counts, overflow_flag, images, depth_out, masks, stream);
 }
 
 }  // extern "C"

@@ -376,3 +376,53 @@ def composite_bwd(means2d, conics, opacities, colors, depths, backgrounds, offse
                                   _ptr(v_conics), _ptr(v_colors), _ptr(v_opac), _ptr(v_depths), _stream()),
                "pm_composite_bwd")
     return v_means2d, v_conics, v_colors, v_opac, v_depths
+
+
+# ------------------------------------------------------------------ module fast path (packed outputs)
+@_instrument("tile_render_fwd", 1)
+def tile_render_packed_fwd(records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height,
+                           d_n=None):
+    """Fused sort-as-you-go forward with the module epilogue: -> images [C,3,H,W] (2 rgb - 1),
+    depth_out [C,1,H,W] (expected depth), masks [C,1,H,W], last_ids [C,H,W], flatten_ids (sorted prefix per
+    tile), sorted_counts [C,th,tw], overflow flag int32[1]. `records` may be a speculative capacity with the
+    true count in d_n[0] (see pm_tile_render_packed_fwd)."""
+    L = _lib.load()
+    C, N = means2d.shape[:2]
+    colors, per_cam, D = _colors_layout(colors, C, N)
+    assert D == 3 and depths is not None
+    dev = means2d.device
+    n = records.numel()
+    images = torch.empty(C, 3, height, width, device=dev)
+    depth_out = torch.empty(C, 1, height, width, device=dev)
+    masks = torch.empty(C, 1, height, width, device=dev)
+    last_ids = torch.empty(C, height, width, dtype=torch.int32, device=dev)
+    flat = torch.empty(n, dtype=torch.int32, device=dev)
+    sorted_counts = torch.empty_like(offsets)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(L.pm_tile_render_packed_fwd(_ptr(records), _ptr(offsets), n, _ptr(d_n), _ptr(means2d), _ptr(conics),
+                                           _ptr(opacities), _ptr(colors), per_cam, _ptr(depths), _ptr(backgrounds), N, C,
+                                           width, height, TILE, _ptr(images), _ptr(depth_out), _ptr(masks),
+                                           _ptr(last_ids), _ptr(flat), _ptr(sorted_counts), _ptr(flag), _stream()),
+               "pm_tile_render_packed_fwd")
+    return images, depth_out, masks, last_ids, flat, sorted_counts, flag
+
+
+@_instrument("composite_bwd", 1)
+def composite_bwd_packed(means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width, height,
+                         masks, depth_out, last_ids, v_images, v_depth_out, v_masks, d_n=None):
+    L = _lib.load()
+    C, N = means2d.shape[:2]
+    colors, per_cam, D = _colors_layout(colors, C, N)
+    v_images, v_depth_out, v_masks = (_opt(t, torch.float32, "grad") for t in (v_images, v_depth_out, v_masks))
+    v_means2d = torch.zeros_like(means2d)
+    v_conics = torch.zeros_like(conics)
+    v_colors = torch.zeros_like(colors)
+    v_opac = torch.zeros_like(opacities)
+    v_depths = torch.zeros_like(depths)
+    _lib.check(L.pm_composite_bwd_packed(_ptr(means2d), _ptr(conics), _ptr(opacities), _ptr(colors), per_cam,
+                                         _ptr(depths), _ptr(backgrounds), _ptr(offsets), _ptr(flatten_ids),
+                                         flatten_ids.numel(), _ptr(d_n), N, C, width, height, TILE, _ptr(masks),
+                                         _ptr(depth_out), _ptr(last_ids), _ptr(v_images), _ptr(v_depth_out),
+                                         _ptr(v_masks), _ptr(v_means2d), _ptr(v_conics), _ptr(v_colors), _ptr(v_opac),
+                                         _ptr(v_depths), _stream()), "pm_composite_bwd_packed")
+    return v_means2d, v_conics, v_colors, v_opac, v_depths

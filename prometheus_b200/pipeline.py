@@ -26,6 +26,7 @@ class DecodeRenderPipeline:
         self._staged = None      # (device inputs, ready event) of the next scene
         self._pending_out = []   # events of D2H copies in flight
         self._dev_out_keepalive = []
+        self._unchecked = []     # (deferred renderer checks, device inputs, host outputs) per scene in flight
 
     def _stage(self, params_h, cams_in_h, cams_out_h):
         assert params_h.is_pinned() and cams_in_h.is_pinned() and cams_out_h.is_pinned(), "pin the host buffers"
@@ -50,9 +51,25 @@ class DecodeRenderPipeline:
         cur.wait_event(ready)
         for t in (params, cin, cout):
             t.record_stream(cur)
-        with torch.no_grad():
-            g = self.conv(params, cin)
-            outs = self.rend(cout, g, bg_color=self.bg, h=self.h, w=self.w)[:3]
+        outs = self._render(params, cin, cout, deferred=True)
+        jobs = self.rend.take_pending()
+        self._copy_out(out_h, outs, cur)
+        # keep what a re-render would need until the scene's deferred checks have been looked at
+        self._unchecked.append((jobs, (params, cin, cout), out_h))
+        while len(self._unchecked) > 4:
+            self._settle(self._unchecked.pop(0))
+
+    def _render(self, params, cin, cout, deferred: bool):
+        prev = self.rend.defer_checks
+        self.rend.defer_checks = deferred
+        try:
+            with torch.no_grad():
+                g = self.conv(params, cin)
+                return self.rend(cout, g, bg_color=self.bg, h=self.h, w=self.w)[:3]
+        finally:
+            self.rend.defer_checks = prev
+
+    def _copy_out(self, out_h, outs, cur) -> None:
         done = torch.cuda.Event()
         done.record(cur)
         with torch.cuda.stream(self.s_out):
@@ -66,9 +83,21 @@ class DecodeRenderPipeline:
         if len(self._pending_out) > 4:
             self._pending_out.pop(0).synchronize()
 
+    def _settle(self, entry) -> None:
+        """Look at a scene's deferred checks (intersection capacity, sort-group overflow); in the rare case
+        one failed, render the scene again with blocking checks and replace its host copy."""
+        jobs, (params, cin, cout), out_h = entry
+        if self.rend.check_jobs(jobs):
+            return
+        cur = torch.cuda.current_stream(self.device)
+        outs = self._render(params, cin, cout, deferred=False)
+        self._copy_out(out_h, outs, cur)
+
     def flush(self) -> None:
         """Make the current stream wait for every outstanding copy (call before reading `out_h`)."""
         cur = torch.cuda.current_stream(self.device)
+        while self._unchecked:
+            self._settle(self._unchecked.pop(0))
         for ev in self._pending_out:
             cur.wait_event(ev)
         self._pending_out = []

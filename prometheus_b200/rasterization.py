@@ -116,6 +116,71 @@ class _TileRender(torch.autograd.Function):
         return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None
 
 
+class _TileRenderPacked(torch.autograd.Function):
+    """Module fast path: fused sort-as-you-go forward with the packed epilogue (images = 2 rgb - 1 in CHW,
+    expected depth, clamped alpha) + the compositing backward that takes the packed cotangents directly."""
+
+    @staticmethod
+    def forward(ctx, means2d, conics, opacities, colors, depths, backgrounds, records, offsets, stats, width, height):
+        means2d, conics = means2d.contiguous(), conics.contiguous()
+        opacities, colors, depths = opacities.contiguous(), colors.contiguous(), depths.contiguous()
+        backgrounds = None if backgrounds is None else backgrounds.contiguous().float()
+        images, depth_out, masks, last_ids, flat, sorted_counts, flag = ops.tile_render_packed_fwd(
+            records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height, d_n=stats)
+        ctx.save_for_backward(means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, masks, depth_out,
+                              last_ids, stats)
+        ctx.dims = (width, height)
+        ctx.mark_non_differentiable(flag, flat, sorted_counts)
+        return images, depth_out, masks, flag, flat, sorted_counts
+
+    @staticmethod
+    def backward(ctx, v_images, v_depth_out, v_masks, _vf, _vflat, _vsc):
+        (means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, masks, depth_out, last_ids,
+         stats) = ctx.saved_tensors
+        width, height = ctx.dims
+        v_means2d, v_conics, v_colors, v_opac, v_depths = ops.composite_bwd_packed(
+            means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, width, height, masks, depth_out,
+            last_ids, v_images, v_depth_out, v_masks, d_n=stats)
+        v_bg = None
+        if backgrounds is not None and ctx.needs_input_grad[5] and v_images is not None:
+            v_bg = (2.0 * v_images * (1.0 - masks)).sum(dim=(2, 3))
+        return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None, None
+
+
+def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, backgrounds, width, height,
+                        capacity=None, near_plane=0.01, far_plane=1e10, radius_clip=0.0, eps2d=0.3):
+    """Fast path behind GaussianRenderer: all C views of one scene, RGB + expected depth, outputs already in the
+    module's layout. -> images [C,3,H,W] in [-1,1], depths [C,1,H,W], masks [C,1,H,W], info.
+
+    `capacity` = speculative size of the intersection buffers. None: read the exact count from the device
+    (one host sync between the tile scan and the scatter, as gsplat does). An int: no host sync at all — the
+    count stays on the device (info["stats"] = {n_isects, max tile count}); the caller must check
+    n_isects <= capacity afterwards and re-render otherwise (GaussianRenderer does)."""
+    N, C = means.shape[0], viewmats.shape[0]
+    if not means.is_cuda:
+        raise RuntimeError("prometheus_b200 needs CUDA tensors: there is no CPU fallback")
+    f32 = lambda t: (t if t.dtype == torch.float32 else t.float()).contiguous()
+    means, quats, scales, opacities, colors, viewmats, Ks = map(f32, (means, quats, scales, opacities, colors, viewmats, Ks))
+    means2d, depths, conics, radii, counts = _Project.apply(means, quats, scales, viewmats, Ks, width, height, eps2d,
+                                                             near_plane, far_plane, radius_clip, True)
+    means2d_views = [v.unsqueeze(0) for v in means2d.unbind(0)]
+    means2d_in = means2d
+    if means2d.requires_grad:
+        for v in means2d_views:
+            v.retain_grad()
+        means2d_in = torch.cat(means2d_views, dim=0)
+    isect_offsets, stats = ops.tile_scan(counts)
+    if capacity is None:
+        capacity = int(stats[0].item())
+    records = ops.bin_scatter(means2d.detach(), radii, depths.detach(), isect_offsets, width, height, int(capacity))
+    images, depth_out, masks, flag, flatten_ids, sorted_counts = _TileRenderPacked.apply(
+        means2d_in, conics, opacities, colors, depths, backgrounds, records, isect_offsets, stats, width, height)
+    info = {"radii": radii, "means2d": means2d, "means2d_views": means2d_views, "depths": depths, "conics": conics,
+            "isect_offsets": isect_offsets, "flatten_ids": flatten_ids, "sorted_counts": sorted_counts,
+            "stats": stats, "overflow_flag": flag, "capacity": int(capacity)}
+    return images, depth_out, masks, info
+
+
 # Largest per-tile group the fused kernel sorts at once (tile_render.cu: kTrCap)
 FUSED_GROUP_CAP = 1024
 

@@ -20,7 +20,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .rasterization import _rasterize_core, rasterization
+from .rasterization import FUSED_GROUP_CAP, _rasterize_core, rasterization, render_views_packed
 
 
 class _Unproject(torch.autograd.Function):
@@ -75,9 +75,18 @@ class GaussianRenderer(nn.Module):
     # cameras rendered per batched launch set: bounds the per-pair / per-intersection buffers
     # (32 B per (camera, Gaussian) pair) when a long trajectory is rendered from a big scene
     view_chunk = 8
-    # render with the fused sort-as-you-go kernel (tile_render.cu): bit-identical images, but only the
-    # part of each tile's list that the compositor consumes gets sorted
+    # render with the fused sort-as-you-go kernel (tile_render.cu) and its packed epilogue: bit-identical
+    # images, but only the part of each tile's list that the compositor consumes gets sorted, and the module's
+    # output layout comes straight out of the kernel
     fused = True
+    # fused path: size the intersection buffers from the previous call of the same shape (x slack) instead of
+    # reading the count back between two kernels; the count is checked once all launches are queued
+    speculative_capacity = True
+    capacity_slack = 1.3
+    # False: forward() returns only after its checks passed (like the reference, which ends with
+    # torch.cuda.synchronize(), :510). True: forward() never blocks; call validate() before trusting the images
+    # (DecodeRenderPipeline does, when it hands the host copies out).
+    defer_checks = False
 
     def __init__(self, sh_degree=0, background=[1, 1, 1]):
         super().__init__()
@@ -85,6 +94,8 @@ class GaussianRenderer(nn.Module):
         self.register_buffer("bg_color", torch.tensor(background).float())
         self.radii: List[torch.Tensor] = []
         self.viewspace_points: List[torch.Tensor] = []
+        self._cap_hint = {}
+        self._pending = []
 
     def _backgrounds(self, bg_color, n_views: int, device) -> torch.Tensor:
         # reference :381-386 — 'random' draws a fresh colour per rendered view
@@ -94,6 +105,48 @@ class GaussianRenderer(nn.Module):
             return self.bg_color.to(device).expand(n_views, 3).contiguous()
         return torch.as_tensor(bg_color, dtype=torch.float32, device=device).reshape(1, 3).expand(n_views, 3).contiguous()
 
+    # ---------------------------------------------------------------- separate-stage path (fused = False)
+    def _render_chunk_unfused(self, xyz, rot, sc, opac, feat, viewmats, Ks, bgs, h, w):
+        render, alphas, info = _rasterize_core(
+            means=xyz, quats=rot, scales=sc, opacities=opac, colors=feat, viewmats=viewmats, Ks=Ks, backgrounds=bgs,
+            width=int(w), height=int(h), render_mode="RGB+ED", packed=False, per_view_means2d=True, fused=False)
+        images = render[..., :3].permute(0, 3, 1, 2) * 2 - 1
+        return images, render[..., 3:].permute(0, 3, 1, 2), alphas.permute(0, 3, 1, 2).clamp(0, 1), info
+
+    # ---------------------------------------------------------------- fused path
+    def _render_chunk_fused(self, args, h, w):
+        xyz, rot, sc, opac, feat, viewmats, Ks, bgs = args
+        key = (xyz.shape[0], viewmats.shape[0], int(h), int(w))
+        cap = self._cap_hint.get(key) if self.speculative_capacity else None
+        images, depths, masks, info = render_views_packed(xyz, rot, sc, opac, feat, viewmats, Ks, bgs, int(w), int(h),
+                                                          capacity=cap)
+        return images, depths, masks, info, key
+
+    def _check(self, job) -> bool:
+        """True if the fused render of `job` is valid; updates the capacity hint."""
+        info, key = job["info"], job["key"]
+        job["event"].synchronize()
+        n_isects, max_count = (int(v) for v in job["stats_host"])
+        self._cap_hint[key] = int(n_isects * self.capacity_slack) + 4096
+        if n_isects > info["capacity"]:
+            return False
+        # a depth sub-bucket larger than the group capacity can only exist if some tile is larger than it
+        return max_count <= FUSED_GROUP_CAP or int(info["overflow_flag"].item()) == 0
+
+    def take_pending(self) -> list:
+        """Deferred-check mode: hand the unchecked jobs of the forward() calls so far to the caller
+        (see check_jobs)."""
+        jobs, self._pending = self._pending, []
+        return jobs
+
+    def check_jobs(self, jobs) -> bool:
+        return all([self._check(j) for j in jobs])
+
+    def validate(self) -> bool:
+        """Deferred-check mode: True if every fused render since the last call was valid (otherwise re-run
+        forward() with defer_checks = False)."""
+        return self.check_jobs(self.take_pending())
+
     def forward(self, cameras, gaussians, scaling_modifier=1.0, bg_color=None, h=256, w=256):
         B, N = cameras.shape[:2]
         xyz, features, opacity, scales, rotations = gaussians
@@ -102,30 +155,55 @@ class GaussianRenderer(nn.Module):
         self.viewspace_points = []
         viewmats, Ks = ops.camera_prep(cameras.reshape(B * N, 18), h, w)
         viewmats, Ks = viewmats.reshape(B, N, 4, 4), Ks.reshape(B, N, 3, 3)
-        images, depths, masks = [], [], []
+        jobs = []
         for i in range(B):
             bgs = self._backgrounds(bg_color, N, device)
             sc = scales[i] if scaling_modifier == 1.0 else scales[i] * scaling_modifier
-            im_i, de_i, ma_i = [], [], []
             for c0 in range(0, N, self.view_chunk):
                 c1 = min(N, c0 + self.view_chunk)
-                render, alphas, info = _rasterize_core(
-                    means=xyz[i], quats=rotations[i], scales=sc, opacities=opacity[i].squeeze(-1),
-                    colors=features[i][:, 0], viewmats=viewmats[i, c0:c1], Ks=Ks[i, c0:c1], backgrounds=bgs[c0:c1],
-                    width=int(w), height=int(h), render_mode="RGB+ED", packed=False, per_view_means2d=True, fused=self.fused)
-                im_i.append(render[..., :3].permute(0, 3, 1, 2))
-                de_i.append(render[..., 3:].permute(0, 3, 1, 2))
-                ma_i.append(alphas.permute(0, 3, 1, 2).clamp(0, 1))
-                for j in range(c1 - c0):
-                    self.radii.append(info["radii"][j])
-                    self.viewspace_points.append(info["means2d_views"][j])
-            images.append(im_i[0] if len(im_i) == 1 else torch.cat(im_i, 0))
-            depths.append(de_i[0] if len(de_i) == 1 else torch.cat(de_i, 0))
-            masks.append(ma_i[0] if len(ma_i) == 1 else torch.cat(ma_i, 0))
-        images = torch.stack(images, dim=0) * 2 - 1
-        depths = torch.stack(depths, dim=0)
-        masks = torch.stack(masks, dim=0)
-        return images, depths, masks, None, None
+                args = (xyz[i], rotations[i], sc, opacity[i].squeeze(-1), features[i][:, 0], viewmats[i, c0:c1],
+                        Ks[i, c0:c1], bgs[c0:c1])
+                if self.fused:
+                    im, de, ma, info, key = self._render_chunk_fused(args, h, w)
+                    stats_host = torch.empty(2, dtype=torch.int32, pin_memory=True)
+                    stats_host.copy_(info["stats"], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    jobs.append(dict(args=args, out=(im, de, ma), info=info, key=key, stats_host=stats_host, event=ev))
+                else:
+                    im, de, ma, info = self._render_chunk_unfused(*args, h, w)
+                    jobs.append(dict(args=args, out=(im, de, ma), info=info, key=None))
+        if self.fused and self.defer_checks:
+            self._pending.extend(jobs)
+        elif self.fused:
+            # every launch is queued; now look at the counts (the GPU is still busy rendering)
+            for job in jobs:
+                if not self._check(job):
+                    a = job["args"]
+                    n_isects = int(job["stats_host"][0])
+                    if n_isects > job["info"]["capacity"]:  # speculative buffers were too small: exact size this time
+                        self._cap_hint.pop(job["key"], None)
+                        im, de, ma, info, _ = self._render_chunk_fused(a, h, w)
+                        ok = int(info["stats"][1].item()) <= FUSED_GROUP_CAP or int(info["overflow_flag"].item()) == 0
+                        self._cap_hint[job["key"]] = int(n_isects * self.capacity_slack) + 4096
+                    else:
+                        ok = False
+                    if not ok:  # a depth sub-bucket beyond the fused kernel's group capacity: separate stages
+                        im, de, ma, info = self._render_chunk_unfused(*a, h, w)
+                    job["out"], job["info"] = (im, de, ma), info
+        images, depths, masks = [], [], []
+        per_scene = len(jobs) // max(B, 1)
+        for i in range(B):
+            sj = jobs[i * per_scene:(i + 1) * per_scene]
+            for job in sj:
+                nv = job["out"][0].shape[0]
+                for j in range(nv):
+                    self.radii.append(job["info"]["radii"][j])
+                    self.viewspace_points.append(job["info"]["means2d_views"][j])
+            for lst, k in ((images, 0), (depths, 1), (masks, 2)):
+                lst.append(sj[0]["out"][k] if len(sj) == 1 else torch.cat([j["out"][k] for j in sj], 0))
+        pack = (lambda l: l[0].unsqueeze(0)) if B == 1 else (lambda l: torch.stack(l, dim=0))
+        return pack(images), pack(depths), pack(masks), None, None
 
 
 def install_as_gsplat() -> None:

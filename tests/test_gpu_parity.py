@@ -675,3 +675,71 @@ def test_project_fused_histogram_scattered_large_image():
         assert torch.equal(x, y)
     assert torch.equal(b[5], ops.bin_count(a[1], a[0], W, H))
     assert int(b[5].sum()) == int(a[4].sum()) > 0
+
+
+# --------------------------------------------------------------------------- packed module path, no-sync capacity
+def _module_scene():
+    from prometheus_b200 import GaussianConverter, scenes
+
+    sc = scenes.make_scene("C1", seed=23, views_in=3, size_in=64, views_out=3, size_out=80)
+    conv = GaussianConverter("mvsplat", z_near=0.01, z_far=100.0, s_min=0.001, s_max=1.0).to(DEV)
+    return sc, conv
+
+
+def test_speculative_capacity_too_small_is_detected_and_rerendered():
+    """The fused module path sizes its intersection buffers from the previous call instead of reading the count
+    back mid-pipeline. A hint that is far too small must be caught by the end-of-forward check and re-rendered
+    with the exact size; a generous hint must give the same bits as the exact size."""
+    from prometheus_b200 import GaussianRenderer
+
+    sc, conv = _module_scene()
+    with torch.no_grad():
+        g = conv(sc.params.to(DEV), sc.cameras_in.to(DEV))
+        ref = GaussianRenderer().to(DEV)
+        ref.fused = False
+        want = ref(sc.cameras_out.to(DEV), g, h=80, w=80)[:3]
+        rend = GaussianRenderer().to(DEV)
+        first = rend(sc.cameras_out.to(DEV), g, h=80, w=80)[:3]          # no hint yet: exact count (one sync)
+        (key, hint), = rend._cap_hint.items()
+        assert hint > 4096
+        second = rend(sc.cameras_out.to(DEV), g, h=80, w=80)[:3]         # speculative, generous
+        rend._cap_hint[key] = 100
+        third = rend(sc.cameras_out.to(DEV), g, h=80, w=80)[:3]          # speculative, far too small
+        assert rend._cap_hint[key] == hint
+    for got in (first, second, third):
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+
+
+def test_deferred_checks_and_pipeline_recover_from_a_bad_hint():
+    """defer_checks: forward() never blocks and validate() reports the bad hint; DecodeRenderPipeline re-renders
+    the affected scene before handing out the host copies."""
+    from prometheus_b200 import DecodeRenderPipeline, GaussianRenderer
+
+    sc, conv = _module_scene()
+    cams = sc.cameras_out.to(DEV)
+    with torch.no_grad():
+        g = conv(sc.params.to(DEV), sc.cameras_in.to(DEV))
+        rend = GaussianRenderer().to(DEV)
+        want = rend(cams, g, h=80, w=80)[:3]
+        (key, hint), = rend._cap_hint.items()
+        rend.defer_checks = True
+        rend(cams, g, h=80, w=80)
+        assert rend.validate()
+        rend._cap_hint[key] = 64
+        rend(cams, g, h=80, w=80)
+        assert not rend.validate()
+        rend.defer_checks = False
+    pipe = DecodeRenderPipeline(conv, rend, 80, 80, device=DEV)
+    ins = tuple(t.pin_memory() for t in (sc.params, sc.cameras_in, sc.cameras_out))
+    outs = [[torch.empty_like(w.cpu()).pin_memory() for w in want] for _ in range(3)]
+    pipe.prefetch(*ins)
+    for i in range(3):
+        if i == 1:
+            rend._cap_hint[key] = 64   # scene 1 renders into buffers that are too small
+        pipe.run(outs[i], next_inputs_h=ins if i < 2 else None)
+    pipe.flush()
+    torch.cuda.synchronize()
+    for o in outs:
+        for a, b in zip(o, want):
+            assert torch.equal(a, b.cpu())
