@@ -121,7 +121,32 @@ __device__ __forceinline__ float butterfly_reduce10(const float (&v)[10], int la
 
 constexpr int kGradStride = 11;  // 10 gradient components per staged Gaussian (+1: bank spread)
 
-__global__ void __launch_bounds__(256)
+#ifndef PM_BWD_MINBLOCKS
+#define PM_BWD_MINBLOCKS 10
+#endif
+#ifndef PM_BWD_WARPS
+#define PM_BWD_WARPS 4
+#endif
+// A CTA replays kBwdWarps of the tile's eight 8x4-pixel warp footprints (8 = the whole tile, 4 = its upper or
+// lower half, ...): smaller CTAs wait for fewer partners at the per-round barrier and more of them fit an SM.
+constexpr int kBwdWarps = PM_BWD_WARPS;
+constexpr int kBwdThreads = 32 * kBwdWarps;
+constexpr int kBwdParts = 8 / kBwdWarps;
+#ifndef PM_BWD_BATCH
+#define PM_BWD_BATCH 128
+#endif
+constexpr int kBwdBatch = PM_BWD_BATCH;  // Gaussians staged (records + gradient accumulators) per CTA round
+
+struct BwdShared {
+  GaussA sA[kBwdBatch];
+  GaussB sB[kBwdBatch];
+  GaussC sC[kBwdBatch];
+  int32_t sF[kBwdBatch];
+  float sG[kBwdBatch * kGradStride];
+  int s_max_last;
+};
+
+__global__ void __launch_bounds__(kBwdThreads, PM_BWD_MINBLOCKS)
 composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict__ conics,
                      const float *__restrict__ opacities, const float *__restrict__ colors,
                      int colors_per_camera, int D, const float *__restrict__ depths,
@@ -135,16 +160,18 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
                      float *__restrict__ v_opacities, float *__restrict__ v_depths,
                      const float *__restrict__ v_images, const float *__restrict__ v_depth_out,
                      const float *__restrict__ v_masks, const float *__restrict__ depth_out, int packed) {
-  __shared__ GaussA sA[kBatch];
-  __shared__ GaussB sB[kBatch];
-  __shared__ GaussC sC[kBatch];
-  __shared__ int32_t sF[kBatch];
-  __shared__ float sG[kBatch * kGradStride];
-  __shared__ int s_max_last;
+  extern __shared__ __align__(16) unsigned char bwd_smem[];
+  BwdShared &sh = *reinterpret_cast<BwdShared *>(bwd_smem);
+  GaussA *sA = sh.sA; GaussB *sB = sh.sB; GaussC *sC = sh.sC;
+  int32_t *sF = sh.sF;
+  float *sG = sh.sG;
+  int &s_max_last = sh.s_max_last;
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (int)(blockIdx.x % kBwdParts) * kBwdWarps + (tid >> 5);  // footprint index inside the tile
   const int n_tiles = tile_width * tile_height;
-  const int ct = blockIdx.x;
+  const int ct = blockIdx.x / kBwdParts;
+  const int n_ct = gridDim.x / kBwdParts;
   const int cam = ct / n_tiles, tile = ct % n_tiles;
   const int tile_y = tile / tile_width, tile_x = tile % tile_width;
   const int wx0 = tile_x * kTile + (warp & 1) * 8, wy0 = tile_y * kTile + (warp >> 1) * 4;
@@ -156,7 +183,7 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
 
   const int64_t n_isects = effective_n(n_host, d_n);
   const int range_start = offsets[ct];
-  const int range_end = (ct == (int)gridDim.x - 1) ? (int)n_isects : offsets[ct + 1];
+  const int range_end = (ct == n_ct - 1) ? (int)n_isects : offsets[ct + 1];
   if (range_end <= range_start) return;
 
   // per-pixel state
@@ -210,42 +237,43 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
 
   if (tid == 0) s_max_last = -1;
   __syncthreads();
-  {
-    int m = my_last;
+  int warp_last = my_last;  // last list position any pixel of this warp replays
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) atomicMax(&s_max_last, m);
-  }
+  for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
+  if (lane == 0) atomicMax(&s_max_last, warp_last);
   __syncthreads();
   const int max_last = s_max_last;
   if (max_last < range_start) return;  // (last_ids are 0 for untouched pixels; 0 >= range_start only in tile 0)
 
   float T = T_final;
   float buf0 = 0.0f, buf1 = 0.0f, buf2 = 0.0f, buf3 = 0.0f;
-  // batches are aligned to the forward pass's batches; walk them back to front
+  // walk the needed prefix of the tile's list back to front in rounds of kBwdBatch staged Gaussians; inside a
+  // round the warps do not wait for each other (a per-256 barrier was 38 % of the stall samples, profiles/r1g_*)
   const int n_needed = max_last - range_start + 1;
-  const int first_batch = (n_needed - 1) / kBatch;
+  const int first_batch = (n_needed - 1) / kBwdBatch;
   for (int bi = first_batch; bi >= 0; --bi) {
-    const int batch_start = range_start + bi * kBatch;
-    const int batch_size = min(kBatch, min(range_end, max_last + 1) - batch_start);
+    const int batch_start = range_start + bi * kBwdBatch;
+    const int batch_size = min(kBwdBatch, min(range_end, max_last + 1) - batch_start);
     __syncthreads();  // previous batch fully flushed
-    if (tid < batch_size) {
-      const int32_t f = flatten_ids[batch_start + tid];
-      sF[tid] = f;
-      gather(f, f - cam * N, means2d, conics, opacities, colors, colors_per_camera, D, depths, sA[tid], sB[tid], sC[tid]);
+    for (int i = tid; i < batch_size; i += kBwdThreads) {
+      const int32_t f = flatten_ids[batch_start + i];
+      sF[i] = f;
+      gather(f, f - cam * N, means2d, conics, opacities, colors, colors_per_camera, D, depths, sA[i], sB[i], sC[i]);
     }
-    for (int i = tid; i < kBatch * kGradStride; i += 256) sG[i] = 0.0f;
+    for (int i = tid; i < batch_size * kGradStride; i += kBwdThreads) sG[i] = 0.0f;
     __syncthreads();
 
-    for (int sub = ((batch_size - 1) / 32) * 32; sub >= 0; sub -= 32) {
+    // nothing at or after warp_last + 1 can be valid for this warp
+    const int warp_n = min(batch_size, warp_last - batch_start + 1);
+    for (int sub = warp_n > 0 ? ((warp_n - 1) / 32) * 32 : -32; sub >= 0; sub -= 32) {
       const int j = sub + lane;
       bool hit = false;
-      if (j < batch_size) {
+      if (j < warp_n) {
         const float4 a = lds128(aA + j * 16);
         hit = fabsf(a.x - wcx) <= a.z + 3.5f && fabsf(a.y - wcy) <= a.w + 1.5f;
       }
       unsigned mask = __ballot_sync(0xffffffffu, hit);
-      while (mask) {
+      while (mask) {  // (a compacted hit queue as in composite_batch_fwd measured 2 % slower here)
         const int bit = 31 - __clz(mask);
         mask &= ~(1u << bit);
         const int t = sub + bit;
@@ -286,9 +314,9 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
     }
     __syncthreads();
     // flush: one global atomic per Gaussian-tile and component
-    if (tid < batch_size) {
-      const float *gr = &sG[tid * kGradStride];
-      const int32_t f = sF[tid];
+    for (int i = tid; i < batch_size; i += kBwdThreads) {
+      const float *gr = &sG[i * kGradStride];
+      const int32_t f = sF[i];
       const int32_t g = f - cam * N;
       float *vc = v_colors + (size_t)(colors_per_camera ? f : g) * D;
       for (int k = 0; k < D; ++k)
@@ -302,6 +330,19 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
       if (gr[9] != 0.0f) atomicAdd(v_opacities + g, gr[9]);
     }
   }
+}
+
+static int bwd_set_attr() {
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(BwdShared)) != cudaSuccess) {
+      set_last_cuda_error(cudaGetLastError());
+      return PM_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  return PM_OK;
 }
 
 static int check_common(const float *means2d, const float *conics, const float *opacities,
@@ -366,7 +407,8 @@ int pm_composite_bwd(const float *means2d, const float *conics, const float *opa
   const int tw = (width + pm::kTile - 1) / pm::kTile, th = (height + pm::kTile - 1) / pm::kTile;
   const int64_t blocks = (int64_t)C * tw * th;
   if (blocks >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
-  pm::composite_bwd_kernel<<<(unsigned)blocks, 256, 0, pm::as_stream(stream)>>>(
+  if (pm::bwd_set_attr() != PM_OK) return PM_ERR_CUDA;
+  pm::composite_bwd_kernel<<<(unsigned)(blocks * pm::kBwdParts), pm::kBwdThreads, sizeof(pm::BwdShared), pm::as_stream(stream)>>>(
       means2d, conics, opacities, colors, colors_per_camera, D, depths, backgrounds, isect_offsets,
       flatten_ids, n_isects, d_n, N, width, height, tw, th, alphas, last_ids, v_render, v_alphas,
       v_means2d, v_conics, v_colors, v_opacities, v_depths, nullptr, nullptr, nullptr, nullptr, 0);
@@ -390,7 +432,8 @@ int pm_composite_bwd_packed(const float *means2d, const float *conics, const flo
   const int tw = (width + pm::kTile - 1) / pm::kTile, th = (height + pm::kTile - 1) / pm::kTile;
   const int64_t blocks = (int64_t)C * tw * th;
   if (blocks >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
-  pm::composite_bwd_kernel<<<(unsigned)blocks, 256, 0, pm::as_stream(stream)>>>(
+  if (pm::bwd_set_attr() != PM_OK) return PM_ERR_CUDA;
+  pm::composite_bwd_kernel<<<(unsigned)(blocks * pm::kBwdParts), pm::kBwdThreads, sizeof(pm::BwdShared), pm::as_stream(stream)>>>(
       means2d, conics, opacities, colors, colors_per_camera, 3, depths, backgrounds, isect_offsets,
       flatten_ids, n_isects, d_n, N, width, height, tw, th, masks, last_ids, nullptr, nullptr,
       v_means2d, v_conics, v_colors, v_opacities, v_depths, v_images, v_depth_out, v_masks, depth_out, 1);
