@@ -124,14 +124,14 @@ class GaussianRenderer(nn.Module):
 
     def _check(self, job) -> bool:
         """True if the fused render of `job` is valid; updates the capacity hint."""
-        info, key = job["info"], job["key"]
-        job["event"].synchronize()
-        n_isects, max_count = (int(v) for v in job["stats_host"])
+        key = job["key"]
+        job["event"].synchronize()  # fires when the render kernel is done; later work (a backward pass) keeps running
+        n_isects, max_count, overflow = (int(v) for v in job["stats_host"])
         self._cap_hint[key] = int(n_isects * self.capacity_slack) + 4096
-        if n_isects > info["capacity"]:
+        if n_isects > job["capacity"]:
             return False
         # a depth sub-bucket larger than the group capacity can only exist if some tile is larger than it
-        return max_count <= FUSED_GROUP_CAP or int(info["overflow_flag"].item()) == 0
+        return max_count <= FUSED_GROUP_CAP or overflow == 0
 
     def take_pending(self) -> list:
         """Deferred-check mode: hand the unchecked jobs of the forward() calls so far to the caller
@@ -165,23 +165,27 @@ class GaussianRenderer(nn.Module):
                         Ks[i, c0:c1], bgs[c0:c1])
                 if self.fused:
                     im, de, ma, info, key = self._render_chunk_fused(args, h, w)
-                    stats_host = torch.empty(2, dtype=torch.int32, pin_memory=True)
-                    stats_host.copy_(info["stats"], non_blocking=True)
+                    stats_host = torch.empty(3, dtype=torch.int32, pin_memory=True)  # n_isects, max tile count, overflow
+                    stats_host[:2].copy_(info["stats"], non_blocking=True)
+                    stats_host[2:].copy_(info["overflow_flag"], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record()
-                    jobs.append(dict(args=args, out=(im, de, ma), info=info, key=key, stats_host=stats_host, event=ev))
+                    jobs.append(dict(args=args, out=(im, de, ma), info=info, key=key, stats_host=stats_host, event=ev,
+                                     capacity=info["capacity"]))
                 else:
                     im, de, ma, info = self._render_chunk_unfused(*args, h, w)
                     jobs.append(dict(args=args, out=(im, de, ma), info=info, key=None))
         if self.fused and self.defer_checks:
-            self._pending.extend(jobs)
+            # only what the check needs: holding the jobs' tensors would pin every step's buffers
+            self._pending.extend(dict(key=j["key"], capacity=j["capacity"], stats_host=j["stats_host"], event=j["event"])
+                                 for j in jobs)
         elif self.fused:
             # every launch is queued; now look at the counts (the GPU is still busy rendering)
             for job in jobs:
                 if not self._check(job):
                     a = job["args"]
                     n_isects = int(job["stats_host"][0])
-                    if n_isects > job["info"]["capacity"]:  # speculative buffers were too small: exact size this time
+                    if n_isects > job["capacity"]:  # speculative buffers were too small: exact size this time
                         self._cap_hint.pop(job["key"], None)
                         im, de, ma, info, _ = self._render_chunk_fused(a, h, w)
                         ok = int(info["stats"][1].item()) <= FUSED_GROUP_CAP or int(info["overflow_flag"].item()) == 0
