@@ -28,8 +28,14 @@ namespace pm {
 
 constexpr int kTrThreads = 256;
 constexpr int kTrWarps = kTrThreads / 32;
-constexpr int kTrItems = 4;
-constexpr int kTrCap = kTrThreads * kTrItems;  // 1024 records per group
+#ifndef PM_TR_MINBLOCKS
+#define PM_TR_MINBLOCKS 4
+#endif
+#ifndef PM_TR_CAP
+#define PM_TR_CAP 768
+#endif
+constexpr int kTrCap = PM_TR_CAP;                                   // records per group
+constexpr int kTrItems = (kTrCap + kTrThreads - 1) / kTrThreads;   // records per thread in the sort / staging loops
 constexpr int kTrRadix = 256;
 #ifndef PM_TR_MLP
 #define PM_TR_MLP 4
@@ -58,7 +64,7 @@ __device__ __forceinline__ unsigned tr_match_digit8(uint32_t d) {
 struct TrShared {
   union {                                    // a group is first sorted, then staged over the same bytes
     struct {
-      uint2 gbuf[kTrCap];                    // group being sorted: {depth bits, flatten id}
+      uint2 gbuf[kTrItems * kTrThreads];     // group being sorted: {depth bits, flatten id} (radix sort pads to a full round)
       uint16_t warp_hist[kTrWarps][kTrRadix];
       uint32_t digit_start[kTrRadix];
     };
@@ -67,6 +73,7 @@ struct TrShared {
   uint32_t queue[kTrWarps][kQueueWords];     // per-warp hit queues of composite_batch_fwd
   uint32_t red[64];
   int bucket[kTrRadix + 1];                  // start of each depth sub-bucket inside the tile's list
+  int bucket2[kTrRadix + 1];                 // second level: sub-buckets of one level-1 bucket that exceeds a group
   int cnt;
   uint32_t kmin, kmax;
 };
@@ -175,7 +182,25 @@ __device__ __forceinline__ void sort_group(TrShared &sh, int m, uint32_t gmin, u
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kTrThreads, 4)
+// Exclusive scan of tbl[1..256] in place (tbl[0] = 0 on entry): tbl[d] = start of bucket d, tbl[256] = total.
+__device__ __forceinline__ void tr_scan_buckets(int *tbl, uint32_t *red) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int v = tbl[tid + 1];
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) red[warp] = (uint32_t)inc;
+  __syncthreads();
+  int wbase = 0;
+  for (int w = 0; w < warp; ++w) wbase += (int)red[w];
+  tbl[tid + 1] = wbase + inc;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kTrThreads, PM_TR_MINBLOCKS)
 tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__restrict__ offsets,
                        int64_t n_host, const int32_t *__restrict__ d_n, const float *__restrict__ means2d,
                        const float *__restrict__ conics, const float *__restrict__ opacities,
@@ -201,7 +226,6 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
   const WarpFootprint fp{(float)ix + 0.5f, (float)iy + 0.5f, (float)wx0 + 4.0f, (float)wy0 + 2.0f};
   PixelState st{inside ? 1.0f : -1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0};
   const uint32_t aS = smem_u32(&sh.stg), aQ = smem_u32(sh.queue[warp]);
-  staged_init_null(sh.stg);
 
   const int64_t n_isects = effective_n(n_host, d_n);
   // (clamped: with a speculative record capacity smaller than the device-side count the result is
@@ -212,14 +236,139 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
   const unsigned long long *src = reinterpret_cast<const unsigned long long *>(records) + start;
   int sorted = 0;
 
-  if (cnt > 0) {
-    // ---- 1. histogram of the tile's records over 256 depth-ordered sub-buckets. The bucket of a key is a
-    // monotone function of it — clamp((key - kmin) >> shift, 0, 255) — so ANY kmin / shift partition the
-    // keys by value; they only steer the bucket sizes. kmin / kmax therefore come from a strided sample
-    // of <= 1024 records (one round of 4 independent loads per thread, exact when the tile has <= 1024
-    // records) instead of a full pass; the few keys outside the sampled range land in buckets 0 / 255.
+  // Histogram of the tile's records with key in [flo, fhi] over the 256 buckets of (kmin_c, shift_c) into tbl,
+  // then the exclusive scan. (Every pass over the tile's records keeps kTrMlp loads per thread in flight.)
+  auto build_table = [&](int *tbl, uint32_t kmin_c, int shift_c, uint32_t flo, uint32_t fhi) {
+    for (int i = tid; i <= kTrRadix; i += kTrThreads) tbl[i] = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < cnt; i0 += kTrMlp * kTrThreads) {
+      uint32_t k[kTrMlp];
+#pragma unroll
+      for (int u = 0; u < kTrMlp; ++u) {
+        const int i = i0 + u * kTrThreads + tid;
+        k[u] = i < cnt ? (uint32_t)__ldg(src + i) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < kTrMlp; ++u)
+        if (i0 + u * kTrThreads + tid < cnt && k[u] >= flo && k[u] <= fhi)
+          atomicAdd(&tbl[tr_bucket(k[u], kmin_c, shift_c) + 1], 1);
+    }
+    __syncthreads();
+    tr_scan_buckets(tbl, sh.red);
+  };
+
+  // One group: the records with key in [flo, fhi] whose bucket under (kmin_c, shift_c) lies in [b0, b1) — at most
+  // kTrCap of them, occupying list positions list_base + tbl[b0] .. list_base + tbl[b1] of the tile.
+  auto process_group = [&](const int *tbl, uint32_t kmin_c, int shift_c, uint32_t flo, uint32_t fhi, int b0, int b1,
+                           int list_base) {
+    const int gs = tbl[b0], m = tbl[b1] - gs;
+    // collect the group straight into bucket order (a counting-sort placement: the position of a record is
+    // its bucket's start + a per-bucket cursor), so that only the short runs of equal bucket remain to be ordered
+    uint32_t *cur = sh.digit_start;
+    for (int bb = b0 + tid; bb < b1; bb += kTrThreads) cur[bb] = 0u;
     if (tid == 0) { sh.kmin = 0xffffffffu; sh.kmax = 0u; }
-    for (int i = tid; i <= kTrRadix; i += kTrThreads) sh.bucket[i] = 0;
+    __syncthreads();
+    uint32_t gmin = 0xffffffffu, gmax = 0u;
+    for (int i0 = 0; i0 < cnt; i0 += kTrMlp * kTrThreads) {
+      unsigned long long r[kTrMlp];
+#pragma unroll
+      for (int u = 0; u < kTrMlp; ++u) {
+        const int i = i0 + u * kTrThreads + tid;
+        r[u] = i < cnt ? __ldg(src + i) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < kTrMlp; ++u) {
+        const uint32_t k = (uint32_t)r[u];
+        const int bb = tr_bucket(k, kmin_c, shift_c);
+        if (i0 + u * kTrThreads + tid < cnt && k >= flo && k <= fhi && bb >= b0 && bb < b1) {
+          const int pos = tbl[bb] - gs + (int)atomicAdd(&cur[bb], 1u);
+          sh.gbuf[pos] = make_uint2(k, (uint32_t)(r[u] >> 32));
+          gmin = min(gmin, k);
+          gmax = max(gmax, k);
+        }
+      }
+    }
+    bool fat = false;  // a run too long for the all-pairs ranking below
+    for (int bb = b0 + tid; bb < b1; bb += kTrThreads) fat |= tbl[bb + 1] - tbl[bb] > kTrRankMax;
+    gmin = __reduce_min_sync(0xffffffffu, gmin);
+    gmax = __reduce_max_sync(0xffffffffu, gmax);
+    if (lane == 0) { atomicMin(&sh.kmin, gmin); atomicMax(&sh.kmax, gmax); }
+    fat = __syncthreads_or(fat);
+    int32_t ids[kTrItems];
+    if (fat) {
+      sort_group(sh, m, sh.kmin, sh.kmax);  // LSD radix sort of the whole group
+#pragma unroll
+      for (int k = 0; k < kTrItems; ++k) {
+        const int slot = k * kTrThreads + tid;
+        ids[k] = slot < m ? (int32_t)sh.gbuf[slot].y : -1;
+      }
+    } else {
+      // rank every record inside its bucket's run by (depth bits, flatten id): runs are ~cnt/256 long,
+      // a warp's 32 consecutive records share one or two runs (broadcast reads), no barrier needed
+      uint32_t *sorted_ids = reinterpret_cast<uint32_t *>(sh.warp_hist);
+#pragma unroll
+      for (int k = 0; k < kTrItems; ++k) {
+        const int e = k * kTrThreads + tid;
+        if (e < m) {
+          const uint2 me = sh.gbuf[e];
+          const int bb = tr_bucket(me.x, kmin_c, shift_c);
+          const int rs = tbl[bb] - gs, re = tbl[bb + 1] - gs;
+          const unsigned long long mine = ((unsigned long long)me.x << 32) | me.y;
+          int rank = rs;
+          for (int j = rs; j < re; ++j) {
+            const uint2 o = sh.gbuf[j];
+            rank += (((unsigned long long)o.x << 32) | o.y) < mine;
+          }
+          sorted_ids[rank] = me.y;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < kTrItems; ++k) {
+        const int slot = k * kTrThreads + tid;
+        ids[k] = slot < m ? (int32_t)sorted_ids[slot] : -1;
+      }
+    }
+    // sorted flatten ids go to their final positions (read again by the backward pass)
+#pragma unroll
+    for (int k = 0; k < kTrItems; ++k) {
+      const int slot = k * kTrThreads + tid;
+      if (slot < m) flatten_ids[(size_t)start + list_base + gs + slot] = ids[k];
+    }
+    sorted = list_base + gs + m;
+    __syncthreads();  // everyone holds its ids: the sort buffers may be overwritten by the staged records
+    staged_init_null(sh.stg);  // (for small group capacities the null slot overlaps the sort buffers)
+#pragma unroll
+    for (int k = 0; k < kTrItems; ++k) {
+      const int slot = k * kTrThreads + tid;
+      if (slot < m)
+        gather(ids[k], ids[k] - cam_base, means2d, conics, opacities, colors, colors_per_camera, D, depths, sh.stg.sA[slot],
+               sh.stg.sB[slot], sh.stg.sC[slot]);
+    }
+    __syncthreads();
+    // composite the whole group; warps do not wait for each other — same arithmetic as composite_fwd_kernel
+    if (!__all_sync(0xffffffffu, pixel_done(st)))
+      composite_batch_fwd<kTrCap>(aS, aQ, m, start + list_base + gs, fp, st);
+  };
+
+  // largest b1 in (b0, 256] with tbl[b1] - tbl[b0] <= capacity (binary search; tbl[] is monotone), b0 + 1 if none
+  auto group_end = [&](const int *tbl, int b0) {
+    const int gs = tbl[b0];
+    int b1 = b0 + 1, hi = kTrRadix;
+    while (b1 < hi) {
+      const int mid = (b1 + hi + 1) >> 1;
+      if (tbl[mid] - gs <= kTrCap) b1 = mid; else hi = mid - 1;
+    }
+    return b1;
+  };
+
+  if (cnt > 0) {
+    // ---- 1. level-1 table: 256 depth-ordered buckets over the tile's key range. The bucket of a key is a
+    // monotone function of it — clamp((key - kmin) >> shift, 0, 255) — so ANY kmin / shift partition the keys by
+    // value; they only steer the bucket sizes. kmin / kmax therefore come from a strided sample of <= 1024
+    // records (one round of 4 independent loads per thread, exact when the tile has <= 1024 records) instead of
+    // a full pass; the few keys outside the sampled range land in buckets 0 / 255.
+    if (tid == 0) { sh.kmin = 0xffffffffu; sh.kmax = 0u; }
     __syncthreads();
     uint32_t kmin = 0xffffffffu, kmax = 0u;
     {
@@ -243,154 +392,67 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
     const uint32_t range = sh.kmax - kmin;
     const int bits = 32 - __clz(range | 1u);
     const int shift = bits > 8 ? bits - 8 : 0;
-    // (every pass over the tile's records keeps kTrMlp loads per thread in flight)
-    for (int i0 = 0; i0 < cnt; i0 += kTrMlp * kTrThreads) {
-      uint32_t k[kTrMlp];
-#pragma unroll
-      for (int u = 0; u < kTrMlp; ++u) {
-        const int i = i0 + u * kTrThreads + tid;
-        k[u] = i < cnt ? (uint32_t)__ldg(src + i) : 0u;
-      }
-#pragma unroll
-      for (int u = 0; u < kTrMlp; ++u)
-        if (i0 + u * kTrThreads + tid < cnt) atomicAdd(&sh.bucket[tr_bucket(k[u], kmin, shift) + 1], 1);
-    }
-    __syncthreads();
-    {  // exclusive scan: bucket[d] = start of sub-bucket d, bucket[256] = cnt
-      const int v = sh.bucket[tid + 1];
-      int inc = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-      }
-      if (lane == 31) sh.red[warp] = (uint32_t)inc;
-      __syncthreads();
-      int wbase = 0;
-      for (int w = 0; w < warp; ++w) wbase += (int)sh.red[w];
-      sh.bucket[tid + 1] = wbase + inc;
-      __syncthreads();
-    }
+    __syncthreads();  // sh.kmin / sh.kmax are reused below
+    build_table(sh.bucket, kmin, shift, 0u, 0xffffffffu);
 
-    // ---- 2. groups of sub-buckets, front to back, until every pixel is done
+    // ---- 2. groups of buckets, front to back, until every pixel is done
+    bool stop = false;
     int g0 = 0;
-    while (g0 < kTrRadix) {
+    while (g0 < kTrRadix && !stop) {
       // group boundary barrier: the staged group of the previous round is dead after it
       if (__syncthreads_count(pixel_done(st)) == kTrThreads) break;
-      // largest g1 with bucket[g1] - bucket[g0] <= capacity (binary search; bucket[] is monotone)
-      const int gs = sh.bucket[g0];
-      int g1 = g0 + 1, hi = kTrRadix;
-      while (g1 < hi) {
-        const int mid = (g1 + hi + 1) >> 1;
-        if (sh.bucket[mid] - gs <= kTrCap) g1 = mid; else hi = mid - 1;
+      const int g1 = group_end(sh.bucket, g0);
+      const int m = sh.bucket[g1] - sh.bucket[g0];
+      if (m <= kTrCap) {
+        if (m > 0) process_group(sh.bucket, kmin, shift, 0u, 0xffffffffu, g0, g1, 0);
+        g0 = g1;
+        continue;
       }
-      const int ge = sh.bucket[g1];
-      const int m = ge - gs;
-      if (m > kTrCap) {  // one depth sub-bucket does not fit: the caller re-renders with the separate stages
-        if (tid == 0) atomicExch(overflow_flag, 1);
-        break;
+      // ---- 3. bucket g0 alone exceeds a group (a thin, dense depth shell): give it its own 256 sub-buckets
+      // over the key range it actually holds and walk those. Only if a sub-bucket still does not fit — more than
+      // kTrCap records within 1/65536 of the tile's depth range, e.g. identical depths — the caller re-renders
+      // with the separate stages.
+      const uint32_t flo = g0 == 0 ? 0u : kmin + ((uint32_t)g0 << shift);
+      const uint32_t fhi = g0 == kTrRadix - 1 ? 0xffffffffu : kmin + (((uint32_t)g0 + 1u) << shift) - 1u;
+      if (tid == 0) { sh.kmin = 0xffffffffu; sh.kmax = 0u; }
+      __syncthreads();
+      uint32_t lo2 = 0xffffffffu, hi2 = 0u;
+      for (int i0 = 0; i0 < cnt; i0 += kTrMlp * kTrThreads) {
+        uint32_t k[kTrMlp];
+#pragma unroll
+        for (int u = 0; u < kTrMlp; ++u) {
+          const int i = i0 + u * kTrThreads + tid;
+          k[u] = i < cnt ? (uint32_t)__ldg(src + i) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < kTrMlp; ++u)
+          if (i0 + u * kTrThreads + tid < cnt && k[u] >= flo && k[u] <= fhi) { lo2 = min(lo2, k[u]); hi2 = max(hi2, k[u]); }
       }
-      if (m > 0) {
-        // collect the group straight into bucket order (a counting-sort placement: the position of a
-        // record is its bucket's start + a per-bucket cursor), so that only the short runs of equal
-        // bucket remain to be ordered
-        uint32_t *cur = sh.digit_start;
-        for (int bb = g0 + tid; bb < g1; bb += kTrThreads) cur[bb] = 0u;
-        if (tid == 0) { sh.kmin = 0xffffffffu; sh.kmax = 0u; }
-        __syncthreads();
-        uint32_t gmin = 0xffffffffu, gmax = 0u;
-        for (int i0 = 0; i0 < cnt; i0 += kTrMlp * kTrThreads) {
-          unsigned long long r[kTrMlp];
-#pragma unroll
-          for (int u = 0; u < kTrMlp; ++u) {
-            const int i = i0 + u * kTrThreads + tid;
-            r[u] = i < cnt ? __ldg(src + i) : 0ull;
-          }
-#pragma unroll
-          for (int u = 0; u < kTrMlp; ++u) {
-            const uint32_t k = (uint32_t)r[u];
-            const int bb = tr_bucket(k, kmin, shift);
-            if (i0 + u * kTrThreads + tid < cnt && bb >= g0 && bb < g1) {
-              const int pos = sh.bucket[bb] - gs + (int)atomicAdd(&cur[bb], 1u);
-              sh.gbuf[pos] = make_uint2(k, (uint32_t)(r[u] >> 32));
-              gmin = min(gmin, k);
-              gmax = max(gmax, k);
-            }
-          }
+      lo2 = __reduce_min_sync(0xffffffffu, lo2);
+      hi2 = __reduce_max_sync(0xffffffffu, hi2);
+      if (lane == 0) { atomicMin(&sh.kmin, lo2); atomicMax(&sh.kmax, hi2); }
+      __syncthreads();
+      const uint32_t kmin2 = sh.kmin;
+      const uint32_t range2 = sh.kmax - kmin2;
+      const int bits2 = 32 - __clz(range2 | 1u);
+      const int shift2 = bits2 > 8 ? bits2 - 8 : 0;
+      __syncthreads();
+      build_table(sh.bucket2, kmin2, shift2, flo, fhi);
+      const int base2 = sh.bucket[g0];
+      int s0 = 0;
+      while (s0 < kTrRadix) {
+        if (s0 > 0 && __syncthreads_count(pixel_done(st)) == kTrThreads) { stop = true; break; }
+        const int s1 = group_end(sh.bucket2, s0);
+        const int m2 = sh.bucket2[s1] - sh.bucket2[s0];
+        if (m2 > kTrCap) {
+          if (tid == 0) atomicExch(overflow_flag, 1);
+          stop = true;
+          break;
         }
-        bool fat = false;  // a run too long for the all-pairs ranking below
-        for (int bb = g0 + tid; bb < g1; bb += kTrThreads) fat |= sh.bucket[bb + 1] - sh.bucket[bb] > kTrRankMax;
-        gmin = __reduce_min_sync(0xffffffffu, gmin);
-        gmax = __reduce_max_sync(0xffffffffu, gmax);
-        if (lane == 0) { atomicMin(&sh.kmin, gmin); atomicMax(&sh.kmax, gmax); }
-        fat = __syncthreads_or(fat);
-        int32_t ids[kTrItems];
-        if (fat) {
-          sort_group(sh, m, sh.kmin, sh.kmax);  // LSD radix sort of the whole group
-#pragma unroll
-          for (int k = 0; k < kTrItems; ++k) {
-            const int slot = k * kTrThreads + tid;
-            ids[k] = slot < m ? (int32_t)sh.gbuf[slot].y : -1;
-          }
-        } else {
-          // rank every record inside its bucket's run by (depth bits, flatten id): runs are ~cnt/256 long,
-          // a warp's 32 consecutive records share one or two runs (broadcast reads), no barrier needed
-          uint32_t *sorted_ids = reinterpret_cast<uint32_t *>(sh.warp_hist);
-#pragma unroll
-          for (int k = 0; k < kTrItems; ++k) {
-            const int e = k * kTrThreads + tid;
-            if (e < m) {
-              const uint2 me = sh.gbuf[e];
-              const int bb = tr_bucket(me.x, kmin, shift);
-              const int rs = sh.bucket[bb] - gs, re = sh.bucket[bb + 1] - gs;
-              const unsigned long long mine = ((unsigned long long)me.x << 32) | me.y;
-              int rank = rs;
-              for (int j = rs; j < re; ++j) {
-                const uint2 o = sh.gbuf[j];
-                rank += (((unsigned long long)o.x << 32) | o.y) < mine;
-              }
-              sorted_ids[rank] = me.y;
-            }
-          }
-          __syncthreads();
-#pragma unroll
-          for (int k = 0; k < kTrItems; ++k) {
-            const int slot = k * kTrThreads + tid;
-            ids[k] = slot < m ? (int32_t)sorted_ids[slot] : -1;
-          }
-        }
-        // sorted flatten ids go to their final positions (read again by the backward pass)
-#pragma unroll
-        for (int k = 0; k < kTrItems; ++k) {
-          const int slot = k * kTrThreads + tid;
-          if (slot < m) flatten_ids[(size_t)start + gs + slot] = ids[k];
-        }
-        sorted = ge;
-        __syncthreads();  // everyone holds its ids: the sort buffers may be overwritten by the staged records
-#if PM_TR_GATHER2
-#pragma unroll
-        for (int k = 0; k < kTrItems; k += 2) {  // two Gaussians' loads in flight per thread
-          const int s0 = k * kTrThreads + tid, s1 = s0 + kTrThreads;
-          GaussRaw r0, r1;
-          if (s0 < m) r0 = gather_load(ids[k], ids[k] - cam_base, means2d, conics, opacities, colors, colors_per_camera, D, depths);
-          if (s1 < m) r1 = gather_load(ids[k + 1], ids[k + 1] - cam_base, means2d, conics, opacities, colors, colors_per_camera, D, depths);
-          if (s0 < m) gather_finish(r0, sh.stg.sA[s0], sh.stg.sB[s0], sh.stg.sC[s0]);
-          if (s1 < m) gather_finish(r1, sh.stg.sA[s1], sh.stg.sB[s1], sh.stg.sC[s1]);
-        }
-#else
-#pragma unroll
-        for (int k = 0; k < kTrItems; ++k) {
-          const int slot = k * kTrThreads + tid;
-          if (slot < m)
-            gather(ids[k], ids[k] - cam_base, means2d, conics, opacities, colors, colors_per_camera, D, depths, sh.stg.sA[slot],
-                   sh.stg.sB[slot], sh.stg.sC[slot]);
-        }
-#endif
-        __syncthreads();
-        // composite the whole group; warps do not wait for each other — same arithmetic as composite_fwd_kernel
-        if (!__all_sync(0xffffffffu, pixel_done(st))) composite_batch_fwd<kTrCap>(aS, aQ, m, start + gs, fp, st);
+        if (m2 > 0) process_group(sh.bucket2, kmin2, shift2, flo, fhi, s0, s1, base2);
+        s0 = s1;
       }
-      g0 = g1;
+      g0 = g0 + 1;
     }
   }
   if (tid == 0) sorted_counts[ct] = sorted;
@@ -449,6 +511,18 @@ static int tile_render_launch(const uint64_t *records, const int32_t *isect_offs
       images, depth_out, masks);
   return pm::check_launch();
 }
+
+#ifdef PM_STATS
+__attribute__((visibility("default"))) int pm_debug_stats(unsigned long long *out, int reset) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out, pm::g_pm_stats, sizeof(unsigned long long) * 8) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(pm::g_pm_stats, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 int pm_tile_render_fwd(const uint64_t *records, const int32_t *isect_offsets, int64_t n_isects,
                        const int32_t *d_n, const float *means2d, const float *conics,

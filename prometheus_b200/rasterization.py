@@ -182,7 +182,7 @@ def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, b
 
 
 # Largest per-tile group the fused kernel sorts at once (tile_render.cu: kTrCap)
-FUSED_GROUP_CAP = 1024
+FUSED_GROUP_CAP = 256  # <= the smallest group capacity any build uses, so the overflow flag is always looked at
 
 
 def isect_tiles(means2d, radii, depths, tiles_per_gauss, width, height, C, force_generic=False):
