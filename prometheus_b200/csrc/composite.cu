@@ -266,12 +266,13 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
     // nothing at or after warp_last + 1 can be valid for this warp
     const int warp_n = min(batch_size, warp_last - batch_start + 1);
     for (int sub = warp_n > 0 ? ((warp_n - 1) / 32) * 32 : -32; sub >= 0; sub -= 32) {
+      // cull against the rectangle of the pixels that still replay something at or after this chunk
+      const unsigned live = __ballot_sync(0xffffffffu, my_last >= batch_start + sub);
+      if (live == 0u) continue;
+      const LiveRect rect = live_rect(live, wcx, wcy);
       const int j = sub + lane;
       bool hit = false;
-      if (j < warp_n) {
-        const float4 a = lds128(aA + j * 16);
-        hit = fabsf(a.x - wcx) <= a.z + 3.5f && fabsf(a.y - wcy) <= a.w + 1.5f;
-      }
+      if (j < warp_n) hit = cull_hit(lds128(aA + j * 16), aB + j * 16, rect);
       unsigned mask = __ballot_sync(0xffffffffu, hit);
       while (mask) {  // (a compacted hit queue as in composite_batch_fwd measured 2 % slower here)
         const int bit = 31 - __clz(mask);

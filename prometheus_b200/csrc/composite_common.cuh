@@ -207,6 +207,51 @@ __device__ __forceinline__ float lg2_approx(float x) {
 #define PM_EXACT_CULL 1
 #endif
 
+// Rectangle spanned by the pixel centres of the lanes in `live` (lane = 8 * row + column of the warp's 8x4 footprint).
+struct LiveRect {
+  float x0, x1, y0, y1;
+};
+__device__ __forceinline__ LiveRect live_rect(unsigned live, float wcx, float wcy) {
+  const unsigned cols = (live | (live >> 8) | (live >> 16) | (live >> 24)) & 0xffu;
+  LiveRect r;
+  r.x0 = wcx - 3.5f + (float)(__ffs(cols) - 1);
+  r.x1 = wcx - 3.5f + (float)(31 - __clz(cols));
+  r.y0 = wcy - 1.5f + (float)((__ffs(live) - 1) >> 3);
+  r.y1 = wcy - 1.5f + (float)((31 - __clz(live)) >> 3);
+  return r;
+}
+
+// Can the staged Gaussian (A record `a`, B record at shared address aB_j) reach alpha >= 1/255 on any point of
+// the rectangle? First the axis-aligned extent of {alpha >= 1/255}, then exactly: the exponent
+// p = Q0 dx^2 + Q1 dx dy + Q2 dy^2 is concave with its maximum (0) at the mean, so over a rectangle that does
+// not contain the mean it peaks on the edge(s) facing the mean; the splat can contribute only if that peak is
+// >= -log2(255 opacity). The margins make rounding err on the side of keeping a splat, so culling never changes
+// a result.
+__device__ __forceinline__ bool cull_hit(const float4 &a, uint32_t aB_j, const LiveRect &r) {
+  const float dx0 = r.x0 - a.x, dx1 = r.x1 - a.x, dy0 = r.y0 - a.y, dy1 = r.y1 - a.y;
+  bool hit = dx0 <= a.z && dx1 >= -a.z && dy0 <= a.w && dy1 >= -a.w;
+#if PM_EXACT_CULL
+  if (hit && a.z < 1e37f) {
+    const float ax = fminf(fmaxf(0.0f, dx0), dx1), by = fminf(fmaxf(0.0f, dy0), dy1);
+    if (ax != 0.0f || by != 0.0f) {
+      const float4 b = lds128(aB_j);
+      float pmax = -3e38f;
+      if (ax != 0.0f) {
+        const float dy = fminf(fmaxf(-0.5f * b.y * ax * rcp_approx(b.z), dy0), dy1);
+        pmax = b.x * ax * ax + b.y * ax * dy + b.z * dy * dy;
+      }
+      if (by != 0.0f) {
+        const float dx = fminf(fmaxf(-0.5f * b.y * by * rcp_approx(b.x), dx0), dx1);
+        pmax = fmaxf(pmax, b.x * dx * dx + b.y * dx * by + b.z * by * by);
+      }
+      const float tau2 = lg2_approx(255.0f * b.w);
+      hit = pmax >= -tau2 * 1.0005f - 2e-3f;
+    }
+  }
+#endif
+  return hit;
+}
+
 template <int CAP>
 __device__ __forceinline__ void composite_batch_fwd(uint32_t aS, uint32_t aQ, int batch_size, int list_pos,
                                                     const WarpFootprint &fp, PixelState &st) {
@@ -214,43 +259,14 @@ __device__ __forceinline__ void composite_batch_fwd(uint32_t aS, uint32_t aQ, in
   const unsigned lt = (1u << lane) - 1u;
   uint32_t last_ga = 0;
   for (int sub = 0; sub < batch_size; sub += 32) {
-    // rectangle spanned by the centres of the warp's LIVE pixels (lane = 8 * row + column): Gaussians are
-    // culled against it, so splats that only cover finished pixels are skipped as well
+    // Gaussians are culled against the rectangle of the warp's LIVE pixels, so splats that only cover finished
+    // pixels are skipped as well
     const unsigned live = __ballot_sync(0xffffffffu, !pixel_done(st));
     if (live == 0u) break;
-    const unsigned cols = (live | (live >> 8) | (live >> 16) | (live >> 24)) & 0xffu;
-    const float rx0 = fp.wcx - 3.5f + (float)(__ffs(cols) - 1), rx1 = fp.wcx - 3.5f + (float)(31 - __clz(cols));
-    const float ry0 = fp.wcy - 1.5f + (float)((__ffs(live) - 1) >> 3), ry1 = fp.wcy - 1.5f + (float)((31 - __clz(live)) >> 3);
+    const LiveRect rect = live_rect(live, fp.wcx, fp.wcy);
     const int j = sub + lane;
     bool hit = false;
-    if (j < batch_size) {
-      const float4 a = lds128(aS + j * 16);
-      // the rectangle relative to the mean; first the axis-aligned extent of {alpha >= 1/255}
-      const float dx0 = rx0 - a.x, dx1 = rx1 - a.x, dy0 = ry0 - a.y, dy1 = ry1 - a.y;
-      hit = dx0 <= a.z && dx1 >= -a.z && dy0 <= a.w && dy1 >= -a.w;
-#if PM_EXACT_CULL
-      if (hit && a.z < 1e37f) {
-        // exact: the exponent p = Q0 dx^2 + Q1 dx dy + Q2 dy^2 is concave with its maximum (0) at the mean, so
-        // over a rectangle that does not contain the mean it peaks on the edge(s) facing the mean; the splat
-        // can reach alpha >= 1/255 only if that peak is >= -log2(255 opacity). Margin: rounding can only keep.
-        const float ax = fminf(fmaxf(0.0f, dx0), dx1), by = fminf(fmaxf(0.0f, dy0), dy1);
-        if (ax != 0.0f || by != 0.0f) {
-          const float4 b = lds128(aS + j * 16 + (CAP + 1) * 16);
-          float pmax = -3e38f;
-          if (ax != 0.0f) {
-            const float dy = fminf(fmaxf(-0.5f * b.y * ax * rcp_approx(b.z), dy0), dy1);
-            pmax = b.x * ax * ax + b.y * ax * dy + b.z * dy * dy;
-          }
-          if (by != 0.0f) {
-            const float dx = fminf(fmaxf(-0.5f * b.y * by * rcp_approx(b.x), dx0), dx1);
-            pmax = fmaxf(pmax, b.x * dx * dx + b.y * dx * by + b.z * by * by);
-          }
-          const float tau2 = lg2_approx(255.0f * b.w);
-          hit = pmax >= -tau2 * 1.0005f - 2e-3f;
-        }
-      }
-#endif
-    }
+    if (j < batch_size) hit = cull_hit(lds128(aS + j * 16), aS + j * 16 + (CAP + 1) * 16, rect);
     const unsigned bal = __ballot_sync(0xffffffffu, hit);
     if (bal == 0u) continue;
     const int n = __popc(bal);
