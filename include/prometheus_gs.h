@@ -300,6 +300,23 @@ PM_API int pm_composite_bwd_packed(const float *means2d, const float *conics, co
                      float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
                      float *v_depths, pm_stream_t stream);
 
+/* ------------------------------------------------------------------------- *
+ * Trajectory rendering: pose sampling along a camera path and
+ * frame packing on the device. Replaces sample_from_dense_cameras
+ * (prometheus/utils/camera.py:134-217, called once per frame by export_video,
+ * prometheus/utils/io.py:167-190) and the per-frame host conversion of io.py:181.
+ * ------------------------------------------------------------------------- */
+
+/* dense_cameras [B,N,18] (c2w 3x4 row-major + fx fy cx cy H W), t [B,M] in [0,1] ->
+ * out [B,M,18]: poses interpolated at arc length t (position lerp + quaternion slerp,
+ * distance = sqrt(|dp|^2 + angle^2)), intrinsics lerped. 2 <= N <= 1024. */
+PM_API int pm_sample_cameras(const float *dense_cameras, const float *t, int B, int N, int M,
+                      float *out, pm_stream_t stream);
+
+/* images [F,3,H,W] fp32 in [-1,1] -> out [F,H,W,3] uint8 = trunc(clamp(x/2+1/2,0,1)*255). */
+PM_API int pm_pack_frames_u8(const float *images, int64_t n_frames, int height, int width,
+                      uint8_t *out, pm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,9 +7,12 @@ Public surface (mirrors the reference, see DESIGN.md / INTEGRATION.md):
   GaussianConverter, GaussianRenderer   module-level mirrors
   install_as_gsplat()           plug the operator under the unmodified reference
   DecodeRenderPipeline          streaming host->device->host decode+render (copies overlap compute)
+  TrajectoryRenderer, sample_from_dense_cameras, export_video   novel-view video along a camera path
 """
 from .rasterization import rasterization  # noqa: F401
 from .renderer import GaussianConverter, GaussianRenderer, install_as_gsplat  # noqa: F401
 from .pipeline import DecodeRenderPipeline  # noqa: F401
+from .trajectory import TrajectoryRenderer, export_video, sample_from_dense_cameras  # noqa: F401
 
-__all__ = ["rasterization", "GaussianConverter", "GaussianRenderer", "install_as_gsplat", "DecodeRenderPipeline"]
+__all__ = ["rasterization", "GaussianConverter", "GaussianRenderer", "install_as_gsplat", "DecodeRenderPipeline",
+           "TrajectoryRenderer", "sample_from_dense_cameras", "export_video"]

@@ -426,3 +426,32 @@ def composite_bwd_packed(means2d, conics, opacities, colors, depths, backgrounds
                                          _ptr(v_masks), _ptr(v_means2d), _ptr(v_conics), _ptr(v_colors), _ptr(v_opac),
                                          _ptr(v_depths), _stream()), "pm_composite_bwd_packed")
     return v_means2d, v_conics, v_colors, v_opac, v_depths
+
+
+# ------------------------------------------------------------------ trajectory row
+@_instrument("sample_cameras", 1)
+def sample_cameras(dense_cameras, t):
+    """dense_cameras [B,N,18], t [B,M] -> [B,M,18] (pm_sample_cameras)."""
+    L = _lib.load()
+    dense_cameras = _req(dense_cameras, torch.float32, "dense_cameras")
+    t = _req(t, torch.float32, "t")
+    B, N, Cc = dense_cameras.shape
+    assert Cc == 18 and t.dim() == 2 and t.shape[0] == B, (tuple(dense_cameras.shape), tuple(t.shape))
+    M = t.shape[1]
+    out = torch.empty(B, M, 18, device=dense_cameras.device)
+    _lib.check(L.pm_sample_cameras(_ptr(dense_cameras), _ptr(t), B, N, M, _ptr(out), _stream()), "pm_sample_cameras")
+    return out
+
+
+@_instrument("pack_frames_u8", 1)
+def pack_frames_u8(images, out=None):
+    """images [F,3,H,W] fp32 in [-1,1] -> uint8 [F,H,W,3] (pm_pack_frames_u8)."""
+    L = _lib.load()
+    images = _req(images, torch.float32, "images")
+    Fn, Cc, H, W = images.shape
+    assert Cc == 3
+    if out is None:
+        out = torch.empty(Fn, H, W, 3, dtype=torch.uint8, device=images.device)
+    assert out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and out.numel() == Fn * H * W * 3
+    _lib.check(L.pm_pack_frames_u8(_ptr(images), Fn, H, W, _ptr(out), _stream()), "pm_pack_frames_u8")
+    return out

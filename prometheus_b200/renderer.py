@@ -122,12 +122,18 @@ class GaussianRenderer(nn.Module):
                                                           capacity=cap)
         return images, depths, masks, info, key
 
+    def _update_hint(self, key, n_isects: int) -> None:
+        """Capacity for the next call of this shape: the latest count with slack, but never much below the
+        previous hint — along a camera trajectory the count varies from chunk to chunk and must not oscillate."""
+        want = int(n_isects * self.capacity_slack) + 4096
+        self._cap_hint[key] = max(want, int(self._cap_hint.get(key, 0) * 0.97))
+
     def _check(self, job) -> bool:
         """True if the fused render of `job` is valid; updates the capacity hint."""
         key = job["key"]
         job["event"].synchronize()  # fires when the render kernel is done; later work (a backward pass) keeps running
         n_isects, max_count, overflow = (int(v) for v in job["stats_host"])
-        self._cap_hint[key] = int(n_isects * self.capacity_slack) + 4096
+        self._update_hint(key, n_isects)
         if n_isects > job["capacity"]:
             return False
         # a depth sub-bucket larger than the group capacity can only exist if some tile is larger than it
@@ -189,7 +195,7 @@ class GaussianRenderer(nn.Module):
                         self._cap_hint.pop(job["key"], None)
                         im, de, ma, info, _ = self._render_chunk_fused(a, h, w)
                         ok = int(info["stats"][1].item()) <= FUSED_GROUP_CAP or int(info["overflow_flag"].item()) == 0
-                        self._cap_hint[job["key"]] = int(n_isects * self.capacity_slack) + 4096
+                        self._update_hint(job["key"], n_isects)
                     else:
                         ok = False
                     if not ok:  # a depth sub-bucket beyond the fused kernel's group capacity: separate stages

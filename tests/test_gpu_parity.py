@@ -743,3 +743,78 @@ def test_deferred_checks_and_pipeline_recover_from_a_bad_hint():
     for o in outs:
         for a, b in zip(o, want):
             assert torch.equal(a, b.cpu())
+
+
+# --------------------------------------------------------------------------- trajectory row
+@pytest.mark.parametrize("name", ["orbit_big", "smooth", "repeat", "video120"])
+def test_sample_cameras_vs_reference_golden(golden_dir, name):
+    """pm_sample_cameras against the reference's own sample_from_dense_cameras outputs (pinned golden), all
+    samples of a trajectory in one launch."""
+    import os
+
+    from prometheus_b200 import sample_from_dense_cameras
+
+    g = np.load(os.path.join(golden_dir, "trajectory.npz"))
+    got = sample_from_dense_cameras(dev(g[name + "_dense"]), dev(g[name + "_t"])).cpu().numpy()
+    want = g[name + "_out"]
+    assert got.shape == want.shape
+    assert np.allclose(got[..., :12], want[..., :12], atol=2e-5, rtol=0)      # float tolerance: sinf / acosf differ by ~1 ulp
+    assert np.allclose(got[..., 12:], want[..., 12:], atol=0, rtol=5e-5)
+
+
+def test_sample_cameras_batched_equals_per_trajectory(golden_dir, oracle):
+    import os
+
+    from oracle import trajectory_oracle as T
+    from prometheus_b200 import ops
+
+    g = np.load(os.path.join(golden_dir, "trajectory.npz"))
+    a, b = g["orbit_big_dense"][0][:8], g["video120_dense"][0][:8]
+    dense = np.stack([a, b])
+    t = np.stack([np.linspace(0, 1, 50, dtype=np.float32), np.random.default_rng(3).uniform(0, 1, 50).astype(np.float32)])
+    got = ops.sample_cameras(dev(dense), dev(t)).cpu().numpy()
+    for i in range(2):
+        want = T.sample_from_dense_cameras(dense[i], t[i])
+        assert np.allclose(got[i, :, :12], want[:, :12], atol=2e-5, rtol=0)
+        assert np.allclose(got[i, :, 12:], want[:, 12:], atol=0, rtol=5e-5)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 16, 32), (3, 3, 9, 7), (1, 3, 5, 4)])
+def test_pack_frames_u8_bit_exact(shape):
+    """Device conversion = export_video's host chain (io.py:181), bit for bit, incl. widths not divisible by 4."""
+    from prometheus_b200 import ops
+
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(*shape, generator=gen) * 0.8
+    x.view(-1)[:4] = torch.tensor([-1.0, 1.0, 0.0, 0.999999])
+    want = torch.stack([f.permute(1, 2, 0).mul(1 / 2).add(1 / 2).clamp(0, 1).mul(255) for f in x]).numpy().astype(np.uint8)
+    got = ops.pack_frames_u8(x.to(DEV)).cpu().numpy()
+    assert np.array_equal(got, want)
+
+
+def test_trajectory_renderer_matches_the_per_frame_loop(golden_dir):
+    """TrajectoryRenderer (all poses in one launch, chunks of cameras, device-side uint8 packing, async copies)
+    vs the reference's export_video loop restated frame by frame on top of the same renderer."""
+    import os
+
+    from prometheus_b200 import GaussianConverter, GaussianRenderer, TrajectoryRenderer, ops, scenes
+
+    sc = scenes.make_scene("C1", seed=31, views_in=3, size_in=48, views_out=2, size_out=64)
+    conv = GaussianConverter("mvsplat", z_near=0.01, z_far=100.0, s_min=0.001, s_max=1.0).to(DEV)
+    rend = GaussianRenderer().to(DEV)
+    rend.view_chunk = 4
+    dense = sc.cameras_in[0].clone()          # the 3 input cameras as a path (OpenGL c2w + intrinsics)
+    n_frames, S = 10, 64
+    with torch.no_grad():
+        g = conv(sc.params.to(DEV), sc.cameras_in.to(DEV))
+        frames, depths = TrajectoryRenderer(rend).render(g, dense.to(DEV), num_frames=n_frames, render_size=S)
+        torch.cuda.synchronize()
+        t = torch.tensor([[i / n_frames for i in range(n_frames)]], dtype=torch.float32)  # io.py:175
+        cams = ops.sample_cameras(dense[None].to(DEV), t.to(DEV))
+        ref = GaussianRenderer().to(DEV)
+        for i in range(n_frames):
+            im, de, _, _, _ = ref(cams[:, i:i + 1], g, h=S, w=S)
+            want = im.reshape(3, S, S).permute(1, 2, 0).cpu().mul(1 / 2).add(1 / 2).clamp(0, 1).mul(255).numpy().astype(np.uint8)
+            assert np.array_equal(frames[i].numpy(), want), i
+            assert np.array_equal(depths[i].numpy(), de.reshape(1, S, S).permute(1, 2, 0).cpu().numpy()), i
+    assert frames.shape == (n_frames, S, S, 3) and frames.numpy().std() > 5

@@ -216,3 +216,35 @@ def test_pixel_aligned_scene_statistics(oracle):
     assert 2.0 < ratio < 4.5
     assert st["alphas"].mean() > 0.99
     assert st["fragile"].mean() < 0.02
+
+
+# --------------------------------------------------------------------------- trajectory row
+@pytest.mark.parametrize("name", ["orbit_big", "smooth", "repeat", "video120"])
+def test_trajectory_oracle_matches_reference_golden(name):
+    """oracle/trajectory_oracle.py against the reference's own sample_from_dense_cameras outputs
+    (tests/golden/trajectory.npz, generated by tests/golden/make_golden_trajectory.py from /root/reference)."""
+    import os
+
+    from oracle import trajectory_oracle as T
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "trajectory.npz"))
+    got = T.sample_from_dense_cameras(g[name + "_dense"][0], g[name + "_t"][0])
+    want = g[name + "_out"][0]
+    assert np.allclose(got[:, :12], want[:, :12], atol=1e-5, rtol=0)
+    assert np.allclose(got[:, 12:], want[:, 12:], atol=0, rtol=2e-5)
+    # t = 0 returns the first pose; t = 1 falls into segment 0 at fraction 1 (the reference's strict `<` test)
+    if name == "orbit_big":
+        d = g[name + "_dense"][0]
+        assert np.allclose(want[0, 12:], d[0, 12:]) and np.allclose(want[-1, 12:], d[1, 12:])
+
+
+def test_pack_frames_oracle_is_the_reference_chain():
+    """export_video's per-frame conversion (io.py:181) restated with torch CPU ops vs the numpy oracle."""
+    import torch
+
+    from oracle import trajectory_oracle as T
+
+    x = torch.randn(3, 3, 9, 7) * 0.8
+    x[0, 0, 0, :4] = torch.tensor([-1.0, 1.0, 0.0, 0.999999])
+    want = torch.stack([f.permute(1, 2, 0).mul(1 / 2).add(1 / 2).clamp(0, 1).mul(255) for f in x]).numpy().astype(np.uint8)
+    assert np.array_equal(T.pack_frames_u8(x.numpy()), want)
