@@ -211,6 +211,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, in front of the JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     if args.config == "C5":
