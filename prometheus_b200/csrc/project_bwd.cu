@@ -27,6 +27,15 @@ __device__ __forceinline__ ProjCam load_proj_cam(const float *__restrict__ vm, c
   return c;
 }
 
+// one camera's constants in fp64, staged in shared memory once per CTA
+struct BwdCam {
+  double R[9];
+  double t[3];
+  double fx, fy;
+  double lim_x_pos, lim_x_neg, lim_y_pos, lim_y_neg;
+};
+constexpr int kBwdMaxCams = 512;  // 72 KB of dynamic shared memory at most
+
 __device__ __forceinline__ double sum3(double a, double b, double c) { return (a + b) + c; }
 __device__ __forceinline__ void quat_to_rotmat_d(double w, double x, double y, double z, double *R) {
   const double inv_norm = 1.0 / sqrt(((x * x + y * y) + z * z) + w * w);
@@ -52,6 +61,24 @@ project_bwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
                    const float *__restrict__ v_means2d, const float *__restrict__ v_depths,
                    const float *__restrict__ v_conics, float *__restrict__ v_means,
                    float *__restrict__ v_quats, float *__restrict__ v_scales) {
+  extern __shared__ __align__(16) unsigned char bwd_cam_smem[];
+  BwdCam *s_cam = reinterpret_cast<BwdCam *>(bwd_cam_smem);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const ProjCam pc = load_proj_cam(viewmats + (size_t)c * 16, Ks + (size_t)c * 9);
+    BwdCam bc;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) bc.R[i] = pc.R[i];
+    bc.t[0] = pc.t[0]; bc.t[1] = pc.t[1]; bc.t[2] = pc.t[2];
+    bc.fx = pc.fx; bc.fy = pc.fy;
+    const double cx = pc.cx, cy = pc.cy;
+    const double tan_fovx = 0.5 * (double)width / bc.fx, tan_fovy = 0.5 * (double)height / bc.fy;
+    bc.lim_x_pos = ((double)width - cx) / bc.fx + 0.3 * tan_fovx;
+    bc.lim_x_neg = cx / bc.fx + 0.3 * tan_fovx;
+    bc.lim_y_pos = ((double)height - cy) / bc.fy + 0.3 * tan_fovy;
+    bc.lim_y_neg = cy / bc.fy + 0.3 * tan_fovy;
+    s_cam[c] = bc;
+  }
+  __syncthreads();
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= N) return;
   const double mx = means[(size_t)g * 3 + 0], my = means[(size_t)g * 3 + 1], mz = means[(size_t)g * 3 + 2];
@@ -75,12 +102,17 @@ project_bwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
 
   for (int cid = 0; cid < C; ++cid) {
     const size_t f = (size_t)cid * N + g;
-    if (radii[f] <= 0) continue;
-    const ProjCam cf = load_proj_cam(viewmats + (size_t)cid * 16, Ks + (size_t)cid * 9);
-    double R[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) R[i] = cf.R[i];
-    const double ct[3] = {cf.t[0], cf.t[1], cf.t[2]};
+    // every input of this (camera, Gaussian) pair is requested up front: one memory latency per camera
+    const int radius = __ldg(radii + f);
+    const float cq0 = __ldg(conics + f * 3 + 0), cq1 = __ldg(conics + f * 3 + 1), cq2 = __ldg(conics + f * 3 + 2);
+    float gc0 = 0.0f, gc1 = 0.0f, gc2 = 0.0f, gm0 = 0.0f, gm1 = 0.0f, gd = 0.0f;
+    if (v_conics) { gc0 = __ldg(v_conics + f * 3 + 0); gc1 = __ldg(v_conics + f * 3 + 1); gc2 = __ldg(v_conics + f * 3 + 2); }
+    if (v_means2d) { gm0 = __ldg(v_means2d + f * 2 + 0); gm1 = __ldg(v_means2d + f * 2 + 1); }
+    if (v_depths) gd = __ldg(v_depths + f);
+    if (radius <= 0) continue;
+    const BwdCam &cf = s_cam[cid];  // per-camera constants (incl. the clamp limits: 6 fp64 divisions) once per CTA
+    const double *R = cf.R;
+    const double *ct = cf.t;
     const double x = sum3(R[0] * mx, R[1] * my, R[2] * mz) + ct[0];
     const double y = sum3(R[3] * mx, R[4] * my, R[5] * mz) + ct[1];
     const double z = sum3(R[6] * mx, R[7] * my, R[8] * mz) + ct[2];
@@ -98,9 +130,8 @@ project_bwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
         Sc[i * 3 + j] = sum3(Tm[i * 3] * R[j * 3], Tm[i * 3 + 1] * R[j * 3 + 1], Tm[i * 3 + 2] * R[j * 3 + 2]);
 
     // conic -> cov2d : G = -Q Vc Q
-    const double q00 = conics[f * 3 + 0], q01 = conics[f * 3 + 1], q11 = conics[f * 3 + 2];
-    double a00 = 0.0, a01 = 0.0, a11 = 0.0;
-    if (v_conics) { a00 = v_conics[f * 3 + 0]; a01 = 0.5 * v_conics[f * 3 + 1]; a11 = v_conics[f * 3 + 2]; }
+    const double q00 = cq0, q01 = cq1, q11 = cq2;
+    const double a00 = gc0, a01 = 0.5 * (double)gc1, a11 = gc2;
     const double t00 = q00 * a00 + q01 * a01, t01 = q00 * a01 + q01 * a11;
     const double t10 = q01 * a00 + q11 * a01, t11 = q01 * a01 + q11 * a11;
     const double G00 = -(t00 * q00 + t01 * q01);
@@ -108,10 +139,8 @@ project_bwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
     const double G10 = -(t10 * q00 + t11 * q01);
     const double G11 = -(t10 * q01 + t11 * q11);
 
-    const double fx = cf.fx, fy = cf.fy, cx = cf.cx, cy = cf.cy;
-    const double tan_fovx = 0.5 * (double)width / fx, tan_fovy = 0.5 * (double)height / fy;
-    const double lim_x_pos = ((double)width - cx) / fx + 0.3 * tan_fovx, lim_x_neg = cx / fx + 0.3 * tan_fovx;
-    const double lim_y_pos = ((double)height - cy) / fy + 0.3 * tan_fovy, lim_y_neg = cy / fy + 0.3 * tan_fovy;
+    const double fx = cf.fx, fy = cf.fy;
+    const double lim_x_pos = cf.lim_x_pos, lim_x_neg = cf.lim_x_neg, lim_y_pos = cf.lim_y_pos, lim_y_neg = cf.lim_y_neg;
     const double rz = 1.0 / z, rz2 = rz * rz, rz3 = rz2 * rz;
     const double xr = x * rz, yr = y * rz;
     const bool x_in = (xr <= lim_x_pos) && (xr >= -lim_x_neg);
@@ -147,15 +176,14 @@ project_bwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
     const double vJ11 = (G10 * JSt[1] + G11 * JSt[4]) + (G01 * JS[1] + G11 * JS[4]);
     const double vJ12 = (G10 * JSt[2] + G11 * JSt[5]) + (G01 * JS[2] + G11 * JS[5]);
 
-    double vm2x = 0.0, vm2y = 0.0;
-    if (v_means2d) { vm2x = v_means2d[f * 2 + 0]; vm2y = v_means2d[f * 2 + 1]; }
+    const double vm2x = gm0, vm2y = gm1;
     double vp0 = fx * rz * vm2x;
     double vp1 = fy * rz * vm2y;
     double vp2 = -(fx * x * vm2x + fy * y * vm2y) * rz2;
     if (x_in) vp0 += -fx * rz2 * vJ02; else vp2 += -fx * rz3 * vJ02 * tx;
     if (y_in) vp1 += -fy * rz2 * vJ12; else vp2 += -fy * rz3 * vJ12 * ty;
     vp2 += -fx * rz2 * vJ00 - fy * rz2 * vJ11 + 2.0 * fx * tx * rz3 * vJ02 + 2.0 * fy * ty * rz3 * vJ12;
-    if (v_depths) vp2 += v_depths[f];
+    vp2 += (double)gd;
 
     // to world: v_mean += R^T vp ; vS += R^T vSc R
 #pragma unroll
@@ -222,7 +250,20 @@ int pm_project_bwd(const float *means, const float *quats, const float *scales, 
     return PM_ERR_BAD_ARG;
   if ((int64_t)N * C >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
   if (N == 0) return PM_OK;
-  pm::project_bwd_kernel<<<(N + 127) / 128, 128, 0, pm::as_stream(stream)>>>(
+  if (C > pm::kBwdMaxCams) return PM_ERR_RANGE;
+  const size_t cam_bytes = sizeof(pm::BwdCam) * (size_t)(C > 0 ? C : 1);
+  if (cam_bytes > 48 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(pm::project_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(sizeof(pm::BwdCam) * pm::kBwdMaxCams)) != cudaSuccess) {
+        pm::set_last_cuda_error(cudaGetLastError());
+        return PM_ERR_CUDA;
+      }
+      attr_set = true;
+    }
+  }
+  pm::project_bwd_kernel<<<(N + 127) / 128, 128, cam_bytes, pm::as_stream(stream)>>>(
       means, quats, scales, viewmats, Ks, N, C, width, height, radii, conics, v_means2d, v_depths,
       v_conics, v_means, v_quats, v_scales);
   return pm::check_launch();
