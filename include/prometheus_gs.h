@@ -317,6 +317,15 @@ PM_API int pm_sample_cameras(const float *dense_cameras, const float *t, int B, 
 PM_API int pm_pack_frames_u8(const float *images, int64_t n_frames, int height, int width,
                       uint8_t *out, pm_stream_t stream);
 
+/* Densification statistics of the SDS++ refiner (prometheus/models/sdspp_refiner.py:275-280,
+ * prometheus/utils/gs_utils.py:247-252) for all C rendered views in one pass, views in order:
+ * vis = radii[c] > 0; is_visible[vis] = 1; max_radii2d[vis] = max(., radii[c]);
+ * xyz_gradient_accum[vis] += |v_means2d[c]|; denom[vis] += 1. radii [C,N] i32, v_means2d [C,N,2]
+ * (the gradient the compositing backward wrote); the four [N] fp32 state arrays are updated in place. */
+PM_API int pm_densify_stats(const int32_t *radii, const float *v_means2d, int C, int N,
+                     float *is_visible, float *max_radii2d, float *xyz_gradient_accum, float *denom,
+                     pm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

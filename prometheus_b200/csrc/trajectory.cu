@@ -171,3 +171,46 @@ int pm_pack_frames_u8(const float *images, int64_t n_frames, int height, int wid
 }
 
 }  // extern "C"
+
+// ---- densification statistics ----------------------------------------------------
+// Replaces the per-view host loop of the SDS++ refiner (prometheus/models/sdspp_refiner.py:275-280) and
+// GaussianModel.add_densification_stats (prometheus/utils/gs_utils.py:247-252): for every rendered view, in
+// order: vis = radii > 0; is_visible[vis] = 1; max_radii2D[vis] = max(max_radii2D[vis], radii[vis]);
+// xyz_gradient_accum[vis] += |grad means2d[vis]|; denom[vis] += 1 — ~10 boolean-mask indexing kernels per view
+// in the reference, one launch for all views here (one thread per Gaussian walks the views in the same order,
+// so the fp32 sums round identically).
+namespace pm {
+
+__global__ void __launch_bounds__(256)
+densify_stats_kernel(const int32_t *__restrict__ radii, const float *__restrict__ v_means2d, int C, int N,
+                     float *__restrict__ is_visible, float *__restrict__ max_radii2d,
+                     float *__restrict__ grad_accum, float *__restrict__ denom) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= N) return;
+  float vis = is_visible[g], mr = max_radii2d[g], acc = grad_accum[g], den = denom[g];
+  for (int c = 0; c < C; ++c) {
+    const size_t f = (size_t)c * N + g;
+    const int r = __ldg(radii + f);
+    const float2 v = __ldg(reinterpret_cast<const float2 *>(v_means2d) + f);
+    if (r > 0) {
+      vis = 1.0f;
+      mr = fmaxf(mr, (float)r);
+      acc = __fadd_rn(acc, sqrtf(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y))));
+      den = __fadd_rn(den, 1.0f);
+    }
+  }
+  is_visible[g] = vis; max_radii2d[g] = mr; grad_accum[g] = acc; denom[g] = den;
+}
+
+}  // namespace pm
+
+extern "C" int pm_densify_stats(const int32_t *radii, const float *v_means2d, int C, int N, float *is_visible,
+                                float *max_radii2d, float *xyz_gradient_accum, float *denom, pm_stream_t stream) {
+  if (C < 0 || N < 0) return PM_ERR_BAD_ARG;
+  if (C == 0 || N == 0) return PM_OK;
+  if (!radii || !v_means2d || !is_visible || !max_radii2d || !xyz_gradient_accum || !denom) return PM_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(v_means2d) & 7) != 0) return PM_ERR_BAD_ARG;
+  pm::densify_stats_kernel<<<(N + 255) / 256, 256, 0, pm::as_stream(stream)>>>(radii, v_means2d, C, N, is_visible,
+                                                                               max_radii2d, xyz_gradient_accum, denom);
+  return pm::check_launch();
+}

@@ -455,3 +455,19 @@ def pack_frames_u8(images, out=None):
     assert out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and out.numel() == Fn * H * W * 3
     _lib.check(L.pm_pack_frames_u8(_ptr(images), Fn, H, W, _ptr(out), _stream()), "pm_pack_frames_u8")
     return out
+
+
+# ------------------------------------------------------------------ densification statistics
+@_instrument("densify_stats", 1)
+def densify_stats(radii, v_means2d, is_visible, max_radii2d, xyz_gradient_accum, denom):
+    """In-place update of the refiner's per-Gaussian state from C rendered views (pm_densify_stats).
+    radii [C,N] int32, v_means2d [C,N,2] fp32; state tensors fp32 with N elements each ([N] or [N,1])."""
+    L = _lib.load()
+    radii = _req(radii, torch.int32, "radii")
+    v_means2d = _req(v_means2d, torch.float32, "v_means2d")
+    C, N = radii.shape
+    assert v_means2d.shape == (C, N, 2)
+    for t in (is_visible, max_radii2d, xyz_gradient_accum, denom):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == N
+    _lib.check(L.pm_densify_stats(_ptr(radii), _ptr(v_means2d), C, N, _ptr(is_visible), _ptr(max_radii2d),
+                                  _ptr(xyz_gradient_accum), _ptr(denom), _stream()), "pm_densify_stats")

@@ -121,7 +121,9 @@ class _TileRenderPacked(torch.autograd.Function):
     expected depth, clamped alpha) + the compositing backward that takes the packed cotangents directly."""
 
     @staticmethod
-    def forward(ctx, means2d, conics, opacities, colors, depths, backgrounds, records, offsets, stats, width, height):
+    def forward(ctx, means2d, conics, opacities, colors, depths, backgrounds, records, offsets, stats, width, height,
+                grad_sink=None):
+        ctx.grad_sink = grad_sink  # dict that receives the contiguous [C,N,2] means2d gradient (densification statistics)
         means2d, conics = means2d.contiguous(), conics.contiguous()
         opacities, colors, depths = opacities.contiguous(), colors.contiguous(), depths.contiguous()
         backgrounds = None if backgrounds is None else backgrounds.contiguous().float()
@@ -141,10 +143,12 @@ class _TileRenderPacked(torch.autograd.Function):
         v_means2d, v_conics, v_colors, v_opac, v_depths = ops.composite_bwd_packed(
             means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, width, height, masks, depth_out,
             last_ids, v_images, v_depth_out, v_masks, d_n=stats)
+        if ctx.grad_sink is not None:
+            ctx.grad_sink["v_means2d"] = v_means2d
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[5] and v_images is not None:
             v_bg = (2.0 * v_images * (1.0 - masks)).sum(dim=(2, 3))
-        return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None, None
+        return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None, None, None
 
 
 def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, backgrounds, width, height,
@@ -173,11 +177,12 @@ def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, b
     if capacity is None:
         capacity = int(stats[0].item())
     records = ops.bin_scatter(means2d.detach(), radii, depths.detach(), isect_offsets, width, height, int(capacity))
+    grad_sink = {}
     images, depth_out, masks, flag, flatten_ids, sorted_counts = _TileRenderPacked.apply(
-        means2d_in, conics, opacities, colors, depths, backgrounds, records, isect_offsets, stats, width, height)
+        means2d_in, conics, opacities, colors, depths, backgrounds, records, isect_offsets, stats, width, height, grad_sink)
     info = {"radii": radii, "means2d": means2d, "means2d_views": means2d_views, "depths": depths, "conics": conics,
             "isect_offsets": isect_offsets, "flatten_ids": flatten_ids, "sorted_counts": sorted_counts,
-            "stats": stats, "overflow_flag": flag, "capacity": int(capacity)}
+            "stats": stats, "overflow_flag": flag, "capacity": int(capacity), "means2d_grad_sink": grad_sink}
     return images, depth_out, masks, info
 
 

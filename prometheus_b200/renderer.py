@@ -96,6 +96,8 @@ class GaussianRenderer(nn.Module):
         self.viewspace_points: List[torch.Tensor] = []
         self._cap_hint = {}
         self._pending = []
+        self._stat_sources = []
+        self._stat_scenes = 0
 
     def _backgrounds(self, bg_color, n_views: int, device) -> torch.Tensor:
         # reference :381-386 — 'random' draws a fresh colour per rendered view
@@ -201,6 +203,9 @@ class GaussianRenderer(nn.Module):
                     if not ok:  # a depth sub-bucket beyond the fused kernel's group capacity: separate stages
                         im, de, ma, info = self._render_chunk_unfused(*a, h, w)
                     job["out"], job["info"] = (im, de, ma), info
+        # (radii [C,N], sink of the contiguous means2d gradient) per rendered chunk, for update_densification_stats
+        self._stat_sources = [(j["info"]["radii"], j["info"].get("means2d_grad_sink"), j["info"]["means2d_views"]) for j in jobs]
+        self._stat_scenes = B
         images, depths, masks = [], [], []
         per_scene = len(jobs) // max(B, 1)
         for i in range(B):
@@ -214,6 +219,23 @@ class GaussianRenderer(nn.Module):
                 lst.append(sj[0]["out"][k] if len(sj) == 1 else torch.cat([j["out"][k] for j in sj], 0))
         pack = (lambda l: l[0].unsqueeze(0)) if B == 1 else (lambda l: torch.stack(l, dim=0))
         return pack(images), pack(depths), pack(masks), None, None
+
+
+def _update_densification_stats(self, is_visible, max_radii2D, xyz_gradient_accum, denom) -> None:
+    """After `loss.backward()`: the SDS++ refiner's per-view bookkeeping (prometheus/models/sdspp_refiner.py:275-280
+    with GaussianModel.add_densification_stats, prometheus/utils/gs_utils.py:247-252) for every view of the last
+    forward(), in one kernel per rendered chunk instead of ~10 boolean-mask kernels per view. The four tensors are
+    the refiner's own state (`new_gaussians.is_visible`, `.max_radii2D`, `.xyz_gradient_accum`, `.denom`), updated
+    in place. One scene per forward (the refiner's case)."""
+    assert self._stat_scenes == 1, "densification statistics are kept per Gaussian set: render one scene per forward()"
+    for radii, sink, views in self._stat_sources:
+        grad = sink.get("v_means2d") if sink else None
+        if grad is None:  # separate-stage path: gather the per-view gradients autograd left on the side tensors
+            grad = torch.cat([v.grad if v.grad is not None else torch.zeros_like(v) for v in views], dim=0)
+        ops.densify_stats(radii, grad, is_visible, max_radii2D, xyz_gradient_accum, denom)
+
+
+GaussianRenderer.update_densification_stats = _update_densification_stats
 
 
 def install_as_gsplat() -> None:

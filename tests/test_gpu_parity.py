@@ -818,3 +818,34 @@ def test_trajectory_renderer_matches_the_per_frame_loop(golden_dir):
             assert np.array_equal(frames[i].numpy(), want), i
             assert np.array_equal(depths[i].numpy(), de.reshape(1, S, S).permute(1, 2, 0).cpu().numpy()), i
     assert frames.shape == (n_frames, S, S, 3) and frames.numpy().std() > 5
+
+
+# --------------------------------------------------------------------------- densification statistics
+@pytest.mark.parametrize("fused", [True, False])
+def test_densification_stats_match_the_refiner_loop(fused):
+    """GaussianRenderer.update_densification_stats vs the refiner's per-view loop restated literally
+    (sdspp_refiner.py:275-280 + gs_utils.py:247-252) on the renderer's own side lists, two refinement steps."""
+    from prometheus_b200 import GaussianConverter, GaussianRenderer, scenes
+
+    sc = scenes.make_scene("C1", seed=41, views_in=3, size_in=48, views_out=4, size_out=64)
+    conv = GaussianConverter("mvsplat", z_near=0.01, z_far=100.0, s_min=0.001, s_max=1.0).to(DEV)
+    rend = GaussianRenderer().to(DEV)
+    rend.fused = fused
+    N = sc.n_gaussians
+    ours = [torch.zeros(N, device=DEV), torch.zeros(N, device=DEV), torch.zeros(N, 1, device=DEV), torch.zeros(N, 1, device=DEV)]
+    ref = [t.clone() for t in ours]
+    for step in range(2):
+        params = (sc.params + 0.01 * step).to(DEV).requires_grad_(True)
+        images, depths, masks, _, _ = rend(sc.cameras_out.to(DEV), conv(params, sc.cameras_in.to(DEV)), bg_color="random", h=64, w=64)
+        (images.square().sum() + masks.sum() + depths.sum()).backward()
+        rend.update_densification_stats(*ours)
+        is_visible, max_radii2D, grad_accum, denom = ref
+        for radii, vp in zip(rend.radii, rend.viewspace_points):          # the reference's loop, literally
+            vis = radii > 0
+            is_visible[vis] = 1
+            max_radii2D[vis] = torch.max(max_radii2D[vis], radii[vis])
+            grad_accum[vis] += torch.norm(vp.grad[0, vis, :2], dim=-1, keepdim=True)
+            denom[vis] += 1
+    assert torch.equal(ours[0], ref[0]) and torch.equal(ours[1], ref[1]) and torch.equal(ours[3], ref[3])
+    assert float(ref[3].max()) == 8.0 and float(ref[2].sum()) > 0
+    assert torch.allclose(ours[2], ref[2], rtol=1e-6, atol=1e-12)
