@@ -326,6 +326,18 @@ PM_API int pm_densify_stats(const int32_t *radii, const float *v_means2d, int C,
                      float *is_visible, float *max_radii2d, float *xyz_gradient_accum, float *denom,
                      pm_stream_t stream);
 
+/* .splat export (prometheus/utils/io.py:25-125, export_ply_for_gaussians): sort keys
+ * -exp(sum log scale) / (1 + exp(-logit opacity)) as order-preserving uint32 in keys[i] (value i in vals[i]),
+ * to be sorted ascending with pm_sort_pairs(end_bit = 32); then the 32-byte records in that order:
+ * xyz 3 x f32, scale 3 x f32, rgba 4 x u8, normalised quaternion * 128 + 128 as 4 x u8. opacity [n], scales [n,3],
+ * xyz [n,3], rgb [n,3], rots [n,4] are the ACTIVATED Gaussians the decoder produces; compatible != 0 replays the
+ * reference's log / logit round trip. */
+PM_API int pm_splat_keys(const float *opacity, const float *scales, int64_t n, int compatible,
+                  int64_t *keys, int32_t *vals, pm_stream_t stream);
+PM_API int pm_splat_pack(const float *xyz, const float *rgb, const float *opacity, const float *scales,
+                  const float *rots, const int32_t *order, int64_t n, int compatible,
+                  uint8_t *out, pm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,3 +116,26 @@ def pack_frames_u8(images):
     x = np.asarray(images, F)
     y = np.clip(x * F(0.5) + F(0.5), F(0), F(1)) * F(255)
     return np.transpose(y, (0, 2, 3, 1)).astype(np.uint8)
+
+
+def pack_splat(xyz, rgb, opacity, scales, rots, compatible=True):
+    """The .splat byte stream of export_ply_for_gaussians (prometheus/utils/io.py:40-121) for activated Gaussians
+    xyz [n,3], rgb [n,3], opacity [n], scales [n,3], rots [n,4]: [n,32] uint8, plus the sort keys (ascending).
+    PINNED: tests/golden/splat.npz holds the reference's own output (tests/golden/make_golden_splat.py)."""
+    xyz, rgb, opacity, scales, rots = (np.asarray(a, F) for a in (xyz, rgb, opacity, scales, rots))
+    if compatible:  # io.py:46-48: inverse_sigmoid (math.py:7) and log(scale + 1e-8)
+        op = np.log(opacity / (F(1) - opacity)).astype(F)
+        ls = np.log(scales + F(1e-8)).astype(F)
+    else:
+        op, ls = opacity, scales
+    keys = (-np.exp(ls[:, 0] + ls[:, 1] + ls[:, 2]) / (F(1) + np.exp(-op))).astype(F)
+    order = np.argsort(keys, kind="stable")
+    out = np.zeros((len(order), 32), np.uint8)
+    out[:, 0:12] = xyz[order].view(np.uint8).reshape(-1, 12)
+    out[:, 12:24] = np.exp(ls[order]).astype(F).view(np.uint8).reshape(-1, 12)
+    color = np.concatenate([rgb[order], (F(1) / (F(1) + np.exp(-op[order])))[:, None]], axis=1).astype(F)
+    out[:, 24:28] = (color * F(255)).clip(0, 255).astype(np.uint8)
+    r = rots[order]
+    rn = np.sqrt(np.sum(r * r, axis=1, keepdims=True, dtype=F)).astype(F)
+    out[:, 28:32] = ((r / rn) * F(128) + F(128)).clip(0, 255).astype(np.uint8)
+    return out, keys[order]

@@ -12,7 +12,8 @@ Public surface (mirrors the reference, see DESIGN.md / INTEGRATION.md):
 from .rasterization import rasterization  # noqa: F401
 from .renderer import GaussianConverter, GaussianRenderer, install_as_gsplat  # noqa: F401
 from .pipeline import DecodeRenderPipeline  # noqa: F401
-from .trajectory import TrajectoryRenderer, export_video, sample_from_dense_cameras  # noqa: F401
+from .trajectory import (TrajectoryRenderer, export_ply_for_gaussians, export_video,  # noqa: F401
+                         sample_from_dense_cameras)
 
 __all__ = ["rasterization", "GaussianConverter", "GaussianRenderer", "install_as_gsplat", "DecodeRenderPipeline",
-           "TrajectoryRenderer", "sample_from_dense_cameras", "export_video"]
+           "TrajectoryRenderer", "sample_from_dense_cameras", "export_video", "export_ply_for_gaussians"]

@@ -471,3 +471,25 @@ def densify_stats(radii, v_means2d, is_visible, max_radii2d, xyz_gradient_accum,
         assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == N
     _lib.check(L.pm_densify_stats(_ptr(radii), _ptr(v_means2d), C, N, _ptr(is_visible), _ptr(max_radii2d),
                                   _ptr(xyz_gradient_accum), _ptr(denom), _stream()), "pm_densify_stats")
+
+
+# ------------------------------------------------------------------ .splat packing
+@_instrument("splat_pack", lambda *a, **k: 8)
+def splat_pack(xyz, rgb, opacity, scales, rots, compatible=True):
+    """Activated Gaussians ([n,3], [n,3], [n], [n,3], [n,4]) -> the .splat byte stream [n,32] uint8 in the
+    reference's order (volume x opacity, descending), all on the device."""
+    L = _lib.load()
+    xyz, rgb, opacity, scales, rots = (_req(t, torch.float32, "gaussians") for t in (xyz, rgb, opacity, scales, rots))
+    n = xyz.shape[0]
+    dev = xyz.device
+    keys = torch.empty(n, dtype=torch.int64, device=dev)
+    vals = torch.empty(n, dtype=torch.int32, device=dev)
+    out = torch.empty(n, 32, dtype=torch.uint8, device=dev)
+    if n == 0:
+        return out
+    _lib.check(L.pm_splat_keys(_ptr(opacity), _ptr(scales), n, int(bool(compatible)), _ptr(keys), _ptr(vals), _stream()),
+               "pm_splat_keys")
+    _, order = sort_pairs(keys, vals, 32)
+    _lib.check(L.pm_splat_pack(_ptr(xyz), _ptr(rgb), _ptr(opacity), _ptr(scales), _ptr(rots), _ptr(order), n,
+                               int(bool(compatible)), _ptr(out), _stream()), "pm_splat_pack")
+    return out

@@ -136,3 +136,25 @@ def export_video(render_fn, save_path, name, dense_cameras, fps=60, num_frames=7
 
         imageio.mimwrite(os.path.join(save_path, f"{name}.mp4"), list(frames), fps=fps, quality=8, macro_block_size=1)
     return frames, depths
+
+
+def export_ply_for_gaussians(path, gaussians, opacity_threshold=0.00, bbox=(-2, 2), compatible=True):
+    """Drop-in for prometheus.utils.io.export_ply_for_gaussians (io.py:25-125): writes `path + '.splat'` — like the
+    reference (its `.ply` write is commented out) — and returns {'pts', 'color', 'alpha'}. The reference sorts with
+    np.argsort and builds every 32-byte record in a Python loop; here the sort keys, the radix sort and the packing
+    run on the device (ops.splat_pack) and one device->host copy feeds the file write. `path=None` skips the file."""
+    xyz, features, opacity, scales, rotations = gaussians
+    means3d, opac = xyz[0].contiguous().float(), opacity[0].contiguous().float()
+    scl, rot, shs = scales[0].contiguous().float(), rotations[0].contiguous().float(), features[0].contiguous().float()
+    if not means3d.is_cuda:
+        raise RuntimeError("prometheus_b200.export_ply_for_gaussians needs CUDA tensors: there is no CPU fallback")
+    mask = opac[..., 0] >= opacity_threshold
+    means3d, opac, scl, rot, shs = means3d[mask], opac[mask], scl[mask], rot[mask], shs[mask]
+    rgb = shs.detach().transpose(1, 2).flatten(start_dim=1).contiguous()
+    splat = ops.splat_pack(means3d.detach(), rgb, opac[:, 0].detach().contiguous(), scl.detach(), rot.detach(), compatible)
+    data = splat.cpu().numpy()
+    if path is not None:
+        with open(path + ".splat", "wb") as f:
+            f.write(data.tobytes())
+    return {"pts": means3d.detach().cpu().numpy(), "color": ((rgb + 1) / 2).cpu().numpy(), "alpha": opac.detach().cpu().numpy(),
+            "splat": data}

@@ -849,3 +849,48 @@ def test_densification_stats_match_the_refiner_loop(fused):
     assert torch.equal(ours[0], ref[0]) and torch.equal(ours[1], ref[1]) and torch.equal(ours[3], ref[3])
     assert float(ref[3].max()) == 8.0 and float(ref[2].sum()) > 0
     assert torch.allclose(ours[2], ref[2], rtol=1e-6, atol=1e-12)
+
+
+# --------------------------------------------------------------------------- .splat export
+@pytest.mark.parametrize("tag,thr", [("all", 0.0), ("pruned", 0.3)])
+def test_splat_export_vs_reference_golden(golden_dir, tag, thr, tmp_path):
+    """Device-side .splat packing against the bytes the reference's export_ply_for_gaussians wrote (pinned golden)."""
+    import os
+
+    from prometheus_b200 import export_ply_for_gaussians
+    from tests.test_oracle import check_splat_against_reference
+
+    g = np.load(os.path.join(golden_dir, "splat.npz"))
+    gauss = tuple(dev(g[k]) for k in ("xyz", "features", "opacity", "scales", "rotations"))
+    ret = export_ply_for_gaussians(str(tmp_path / "g"), gauss, opacity_threshold=thr)
+    data = np.frombuffer(open(str(tmp_path / "g.splat"), "rb").read(), np.uint8)
+    n = int((g["opacity"][0, :, 0] >= thr).sum())
+    check_splat_against_reference(data, g["splat_" + tag], n)
+    assert np.array_equal(ret["pts"], g["ret_%s_pts" % tag])
+    assert np.allclose(ret["color"], g["ret_%s_color" % tag], atol=1e-6)
+
+
+def test_splat_pack_large_is_sorted_and_complete(oracle):
+    """2^20 Gaussians: keys non-increasing in volume x opacity, every Gaussian present exactly once."""
+    from oracle import trajectory_oracle as T
+    from prometheus_b200 import ops
+
+    gen = torch.Generator().manual_seed(8)
+    n = 1 << 20
+    xyz = torch.randn(n, 3, generator=gen)
+    rgb = torch.rand(n, 3, generator=gen)
+    opa = torch.sigmoid(torch.randn(n, generator=gen) * 2)
+    scl = 0.001 + 0.3 * torch.rand(n, 3, generator=gen) ** 2
+    rot = torch.randn(n, 4, generator=gen)
+    out = ops.splat_pack(*(t.to(DEV) for t in (xyz, rgb, opa, scl, rot))).cpu().numpy()
+    pos = out[:, :12].copy().view(np.float32)
+    # every Gaussian exactly once: match the stream back to its source through the positions
+    X = xyz.numpy()
+    i_src, i_out = np.lexsort(X.T[::-1]), np.lexsort(pos.T[::-1])
+    assert np.array_equal(X[i_src], pos[i_out])
+    src = np.empty(n, np.int64)
+    src[i_out] = i_src
+    # ... in the reference's order: volume x opacity (io.py:76-79), evaluated here in fp64
+    vol = (scl.numpy().astype(np.float64) + 1e-8).prod(axis=1) * opa.numpy().astype(np.float64)
+    key = vol[src]
+    assert np.all(key[1:] <= key[:-1] * (1 + 1e-5))

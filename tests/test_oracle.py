@@ -248,3 +248,43 @@ def test_pack_frames_oracle_is_the_reference_chain():
     x[0, 0, 0, :4] = torch.tensor([-1.0, 1.0, 0.0, 0.999999])
     want = torch.stack([f.permute(1, 2, 0).mul(1 / 2).add(1 / 2).clamp(0, 1).mul(255) for f in x]).numpy().astype(np.uint8)
     assert np.array_equal(T.pack_frames_u8(x.numpy()), want)
+
+
+def _splat_records(buf):
+    """[n,32] uint8 -> (xyz f32 [n,3], scales f32 [n,3], rgba u8 [n,4], rot u8 [n,4])"""
+    buf = np.ascontiguousarray(buf).reshape(-1, 32)
+    return (buf[:, 0:12].copy().view(np.float32), buf[:, 12:24].copy().view(np.float32), buf[:, 24:28], buf[:, 28:32])
+
+
+def check_splat_against_reference(got, want, n_expected):
+    """Record-level parity with the reference's byte stream: same Gaussians (positions bit-exact), scales to fp32
+    round-off of the exp(log(.)) round trip, 8-bit fields within one code (libm vs numpy exp / log differ by an ulp),
+    and the same volume x opacity ordering up to swaps of near-equal keys."""
+    gx, gs, gc, gr = _splat_records(got)
+    wx, ws, wc, wr = _splat_records(want)
+    assert len(gx) == len(wx) == n_expected
+    gi = np.lexsort(gx.T[::-1])
+    wi = np.lexsort(wx.T[::-1])
+    assert np.array_equal(gx[gi], wx[wi])
+    assert np.allclose(gs[gi], ws[wi], rtol=2e-6, atol=0)
+    assert np.abs(gc[gi].astype(int) - wc[wi].astype(int)).max() <= 1
+    assert np.abs(gr[gi].astype(int) - wr[wi].astype(int)).max() <= 1
+    # ordering: rank of every Gaussian in both streams differs only where keys are (nearly) tied
+    rank_g = np.empty(len(gi), int); rank_g[gi] = np.arange(len(gi))
+    rank_w = np.empty(len(wi), int); rank_w[wi] = np.arange(len(wi))
+    assert np.abs(np.argsort(rank_g) - np.argsort(rank_w)).max() <= 2 or np.mean(np.argsort(rank_g) == np.argsort(rank_w)) > 0.99
+
+
+@pytest.mark.parametrize("tag,thr", [("all", 0.0), ("pruned", 0.3)])
+def test_splat_oracle_matches_reference_golden(tag, thr):
+    """oracle pack_splat vs the reference exporter's own bytes (tests/golden/splat.npz)."""
+    import os
+
+    from oracle import trajectory_oracle as T
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "splat.npz"))
+    keep = g["opacity"][0, :, 0] >= thr
+    got, keys = T.pack_splat(g["xyz"][0][keep], g["features"][0][keep][:, 0], g["opacity"][0][keep][:, 0], g["scales"][0][keep],
+                             g["rotations"][0][keep])
+    assert np.all(np.diff(keys) >= 0)
+    check_splat_against_reference(got, g["splat_" + tag], int(keep.sum()))
