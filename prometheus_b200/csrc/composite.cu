@@ -21,7 +21,11 @@
 // loaded. The backward pass replays the same culled lists back to front, reduces
 // each Gaussian's gradient across the warp with a 12-shuffle halving butterfly and
 // issues one fire-and-forget global reduction per (warp, Gaussian, component) —
-// no per-pixel global atomics. (Accumulating the CTA's warps in shared memory first,
+// no per-pixel global atomics. The warps of the backward are AUTONOMOUS: each stages
+// its own 32-Gaussian chunks (lane j gathers Gaussian j; the other warps of the tile
+// hit the same lines in L1/L2) and walks only the prefix its own pixels need, so there
+// is no CTA barrier at all — the per-round barrier of the CTA-wide version was 36 % of
+// its stall samples (profiles/r1j_composite_bwd_lines.txt). (Accumulating the CTA's warps in shared memory first,
 // PM_BWD_GLOBAL_RED=0, measured 3.5 % slower: shared atomics return a value and the
 // flush needs a barrier.)
 #include "composite_common.cuh"
@@ -134,6 +138,9 @@ __device__ __forceinline__ float butterfly_reduce10(const float (&v)[10], int la
 #ifndef PM_BWD_GLOBAL_RED
 #define PM_BWD_GLOBAL_RED 1
 #endif
+#ifndef PM_BWD_AUTONOMOUS
+#define PM_BWD_AUTONOMOUS 1  // every warp stages its own 32-Gaussian chunks, no CTA barrier (needs GLOBAL_RED); 0: CTA-wide rounds
+#endif
 constexpr int kBwdWarps = PM_BWD_WARPS;
 constexpr int kBwdThreads = 32 * kBwdWarps;
 constexpr int kBwdParts = 8 / kBwdWarps;
@@ -142,11 +149,16 @@ constexpr int kBwdParts = 8 / kBwdWarps;
 #endif
 constexpr int kBwdBatch = PM_BWD_BATCH;  // Gaussians staged (records + gradient accumulators) per CTA round
 
+#if PM_BWD_AUTONOMOUS
+constexpr int kBwdStage = 32 * kBwdWarps;  // one private 32-Gaussian chunk per warp
+#else
+constexpr int kBwdStage = kBwdBatch;
+#endif
 struct BwdShared {
-  GaussA sA[kBwdBatch];
-  GaussB sB[kBwdBatch];
-  GaussC sC[kBwdBatch];
-  int32_t sF[kBwdBatch];
+  GaussA sA[kBwdStage];
+  GaussB sB[kBwdStage];
+  GaussC sC[kBwdStage];
+  int32_t sF[kBwdStage];
 #if !PM_BWD_GLOBAL_RED
   float sG[kBwdBatch * kGradStride];
 #endif
@@ -259,6 +271,78 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
 #endif
   const uint32_t aA = smem_u32(sA), aB = smem_u32(sB), aC = smem_u32(sC);
 
+#if PM_BWD_AUTONOMOUS
+  {
+    // Warp-autonomous replay: no CTA barrier anywhere. Each warp walks the prefix of the tile's list ITS pixels
+    // need, back to front, 32 Gaussians at a time: lane j gathers Gaussian j into the warp's private staging
+    // slots (the gathers of the warps of a tile hit L1/L2), then the warp culls and replays the chunk.
+    int wl = my_last;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wl = max(wl, __shfl_xor_sync(0xffffffffu, wl, o));
+    if (wl < range_start) return;
+    const int w = tid >> 5;
+    GaussA *wA = sA + w * 32; GaussB *wB = sB + w * 32; GaussC *wC = sC + w * 32;
+    const uint32_t qA = smem_u32(wA), qB = smem_u32(wB), qC = smem_u32(wC);
+    const int n_w = min(range_end, wl + 1) - range_start;
+    float T = T_final;
+    float buf0 = 0.0f, buf1 = 0.0f, buf2 = 0.0f, buf3 = 0.0f;
+    for (int c0 = ((n_w - 1) / 32) * 32; c0 >= 0; c0 -= 32) {
+      const int cnt = min(32, n_w - c0);
+      const int chunk_start = range_start + c0;
+      int32_t f = 0;
+      __syncwarp();
+      if (lane < cnt) {
+        f = flatten_ids[chunk_start + lane];
+        gather(f, f - cam * N, means2d, conics, opacities, colors, colors_per_camera, D, depths, wA[lane], wB[lane], wC[lane]);
+      }
+      __syncwarp();
+      const unsigned live = __ballot_sync(0xffffffffu, my_last >= chunk_start);
+      const LiveRect rect = live_rect(live, wcx, wcy);
+      bool hit = false;
+      if (lane < cnt) hit = cull_hit(lds128(qA + lane * 16), qB + lane * 16, rect);
+      unsigned mask = __ballot_sync(0xffffffffu, hit);
+      while (mask) {
+        const int t = 31 - __clz(mask);
+        mask &= ~(1u << t);
+        const float2 m = lds64(qA + t * 16);
+        const float4 b = lds128(qB + t * 16);
+        const float dx = m.x - px, dy = m.y - py;
+        const float p = power2(b.x, b.y, b.z, dx, dy);
+        const float vis = ex2_approx(p);
+        const float alpha = fminf(0.999f, b.w * vis);
+        const bool valid = (chunk_start + t <= my_last) && !(p > 0.0f) && alpha >= kAlphaMin;
+        if (!__any_sync(0xffffffffu, valid)) continue;
+        float gv[10] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        if (valid) {
+          const float4 c = lds128(qC + t * 16);
+          const float ra = rcp_approx(1.0f - alpha);
+          T *= ra;
+          const float fac = alpha * T;
+          gv[0] = fac * vr[0]; gv[1] = fac * vr[1]; gv[2] = fac * vr[2]; gv[3] = fac * vr[3];
+          float v_alpha = (c.x * T - buf0 * ra) * vr[0] + (c.y * T - buf1 * ra) * vr[1] +
+                          (c.z * T - buf2 * ra) * vr[2] + (c.w * T - buf3 * ra) * vr[3];
+          v_alpha += va_seed * ra;
+          if (b.w * vis <= 0.999f) {
+            const float v_sigma = -b.w * vis * v_alpha;
+            gv[4] = 0.5f * v_sigma * dx * dx;
+            gv[5] = v_sigma * dx * dy;
+            gv[6] = 0.5f * v_sigma * dy * dy;
+            const float s2 = v_sigma * (-1.0f / kLog2e);
+            gv[7] = s2 * (2.0f * b.x * dx + b.y * dy);
+            gv[8] = s2 * (b.y * dx + 2.0f * b.z * dy);
+            gv[9] = vis * v_alpha;
+          }
+          buf0 += c.x * fac; buf1 += c.y * fac; buf2 += c.z * fac; buf3 += c.w * fac;
+        }
+        const float total = butterfly_reduce10(gv, lane);
+        const int32_t ft = __shfl_sync(0xffffffffu, f, t);
+        if (my_comp_live >= 0 && total != 0.0f)
+          atomicAdd(red_base + (size_t)(red_by_pair ? ft : ft - cam * N) * red_mult, total);
+      }
+    }
+    return;
+  }
+#endif
   if (tid == 0) s_max_last = -1;
   __syncthreads();
   int warp_last = my_last;  // last list position any pixel of this warp replays
