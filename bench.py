@@ -261,9 +261,19 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup, profile=False):
+        import gc
+
         for _ in range(warmup):
             fn()
         barrier()
+        gc.collect()
+        gc.disable()  # as timeit does: a generation-2 collection in the middle of a step starves the GPU for milliseconds
+        try:
+            return _timed_body(fn, steps, profile)
+        finally:
+            gc.enable()
+
+    def _timed_body(fn, steps, profile):
         ops.PROFILE = [] if profile else None
         n0 = ops.LAUNCHES
         evs = []
@@ -391,11 +401,16 @@ def main():
     e2e_loop(max(3, args.warmup))
     barrier()
     flush_buf.fill_(1)
+    import gc
+
+    gc.collect()
+    gc.disable()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     e2e_loop(args.steps)
     e1.record()
     barrier()
+    gc.enable()
     e2e_ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
