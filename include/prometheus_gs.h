@@ -181,9 +181,10 @@ PM_API int pm_bin_count(const float *means2d, const int32_t *radii, int N, int C
                         int tile_width, int tile_height, int32_t *tile_counts, pm_stream_t stream);
 
 /* Exclusive scan of tile_counts [T] -> isect_offsets [T]; stats_out (device, 2 x
- * int32) receives {n_isects, max tile count}. */
+ * int32) receives {n_isects, max tile count}. tile_order [T] (may be NULL) receives the
+ * tile indices heaviest first — the launch order of pm_tile_render_*_fwd. */
 PM_API int pm_tile_scan(const int32_t *tile_counts, int64_t T, int32_t *isect_offsets,
-                        int32_t *stats_out, pm_stream_t stream);
+                        int32_t *stats_out, int32_t *tile_order, pm_stream_t stream);
 
 /* Scatter every (pair, tile) intersection into its tile segment as a packed
  * 8-byte record {depth bits (low 32), flatten id (high 32)}. cursors [T] must be
@@ -247,7 +248,8 @@ PM_API int pm_composite_fwd(const float *means2d, const float *conics, const flo
  * sorted_counts[c,ty,tx] entries of each tile only (all that pm_composite_bwd
  * reads). *overflow_flag (device int32, caller zero-fills) is set if a depth
  * sub-bucket of some tile exceeds the 1024-record group capacity: the caller
- * must then redo the call with pm_tile_sort + pm_composite_fwd. */
+ * must then redo the call with pm_tile_sort + pm_composite_fwd. tile_order (may be NULL): the
+ * (camera, tile) index each CTA takes, e.g. heaviest first from pm_tile_scan. */
 PM_API int pm_tile_render_fwd(const uint64_t *records, const int32_t *isect_offsets, int64_t n_isects,
                               const int32_t *d_n, const float *means2d, const float *conics,
                               const float *opacities, const float *colors, int colors_per_camera, int D,
@@ -255,7 +257,7 @@ PM_API int pm_tile_render_fwd(const uint64_t *records, const int32_t *isect_offs
                               int width, int height, int tile_size,
                               float *render, float *alphas, int32_t *last_ids,
                               int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
-                              pm_stream_t stream);
+                              const int32_t *tile_order, pm_stream_t stream);
 
 /* The same kernel with the module-level epilogue fused in (RGB + expected depth, D = 3): writes
  * what GaussianRenderer.forward returns (gaussians_renderer.py:437-440, :507-509) —
@@ -271,7 +273,7 @@ PM_API int pm_tile_render_packed_fwd(const uint64_t *records, const int32_t *ise
                               int width, int height, int tile_size,
                               float *images, float *depth_out, float *masks, int32_t *last_ids,
                               int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
-                              pm_stream_t stream);
+                              const int32_t *tile_order, pm_stream_t stream);
 
 /* Backward. v_render [C,H,W,CD], v_alphas [C,H,W] (either may be NULL).
  * Gradients are ACCUMULATED (+=) into v_means2d [C,N,2], v_conics [C,N,3],

@@ -33,7 +33,7 @@ SIGNATURES = {
     "pm_project_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P]),
     "pm_project_count_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
     "pm_bin_count": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
-    "pm_tile_scan": (c_int, [_P, _L, _P, _P, _P]),
+    "pm_tile_scan": (c_int, [_P, _L, _P, _P, _P, _P]),
     "pm_bin_scatter": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _L, _P]),
     "pm_tile_sort_capacity": (c_int, []),
     "pm_tile_sort": (c_int, [_P, _P, _P, _L, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
@@ -45,8 +45,8 @@ SIGNATURES = {
     "pm_sort_pairs": (c_int, [_P, _P, _P, _P, _L, _P, _I, _P, _S, POINTER(c_int), _P]),
     "pm_tile_offsets": (c_int, [_P, _L, _P, _I, _I, _I, _P, _P]),
     "pm_composite_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
-    "pm_tile_render_fwd": (c_int, [_P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
-    "pm_tile_render_packed_fwd": (c_int, [_P, _P, _L, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pm_tile_render_fwd": (c_int, [_P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pm_tile_render_packed_fwd": (c_int, [_P, _P, _L, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pm_composite_bwd_packed": (c_int, [_P, _P, _P, _P, _I, _P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I,
                                         _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pm_splat_keys": (c_int, [_P, _P, _L, _I, _P, _P, _P]),

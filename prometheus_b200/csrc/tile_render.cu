@@ -210,12 +210,13 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
                        float *__restrict__ alphas, int32_t *__restrict__ last_ids,
                        int32_t *__restrict__ flatten_ids, int32_t *__restrict__ sorted_counts,
                        int32_t *__restrict__ overflow_flag, float *__restrict__ images,
-                       float *__restrict__ depth_out, float *__restrict__ masks) {
+                       float *__restrict__ depth_out, float *__restrict__ masks,
+                       const int32_t *__restrict__ tile_order) {
   extern __shared__ __align__(16) unsigned char tr_smem[];
   TrShared &sh = *reinterpret_cast<TrShared *>(tr_smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_tiles = tile_width * tile_height;
-  const int ct = blockIdx.x;
+  const int ct = tile_order ? tile_order[blockIdx.x] : (int)blockIdx.x;  // heaviest tiles first (pm_tile_scan)
   const int cam = ct / n_tiles, tile = ct % n_tiles;
   const int tile_y = tile / tile_width, tile_x = tile % tile_width;
   const int wx0 = tile_x * kTile + (warp & 1) * 8, wy0 = tile_y * kTile + (warp >> 1) * 4;
@@ -474,7 +475,7 @@ static int tile_render_launch(const uint64_t *records, const int32_t *isect_offs
                               const float *backgrounds, int N, int C, int width, int height, int tile_size,
                               float *render, float *alphas, int32_t *last_ids, int32_t *flatten_ids,
                               int32_t *sorted_counts, int32_t *overflow_flag, float *images, float *depth_out,
-                              float *masks, pm_stream_t stream) {
+                              float *masks, const int32_t *tile_order, pm_stream_t stream) {
   if (N < 0 || C < 0 || width <= 0 || height <= 0 || n_isects < 0 || D < 0) return PM_ERR_BAD_ARG;
   if (tile_size != pm::kTile) return PM_ERR_UNSUPPORTED;
   const int CD = D + (depths ? 1 : 0);
@@ -508,7 +509,7 @@ static int tile_render_launch(const uint64_t *records, const int32_t *isect_offs
   pm::tile_render_fwd_kernel<<<(unsigned)blocks, pm::kTrThreads, pm::kTrSmemBytes, pm::as_stream(stream)>>>(
       records, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera, D, depths,
       backgrounds, N, width, height, tw, th, render, alphas, last_ids, flatten_ids, sorted_counts, overflow_flag,
-      images, depth_out, masks);
+      images, depth_out, masks, tile_order);
   return pm::check_launch();
 }
 
@@ -530,10 +531,10 @@ int pm_tile_render_fwd(const uint64_t *records, const int32_t *isect_offsets, in
                        const float *depths, const float *backgrounds, int N, int C, int width, int height,
                        int tile_size, float *render, float *alphas, int32_t *last_ids,
                        int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
-                       pm_stream_t stream) {
+                       const int32_t *tile_order, pm_stream_t stream) {
   return tile_render_launch(records, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera,
                             D, depths, backgrounds, N, C, width, height, tile_size, render, alphas, last_ids,
-                            flatten_ids, sorted_counts, overflow_flag, nullptr, nullptr, nullptr, stream);
+                            flatten_ids, sorted_counts, overflow_flag, nullptr, nullptr, nullptr, tile_order, stream);
 }
 
 int pm_tile_render_packed_fwd(const uint64_t *records, const int32_t *isect_offsets, int64_t n_isects,
@@ -542,11 +543,11 @@ int pm_tile_render_packed_fwd(const uint64_t *records, const int32_t *isect_offs
                               const float *depths, const float *backgrounds, int N, int C, int width, int height,
                               int tile_size, float *images, float *depth_out, float *masks, int32_t *last_ids,
                               int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
-                              pm_stream_t stream) {
+                              const int32_t *tile_order, pm_stream_t stream) {
   if (!images) return PM_ERR_BAD_ARG;
   return tile_render_launch(records, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera,
                             3, depths, backgrounds, N, C, width, height, tile_size, nullptr, nullptr, last_ids,
-                            flatten_ids, sorted_counts, overflow_flag, images, depth_out, masks, stream);
+                            flatten_ids, sorted_counts, overflow_flag, images, depth_out, masks, tile_order, stream);
 }
 
 }  // extern "C"

@@ -222,15 +222,17 @@ def bin_count(means2d, radii, width, height):
 
 
 @_instrument("tile_scan", 1)
-def tile_scan(tile_counts):
+def tile_scan(tile_counts, want_order=False):
     """Exclusive scan of the per-tile histogram -> (isect_offsets like tile_counts, stats int32[2] =
-    {n_isects, max tile count}, both on the device)."""
+    {n_isects, max tile count}, both on the device) [, tile_order int32[T]: tile indices heaviest first]."""
     L = _lib.load()
     assert tile_counts.dtype == torch.int32 and tile_counts.is_contiguous() and tile_counts.is_cuda
     offsets = torch.empty_like(tile_counts)
     stats = torch.empty(2, dtype=torch.int32, device=tile_counts.device)
-    _lib.check(L.pm_tile_scan(_ptr(tile_counts), tile_counts.numel(), _ptr(offsets), _ptr(stats), _stream()), "pm_tile_scan")
-    return offsets, stats
+    order = torch.empty(tile_counts.numel(), dtype=torch.int32, device=tile_counts.device) if want_order else None
+    _lib.check(L.pm_tile_scan(_ptr(tile_counts), tile_counts.numel(), _ptr(offsets), _ptr(stats), _ptr(order), _stream()),
+               "pm_tile_scan")
+    return (offsets, stats, order) if want_order else (offsets, stats)
 
 
 @_instrument("bin_scatter", 1)
@@ -334,7 +336,8 @@ def composite_fwd(means2d, conics, opacities, colors, depths, backgrounds, offse
 
 
 @_instrument("tile_render_fwd", 1)
-def tile_render_fwd(records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height, d_n=None):
+def tile_render_fwd(records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height, d_n=None,
+                    tile_order=None):
     """Fused sort-as-you-go forward -> render, alphas, last_ids, flatten_ids (sorted prefix per tile),
     sorted_counts [C,th,tw], overflow flag int32[1]."""
     L = _lib.load()
@@ -352,7 +355,7 @@ def tile_render_fwd(records, offsets, means2d, conics, opacities, colors, depths
     _lib.check(L.pm_tile_render_fwd(_ptr(records), _ptr(offsets), n, _ptr(d_n), _ptr(means2d), _ptr(conics),
                                     _ptr(opacities), _ptr(colors), per_cam, D, _ptr(depths), _ptr(backgrounds), N, C,
                                     width, height, TILE, _ptr(render), _ptr(alphas), _ptr(last_ids), _ptr(flat),
-                                    _ptr(sorted_counts), _ptr(flag), _stream()), "pm_tile_render_fwd")
+                                    _ptr(sorted_counts), _ptr(flag), _ptr(tile_order), _stream()), "pm_tile_render_fwd")
     return render, alphas, last_ids, flat, sorted_counts, flag
 
 
@@ -381,7 +384,7 @@ def composite_bwd(means2d, conics, opacities, colors, depths, backgrounds, offse
 # ------------------------------------------------------------------ module fast path (packed outputs)
 @_instrument("tile_render_fwd", 1)
 def tile_render_packed_fwd(records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height,
-                           d_n=None):
+                           d_n=None, tile_order=None):
     """Fused sort-as-you-go forward with the module epilogue: -> images [C,3,H,W] (2 rgb - 1),
     depth_out [C,1,H,W] (expected depth), masks [C,1,H,W], last_ids [C,H,W], flatten_ids (sorted prefix per
     tile), sorted_counts [C,th,tw], overflow flag int32[1]. `records` may be a speculative capacity with the
@@ -402,7 +405,8 @@ def tile_render_packed_fwd(records, offsets, means2d, conics, opacities, colors,
     _lib.check(L.pm_tile_render_packed_fwd(_ptr(records), _ptr(offsets), n, _ptr(d_n), _ptr(means2d), _ptr(conics),
                                            _ptr(opacities), _ptr(colors), per_cam, _ptr(depths), _ptr(backgrounds), N, C,
                                            width, height, TILE, _ptr(images), _ptr(depth_out), _ptr(masks),
-                                           _ptr(last_ids), _ptr(flat), _ptr(sorted_counts), _ptr(flag), _stream()),
+                                           _ptr(last_ids), _ptr(flat), _ptr(sorted_counts), _ptr(flag), _ptr(tile_order),
+                                           _stream()),
                "pm_tile_render_packed_fwd")
     return images, depth_out, masks, last_ids, flat, sorted_counts, flag
 

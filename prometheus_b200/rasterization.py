@@ -122,13 +122,14 @@ class _TileRenderPacked(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means2d, conics, opacities, colors, depths, backgrounds, records, offsets, stats, width, height,
-                grad_sink=None):
+                grad_sink=None, tile_order=None):
         ctx.grad_sink = grad_sink  # dict that receives the contiguous [C,N,2] means2d gradient (densification statistics)
         means2d, conics = means2d.contiguous(), conics.contiguous()
         opacities, colors, depths = opacities.contiguous(), colors.contiguous(), depths.contiguous()
         backgrounds = None if backgrounds is None else backgrounds.contiguous().float()
         images, depth_out, masks, last_ids, flat, sorted_counts, flag = ops.tile_render_packed_fwd(
-            records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height, d_n=stats)
+            records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height, d_n=stats,
+            tile_order=tile_order)
         ctx.save_for_backward(means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, masks, depth_out,
                               last_ids, stats)
         ctx.dims = (width, height)
@@ -148,7 +149,7 @@ class _TileRenderPacked(torch.autograd.Function):
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[5] and v_images is not None:
             v_bg = (2.0 * v_images * (1.0 - masks)).sum(dim=(2, 3))
-        return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None, None, None
+        return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None, None, None, None
 
 
 def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, backgrounds, width, height,
@@ -173,13 +174,14 @@ def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, b
         for v in means2d_views:
             v.retain_grad()
         means2d_in = torch.cat(means2d_views, dim=0)
-    isect_offsets, stats = ops.tile_scan(counts)
+    isect_offsets, stats, tile_order = ops.tile_scan(counts, want_order=True)
     if capacity is None:
         capacity = int(stats[0].item())
     records = ops.bin_scatter(means2d.detach(), radii, depths.detach(), isect_offsets, width, height, int(capacity))
     grad_sink = {}
     images, depth_out, masks, flag, flatten_ids, sorted_counts = _TileRenderPacked.apply(
-        means2d_in, conics, opacities, colors, depths, backgrounds, records, isect_offsets, stats, width, height, grad_sink)
+        means2d_in, conics, opacities, colors, depths, backgrounds, records, isect_offsets, stats, width, height, grad_sink,
+        tile_order)
     info = {"radii": radii, "means2d": means2d, "means2d_views": means2d_views, "depths": depths, "conics": conics,
             "isect_offsets": isect_offsets, "flatten_ids": flatten_ids, "sorted_counts": sorted_counts,
             "stats": stats, "overflow_flag": flag, "capacity": int(capacity), "means2d_grad_sink": grad_sink}

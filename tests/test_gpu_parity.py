@@ -894,3 +894,19 @@ def test_splat_pack_large_is_sorted_and_complete(oracle):
     vol = (scl.numpy().astype(np.float64) + 1e-8).prod(axis=1) * opa.numpy().astype(np.float64)
     key = vol[src]
     assert np.all(key[1:] <= key[:-1] * (1 + 1e-5))
+
+
+def test_tile_order_is_a_heaviest_first_permutation():
+    """pm_tile_scan's launch order: a permutation of the tiles, counts non-increasing up to the 1024-class quantisation."""
+    from prometheus_b200 import ops
+
+    gen = torch.Generator().manual_seed(2)
+    counts = (torch.rand(3, 20, 17, generator=gen) ** 3 * 9000).to(torch.int32).to(DEV)
+    off, stats, order = ops.tile_scan(counts, want_order=True)
+    o = order.cpu().numpy()
+    c = counts.reshape(-1).cpu().numpy()
+    assert np.array_equal(np.sort(o), np.arange(c.size))
+    shift = max(0, int(c.max()).bit_length() - 10)
+    cls = c[o] >> shift
+    assert np.all(np.diff(cls) <= 0)
+    assert int(stats[0]) == int(c.sum()) and int(stats[1]) == int(c.max())
