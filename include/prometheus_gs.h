@@ -291,7 +291,8 @@ PM_API int pm_composite_bwd(const float *means2d, const float *conics, const flo
                      float *v_opacities, float *v_depths, pm_stream_t stream);
 
 /* Backward of pm_tile_render_packed_fwd: cotangents of the packed outputs (any may be NULL) in,
- * the same accumulated per-Gaussian gradients out. masks / depth_out are the forward's outputs. */
+ * the same accumulated per-Gaussian gradients out. masks / depth_out are the forward's outputs.
+ * tile_order (may be NULL): launch order of the tiles, e.g. pm_tile_scan over the forward's sorted_counts. */
 PM_API int pm_composite_bwd_packed(const float *means2d, const float *conics, const float *opacities,
                      const float *colors, int colors_per_camera, const float *depths,
                      const float *backgrounds, const int32_t *isect_offsets,
@@ -300,7 +301,7 @@ PM_API int pm_composite_bwd_packed(const float *means2d, const float *conics, co
                      const float *masks, const float *depth_out, const int32_t *last_ids,
                      const float *v_images, const float *v_depth_out, const float *v_masks,
                      float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
-                     float *v_depths, pm_stream_t stream);
+                     float *v_depths, const int32_t *tile_order, pm_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
  * Trajectory rendering: pose sampling along a camera path and

@@ -48,7 +48,7 @@ SIGNATURES = {
     "pm_tile_render_fwd": (c_int, [_P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pm_tile_render_packed_fwd": (c_int, [_P, _P, _L, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pm_composite_bwd_packed": (c_int, [_P, _P, _P, _P, _I, _P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I,
-                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pm_splat_keys": (c_int, [_P, _P, _L, _I, _P, _P, _P]),
     "pm_splat_pack": (c_int, [_P, _P, _P, _P, _P, _P, _L, _I, _P, _P]),
     "pm_densify_stats": (c_int, [_P, _P, _I, _I, _P, _P, _P, _P, _P]),

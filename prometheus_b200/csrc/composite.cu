@@ -178,7 +178,8 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
                      float *__restrict__ v_conics, float *__restrict__ v_colors,
                      float *__restrict__ v_opacities, float *__restrict__ v_depths,
                      const float *__restrict__ v_images, const float *__restrict__ v_depth_out,
-                     const float *__restrict__ v_masks, const float *__restrict__ depth_out, int packed) {
+                     const float *__restrict__ v_masks, const float *__restrict__ depth_out, int packed,
+                     const int32_t *__restrict__ tile_order) {
   extern __shared__ __align__(16) unsigned char bwd_smem[];
   BwdShared &sh = *reinterpret_cast<BwdShared *>(bwd_smem);
   GaussA *sA = sh.sA; GaussB *sB = sh.sB; GaussC *sC = sh.sC;
@@ -191,8 +192,8 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = (int)(blockIdx.x % kBwdParts) * kBwdWarps + (tid >> 5);  // footprint index inside the tile
   const int n_tiles = tile_width * tile_height;
-  const int ct = blockIdx.x / kBwdParts;
   const int n_ct = gridDim.x / kBwdParts;
+  const int ct = tile_order ? tile_order[blockIdx.x / kBwdParts] : (int)(blockIdx.x / kBwdParts);  // longest lists first
   const int cam = ct / n_tiles, tile = ct % n_tiles;
   const int tile_y = tile / tile_width, tile_x = tile % tile_width;
   const int wx0 = tile_x * kTile + (warp & 1) * 8, wy0 = tile_y * kTile + (warp >> 1) * 4;
@@ -532,7 +533,7 @@ int pm_composite_bwd(const float *means2d, const float *conics, const float *opa
   pm::composite_bwd_kernel<<<(unsigned)(blocks * pm::kBwdParts), pm::kBwdThreads, sizeof(pm::BwdShared), pm::as_stream(stream)>>>(
       means2d, conics, opacities, colors, colors_per_camera, D, depths, backgrounds, isect_offsets,
       flatten_ids, n_isects, d_n, N, width, height, tw, th, alphas, last_ids, v_render, v_alphas,
-      v_means2d, v_conics, v_colors, v_opacities, v_depths, nullptr, nullptr, nullptr, nullptr, 0);
+      v_means2d, v_conics, v_colors, v_opacities, v_depths, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
   return pm::check_launch();
 }
 
@@ -543,7 +544,7 @@ int pm_composite_bwd_packed(const float *means2d, const float *conics, const flo
                             int width, int height, int tile_size, const float *masks, const float *depth_out,
                             const int32_t *last_ids, const float *v_images, const float *v_depth_out,
                             const float *v_masks, float *v_means2d, float *v_conics, float *v_colors,
-                            float *v_opacities, float *v_depths, pm_stream_t stream) {
+                            float *v_opacities, float *v_depths, const int32_t *tile_order, pm_stream_t stream) {
   const int rc = pm::check_common(means2d, conics, opacities, colors, 3, depths, isect_offsets, flatten_ids,
                                   n_isects, N, C, width, height, tile_size);
   if (rc != PM_OK) return rc;
@@ -557,7 +558,7 @@ int pm_composite_bwd_packed(const float *means2d, const float *conics, const flo
   pm::composite_bwd_kernel<<<(unsigned)(blocks * pm::kBwdParts), pm::kBwdThreads, sizeof(pm::BwdShared), pm::as_stream(stream)>>>(
       means2d, conics, opacities, colors, colors_per_camera, 3, depths, backgrounds, isect_offsets,
       flatten_ids, n_isects, d_n, N, width, height, tw, th, masks, last_ids, nullptr, nullptr,
-      v_means2d, v_conics, v_colors, v_opacities, v_depths, v_images, v_depth_out, v_masks, depth_out, 1);
+      v_means2d, v_conics, v_colors, v_opacities, v_depths, v_images, v_depth_out, v_masks, depth_out, 1, tile_order);
   return pm::check_launch();
 }
 

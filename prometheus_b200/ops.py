@@ -413,7 +413,7 @@ def tile_render_packed_fwd(records, offsets, means2d, conics, opacities, colors,
 
 @_instrument("composite_bwd", 1)
 def composite_bwd_packed(means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width, height,
-                         masks, depth_out, last_ids, v_images, v_depth_out, v_masks, d_n=None):
+                         masks, depth_out, last_ids, v_images, v_depth_out, v_masks, d_n=None, tile_order=None):
     L = _lib.load()
     C, N = means2d.shape[:2]
     colors, per_cam, D = _colors_layout(colors, C, N)
@@ -428,7 +428,7 @@ def composite_bwd_packed(means2d, conics, opacities, colors, depths, backgrounds
                                          flatten_ids.numel(), _ptr(d_n), N, C, width, height, TILE, _ptr(masks),
                                          _ptr(depth_out), _ptr(last_ids), _ptr(v_images), _ptr(v_depth_out),
                                          _ptr(v_masks), _ptr(v_means2d), _ptr(v_conics), _ptr(v_colors), _ptr(v_opac),
-                                         _ptr(v_depths), _stream()), "pm_composite_bwd_packed")
+                                         _ptr(v_depths), _ptr(tile_order), _stream()), "pm_composite_bwd_packed")
     return v_means2d, v_conics, v_colors, v_opac, v_depths
 
 

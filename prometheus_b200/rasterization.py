@@ -131,7 +131,7 @@ class _TileRenderPacked(torch.autograd.Function):
             records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height, d_n=stats,
             tile_order=tile_order)
         ctx.save_for_backward(means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, masks, depth_out,
-                              last_ids, stats)
+                              last_ids, stats, sorted_counts)
         ctx.dims = (width, height)
         ctx.mark_non_differentiable(flag, flat, sorted_counts)
         return images, depth_out, masks, flag, flat, sorted_counts
@@ -139,11 +139,13 @@ class _TileRenderPacked(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_images, v_depth_out, v_masks, _vf, _vflat, _vsc):
         (means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, masks, depth_out, last_ids,
-         stats) = ctx.saved_tensors
+         stats, sorted_counts) = ctx.saved_tensors
         width, height = ctx.dims
+        # the backward replays what the forward sorted: tiles with the longest sorted prefix go first
+        order = ops.tile_scan(sorted_counts, want_order=True)[2]
         v_means2d, v_conics, v_colors, v_opac, v_depths = ops.composite_bwd_packed(
             means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, width, height, masks, depth_out,
-            last_ids, v_images, v_depth_out, v_masks, d_n=stats)
+            last_ids, v_images, v_depth_out, v_masks, d_n=stats, tile_order=order)
         if ctx.grad_sink is not None:
             ctx.grad_sink["v_means2d"] = v_means2d
         v_bg = None
