@@ -100,7 +100,7 @@ bin_kernel(const float *__restrict__ means2d, const int32_t *__restrict__ radii,
       if (c > 0) {
         const int t = (wy0 + i / ww) * tile_width + wx0 + i % ww;
         const int b = atomicAdd(gl + t, c);
-        if (SCATTER) { win_base[i] = b; win[i] = 0; }
+        if (SCATTER) { win_base[i] = off[t] + b; win[i] = 0; }  // absolute slot of the CTA's first record in this tile
       }
     }
     if (!SCATTER) return;
@@ -108,8 +108,7 @@ bin_kernel(const float *__restrict__ means2d, const int32_t *__restrict__ radii,
     for (int y = y0; y < y1; ++y)
       for (int x = x0; x < x1; ++x) {
         const int cell = (y - wy0) * ww + (x - wx0);
-        const int pos = win_base[cell] + atomicAdd(&win[cell], 1);
-        const int64_t slot = (int64_t)off[y * tile_width + x] + pos;
+        const int64_t slot = (int64_t)win_base[cell] + atomicAdd(&win[cell], 1);
         if (slot < capacity) records[slot] = rec;
       }
     return;
