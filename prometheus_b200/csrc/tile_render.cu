@@ -38,7 +38,7 @@ constexpr int kTrCap = PM_TR_CAP;                                   // records p
 constexpr int kTrItems = (kTrCap + kTrThreads - 1) / kTrThreads;   // records per thread in the sort / staging loops
 constexpr int kTrRadix = 256;
 #ifndef PM_TR_MLP
-#define PM_TR_MLP 4
+#define PM_TR_MLP 8
 #endif
 #ifndef PM_TR_GATHER2
 #define PM_TR_GATHER2 0
