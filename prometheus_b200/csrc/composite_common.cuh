@@ -235,17 +235,22 @@ __device__ __forceinline__ bool cull_hit(const float4 &a, uint32_t aB_j, const L
     const float ax = fminf(fmaxf(0.0f, dx0), dx1), by = fminf(fmaxf(0.0f, dy0), dy1);
     if (ax != 0.0f || by != 0.0f) {
       const float4 b = lds128(aB_j);
-      float pmax = -3e38f;
+      // (slack = a relative bound on the rounding of the three products: strongly anisotropic conics cancel)
+      float pmax = -3e38f, slack = 0.0f;
       if (ax != 0.0f) {
         const float dy = fminf(fmaxf(-0.5f * b.y * ax * rcp_approx(b.z), dy0), dy1);
-        pmax = b.x * ax * ax + b.y * ax * dy + b.z * dy * dy;
+        const float t0 = b.x * ax * ax, t1 = b.y * ax * dy, t2 = b.z * dy * dy;
+        pmax = t0 + t1 + t2;
+        slack = fabsf(t0) + fabsf(t1) + fabsf(t2);
       }
       if (by != 0.0f) {
         const float dx = fminf(fmaxf(-0.5f * b.y * by * rcp_approx(b.x), dx0), dx1);
-        pmax = fmaxf(pmax, b.x * dx * dx + b.y * dx * by + b.z * by * by);
+        const float t0 = b.x * dx * dx, t1 = b.y * dx * by, t2 = b.z * by * by;
+        pmax = fmaxf(pmax, t0 + t1 + t2);
+        slack = fmaxf(slack, fabsf(t0) + fabsf(t1) + fabsf(t2));
       }
       const float tau2 = lg2_approx(255.0f * b.w);
-      hit = pmax >= -tau2 * 1.0005f - 2e-3f;
+      hit = pmax + 4e-6f * slack >= -tau2 * 1.0005f - 2e-3f;
     }
   }
 #endif
