@@ -208,6 +208,12 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     assert torch.cuda.is_available(), "bench.py (ours) needs a GPU: there is no CPU fallback"
+    if world > 1:
+        from prometheus_b200 import parallel as _par
+
+        numa_bound = _par.bind_to_gpu_numa(local_rank)  # pinned host buffers of each rank on the NUMA node of its GPU
+    else:
+        numa_bound = False
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -478,6 +484,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": workload_name(args.config, scene), "parallelism": "scene-sharded x%d" % world,
+                       "numa_bound": numa_bound,
                        "l2": "256 MiB buffer written between timed steps (L2 flush, outside the events)",
                        "checks": "intersection-capacity / sort-overflow checks deferred and validated after the timed "
                                  "loop (fwd) or after loss.backward() is queued (fwd+bwd); all passed"},

@@ -67,3 +67,26 @@ def render_sharded_views(render_fn: Callable[[torch.Tensor], Tuple[torch.Tensor,
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     s, e = shard_range(cameras.shape[0], world, rank)
     return (s, e), render_fn(cameras[s:e])
+
+
+def bind_to_gpu_numa(device_index: int) -> bool:
+    """Pin this process to the CPU cores NVML reports as local to `device_index` (one process per GPU). Pinned
+    host buffers allocated afterwards are first-touched on that NUMA node, so the host->device copies of the 8
+    ranks of a box do not all pull from one socket's memory. Best effort: returns False if NVML or the affinity
+    call is unavailable."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:  # noqa: BLE001
+        return False
