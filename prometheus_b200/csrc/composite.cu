@@ -125,44 +125,23 @@ __device__ __forceinline__ float butterfly_reduce10(const float (&v)[10], int la
   return d;
 }
 
-[[maybe_unused]] constexpr int kGradStride = 11;  // 10 gradient components per staged Gaussian (+1: bank spread)
-
 #ifndef PM_BWD_MINBLOCKS
 #define PM_BWD_MINBLOCKS 10
 #endif
 #ifndef PM_BWD_WARPS
 #define PM_BWD_WARPS 4
 #endif
-// A CTA replays kBwdWarps of the tile's eight 8x4-pixel warp footprints (8 = the whole tile, 4 = its upper or
-// lower half, ...): smaller CTAs wait for fewer partners at the per-round barrier and more of them fit an SM.
-#ifndef PM_BWD_GLOBAL_RED
-#define PM_BWD_GLOBAL_RED 1
-#endif
-#ifndef PM_BWD_AUTONOMOUS
-#define PM_BWD_AUTONOMOUS 1  // every warp stages its own 32-Gaussian chunks, no CTA barrier (needs GLOBAL_RED); 0: CTA-wide rounds
-#endif
+// A CTA holds kBwdWarps of the tile's eight 8x4-pixel warp footprints (4 = its upper or lower half). The warps of
+// a CTA share nothing but the launch: each has its own staging slots and there is no barrier.
 constexpr int kBwdWarps = PM_BWD_WARPS;
 constexpr int kBwdThreads = 32 * kBwdWarps;
 constexpr int kBwdParts = 8 / kBwdWarps;
-#ifndef PM_BWD_BATCH
-#define PM_BWD_BATCH 256
-#endif
-constexpr int kBwdBatch = PM_BWD_BATCH;  // Gaussians staged (records + gradient accumulators) per CTA round
-
-#if PM_BWD_AUTONOMOUS
 constexpr int kBwdStage = 32 * kBwdWarps;  // one private 32-Gaussian chunk per warp
-#else
-constexpr int kBwdStage = kBwdBatch;
-#endif
+
 struct BwdShared {
   GaussA sA[kBwdStage];
   GaussB sB[kBwdStage];
   GaussC sC[kBwdStage];
-  int32_t sF[kBwdStage];
-#if !PM_BWD_GLOBAL_RED
-  float sG[kBwdBatch * kGradStride];
-#endif
-  int s_max_last;
 };
 
 __global__ void __launch_bounds__(kBwdThreads, PM_BWD_MINBLOCKS)
@@ -183,11 +162,6 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
   extern __shared__ __align__(16) unsigned char bwd_smem[];
   BwdShared &sh = *reinterpret_cast<BwdShared *>(bwd_smem);
   GaussA *sA = sh.sA; GaussB *sB = sh.sB; GaussC *sC = sh.sC;
-  int32_t *sF = sh.sF;
-#if !PM_BWD_GLOBAL_RED
-  float *sG = sh.sG;
-#endif
-  int &s_max_last = sh.s_max_last;
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = (int)(blockIdx.x % kBwdParts) * kBwdWarps + (tid >> 5);  // footprint index inside the tile
@@ -255,7 +229,6 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
   }
   const float va_seed = T_final * (va - bg_dot);
   const int my_comp = comp_of_lane(lane);
-#if PM_BWD_GLOBAL_RED
   // where this lane's component goes: c0..c3 (colour, depth), q0..q2, mx, my, opacity
   float *red_base = nullptr;
   int red_mult = 0;
@@ -269,188 +242,73 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
     else { red_base = v_opacities; red_mult = 1; red_by_pair = false; }
   }
   const int my_comp_live = red_base ? my_comp : -1;
-#endif
-  const uint32_t aA = smem_u32(sA), aB = smem_u32(sB), aC = smem_u32(sC);
 
-#if PM_BWD_AUTONOMOUS
-  {
-    // Warp-autonomous replay: no CTA barrier anywhere. Each warp walks the prefix of the tile's list ITS pixels
-    // need, back to front, 32 Gaussians at a time: lane j gathers Gaussian j into the warp's private staging
-    // slots (the gathers of the warps of a tile hit L1/L2), then the warp culls and replays the chunk.
-    int wl = my_last;
+  // Warp-autonomous replay: no CTA barrier anywhere. Each warp walks the prefix of the tile's list ITS pixels
+  // need, back to front, 32 Gaussians at a time: lane j gathers Gaussian j into the warp's private staging
+  // slots (the gathers of the warps of a tile hit L1/L2), then the warp culls and replays the chunk.
+  int wl = my_last;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wl = max(wl, __shfl_xor_sync(0xffffffffu, wl, o));
-    if (wl < range_start) return;
-    const int w = tid >> 5;
-    GaussA *wA = sA + w * 32; GaussB *wB = sB + w * 32; GaussC *wC = sC + w * 32;
-    const uint32_t qA = smem_u32(wA), qB = smem_u32(wB), qC = smem_u32(wC);
-    const int n_w = min(range_end, wl + 1) - range_start;
-    float T = T_final;
-    float buf0 = 0.0f, buf1 = 0.0f, buf2 = 0.0f, buf3 = 0.0f;
-    for (int c0 = ((n_w - 1) / 32) * 32; c0 >= 0; c0 -= 32) {
-      const int cnt = min(32, n_w - c0);
-      const int chunk_start = range_start + c0;
-      int32_t f = 0;
-      __syncwarp();
-      if (lane < cnt) {
-        f = flatten_ids[chunk_start + lane];
-        gather(f, f - cam * N, means2d, conics, opacities, colors, colors_per_camera, D, depths, wA[lane], wB[lane], wC[lane]);
-      }
-      __syncwarp();
-      const unsigned live = __ballot_sync(0xffffffffu, my_last >= chunk_start);
-      const LiveRect rect = live_rect(live, wcx, wcy);
-      bool hit = false;
-      if (lane < cnt) hit = cull_hit(lds128(qA + lane * 16), qB + lane * 16, rect);
-      unsigned mask = __ballot_sync(0xffffffffu, hit);
-      while (mask) {
-        const int t = 31 - __clz(mask);
-        mask &= ~(1u << t);
-        const float2 m = lds64(qA + t * 16);
-        const float4 b = lds128(qB + t * 16);
-        const float dx = m.x - px, dy = m.y - py;
-        const float p = power2(b.x, b.y, b.z, dx, dy);
-        const float vis = ex2_approx(p);
-        const float alpha = fminf(0.999f, b.w * vis);
-        const bool valid = (chunk_start + t <= my_last) && !(p > 0.0f) && alpha >= kAlphaMin;
-        if (!__any_sync(0xffffffffu, valid)) continue;
-        float gv[10] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-        if (valid) {
-          const float4 c = lds128(qC + t * 16);
-          const float ra = rcp_approx(1.0f - alpha);
-          T *= ra;
-          const float fac = alpha * T;
-          gv[0] = fac * vr[0]; gv[1] = fac * vr[1]; gv[2] = fac * vr[2]; gv[3] = fac * vr[3];
-          float v_alpha = (c.x * T - buf0 * ra) * vr[0] + (c.y * T - buf1 * ra) * vr[1] +
-                          (c.z * T - buf2 * ra) * vr[2] + (c.w * T - buf3 * ra) * vr[3];
-          v_alpha += va_seed * ra;
-          if (b.w * vis <= 0.999f) {
-            const float v_sigma = -b.w * vis * v_alpha;
-            gv[4] = 0.5f * v_sigma * dx * dx;
-            gv[5] = v_sigma * dx * dy;
-            gv[6] = 0.5f * v_sigma * dy * dy;
-            const float s2 = v_sigma * (-1.0f / kLog2e);
-            gv[7] = s2 * (2.0f * b.x * dx + b.y * dy);
-            gv[8] = s2 * (b.y * dx + 2.0f * b.z * dy);
-            gv[9] = vis * v_alpha;
-          }
-          buf0 += c.x * fac; buf1 += c.y * fac; buf2 += c.z * fac; buf3 += c.w * fac;
-        }
-        const float total = butterfly_reduce10(gv, lane);
-        const int32_t ft = __shfl_sync(0xffffffffu, f, t);
-        if (my_comp_live >= 0 && total != 0.0f)
-          atomicAdd(red_base + (size_t)(red_by_pair ? ft : ft - cam * N) * red_mult, total);
-      }
-    }
-    return;
-  }
-#endif
-  if (tid == 0) s_max_last = -1;
-  __syncthreads();
-  int warp_last = my_last;  // last list position any pixel of this warp replays
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
-  if (lane == 0) atomicMax(&s_max_last, warp_last);
-  __syncthreads();
-  const int max_last = s_max_last;
-  if (max_last < range_start) return;  // (last_ids are 0 for untouched pixels; 0 >= range_start only in tile 0)
-
+  for (int o = 16; o > 0; o >>= 1) wl = max(wl, __shfl_xor_sync(0xffffffffu, wl, o));
+  if (wl < range_start) return;
+  const int w = tid >> 5;
+  GaussA *wA = sA + w * 32; GaussB *wB = sB + w * 32; GaussC *wC = sC + w * 32;
+  const uint32_t qA = smem_u32(wA), qB = smem_u32(wB), qC = smem_u32(wC);
+  const int n_w = min(range_end, wl + 1) - range_start;
   float T = T_final;
   float buf0 = 0.0f, buf1 = 0.0f, buf2 = 0.0f, buf3 = 0.0f;
-  // walk the needed prefix of the tile's list back to front in rounds of kBwdBatch staged Gaussians; inside a
-  // round the warps do not wait for each other (a per-256 barrier was 38 % of the stall samples, profiles/r1g_*)
-  const int n_needed = max_last - range_start + 1;
-  const int first_batch = (n_needed - 1) / kBwdBatch;
-  for (int bi = first_batch; bi >= 0; --bi) {
-    const int batch_start = range_start + bi * kBwdBatch;
-    const int batch_size = min(kBwdBatch, min(range_end, max_last + 1) - batch_start);
-    __syncthreads();  // previous batch fully flushed
-    for (int i = tid; i < batch_size; i += kBwdThreads) {
-      const int32_t f = flatten_ids[batch_start + i];
-      sF[i] = f;
-      gather(f, f - cam * N, means2d, conics, opacities, colors, colors_per_camera, D, depths, sA[i], sB[i], sC[i]);
+  for (int c0 = ((n_w - 1) / 32) * 32; c0 >= 0; c0 -= 32) {
+    const int cnt = min(32, n_w - c0);
+    const int chunk_start = range_start + c0;
+    int32_t f = 0;
+    __syncwarp();
+    if (lane < cnt) {
+      f = flatten_ids[chunk_start + lane];
+      gather(f, f - cam * N, means2d, conics, opacities, colors, colors_per_camera, D, depths, wA[lane], wB[lane], wC[lane]);
     }
-#if !PM_BWD_GLOBAL_RED
-    for (int i = tid; i < batch_size * kGradStride; i += kBwdThreads) sG[i] = 0.0f;
-#endif
-    __syncthreads();
-
-    // nothing at or after warp_last + 1 can be valid for this warp
-    const int warp_n = min(batch_size, warp_last - batch_start + 1);
-    for (int sub = warp_n > 0 ? ((warp_n - 1) / 32) * 32 : -32; sub >= 0; sub -= 32) {
-      // cull against the rectangle of the pixels that still replay something at or after this chunk
-      const unsigned live = __ballot_sync(0xffffffffu, my_last >= batch_start + sub);
-      if (live == 0u) continue;
-      const LiveRect rect = live_rect(live, wcx, wcy);
-      const int j = sub + lane;
-      bool hit = false;
-      if (j < warp_n) hit = cull_hit(lds128(aA + j * 16), aB + j * 16, rect);
-      unsigned mask = __ballot_sync(0xffffffffu, hit);
-      while (mask) {  // (a compacted hit queue as in composite_batch_fwd measured 2 % slower here)
-        const int bit = 31 - __clz(mask);
-        mask &= ~(1u << bit);
-        const int t = sub + bit;
-        const float2 m = lds64(aA + t * 16);
-        const float4 b = lds128(aB + t * 16);  // pre-scaled conic (see gather) + opacity
-        const float dx = m.x - px, dy = m.y - py;
-        const float p = power2(b.x, b.y, b.z, dx, dy);  // same expression as the forward: identical alpha bits
-        const float vis = ex2_approx(p);
-        const float alpha = fminf(0.999f, b.w * vis);
-        const bool valid = (batch_start + t <= my_last) && !(p > 0.0f) && alpha >= kAlphaMin;
-        if (!__any_sync(0xffffffffu, valid)) continue;
-        float gv[10] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};  // c0..c3, q0..q2, mx, my, o
-        if (valid) {
-          const float4 c = lds128(aC + t * 16);
-          const float ra = rcp_approx(1.0f - alpha);  // 1 - alpha >= 1e-3: MUFU.RCP (1 ulp) instead of the IEEE divide sequence
-          T *= ra;
-          const float fac = alpha * T;
-          gv[0] = fac * vr[0]; gv[1] = fac * vr[1]; gv[2] = fac * vr[2]; gv[3] = fac * vr[3];
-          float v_alpha = (c.x * T - buf0 * ra) * vr[0] + (c.y * T - buf1 * ra) * vr[1] +
-                          (c.z * T - buf2 * ra) * vr[2] + (c.w * T - buf3 * ra) * vr[3];
-          v_alpha += va_seed * ra;
-          if (b.w * vis <= 0.999f) {
-            const float v_sigma = -b.w * vis * v_alpha;
-            gv[4] = 0.5f * v_sigma * dx * dx;
-            gv[5] = v_sigma * dx * dy;
-            gv[6] = 0.5f * v_sigma * dy * dy;
-            // conic.x dx + conic.y dy etc. from the pre-scaled values: conic.x = -2/log2e * b.x, conic.y = -1/log2e * b.y
-            const float s2 = v_sigma * (-1.0f / kLog2e);
-            gv[7] = s2 * (2.0f * b.x * dx + b.y * dy);
-            gv[8] = s2 * (b.y * dx + 2.0f * b.z * dy);
-            gv[9] = vis * v_alpha;
-          }
-          buf0 += c.x * fac; buf1 += c.y * fac; buf2 += c.z * fac; buf3 += c.w * fac;
+    __syncwarp();
+    const unsigned live = __ballot_sync(0xffffffffu, my_last >= chunk_start);
+    const LiveRect rect = live_rect(live, wcx, wcy);
+    bool hit = false;
+    if (lane < cnt) hit = cull_hit(lds128(qA + lane * 16), qB + lane * 16, rect);
+    unsigned mask = __ballot_sync(0xffffffffu, hit);
+    while (mask) {
+      const int t = 31 - __clz(mask);
+      mask &= ~(1u << t);
+      const float2 m = lds64(qA + t * 16);
+      const float4 b = lds128(qB + t * 16);
+      const float dx = m.x - px, dy = m.y - py;
+      const float p = power2(b.x, b.y, b.z, dx, dy);
+      const float vis = ex2_approx(p);
+      const float alpha = fminf(0.999f, b.w * vis);
+      const bool valid = (chunk_start + t <= my_last) && !(p > 0.0f) && alpha >= kAlphaMin;
+      if (!__any_sync(0xffffffffu, valid)) continue;
+      float gv[10] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+      if (valid) {
+        const float4 c = lds128(qC + t * 16);
+        const float ra = rcp_approx(1.0f - alpha);
+        T *= ra;
+        const float fac = alpha * T;
+        gv[0] = fac * vr[0]; gv[1] = fac * vr[1]; gv[2] = fac * vr[2]; gv[3] = fac * vr[3];
+        float v_alpha = (c.x * T - buf0 * ra) * vr[0] + (c.y * T - buf1 * ra) * vr[1] +
+                        (c.z * T - buf2 * ra) * vr[2] + (c.w * T - buf3 * ra) * vr[3];
+        v_alpha += va_seed * ra;
+        if (b.w * vis <= 0.999f) {
+          const float v_sigma = -b.w * vis * v_alpha;
+          gv[4] = 0.5f * v_sigma * dx * dx;
+          gv[5] = v_sigma * dx * dy;
+          gv[6] = 0.5f * v_sigma * dy * dy;
+          const float s2 = v_sigma * (-1.0f / kLog2e);
+          gv[7] = s2 * (2.0f * b.x * dx + b.y * dy);
+          gv[8] = s2 * (b.y * dx + 2.0f * b.z * dy);
+          gv[9] = vis * v_alpha;
         }
-        const float total = butterfly_reduce10(gv, lane);
-#if PM_BWD_GLOBAL_RED
-        // one fire-and-forget global reduction per (warp, Gaussian, component)
-        if (my_comp_live >= 0 && total != 0.0f) {
-          const int32_t f = sF[t];
-          atomicAdd(red_base + (size_t)(red_by_pair ? f : f - cam * N) * red_mult, total);
-        }
-#else
-        if (my_comp >= 0) atomicAdd(&sG[t * kGradStride + my_comp], total);
-#endif
+        buf0 += c.x * fac; buf1 += c.y * fac; buf2 += c.z * fac; buf3 += c.w * fac;
       }
+      const float total = butterfly_reduce10(gv, lane);
+      const int32_t ft = __shfl_sync(0xffffffffu, f, t);
+      if (my_comp_live >= 0 && total != 0.0f)
+        atomicAdd(red_base + (size_t)(red_by_pair ? ft : ft - cam * N) * red_mult, total);
     }
-#if !PM_BWD_GLOBAL_RED
-    __syncthreads();
-    // flush: one global atomic per Gaussian-tile and component
-    for (int i = tid; i < batch_size; i += kBwdThreads) {
-      const float *gr = &sG[i * kGradStride];
-      const int32_t f = sF[i];
-      const int32_t g = f - cam * N;
-      float *vc = v_colors + (size_t)(colors_per_camera ? f : g) * D;
-      for (int k = 0; k < D; ++k)
-        if (gr[k] != 0.0f) atomicAdd(vc + k, gr[k]);
-      if (depths && gr[D] != 0.0f) atomicAdd(v_depths + f, gr[D]);
-      if (gr[4] != 0.0f) atomicAdd(v_conics + (size_t)f * 3 + 0, gr[4]);
-      if (gr[5] != 0.0f) atomicAdd(v_conics + (size_t)f * 3 + 1, gr[5]);
-      if (gr[6] != 0.0f) atomicAdd(v_conics + (size_t)f * 3 + 2, gr[6]);
-      if (gr[7] != 0.0f) atomicAdd(v_means2d + (size_t)f * 2 + 0, gr[7]);
-      if (gr[8] != 0.0f) atomicAdd(v_means2d + (size_t)f * 2 + 1, gr[8]);
-      if (gr[9] != 0.0f) atomicAdd(v_opacities + g, gr[9]);
-    }
-#endif
   }
 }
 

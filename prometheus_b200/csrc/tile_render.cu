@@ -8,8 +8,8 @@
 // tile. This kernel sorts only what the compositor consumes: one CTA per (camera, tile)
 //   1. reads the tile's unsorted {depth bits, flatten id} records (written by bin_scatter),
 //      finds the depth range and histograms the records into 256 depth-ordered sub-buckets;
-//   2. walks the sub-buckets front to back in groups of <= 1024 records: collect the group into
-//      shared memory, radix-sort it there by (depth bits, flatten id), write the sorted flatten ids
+//   2. walks the sub-buckets front to back in groups of <= 768 records: collect the group into shared memory in
+//      bucket order, rank each bucket's short run by (depth bits, flatten id), write the sorted flatten ids
 //      to their final positions (the backward pass replays them), stage the WHOLE group's Gaussian
 //      records (mean/extent, conic/opacity, colour: 48 B each, over the sort buffers) and let the 8
 //      warps composite it with no CTA barrier in between — each warp runs at its own pace through
@@ -38,10 +38,7 @@ constexpr int kTrCap = PM_TR_CAP;                                   // records p
 constexpr int kTrItems = (kTrCap + kTrThreads - 1) / kTrThreads;   // records per thread in the sort / staging loops
 constexpr int kTrRadix = 256;
 #ifndef PM_TR_MLP
-#define PM_TR_MLP 8
-#endif
-#ifndef PM_TR_GATHER2
-#define PM_TR_GATHER2 0
+#define PM_TR_MLP 8  // record loads in flight per thread in the passes over a tile's segment
 #endif
 constexpr int kTrMlp = PM_TR_MLP;
 constexpr int kTrRankMax = 128;  // longest bucket run ordered by all-pairs ranking (longer: radix sort of the group)
@@ -49,7 +46,7 @@ constexpr int kTrRankMax = 128;  // longest bucket run ordered by all-pairs rank
 // depth sub-bucket of a key: monotone in the key for any kmin / shift
 __device__ __forceinline__ int tr_bucket(uint32_t k, uint32_t kmin, int shift) {
   return k <= kmin ? 0 : (int)min((k - kmin) >> shift, 255u);
-}  // record loads in flight per thread in the passes over a tile's segment
+}
 
 __device__ __forceinline__ unsigned tr_match_digit8(uint32_t d) {
   unsigned peers = 0xffffffffu;
