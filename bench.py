@@ -381,7 +381,18 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom) if args.config == "C2" else None
     except Exception:  # noqa: BLE001
         pass
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+    # the kernel's real ceiling is instruction issue: warp instructions of the committed ncu capture /
+    # (live launch time x 148 SMs x 4 schedulers x sampled SM clock)
+    issue = None
+    try:
+        wi = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("_warp_instructions", {}).get(dom)
+        if wi and args.config == "C2" and clocks.get("sm_mhz"):
+            peak_issue = 148 * 4 * clocks["sm_mhz"] * 1e6
+            issue = {"warp_instructions": wi, "peak_warp_inst_per_s": peak_issue,
+                     "frac": round(wi / (dom_ms * 1e-3) / peak_issue, 4), "source": "ncu smsp__inst_executed.sum (profiles/)"}
+    except Exception:  # noqa: BLE001
+        pass
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "issue": issue,
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "avg_launch_ms": round(dom_ms, 4),
                 "alg_bytes_per_launch": int(dom_bytes),
