@@ -910,3 +910,46 @@ def test_tile_order_is_a_heaviest_first_permutation():
     cls = c[o] >> shift
     assert np.all(np.diff(cls) <= 0)
     assert int(stats[0]) == int(c.sum()) and int(stats[1]) == int(c.max())
+
+
+# --------------------------------------------------------------------------- edge cases of the module fast path
+def test_fast_path_nothing_visible_renders_background():
+    """All Gaussians behind the cameras: zero intersections, images = 2 * background - 1, masks = 0, depth = 0."""
+    from prometheus_b200 import GaussianRenderer
+
+    n = 500
+    g = torch.Generator().manual_seed(1)
+    xyz = torch.randn(1, n, 3, generator=g)
+    xyz[..., 2] = 5.0  # OpenGL cameras look down -z: +z is behind them
+    gauss = (xyz, torch.rand(1, n, 1, 3, generator=g), torch.rand(1, n, 1, generator=g), torch.full((1, n, 3), 0.05),
+             torch.tensor([1.0, 0, 0, 0]).repeat(1, n, 1))
+    cams = torch.zeros(1, 2, 18)
+    cams[..., :12] = torch.eye(4)[:3].reshape(-1)
+    cams[..., 12:] = torch.tensor([60.0, 60.0, 35.0, 25.0, 50.0, 70.0])
+    rend = GaussianRenderer(background=[0.2, 0.5, 0.9]).to(DEV)
+    for _ in range(2):  # second call goes through the speculative-capacity path with a zero count
+        images, depths, masks, _, _ = rend(cams.to(DEV), tuple(t.to(DEV) for t in gauss), h=50, w=70)
+    want = 2 * torch.tensor([0.2, 0.5, 0.9], device=DEV).view(1, 1, 3, 1, 1) - 1
+    assert images.shape == (1, 2, 3, 50, 70) and torch.allclose(images, want.expand_as(images), atol=1e-7)
+    assert float(masks.abs().max()) == 0.0 and float(depths.abs().max()) == 0.0
+    assert all(int((r > 0).sum()) == 0 for r in rend.radii)
+
+
+@pytest.mark.parametrize("C,h,w", [(1, 50, 70), (33, 37, 41)])
+def test_fast_path_odd_sizes_and_many_cameras(C, h, w):
+    """Image sizes that are not multiples of 16 and more cameras than one projection launch handles (32):
+    fused packed path == separate stages, bit for bit."""
+    from prometheus_b200 import GaussianConverter, GaussianRenderer, scenes
+
+    sc = scenes.make_scene("C1", seed=51, views_in=2, size_in=40, views_out=C, size_out=64)
+    conv = GaussianConverter("mvsplat", z_near=0.01, z_far=100.0, s_min=0.001, s_max=1.0).to(DEV)
+    outs = []
+    with torch.no_grad():
+        g = conv(sc.params.to(DEV), sc.cameras_in.to(DEV))
+        for fused in (True, False):
+            rend = GaussianRenderer().to(DEV)
+            rend.fused, rend.view_chunk = fused, 40
+            outs.append(rend(sc.cameras_out.to(DEV), g, bg_color=(0.3, 0.1, 0.7), h=h, w=w)[:3] + (torch.stack(rend.radii),))
+    for a, b in zip(*outs):
+        assert a.shape == b.shape and torch.equal(a, b)
+    assert outs[0][0].shape == (1, C, 3, h, w) and float(outs[0][2].mean()) > 0.05
