@@ -116,10 +116,14 @@ PM_API int pm_project_fwd(const float *means, const float *quats, const float *s
 
 /* pm_project_fwd + pm_bin_count in one pass: additionally ACCUMULATES the per-(camera, tile)
  * intersection histogram into tile_counts [C, tile_height, tile_width] int32 (caller zero-fills)
- * while each pair's tile AABB is still in registers. Same outputs, bit for bit, as the two calls. */
+ * while each pair's tile AABB is still in registers. Same outputs, bit for bit, as the two calls.
+ * SCENE BATCHING (this and the other fast-path entry points): views_per_scene = V > 0 with C = S * V renders
+ * S independent scenes in one launch set — means / quats / scales (and opacities / colours downstream) hold S
+ * blocks of N Gaussians, camera c sees only block c / V; pair arrays stay [C, N]. Needs N % 256 == 0 when
+ * S > 1. views_per_scene = 0 means one scene (V = C). */
 PM_API int pm_project_count_fwd(const float *means, const float *quats, const float *scales,
                    const float *viewmats, const float *Ks,
-                   int N, int C, int width, int height, int tile_size,
+                   int N, int C, int views_per_scene, int width, int height, int tile_size,
                    float eps2d, float near_plane, float far_plane, float radius_clip,
                    int32_t *radii, float *means2d, float *depths, float *conics,
                    int32_t *tiles_per_gauss, int32_t *tile_counts, pm_stream_t stream);
@@ -129,7 +133,7 @@ PM_API int pm_project_count_fwd(const float *means, const float *quats, const fl
  * cameras, fully overwritten. viewmats/Ks carry no gradient on this path. */
 PM_API int pm_project_bwd(const float *means, const float *quats, const float *scales,
                    const float *viewmats, const float *Ks,
-                   int N, int C, int width, int height, float eps2d,
+                   int N, int C, int views_per_scene, int width, int height, float eps2d,
                    const int32_t *radii, const float *conics,
                    const float *v_means2d, const float *v_depths, const float *v_conics,
                    float *v_means, float *v_quats, float *v_scales, pm_stream_t stream);
@@ -273,7 +277,7 @@ PM_API int pm_tile_render_packed_fwd(const uint64_t *records, const int32_t *ise
                               int width, int height, int tile_size,
                               float *images, float *depth_out, float *masks, int32_t *last_ids,
                               int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
-                              const int32_t *tile_order, pm_stream_t stream);
+                              const int32_t *tile_order, int views_per_scene, pm_stream_t stream);
 
 /* Backward. v_render [C,H,W,CD], v_alphas [C,H,W] (either may be NULL).
  * Gradients are ACCUMULATED (+=) into v_means2d [C,N,2], v_conics [C,N,3],
@@ -301,7 +305,7 @@ PM_API int pm_composite_bwd_packed(const float *means2d, const float *conics, co
                      const float *masks, const float *depth_out, const int32_t *last_ids,
                      const float *v_images, const float *v_depth_out, const float *v_masks,
                      float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
-                     float *v_depths, const int32_t *tile_order, pm_stream_t stream);
+                     float *v_depths, const int32_t *tile_order, int views_per_scene, pm_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
  * Trajectory rendering: pose sampling along a camera path and

@@ -31,13 +31,13 @@ SIGNATURES = {
     "pm_unproject_bwd": (c_int, [_P, _P, _P, _I, _F, _F, _F, _F, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "pm_camera_prep": (c_int, [_P, _I, _I, _I, _P, _P, _P]),
     "pm_project_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P]),
-    "pm_project_count_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
+    "pm_project_count_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
     "pm_bin_count": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "pm_tile_scan": (c_int, [_P, _L, _P, _P, _P, _P]),
     "pm_bin_scatter": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _L, _P]),
     "pm_tile_sort_capacity": (c_int, []),
     "pm_tile_sort": (c_int, [_P, _P, _P, _L, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
-    "pm_project_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pm_project_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pm_scan_workspace_bytes": (c_size_t, [_L]),
     "pm_scan_tiles": (c_int, [_P, _L, _P, _P, _P, _S, _P]),
     "pm_bin_emit": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _L, _P]),
@@ -46,9 +46,9 @@ SIGNATURES = {
     "pm_tile_offsets": (c_int, [_P, _L, _P, _I, _I, _I, _P, _P]),
     "pm_composite_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "pm_tile_render_fwd": (c_int, [_P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "pm_tile_render_packed_fwd": (c_int, [_P, _P, _L, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pm_tile_render_packed_fwd": (c_int, [_P, _P, _L, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "pm_composite_bwd_packed": (c_int, [_P, _P, _P, _P, _I, _P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I,
-                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "pm_splat_keys": (c_int, [_P, _P, _L, _I, _P, _P, _P]),
     "pm_splat_pack": (c_int, [_P, _P, _P, _P, _P, _P, _L, _I, _P, _P]),
     "pm_densify_stats": (c_int, [_P, _P, _I, _I, _P, _P, _P, _P, _P]),

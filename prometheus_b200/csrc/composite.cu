@@ -158,7 +158,7 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
                      float *__restrict__ v_opacities, float *__restrict__ v_depths,
                      const float *__restrict__ v_images, const float *__restrict__ v_depth_out,
                      const float *__restrict__ v_masks, const float *__restrict__ depth_out, int packed,
-                     const int32_t *__restrict__ tile_order) {
+                     const int32_t *__restrict__ tile_order, int views_per_scene) {
   extern __shared__ __align__(16) unsigned char bwd_smem[];
   BwdShared &sh = *reinterpret_cast<BwdShared *>(bwd_smem);
   GaussA *sA = sh.sA; GaussB *sB = sh.sB; GaussC *sC = sh.sC;
@@ -176,6 +176,8 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
   const float wcx = (float)wx0 + 4.0f, wcy = (float)wy0 + 2.0f;
   const bool inside = ix < width && iy < height;
   const int CD = D + (depths ? 1 : 0);
+  // flatten id f = cam * N + g; per-Gaussian arrays hold one block of N per scene (scene = cam / views_per_scene)
+  const int g_base = cam * N - (cam / views_per_scene) * N;
 
   const int64_t n_isects = effective_n(n_host, d_n);
   const int range_start = offsets[ct];
@@ -263,7 +265,7 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
     __syncwarp();
     if (lane < cnt) {
       f = flatten_ids[chunk_start + lane];
-      gather(f, f - cam * N, means2d, conics, opacities, colors, colors_per_camera, D, depths, wA[lane], wB[lane], wC[lane]);
+      gather(f, f - g_base, means2d, conics, opacities, colors, colors_per_camera, D, depths, wA[lane], wB[lane], wC[lane]);
     }
     __syncwarp();
     const unsigned live = __ballot_sync(0xffffffffu, my_last >= chunk_start);
@@ -307,7 +309,7 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
       const float total = butterfly_reduce10(gv, lane);
       const int32_t ft = __shfl_sync(0xffffffffu, f, t);
       if (my_comp_live >= 0 && total != 0.0f)
-        atomicAdd(red_base + (size_t)(red_by_pair ? ft : ft - cam * N) * red_mult, total);
+        atomicAdd(red_base + (size_t)(red_by_pair ? ft : ft - g_base) * red_mult, total);
     }
   }
 }
@@ -391,7 +393,7 @@ int pm_composite_bwd(const float *means2d, const float *conics, const float *opa
   pm::composite_bwd_kernel<<<(unsigned)(blocks * pm::kBwdParts), pm::kBwdThreads, sizeof(pm::BwdShared), pm::as_stream(stream)>>>(
       means2d, conics, opacities, colors, colors_per_camera, D, depths, backgrounds, isect_offsets,
       flatten_ids, n_isects, d_n, N, width, height, tw, th, alphas, last_ids, v_render, v_alphas,
-      v_means2d, v_conics, v_colors, v_opacities, v_depths, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
+      v_means2d, v_conics, v_colors, v_opacities, v_depths, nullptr, nullptr, nullptr, nullptr, 0, nullptr, C);
   return pm::check_launch();
 }
 
@@ -402,7 +404,8 @@ int pm_composite_bwd_packed(const float *means2d, const float *conics, const flo
                             int width, int height, int tile_size, const float *masks, const float *depth_out,
                             const int32_t *last_ids, const float *v_images, const float *v_depth_out,
                             const float *v_masks, float *v_means2d, float *v_conics, float *v_colors,
-                            float *v_opacities, float *v_depths, const int32_t *tile_order, pm_stream_t stream) {
+                            float *v_opacities, float *v_depths, const int32_t *tile_order, int views_per_scene,
+                            pm_stream_t stream) {
   const int rc = pm::check_common(means2d, conics, opacities, colors, 3, depths, isect_offsets, flatten_ids,
                                   n_isects, N, C, width, height, tile_size);
   if (rc != PM_OK) return rc;
@@ -416,7 +419,8 @@ int pm_composite_bwd_packed(const float *means2d, const float *conics, const flo
   pm::composite_bwd_kernel<<<(unsigned)(blocks * pm::kBwdParts), pm::kBwdThreads, sizeof(pm::BwdShared), pm::as_stream(stream)>>>(
       means2d, conics, opacities, colors, colors_per_camera, 3, depths, backgrounds, isect_offsets,
       flatten_ids, n_isects, d_n, N, width, height, tw, th, masks, last_ids, nullptr, nullptr,
-      v_means2d, v_conics, v_colors, v_opacities, v_depths, v_images, v_depth_out, v_masks, depth_out, 1, tile_order);
+      v_means2d, v_conics, v_colors, v_opacities, v_depths, v_images, v_depth_out, v_masks, depth_out, 1, tile_order,
+      views_per_scene > 0 ? views_per_scene : C);
   return pm::check_launch();
 }
 

@@ -81,33 +81,40 @@ template <bool COUNT>
 __global__ void __launch_bounds__(256)
 project_fwd_kernel(const float *__restrict__ means, const float *__restrict__ quats,
                    const float *__restrict__ scales, const float *__restrict__ viewmats,
-                   const float *__restrict__ Ks, int N, int cam0, int n_cams, int chunk_stride, int width, int height,
+                   const float *__restrict__ Ks, int N, int views_per_scene, int cam0, int n_cams, int chunk_stride,
+                   int width, int height,
                    int tile_width, int tile_height, float eps2d, float near_plane, float far_plane,
                    float radius_clip, int32_t *__restrict__ radii, float *__restrict__ means2d,
                    float *__restrict__ depths, float *__restrict__ conics,
                    int32_t *__restrict__ tiles_per_gauss, int32_t *__restrict__ tile_counts) {
   __shared__ ProjCamS s_cam[kProjCamChunk];
   __shared__ TileCountSmem s_cnt[1];  // (unused and optimised away when !COUNT)
+  // strided CTA order (see binning_common.cuh): concurrently resident CTAs touch far-apart tiles
+  const int chunk = (int)(((int64_t)blockIdx.x * chunk_stride) % gridDim.x);
+  // scene batching: the Gaussian arrays hold S scenes of N Gaussians, camera c belongs to scene c / views_per_scene
+  // and sees only that scene. With S > 1 the launcher guarantees N % 256 == 0, so a CTA never straddles two scenes.
+  const int chunks_per_scene = (N + 255) / 256;
+  const int scene = chunk / chunks_per_scene;
+  const int g = (chunk - scene * chunks_per_scene) * blockDim.x + threadIdx.x;  // Gaussian index inside the scene
+  const bool in_range = g < N;
+  const size_t gg = (size_t)scene * N + (in_range ? g : 0);                     // index into the Gaussian arrays
+  const int cam_first = scene * views_per_scene + cam0;                         // first camera of this launch, absolute
   for (int i = threadIdx.x; i < n_cams; i += blockDim.x) {
     ProjCamS pc;
-    pc.c = load_proj_cam(viewmats + (size_t)(cam0 + i) * 16, Ks + (size_t)(cam0 + i) * 9);
+    pc.c = load_proj_cam(viewmats + (size_t)(cam_first + i) * 16, Ks + (size_t)(cam_first + i) * 9);
     pc.lims = proj_lims(pc.c, width, height);
     s_cam[i] = pc;
   }
   __syncthreads();
-  // strided CTA order (see binning_common.cuh): concurrently resident CTAs touch far-apart tiles
-  const int chunk = (int)(((int64_t)blockIdx.x * chunk_stride) % gridDim.x);
-  const int g = chunk * blockDim.x + threadIdx.x;
-  const bool in_range = g < N;
 
   float mx = 0.0f, my = 0.0f, mz = 0.0f;
   float S[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) S[i] = 0.0f;
   if (in_range) {
-    mx = means[(size_t)g * 3 + 0]; my = means[(size_t)g * 3 + 1]; mz = means[(size_t)g * 3 + 2];
-    const float4 q = reinterpret_cast<const float4 *>(quats)[g];
-    const float s0 = scales[(size_t)g * 3 + 0], s1 = scales[(size_t)g * 3 + 1], s2 = scales[(size_t)g * 3 + 2];
+    mx = means[gg * 3 + 0]; my = means[gg * 3 + 1]; mz = means[gg * 3 + 2];
+    const float4 q = reinterpret_cast<const float4 *>(quats)[gg];
+    const float s0 = scales[gg * 3 + 0], s1 = scales[gg * 3 + 1], s2 = scales[gg * 3 + 2];
     float Rq[9], M[9];
     quat_to_rotmat(q.x, q.y, q.z, q.w, Rq);
 #pragma unroll
@@ -128,7 +135,7 @@ project_fwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
   for (int ci = 0; ci < n_cams; ++ci) {
     const ProjCam &c = s_cam[ci].c;
     const float *R = c.R;
-    const size_t f = (size_t)(cam0 + ci) * N + (in_range ? g : 0);
+    const size_t f = (size_t)(cam_first + ci) * N + (in_range ? g : 0);
     int radius_i = 0;
     float m2x = 0.0f, m2y = 0.0f, depth = 0.0f, q0 = 0.0f, q1 = 0.0f, q2 = 0.0f;
     do {
@@ -196,7 +203,7 @@ project_fwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
       if (tiles_per_gauss != nullptr) tiles_per_gauss[f] = (x1 - x0) * (y1 - y0);
     }
     if (COUNT)
-      cta_tile_count(s_cnt[0], x0, x1, y0, y1, tile_counts + (size_t)(cam0 + ci) * tile_width * tile_height, tile_width);
+      cta_tile_count(s_cnt[0], x0, x1, y0, y1, tile_counts + (size_t)(cam_first + ci) * tile_width * tile_height, tile_width);
   }
 }
 
@@ -205,7 +212,8 @@ project_fwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
 extern "C" {
 
 static int project_fwd_launch(const float *means, const float *quats, const float *scales, const float *viewmats,
-                              const float *Ks, int N, int C, int width, int height, int tile_size, float eps2d,
+                              const float *Ks, int N, int C, int views_per_scene, int width, int height, int tile_size,
+                              float eps2d,
                               float near_plane, float far_plane, float radius_clip, int32_t *radii, float *means2d,
                               float *depths, float *conics, int32_t *tiles_per_gauss, int32_t *tile_counts,
                               pm_stream_t stream) {
@@ -217,18 +225,22 @@ static int project_fwd_launch(const float *means, const float *quats, const floa
     return PM_ERR_BAD_ARG;
   if (C > 65535 || (int64_t)N * C >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
   if (N == 0 || C == 0) return PM_OK;
+  const int Nv = views_per_scene > 0 ? views_per_scene : C;
+  if (C % Nv != 0) return PM_ERR_BAD_ARG;
+  const int n_scenes = C / Nv;
+  if (n_scenes > 1 && N % 256 != 0) return PM_ERR_UNSUPPORTED;  // a 256-Gaussian CTA must not straddle two scenes
   const int tw = (width + pm::kTile - 1) / pm::kTile, th = (height + pm::kTile - 1) / pm::kTile;
-  const int nb = (N + 255) / 256;
+  const int nb = n_scenes * ((N + 255) / 256);
   const int stride = pm::coprime_stride(nb);
-  for (int cam0 = 0; cam0 < C; cam0 += pm::kProjCamChunk) {
-    const int n_cams = C - cam0 < pm::kProjCamChunk ? C - cam0 : pm::kProjCamChunk;
+  for (int cam0 = 0; cam0 < Nv; cam0 += pm::kProjCamChunk) {
+    const int n_cams = Nv - cam0 < pm::kProjCamChunk ? Nv - cam0 : pm::kProjCamChunk;
     if (tile_counts)
       pm::project_fwd_kernel<true><<<nb, 256, 0, pm::as_stream(stream)>>>(
-          means, quats, scales, viewmats, Ks, N, cam0, n_cams, stride, width, height, tw, th, eps2d, near_plane,
+          means, quats, scales, viewmats, Ks, N, Nv, cam0, n_cams, stride, width, height, tw, th, eps2d, near_plane,
           far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, tile_counts);
     else
       pm::project_fwd_kernel<false><<<nb, 256, 0, pm::as_stream(stream)>>>(
-          means, quats, scales, viewmats, Ks, N, cam0, n_cams, stride, width, height, tw, th, eps2d, near_plane,
+          means, quats, scales, viewmats, Ks, N, Nv, cam0, n_cams, stride, width, height, tw, th, eps2d, near_plane,
           far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, nullptr);
   }
   return pm::check_launch();
@@ -238,17 +250,17 @@ int pm_project_fwd(const float *means, const float *quats, const float *scales, 
                    const float *Ks, int N, int C, int width, int height, int tile_size, float eps2d,
                    float near_plane, float far_plane, float radius_clip, int32_t *radii, float *means2d,
                    float *depths, float *conics, int32_t *tiles_per_gauss, pm_stream_t stream) {
-  return project_fwd_launch(means, quats, scales, viewmats, Ks, N, C, width, height, tile_size, eps2d, near_plane,
+  return project_fwd_launch(means, quats, scales, viewmats, Ks, N, C, C, width, height, tile_size, eps2d, near_plane,
                             far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, nullptr, stream);
 }
 
 int pm_project_count_fwd(const float *means, const float *quats, const float *scales, const float *viewmats,
-                         const float *Ks, int N, int C, int width, int height, int tile_size, float eps2d,
+                         const float *Ks, int N, int C, int views_per_scene, int width, int height, int tile_size, float eps2d,
                          float near_plane, float far_plane, float radius_clip, int32_t *radii, float *means2d,
                          float *depths, float *conics, int32_t *tiles_per_gauss, int32_t *tile_counts,
                          pm_stream_t stream) {
   if (!tile_counts) return PM_ERR_BAD_ARG;
-  return project_fwd_launch(means, quats, scales, viewmats, Ks, N, C, width, height, tile_size, eps2d, near_plane,
+  return project_fwd_launch(means, quats, scales, viewmats, Ks, N, C, views_per_scene, width, height, tile_size, eps2d, near_plane,
                             far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, tile_counts,
                             stream);
 }

@@ -56,7 +56,7 @@ __device__ __forceinline__ void quat_to_rotmat_d(double w, double x, double y, d
 __global__ void __launch_bounds__(128)
 project_bwd_kernel(const float *__restrict__ means, const float *__restrict__ quats,
                    const float *__restrict__ scales, const float *__restrict__ viewmats,
-                   const float *__restrict__ Ks, int N, int C, int width, int height,
+                   const float *__restrict__ Ks, int N, int C, int views_per_scene, int width, int height,
                    const int32_t *__restrict__ radii, const float *__restrict__ conics,
                    const float *__restrict__ v_means2d, const float *__restrict__ v_depths,
                    const float *__restrict__ v_conics, float *__restrict__ v_means,
@@ -79,12 +79,16 @@ project_bwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
     s_cam[c] = bc;
   }
   __syncthreads();
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= N) return;
-  const double mx = means[(size_t)g * 3 + 0], my = means[(size_t)g * 3 + 1], mz = means[(size_t)g * 3 + 2];
-  const float4 q4 = reinterpret_cast<const float4 *>(quats)[g];
+  // scene batching (see project.cu): thread gg owns Gaussian g of scene gg / N and loops over that scene's cameras
+  const int64_t gg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_scenes = C > 0 ? C / views_per_scene : 1;
+  if (gg >= (int64_t)N * n_scenes) return;
+  const int scene = (int)(gg / N);
+  const int g = (int)(gg - (int64_t)scene * N);
+  const double mx = means[(size_t)gg * 3 + 0], my = means[(size_t)gg * 3 + 1], mz = means[(size_t)gg * 3 + 2];
+  const float4 q4 = reinterpret_cast<const float4 *>(quats)[gg];
   const double4 q = make_double4(q4.x, q4.y, q4.z, q4.w);
-  const double sc[3] = {scales[(size_t)g * 3 + 0], scales[(size_t)g * 3 + 1], scales[(size_t)g * 3 + 2]};
+  const double sc[3] = {scales[(size_t)gg * 3 + 0], scales[(size_t)gg * 3 + 1], scales[(size_t)gg * 3 + 2]};
   double Rq[9], M[9], S[9];
   quat_to_rotmat_d(q.x, q.y, q.z, q.w, Rq);
 #pragma unroll
@@ -100,7 +104,7 @@ project_bwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
   double vmean[3] = {0, 0, 0};
   double vS[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // d loss / d Sigma (world), summed over cameras
 
-  for (int cid = 0; cid < C; ++cid) {
+  for (int cid = scene * views_per_scene; cid < min(C, (scene + 1) * views_per_scene); ++cid) {
     const size_t f = (size_t)cid * N + g;
     // every input of this (camera, Gaussian) pair is requested up front: one memory latency per camera
     const int radius = __ldg(radii + f);
@@ -216,7 +220,7 @@ project_bwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
     for (int j = 0; j < 3; ++j) vR[i * 3 + j] = vM[i * 3 + j] * sc[j];
 #pragma unroll
   for (int j = 0; j < 3; ++j)
-    v_scales[(size_t)g * 3 + j] = (float)(Rq[0 * 3 + j] * vM[0 * 3 + j] + Rq[1 * 3 + j] * vM[1 * 3 + j] + Rq[2 * 3 + j] * vM[2 * 3 + j]);
+    v_scales[(size_t)gg * 3 + j] = (float)(Rq[0 * 3 + j] * vM[0 * 3 + j] + Rq[1 * 3 + j] * vM[1 * 3 + j] + Rq[2 * 3 + j] * vM[2 * 3 + j]);
 
   const double inv = 1.0 / sqrt(((q.y * q.y + q.z * q.z) + q.w * q.w) + q.x * q.x);
   const double w = q.x * inv, xq = q.y * inv, yq = q.z * inv, zq = q.w * inv;
@@ -226,11 +230,11 @@ project_bwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
   vq[2] = 2.0 * (-2.0 * yq * vR[0] + xq * vR[1] + w * vR[2] + xq * vR[3] + zq * vR[5] - w * vR[6] + zq * vR[7] - 2.0 * yq * vR[8]);
   vq[3] = 2.0 * (-2.0 * zq * vR[0] - w * vR[1] + xq * vR[2] + w * vR[3] - 2.0 * zq * vR[4] + yq * vR[5] + xq * vR[6] + yq * vR[7]);
   const double dotp = vq[0] * w + vq[1] * xq + vq[2] * yq + vq[3] * zq;
-  reinterpret_cast<float4 *>(v_quats)[g] =
+  reinterpret_cast<float4 *>(v_quats)[gg] =
       make_float4((float)((vq[0] - dotp * w) * inv), (float)((vq[1] - dotp * xq) * inv), (float)((vq[2] - dotp * yq) * inv), (float)((vq[3] - dotp * zq) * inv));
-  v_means[(size_t)g * 3 + 0] = (float)vmean[0];
-  v_means[(size_t)g * 3 + 1] = (float)vmean[1];
-  v_means[(size_t)g * 3 + 2] = (float)vmean[2];
+  v_means[(size_t)gg * 3 + 0] = (float)vmean[0];
+  v_means[(size_t)gg * 3 + 1] = (float)vmean[1];
+  v_means[(size_t)gg * 3 + 2] = (float)vmean[2];
 }
 
 }  // namespace pm
@@ -238,7 +242,7 @@ project_bwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
 extern "C" {
 
 int pm_project_bwd(const float *means, const float *quats, const float *scales, const float *viewmats,
-                   const float *Ks, int N, int C, int width, int height, float eps2d,
+                   const float *Ks, int N, int C, int views_per_scene, int width, int height, float eps2d,
                    const int32_t *radii, const float *conics, const float *v_means2d,
                    const float *v_depths, const float *v_conics, float *v_means, float *v_quats,
                    float *v_scales, pm_stream_t stream) {
@@ -251,6 +255,9 @@ int pm_project_bwd(const float *means, const float *quats, const float *scales, 
   if ((int64_t)N * C >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
   if (N == 0) return PM_OK;
   if (C > pm::kBwdMaxCams) return PM_ERR_RANGE;
+  const int Nv = views_per_scene > 0 ? views_per_scene : (C > 0 ? C : 1);
+  if (C % Nv != 0) return PM_ERR_BAD_ARG;
+  const int64_t total = (int64_t)N * (C > 0 ? C / Nv : 1);
   const size_t cam_bytes = sizeof(pm::BwdCam) * (size_t)(C > 0 ? C : 1);
   if (cam_bytes > 48 * 1024) {
     static bool attr_set = false;
@@ -263,8 +270,8 @@ int pm_project_bwd(const float *means, const float *quats, const float *scales, 
       attr_set = true;
     }
   }
-  pm::project_bwd_kernel<<<(N + 127) / 128, 128, cam_bytes, pm::as_stream(stream)>>>(
-      means, quats, scales, viewmats, Ks, N, C, width, height, radii, conics, v_means2d, v_depths,
+  pm::project_bwd_kernel<<<(unsigned)((total + 127) / 128), 128, cam_bytes, pm::as_stream(stream)>>>(
+      means, quats, scales, viewmats, Ks, N, C, Nv, width, height, radii, conics, v_means2d, v_depths,
       v_conics, v_means, v_quats, v_scales);
   return pm::check_launch();
 }

@@ -208,7 +208,7 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
                        int32_t *__restrict__ flatten_ids, int32_t *__restrict__ sorted_counts,
                        int32_t *__restrict__ overflow_flag, float *__restrict__ images,
                        float *__restrict__ depth_out, float *__restrict__ masks,
-                       const int32_t *__restrict__ tile_order) {
+                       const int32_t *__restrict__ tile_order, int views_per_scene) {
   extern __shared__ __align__(16) unsigned char tr_smem[];
   TrShared &sh = *reinterpret_cast<TrShared *>(tr_smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -220,7 +220,8 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
   const int ix = wx0 + (lane & 7), iy = wy0 + (lane >> 3);
   const bool inside = ix < width && iy < height;
   const int CD = D + (depths ? 1 : 0);
-  const int cam_base = cam * N;
+  // flatten id f = cam * N + g; the per-Gaussian arrays hold one block of N per scene (scene = cam / views_per_scene)
+  const int cam_base = cam * N - (cam / views_per_scene) * N;
   const WarpFootprint fp{(float)ix + 0.5f, (float)iy + 0.5f, (float)wx0 + 4.0f, (float)wy0 + 2.0f};
   PixelState st{inside ? 1.0f : -1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0};
   const uint32_t aS = smem_u32(&sh.stg), aQ = smem_u32(sh.queue[warp]);
@@ -472,7 +473,7 @@ static int tile_render_launch(const uint64_t *records, const int32_t *isect_offs
                               const float *backgrounds, int N, int C, int width, int height, int tile_size,
                               float *render, float *alphas, int32_t *last_ids, int32_t *flatten_ids,
                               int32_t *sorted_counts, int32_t *overflow_flag, float *images, float *depth_out,
-                              float *masks, const int32_t *tile_order, pm_stream_t stream) {
+                              float *masks, const int32_t *tile_order, int views_per_scene, pm_stream_t stream) {
   if (N < 0 || C < 0 || width <= 0 || height <= 0 || n_isects < 0 || D < 0) return PM_ERR_BAD_ARG;
   if (tile_size != pm::kTile) return PM_ERR_UNSUPPORTED;
   const int CD = D + (depths ? 1 : 0);
@@ -491,6 +492,7 @@ static int tile_render_launch(const uint64_t *records, const int32_t *isect_offs
   if ((reinterpret_cast<uintptr_t>(means2d) & 7) != 0) return PM_ERR_BAD_ARG;
   if (n_isects >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
   if (C == 0) return PM_OK;
+  if (views_per_scene > 0 && C % views_per_scene != 0) return PM_ERR_BAD_ARG;
   const int tw = (width + pm::kTile - 1) / pm::kTile, th = (height + pm::kTile - 1) / pm::kTile;
   const int64_t blocks = (int64_t)C * tw * th;
   if (blocks >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
@@ -506,7 +508,7 @@ static int tile_render_launch(const uint64_t *records, const int32_t *isect_offs
   pm::tile_render_fwd_kernel<<<(unsigned)blocks, pm::kTrThreads, pm::kTrSmemBytes, pm::as_stream(stream)>>>(
       records, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera, D, depths,
       backgrounds, N, width, height, tw, th, render, alphas, last_ids, flatten_ids, sorted_counts, overflow_flag,
-      images, depth_out, masks, tile_order);
+      images, depth_out, masks, tile_order, views_per_scene > 0 ? views_per_scene : C);
   return pm::check_launch();
 }
 
@@ -531,7 +533,7 @@ int pm_tile_render_fwd(const uint64_t *records, const int32_t *isect_offsets, in
                        const int32_t *tile_order, pm_stream_t stream) {
   return tile_render_launch(records, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera,
                             D, depths, backgrounds, N, C, width, height, tile_size, render, alphas, last_ids,
-                            flatten_ids, sorted_counts, overflow_flag, nullptr, nullptr, nullptr, tile_order, stream);
+                            flatten_ids, sorted_counts, overflow_flag, nullptr, nullptr, nullptr, tile_order, 0, stream);
 }
 
 int pm_tile_render_packed_fwd(const uint64_t *records, const int32_t *isect_offsets, int64_t n_isects,
@@ -540,11 +542,11 @@ int pm_tile_render_packed_fwd(const uint64_t *records, const int32_t *isect_offs
                               const float *depths, const float *backgrounds, int N, int C, int width, int height,
                               int tile_size, float *images, float *depth_out, float *masks, int32_t *last_ids,
                               int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
-                              const int32_t *tile_order, pm_stream_t stream) {
+                              const int32_t *tile_order, int views_per_scene, pm_stream_t stream) {
   if (!images) return PM_ERR_BAD_ARG;
   return tile_render_launch(records, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera,
                             3, depths, backgrounds, N, C, width, height, tile_size, nullptr, nullptr, last_ids,
-                            flatten_ids, sorted_counts, overflow_flag, images, depth_out, masks, tile_order, stream);
+                            flatten_ids, sorted_counts, overflow_flag, images, depth_out, masks, tile_order, views_per_scene, stream);
 }
 
 }  // extern "C"

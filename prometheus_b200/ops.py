@@ -137,13 +137,18 @@ def camera_prep(cameras, h: int, w: int):
 # ------------------------------------------------------------------ stage 2
 @_instrument("project_fwd", lambda means, quats, scales, viewmats, *a, **k: (viewmats.shape[0] + 31) // 32)
 def project_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d=0.3, near_plane=0.01,
-                far_plane=1e10, radius_clip=0.0, count_tiles=True, tile_histogram=False):
+                far_plane=1e10, radius_clip=0.0, count_tiles=True, tile_histogram=False, views_per_scene=0):
     """-> radii, means2d, depths, conics, tiles_per_gauss (None unless count_tiles)
-    [, tile_counts [C,th,tw] int32 when tile_histogram: the fused pm_bin_count]."""
+    [, tile_counts [C,th,tw] int32 when tile_histogram: the fused pm_bin_count].
+    views_per_scene = V > 0 (tile_histogram only): scene batching — means / quats / scales hold C / V blocks of
+    N Gaussians and camera c sees block c / V; the pair outputs are [C, N]."""
     L = _lib.load()
     means, quats, scales = (_req(t, torch.float32, n) for t, n in ((means, "means"), (quats, "quats"), (scales, "scales")))
     viewmats, Ks = _req(viewmats, torch.float32, "viewmats"), _req(Ks, torch.float32, "Ks")
-    N, C = means.shape[0], viewmats.shape[0]
+    C = viewmats.shape[0]
+    n_scenes = C // views_per_scene if views_per_scene else 1
+    assert means.shape[0] % n_scenes == 0 and (not views_per_scene or tile_histogram)
+    N = means.shape[0] // n_scenes
     dev = means.device
     radii = torch.empty(C, N, dtype=torch.int32, device=dev)
     means2d = torch.empty(C, N, 2, device=dev)
@@ -153,8 +158,8 @@ def project_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d=0.3, ne
     if tile_histogram:
         tw, th = tile_grid(width, height)
         counts = torch.zeros(C, th, tw, dtype=torch.int32, device=dev)
-        _lib.check(L.pm_project_count_fwd(_ptr(means), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks), N, C, width,
-                                          height, TILE, eps2d, near_plane, far_plane, radius_clip, _ptr(radii),
+        _lib.check(L.pm_project_count_fwd(_ptr(means), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks), N, C,
+                                          int(views_per_scene), width, height, TILE, eps2d, near_plane, far_plane, radius_clip, _ptr(radii),
                                           _ptr(means2d), _ptr(depths), _ptr(conics), _ptr(tpg), _ptr(counts), _stream()),
                    "pm_project_count_fwd")
         return radii, means2d, depths, conics, tpg, counts
@@ -167,15 +172,16 @@ def project_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d=0.3, ne
 
 @_instrument("project_bwd", 1)
 def project_bwd(means, quats, scales, viewmats, Ks, width, height, radii, conics, v_means2d, v_depths,
-                v_conics, eps2d=0.3):
+                v_conics, eps2d=0.3, views_per_scene=0):
     L = _lib.load()
     means, quats, scales = (_req(t, torch.float32, "in") for t in (means, quats, scales))
     viewmats, Ks = _req(viewmats, torch.float32, "viewmats"), _req(Ks, torch.float32, "Ks")
-    N, C = means.shape[0], viewmats.shape[0]
+    C = viewmats.shape[0]
+    N = means.shape[0] // (C // views_per_scene if views_per_scene else 1)
     v_means2d, v_depths, v_conics = (_opt(t, torch.float32, "grad") for t in (v_means2d, v_depths, v_conics))
     v_means, v_quats, v_scales = torch.empty_like(means), torch.empty_like(quats), torch.empty_like(scales)
-    _lib.check(L.pm_project_bwd(_ptr(means), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks), N, C, width,
-                                height, eps2d, _ptr(radii), _ptr(conics), _ptr(v_means2d), _ptr(v_depths),
+    _lib.check(L.pm_project_bwd(_ptr(means), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks), N, C,
+                                int(views_per_scene), width, height, eps2d, _ptr(radii), _ptr(conics), _ptr(v_means2d), _ptr(v_depths),
                                 _ptr(v_conics), _ptr(v_means), _ptr(v_quats), _ptr(v_scales), _stream()),
                "pm_project_bwd")
     return v_means, v_quats, v_scales
@@ -384,15 +390,16 @@ def composite_bwd(means2d, conics, opacities, colors, depths, backgrounds, offse
 # ------------------------------------------------------------------ module fast path (packed outputs)
 @_instrument("tile_render_fwd", 1)
 def tile_render_packed_fwd(records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height,
-                           d_n=None, tile_order=None):
+                           d_n=None, tile_order=None, views_per_scene=0):
     """Fused sort-as-you-go forward with the module epilogue: -> images [C,3,H,W] (2 rgb - 1),
     depth_out [C,1,H,W] (expected depth), masks [C,1,H,W], last_ids [C,H,W], flatten_ids (sorted prefix per
     tile), sorted_counts [C,th,tw], overflow flag int32[1]. `records` may be a speculative capacity with the
     true count in d_n[0] (see pm_tile_render_packed_fwd)."""
     L = _lib.load()
     C, N = means2d.shape[:2]
-    colors, per_cam, D = _colors_layout(colors, C, N)
-    assert D == 3 and depths is not None
+    n_scenes = C // views_per_scene if views_per_scene else 1
+    colors, per_cam, D = _colors_layout(colors, C, N * n_scenes)
+    assert D == 3 and depths is not None and opacities.numel() == N * n_scenes
     dev = means2d.device
     n = records.numel()
     images = torch.empty(C, 3, height, width, device=dev)
@@ -406,17 +413,18 @@ def tile_render_packed_fwd(records, offsets, means2d, conics, opacities, colors,
                                            _ptr(opacities), _ptr(colors), per_cam, _ptr(depths), _ptr(backgrounds), N, C,
                                            width, height, TILE, _ptr(images), _ptr(depth_out), _ptr(masks),
                                            _ptr(last_ids), _ptr(flat), _ptr(sorted_counts), _ptr(flag), _ptr(tile_order),
-                                           _stream()),
+                                           int(views_per_scene), _stream()),
                "pm_tile_render_packed_fwd")
     return images, depth_out, masks, last_ids, flat, sorted_counts, flag
 
 
 @_instrument("composite_bwd", 1)
 def composite_bwd_packed(means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width, height,
-                         masks, depth_out, last_ids, v_images, v_depth_out, v_masks, d_n=None, tile_order=None):
+                         masks, depth_out, last_ids, v_images, v_depth_out, v_masks, d_n=None, tile_order=None,
+                         views_per_scene=0):
     L = _lib.load()
     C, N = means2d.shape[:2]
-    colors, per_cam, D = _colors_layout(colors, C, N)
+    colors, per_cam, D = _colors_layout(colors, C, N * (C // views_per_scene if views_per_scene else 1))
     v_images, v_depth_out, v_masks = (_opt(t, torch.float32, "grad") for t in (v_images, v_depth_out, v_masks))
     v_means2d = torch.zeros_like(means2d)
     v_conics = torch.zeros_like(conics)
@@ -428,7 +436,8 @@ def composite_bwd_packed(means2d, conics, opacities, colors, depths, backgrounds
                                          flatten_ids.numel(), _ptr(d_n), N, C, width, height, TILE, _ptr(masks),
                                          _ptr(depth_out), _ptr(last_ids), _ptr(v_images), _ptr(v_depth_out),
                                          _ptr(v_masks), _ptr(v_means2d), _ptr(v_conics), _ptr(v_colors), _ptr(v_opac),
-                                         _ptr(v_depths), _ptr(tile_order), _stream()), "pm_composite_bwd_packed")
+                                         _ptr(v_depths), _ptr(tile_order), int(views_per_scene), _stream()),
+               "pm_composite_bwd_packed")
     return v_means2d, v_conics, v_colors, v_opac, v_depths
 
 

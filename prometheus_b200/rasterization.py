@@ -31,10 +31,12 @@ FORCE_GENERIC_SORT = False
 class _Project(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
-                radius_clip, fused_count=False):
+                radius_clip, fused_count=False, views_per_scene=0):
         """fused_count (module fast path): skip tiles_per_gauss, return the per-tile histogram instead."""
         out = ops.project_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
-                              radius_clip, count_tiles=not fused_count, tile_histogram=fused_count)
+                              radius_clip, count_tiles=not fused_count, tile_histogram=fused_count,
+                              views_per_scene=views_per_scene)
+        ctx.views_per_scene = views_per_scene
         radii, means2d, depths, conics, tpg = out[:5]
         aux = out[5] if fused_count else tpg
         ctx.save_for_backward(means, quats, scales, viewmats, Ks, radii, conics)
@@ -47,8 +49,9 @@ class _Project(torch.autograd.Function):
         means, quats, scales, viewmats, Ks, radii, conics = ctx.saved_tensors
         width, height, eps2d = ctx.dims
         v_means, v_quats, v_scales = ops.project_bwd(means, quats, scales, viewmats, Ks, width, height, radii,
-                                                     conics, v_means2d, v_depths, v_conics, eps2d)
-        return (v_means, v_quats, v_scales) + (None,) * 9
+                                                     conics, v_means2d, v_depths, v_conics, eps2d,
+                                                     views_per_scene=ctx.views_per_scene)
+        return (v_means, v_quats, v_scales) + (None,) * 10
 
 
 class _Composite(torch.autograd.Function):
@@ -122,14 +125,15 @@ class _TileRenderPacked(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means2d, conics, opacities, colors, depths, backgrounds, records, offsets, stats, width, height,
-                grad_sink=None, tile_order=None):
+                grad_sink=None, tile_order=None, views_per_scene=0):
+        ctx.views_per_scene = views_per_scene
         ctx.grad_sink = grad_sink  # dict that receives the contiguous [C,N,2] means2d gradient (densification statistics)
         means2d, conics = means2d.contiguous(), conics.contiguous()
         opacities, colors, depths = opacities.contiguous(), colors.contiguous(), depths.contiguous()
         backgrounds = None if backgrounds is None else backgrounds.contiguous().float()
         images, depth_out, masks, last_ids, flat, sorted_counts, flag = ops.tile_render_packed_fwd(
             records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height, d_n=stats,
-            tile_order=tile_order)
+            tile_order=tile_order, views_per_scene=views_per_scene)
         ctx.save_for_backward(means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, masks, depth_out,
                               last_ids, stats, sorted_counts)
         ctx.dims = (width, height)
@@ -145,31 +149,34 @@ class _TileRenderPacked(torch.autograd.Function):
         order = ops.tile_scan(sorted_counts, want_order=True)[2]
         v_means2d, v_conics, v_colors, v_opac, v_depths = ops.composite_bwd_packed(
             means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, width, height, masks, depth_out,
-            last_ids, v_images, v_depth_out, v_masks, d_n=stats, tile_order=order)
+            last_ids, v_images, v_depth_out, v_masks, d_n=stats, tile_order=order, views_per_scene=ctx.views_per_scene)
         if ctx.grad_sink is not None:
             ctx.grad_sink["v_means2d"] = v_means2d
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[5] and v_images is not None:
             v_bg = (2.0 * v_images * (1.0 - masks)).sum(dim=(2, 3))
-        return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None, None, None, None
+        return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None, None, None, None, None
 
 
 def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, backgrounds, width, height,
-                        capacity=None, near_plane=0.01, far_plane=1e10, radius_clip=0.0, eps2d=0.3):
+                        capacity=None, near_plane=0.01, far_plane=1e10, radius_clip=0.0, eps2d=0.3, views_per_scene=0):
     """Fast path behind GaussianRenderer: all C views of one scene, RGB + expected depth, outputs already in the
     module's layout. -> images [C,3,H,W] in [-1,1], depths [C,1,H,W], masks [C,1,H,W], info.
 
     `capacity` = speculative size of the intersection buffers. None: read the exact count from the device
     (one host sync between the tile scan and the scatter, as gsplat does). An int: no host sync at all — the
     count stays on the device (info["stats"] = {n_isects, max tile count}); the caller must check
-    n_isects <= capacity afterwards and re-render otherwise (GaussianRenderer does)."""
-    N, C = means.shape[0], viewmats.shape[0]
+    n_isects <= capacity afterwards and re-render otherwise (GaussianRenderer does).
+
+    `views_per_scene` = V > 0: SCENE BATCHING — the Gaussian tensors hold C / V scenes back to back (N Gaussians
+    each, N % 256 == 0) and camera c renders scene c / V: one launch set for a whole training batch."""
+    C = viewmats.shape[0]
     if not means.is_cuda:
         raise RuntimeError("prometheus_b200 needs CUDA tensors: there is no CPU fallback")
     f32 = lambda t: (t if t.dtype == torch.float32 else t.float()).contiguous()
     means, quats, scales, opacities, colors, viewmats, Ks = map(f32, (means, quats, scales, opacities, colors, viewmats, Ks))
     means2d, depths, conics, radii, counts = _Project.apply(means, quats, scales, viewmats, Ks, width, height, eps2d,
-                                                             near_plane, far_plane, radius_clip, True)
+                                                             near_plane, far_plane, radius_clip, True, views_per_scene)
     means2d_views = [v.unsqueeze(0) for v in means2d.unbind(0)]
     means2d_in = means2d
     if means2d.requires_grad:
@@ -183,7 +190,7 @@ def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, b
     grad_sink = {}
     images, depth_out, masks, flag, flatten_ids, sorted_counts = _TileRenderPacked.apply(
         means2d_in, conics, opacities, colors, depths, backgrounds, records, isect_offsets, stats, width, height, grad_sink,
-        tile_order)
+        tile_order, views_per_scene)
     info = {"radii": radii, "means2d": means2d, "means2d_views": means2d_views, "depths": depths, "conics": conics,
             "isect_offsets": isect_offsets, "flatten_ids": flatten_ids, "sorted_counts": sorted_counts,
             "stats": stats, "overflow_flag": flag, "capacity": int(capacity), "means2d_grad_sink": grad_sink}

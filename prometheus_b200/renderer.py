@@ -87,6 +87,9 @@ class GaussianRenderer(nn.Module):
     # torch.cuda.synchronize(), :510). True: forward() never blocks; call validate() before trusting the images
     # (DecodeRenderPipeline does, when it hands the host copies out).
     defer_checks = False
+    # several scenes per forward (a training batch): render them in ONE launch set when every scene's views fit a
+    # chunk and the per-scene Gaussian count is a multiple of 256 (always, for pixel-aligned maps)
+    scene_batch = True
 
     def __init__(self, sh_degree=0, background=[1, 1, 1]):
         super().__init__()
@@ -155,6 +158,42 @@ class GaussianRenderer(nn.Module):
         forward() with defer_checks = False)."""
         return self.check_jobs(self.take_pending())
 
+    def _job_for(self, args, out, info, key):
+        """Queue the device-side counts of a fused render for the later check: {n_isects, max tile count, overflow
+        flag} travel to pinned memory behind the render kernel."""
+        stats_host = torch.empty(3, dtype=torch.int32, pin_memory=True)
+        stats_host[:2].copy_(info["stats"], non_blocking=True)
+        stats_host[2:].copy_(info["overflow_flag"], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return dict(args=args, out=out, info=info, key=key, stats_host=stats_host, event=ev, capacity=info["capacity"])
+
+    def _forward_batched(self, viewmats, Ks, gaussians, scaling_modifier, bg_color, h, w):
+        """All B scenes of a training batch in ONE launch set (scene batching, `views_per_scene`): the B x N cameras
+        become one camera list, camera c sees the Gaussians of scene c // N. Returns None if the deferred-free
+        check fails (the caller then renders scene by scene)."""
+        B, N = viewmats.shape[:2]
+        xyz, features, opacity, scales, rotations = gaussians
+        G = xyz.shape[1]
+        sc = scales if scaling_modifier == 1.0 else scales * scaling_modifier
+        args = (xyz.reshape(B * G, 3), rotations.reshape(B * G, 4), sc.reshape(B * G, 3), opacity.reshape(B * G),
+                features[:, :, 0].reshape(B * G, 3), viewmats.reshape(B * N, 4, 4), Ks.reshape(B * N, 3, 3),
+                self._backgrounds(bg_color, B * N, xyz.device))
+        key = (G, B * N, int(h), int(w), B)
+        cap = self._cap_hint.get(key) if self.speculative_capacity else None
+        im, de, ma, info = render_views_packed(*args, int(w), int(h), capacity=cap, views_per_scene=N)
+        job = self._job_for(args, (im, de, ma), info, key)
+        if self.defer_checks:
+            self._pending.append(dict(key=key, capacity=job["capacity"], stats_host=job["stats_host"], event=job["event"]))
+        elif not self._check(job):
+            return None
+        self._stat_sources = [(info["radii"], info.get("means2d_grad_sink"), info["means2d_views"])]
+        self._stat_scenes = B
+        for j in range(B * N):
+            self.radii.append(info["radii"][j])
+            self.viewspace_points.append(info["means2d_views"][j])
+        return (im.reshape(B, N, 3, h, w), de.reshape(B, N, 1, h, w), ma.reshape(B, N, 1, h, w), None, None)
+
     def forward(self, cameras, gaussians, scaling_modifier=1.0, bg_color=None, h=256, w=256):
         B, N = cameras.shape[:2]
         xyz, features, opacity, scales, rotations = gaussians
@@ -163,6 +202,11 @@ class GaussianRenderer(nn.Module):
         self.viewspace_points = []
         viewmats, Ks = ops.camera_prep(cameras.reshape(B * N, 18), h, w)
         viewmats, Ks = viewmats.reshape(B, N, 4, 4), Ks.reshape(B, N, 3, 3)
+        if self.fused and self.scene_batch and B > 1 and N <= self.view_chunk and xyz.shape[1] % 256 == 0:
+            out = self._forward_batched(viewmats, Ks, gaussians, scaling_modifier, bg_color, h, w)
+            if out is not None:
+                return out
+            self.radii, self.viewspace_points = [], []  # a check failed: scene by scene below (exact sizes, fallbacks)
         jobs = []
         for i in range(B):
             bgs = self._backgrounds(bg_color, N, device)
@@ -173,13 +217,7 @@ class GaussianRenderer(nn.Module):
                         Ks[i, c0:c1], bgs[c0:c1])
                 if self.fused:
                     im, de, ma, info, key = self._render_chunk_fused(args, h, w)
-                    stats_host = torch.empty(3, dtype=torch.int32, pin_memory=True)  # n_isects, max tile count, overflow
-                    stats_host[:2].copy_(info["stats"], non_blocking=True)
-                    stats_host[2:].copy_(info["overflow_flag"], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record()
-                    jobs.append(dict(args=args, out=(im, de, ma), info=info, key=key, stats_host=stats_host, event=ev,
-                                     capacity=info["capacity"]))
+                    jobs.append(self._job_for(args, (im, de, ma), info, key))
                 else:
                     im, de, ma, info = self._render_chunk_unfused(*args, h, w)
                     jobs.append(dict(args=args, out=(im, de, ma), info=info, key=None))

@@ -953,3 +953,27 @@ def test_fast_path_odd_sizes_and_many_cameras(C, h, w):
     for a, b in zip(*outs):
         assert a.shape == b.shape and torch.equal(a, b)
     assert outs[0][0].shape == (1, C, 3, h, w) and float(outs[0][2].mean()) > 0.05
+
+
+def test_scene_batched_forward_backward_equals_per_scene():
+    """B scenes in one launch set (views_per_scene) vs the scene-by-scene loop: images / depths / masks / radii bit
+    for bit, parameter gradients to summation order; 'random' backgrounds draw B*N colours either way."""
+    from prometheus_b200 import GaussianConverter, GaussianRenderer, scenes
+
+    sc = scenes.make_scene("C1", seed=61, views_in=4, size_in=32, views_out=3, size_out=56, scenes=3)   # G = 4096 per scene
+    conv = GaussianConverter("mvsplat", z_near=0.01, z_far=100.0, s_min=0.001, s_max=1.0).to(DEV)
+    outs = []
+    for batched in (True, False):
+        rend = GaussianRenderer().to(DEV)
+        rend.scene_batch = batched
+        params = sc.params.to(DEV).requires_grad_(True)
+        images, depths, masks, _, _ = rend(sc.cameras_out.to(DEV), conv(params, sc.cameras_in.to(DEV)), bg_color=(0.2, 0.4, 0.9), h=56, w=56)
+        (scenes.render_loss(images, depths, masks, torch.zeros_like(images)) * images.numel()).backward()
+        outs.append((images.detach(), depths.detach(), masks.detach(), torch.stack(rend.radii), params.grad.clone(),
+                     torch.cat([v.grad for v in rend.viewspace_points])))
+    a, b = outs
+    assert a[0].shape == (3, 3, 3, 56, 56)
+    for x, y in zip(a[:4], b[:4]):
+        assert torch.equal(x, y)
+    assert grad_close(a[4].cpu().numpy(), b[4].cpu().numpy(), atol=1e-5, rtol=1e-4)
+    assert grad_close(a[5].cpu().numpy(), b[5].cpu().numpy(), atol=1e-5, rtol=1e-4)
