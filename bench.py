@@ -227,8 +227,13 @@ def main():
             dist.destroy_process_group()
         return
 
-    # every rank owns one scene of the named config (scene sharding; seeds differ per rank)
-    scene = scenes.make_scene(args.config, seed=1234 + 1000 * rank)
+    # every rank owns one scene of the named config (scene sharding; seeds differ per rank). C4 (text-to-3D batch of
+    # 64 scenes) is split over the ranks instead: 64 / N scenes each, a fixed total => strong scaling.
+    if args.config == "C4":
+        assert 64 % world == 0
+        scene = scenes.make_scene("C4", seed=1234 + 1000 * rank, scenes=64 // world)
+    else:
+        scene = scenes.make_scene(args.config, seed=1234 + 1000 * rank)
     S = scene.size_out
     B, V_out = scene.cameras_out.shape[:2]
     pixels = B * V_out * S * S
@@ -492,7 +497,8 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.config == "C4" else "weak",
+            "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": workload_name(args.config, scene), "parallelism": "scene-sharded x%d" % world,
                        "numa_bound": numa_bound,

@@ -90,6 +90,7 @@ class GaussianRenderer(nn.Module):
     # several scenes per forward (a training batch): render them in ONE launch set when every scene's views fit a
     # chunk and the per-scene Gaussian count is a multiple of 256 (always, for pixel-aligned maps)
     scene_batch = True
+    scene_chunk = 8  # scenes per launch set
 
     def __init__(self, sh_degree=0, background=[1, 1, 1]):
         super().__init__()
@@ -203,9 +204,20 @@ class GaussianRenderer(nn.Module):
         viewmats, Ks = ops.camera_prep(cameras.reshape(B * N, 18), h, w)
         viewmats, Ks = viewmats.reshape(B, N, 4, 4), Ks.reshape(B, N, 3, 3)
         if self.fused and self.scene_batch and B > 1 and N <= self.view_chunk and xyz.shape[1] % 256 == 0:
-            out = self._forward_batched(viewmats, Ks, gaussians, scaling_modifier, bg_color, h, w)
-            if out is not None:
-                return out
+            outs, sources = [], []
+            for b0 in range(0, B, self.scene_chunk):  # bounded per-pair / per-intersection buffers for big batches
+                b1 = min(B, b0 + self.scene_chunk)
+                out = self._forward_batched(viewmats[b0:b1], Ks[b0:b1], tuple(t[b0:b1] for t in gaussians),
+                                            scaling_modifier, bg_color, h, w)
+                if out is None:
+                    break
+                outs.append(out)
+                sources.extend(self._stat_sources)
+            if len(outs) * self.scene_chunk >= B:
+                self._stat_sources, self._stat_scenes = sources, B
+                if len(outs) == 1:
+                    return outs[0]
+                return tuple(torch.cat([o[k] for o in outs], 0) for k in range(3)) + (None, None)
             self.radii, self.viewspace_points = [], []  # a check failed: scene by scene below (exact sizes, fallbacks)
         jobs = []
         for i in range(B):
