@@ -10,7 +10,7 @@ import torch  # noqa: E402
 from prometheus_b200 import DecodeRenderPipeline, GaussianConverter, GaussianRenderer, scenes  # noqa: E402
 
 dev = torch.device("cuda", 0)
-sc = scenes.make_scene("C2")
+sc = scenes.make_scene(sys.argv[1] if len(sys.argv) > 1 else "C2")
 S = sc.size_out
 conv = GaussianConverter("mvsplat", z_near=scenes.Z_NEAR, z_far=scenes.Z_FAR, s_min=scenes.S_MIN, s_max=scenes.S_MAX).to(dev)
 rend = GaussianRenderer(background=[1, 1, 1]).to(dev)
