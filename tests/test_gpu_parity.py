@@ -977,3 +977,27 @@ def test_scene_batched_forward_backward_equals_per_scene():
         assert torch.equal(x, y)
     assert grad_close(a[4].cpu().numpy(), b[4].cpu().numpy(), atol=1e-5, rtol=1e-4)
     assert grad_close(a[5].cpu().numpy(), b[5].cpu().numpy(), atol=1e-5, rtol=1e-4)
+
+
+def test_scene_batched_bad_hint_falls_back_to_per_scene():
+    """A too-small speculative capacity on the scene-batched launch set is caught and the batch re-rendered scene by
+    scene: same images as the unbatched renderer."""
+    from prometheus_b200 import GaussianConverter, GaussianRenderer, scenes
+
+    sc = scenes.make_scene("C1", seed=62, views_in=4, size_in=32, views_out=2, size_out=48, scenes=2)
+    conv = GaussianConverter("mvsplat", z_near=0.01, z_far=100.0, s_min=0.001, s_max=1.0).to(DEV)
+    with torch.no_grad():
+        g = conv(sc.params.to(DEV), sc.cameras_in.to(DEV))
+        ref = GaussianRenderer().to(DEV)
+        ref.scene_batch = False
+        want = ref(sc.cameras_out.to(DEV), g, h=48, w=48)[:3]
+        rend = GaussianRenderer().to(DEV)
+        first = rend(sc.cameras_out.to(DEV), g, h=48, w=48)[:3]
+        key = [k for k in rend._cap_hint if len(k) == 5][0]
+        rend._cap_hint[key] = 128
+        second = rend(sc.cameras_out.to(DEV), g, h=48, w=48)[:3]
+        assert rend._cap_hint[key] > 128 and len(rend.radii) == 4
+        third = rend(sc.cameras_out.to(DEV), g, h=48, w=48)[:3]
+    for got in (first, second, third):
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
