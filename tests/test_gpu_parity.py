@@ -1001,3 +1001,15 @@ def test_scene_batched_bad_hint_falls_back_to_per_scene():
     for got in (first, second, third):
         for a, b in zip(got, want):
             assert torch.equal(a, b)
+
+
+def test_randomised_fused_vs_separate_stages():
+    """tools/stress_fused.py on 15 random configurations (volumes, thin shells, repeated depths, huge per-tile lists,
+    shells + outliers): fused and packed fast paths == separate stages, bit for bit."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_fused.py"), "15"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "mismatches: 0" in p.stdout
