@@ -84,6 +84,14 @@ PM_API int pm_unproject_fwd(const float *params, const float *cameras, const flo
 /* VJP of pm_unproject_fwd w.r.t. params (cameras carry no gradient in the
  * reference: gs_decoder_system.py:200 feeds dataset cameras). Any v_* input may
  * be NULL (treated as zero). v_params [V,14,h,w] is fully overwritten. */
+/* pm_unproject_fwd with n_dst (1..8) destination sets: dst_ptrs is a HOST array of 5 * n_dst device pointers
+ * {xyz, rgb, opacity, scales, quats} per destination. With peer-mapped pointers (NVLink P2P / symmetric memory)
+ * this is the fused "unproject + all-gather" of the view-sharded decode: every rank stores its Gaussians straight
+ * into its slot of every peer's gather buffer; the caller brackets it with cross-rank barriers. */
+PM_API int pm_unproject_fwd_multi(const float *params, const float *cameras, const float *muls,
+                     int mode, float z_near, float z_far, float s_min, float s_max,
+                     int n_views, int h, int w, int n_dst, float *const *dst_ptrs, pm_stream_t stream);
+
 PM_API int pm_unproject_bwd(const float *params, const float *cameras, const float *muls,
                      int mode, float z_near, float z_far, float s_min, float s_max,
                      int n_views, int h, int w,

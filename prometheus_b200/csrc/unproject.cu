@@ -42,12 +42,23 @@ constexpr float kDirector3dOpacityOffset = -4.59511985013459f;  // log(0.01/0.99
 constexpr float kDirector3dScaleOffset = -4.60517018598809f;    // log(1/100)
 constexpr float kDirector3dRgbDiv = 2.0f * 0.28209479177387814f;
 
+// Where the Gaussians go: one set of the five output arrays per destination. n = 1 is the plain operator;
+// n > 1 is the fused "unproject + all-gather" of the view-sharded decode (config C5): destination k is this
+// rank's slot of the gather buffer on GPU k, reached with plain stores over NVLink peer mappings, so the
+// exchange step needs no separate collective and no local staging copy.
+constexpr int kMaxUnprojDst = 8;
+struct UnprojDst {
+  float *xyz, *rgb, *opacity, *scales, *quats;
+};
+struct UnprojDstSet {
+  UnprojDst d[kMaxUnprojDst];
+  int n;
+};
+
 __global__ void __launch_bounds__(256)
 unproject_fwd_kernel(const float *__restrict__ params, const float *__restrict__ cameras,
                      const float *__restrict__ muls, int mode, float z_near, float z_far,
-                     float s_min, float s_max, int h, int w,
-                     float *__restrict__ xyz, float *__restrict__ rgb, float *__restrict__ opacity,
-                     float *__restrict__ scales, float *__restrict__ quats) {
+                     float s_min, float s_max, int h, int w, const UnprojDstSet dst) {
   const int hw = h * w;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   const int v = blockIdx.y;
@@ -102,13 +113,16 @@ unproject_fwd_kernel(const float *__restrict__ params, const float *__restrict__
   const float qn = fmaxf(sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3), 1e-12f);
 
   const size_t g = (size_t)v * hw + pix;
-  xyz[g * 3 + 0] = c.t[0] + depth * d0;
-  xyz[g * 3 + 1] = c.t[1] + depth * d1;
-  xyz[g * 3 + 2] = c.t[2] + depth * d2;
-  rgb[g * 3 + 0] = c0; rgb[g * 3 + 1] = c1; rgb[g * 3 + 2] = c2;
-  opacity[g] = op;
-  scales[g * 3 + 0] = s0; scales[g * 3 + 1] = s1; scales[g * 3 + 2] = s2;
-  reinterpret_cast<float4 *>(quats)[g] = make_float4(q0 / qn, q1 / qn, q2 / qn, q3 / qn);
+  const float x0 = c.t[0] + depth * d0, x1 = c.t[1] + depth * d1, x2 = c.t[2] + depth * d2;
+  const float4 qv = make_float4(q0 / qn, q1 / qn, q2 / qn, q3 / qn);
+  for (int k = 0; k < dst.n; ++k) {
+    const UnprojDst &o = dst.d[k];
+    o.xyz[g * 3 + 0] = x0; o.xyz[g * 3 + 1] = x1; o.xyz[g * 3 + 2] = x2;
+    o.rgb[g * 3 + 0] = c0; o.rgb[g * 3 + 1] = c1; o.rgb[g * 3 + 2] = c2;
+    o.opacity[g] = op;
+    o.scales[g * 3 + 0] = s0; o.scales[g * 3 + 1] = s1; o.scales[g * 3 + 2] = s2;
+    reinterpret_cast<float4 *>(o.quats)[g] = qv;
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -288,8 +302,34 @@ int pm_unproject_fwd(const float *params, const float *cameras, const float *mul
   if (n_views == 0) return PM_OK;
   const int hw = h * w;
   dim3 grid((hw + 255) / 256, n_views);
+  pm::UnprojDstSet dst;
+  dst.n = 1;
+  dst.d[0] = pm::UnprojDst{xyz, rgb, opacity, scales, quats};
   pm::unproject_fwd_kernel<<<grid, 256, 0, pm::as_stream(stream)>>>(
-      params, cameras, muls, mode, z_near, z_far, s_min, s_max, h, w, xyz, rgb, opacity, scales, quats);
+      params, cameras, muls, mode, z_near, z_far, s_min, s_max, h, w, dst);
+  return pm::check_launch();
+}
+
+int pm_unproject_fwd_multi(const float *params, const float *cameras, const float *muls, int mode,
+                           float z_near, float z_far, float s_min, float s_max, int n_views, int h, int w,
+                           int n_dst, float *const *dst_ptrs, pm_stream_t stream) {
+  if (!params || !cameras || !muls || !dst_ptrs) return PM_ERR_BAD_ARG;
+  if (n_dst < 1 || n_dst > pm::kMaxUnprojDst) return PM_ERR_RANGE;
+  if (n_views < 0 || h <= 0 || w <= 0) return PM_ERR_BAD_ARG;
+  if (mode < PM_MODE_MVSPLAT || mode > PM_MODE_DIRECTOR3D) return PM_ERR_UNSUPPORTED;
+  if ((int64_t)h * w > (int64_t)1 << 30 || n_views > 65535) return PM_ERR_RANGE;
+  pm::UnprojDstSet dst;
+  dst.n = n_dst;
+  for (int k = 0; k < n_dst; ++k) {
+    float *const *p = dst_ptrs + 5 * k;
+    if (!p[0] || !p[1] || !p[2] || !p[3] || !p[4] || (reinterpret_cast<uintptr_t>(p[4]) & 15) != 0) return PM_ERR_BAD_ARG;
+    dst.d[k] = pm::UnprojDst{p[0], p[1], p[2], p[3], p[4]};
+  }
+  if (n_views == 0) return PM_OK;
+  const int hw = h * w;
+  dim3 grid((hw + 255) / 256, n_views);
+  pm::unproject_fwd_kernel<<<grid, 256, 0, pm::as_stream(stream)>>>(
+      params, cameras, muls, mode, z_near, z_far, s_min, s_max, h, w, dst);
   return pm::check_launch();
 }
 

@@ -106,6 +106,20 @@ def unproject_fwd(params, cameras, muls, mode, z_near, z_far, s_min, s_max, out=
     return xyz, rgb, opacity, scales, quats
 
 
+@_instrument("unproject_fwd", 1)
+def unproject_fwd_multi(params, cameras, muls, mode, z_near, z_far, s_min, s_max, n_dst, dst_ptrs):
+    """Unproject this rank's views into n_dst destination sets (pm_unproject_fwd_multi): `dst_ptrs` is a ctypes
+    array of 5 * n_dst device pointers {xyz, rgb, opacity, scales, quats} — see parallel.PeerGather."""
+    L = _lib.load()
+    params = _req(params, torch.float32, "params")
+    cameras = _req(cameras, torch.float32, "cameras")
+    muls = _req(muls, torch.float32, "muls").reshape(-1)
+    V, Cc, h, w = params.shape
+    assert Cc == 14 and cameras.shape == (V, 18) and muls.numel() == 14
+    _lib.check(L.pm_unproject_fwd_multi(_ptr(params), _ptr(cameras), _ptr(muls), MODES[mode], z_near, z_far, s_min, s_max,
+                                        V, h, w, int(n_dst), dst_ptrs, _stream()), "pm_unproject_fwd_multi")
+
+
 @_instrument("unproject_bwd", 1)
 def unproject_bwd(params, cameras, muls, mode, z_near, z_far, s_min, s_max, v_xyz, v_rgb, v_opacity,
                   v_scales, v_quats):

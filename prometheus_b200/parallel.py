@@ -90,3 +90,44 @@ def bind_to_gpu_numa(device_index: int) -> bool:
         return True
     except Exception:  # noqa: BLE001
         return False
+
+
+class PeerGather:
+    """The exchange step of the view-sharded decode (config C5) as ONE kernel over NVLink peer memory: every
+    rank's unproject kernel stores its Gaussians straight into its slot of EVERY rank's gather buffer
+    (`pm_unproject_fwd_multi`, plain stores through peer mappings of a torch symmetric-memory allocation), so
+    there is no separate all-gather and no staging copy on either side. Two device-side cross-rank barriers
+    bracket it: before (all ranks are done reading the previous scene) and after (all stores have landed).
+
+    The buffer is field-major — xyz of all ranks, then rgb, ... — so the gathered scene is five contiguous
+    views, in the order a single-GPU unproject of all (contiguously sharded) views produces."""
+
+    def __init__(self, n_local: int, device, group: Optional[dist.ProcessGroup] = None):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm
+
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank, self.n_local = dist.get_world_size(group), dist.get_rank(group), n_local
+        assert 1 <= self.world <= 8 and n_local % 4 == 0
+        G = self.world * n_local
+        self.buf = symm.empty(FLOATS_PER_GAUSSIAN * G, dtype=torch.float32, device=device)
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.full, ptrs, o = [], [[] for _ in range(self.world)], 0
+        for _, k in FIELDS:
+            t = self.buf[o:o + k * G]
+            self.full.append(t.view(G, k) if k > 1 else t.view(G))
+            for p in range(self.world):  # this rank's slot of field `k` inside peer p's buffer
+                ptrs[p].append(int(self.hdl.buffer_ptrs[p]) + 4 * (o + self.rank * n_local * k))
+            o += k * G
+        flat = [a for p in ptrs for a in p]
+        self.dst_ptrs = (ctypes.c_void_p * len(flat))(*flat)
+        self.full = tuple(self.full)
+
+    def gather(self, unproject_multi: Callable[[int, object], None]):
+        """`unproject_multi(n_dst, dst_ptrs)` launches the multi-destination unproject of this rank's views
+        (ops.unproject_fwd_multi). Returns the full scene (views of the local symmetric buffer)."""
+        self.hdl.barrier(channel=0)
+        unproject_multi(self.world, self.dst_ptrs)
+        self.hdl.barrier(channel=1)
+        return self.full

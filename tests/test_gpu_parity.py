@@ -1013,3 +1013,18 @@ def test_randomised_fused_vs_separate_stages():
     p = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_fused.py"), "15"], capture_output=True, text=True)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "mismatches: 0" in p.stdout
+
+
+def test_peer_gather_on_two_gpus():
+    """Fused unproject + all-gather over NVLink peer memory (parallel.PeerGather) == NCCL all-gather == single-GPU
+    unproject, bit for bit. Needs two GPUs (skipped on the single-GPU test box; run with gpurun --gpus 2)."""
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29577", os.path.join(root, "tools", "p2p_gather_check.py"), "64"],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "p2p gather ok" in p.stdout, p.stdout[-1500:] + p.stderr[-1500:]
