@@ -102,7 +102,8 @@ class PeerGather:
     The buffer is field-major — xyz of all ranks, then rgb, ... — so the gathered scene is five contiguous
     views, in the order a single-GPU unproject of all (contiguously sharded) views produces."""
 
-    def __init__(self, n_local: int, device, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, n_local: int, device, group: Optional[dist.ProcessGroup] = None, multicast: bool = True,
+                 force_multicast: bool = False):
         import ctypes
 
         import torch.distributed._symmetric_memory as symm
@@ -121,6 +122,18 @@ class PeerGather:
                 ptrs[p].append(int(self.hdl.buffer_ptrs[p]) + 4 * (o + self.rank * n_local * k))
             o += k * G
         flat = [a for p in ptrs for a in p]
+        self.n_dst = self.world
+        # NVSwitch multicast (NVLS): a store to the multicast mapping of the allocation is replicated to every GPU
+        # by the switch, so each rank sends its block ONCE instead of once per peer
+        # (measured, 59 MB per rank: 2 GPUs peer stores 0.13 ms vs multicast 0.22 ms; 8 GPUs 0.98 vs 0.95 ms)
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0) if (multicast and (self.world >= 4 or force_multicast)) else 0
+        self.multicast = mc != 0
+        if self.multicast:
+            flat, o = [], 0
+            for _, k in FIELDS:
+                flat.append(mc + 4 * (o + self.rank * n_local * k))
+                o += k * G
+            self.n_dst = 1
         self.dst_ptrs = (ctypes.c_void_p * len(flat))(*flat)
         self.full = tuple(self.full)
 
@@ -128,6 +141,6 @@ class PeerGather:
         """`unproject_multi(n_dst, dst_ptrs)` launches the multi-destination unproject of this rank's views
         (ops.unproject_fwd_multi). Returns the full scene (views of the local symmetric buffer)."""
         self.hdl.barrier(channel=0)
-        unproject_multi(self.world, self.dst_ptrs)
+        unproject_multi(self.n_dst, self.dst_ptrs)
         self.hdl.barrier(channel=1)
         return self.full

@@ -26,12 +26,17 @@ n_local = (v1 - v0) * S_in * S_in
 cfg = ("mvsplat", scenes.Z_NEAR, scenes.Z_FAR, scenes.S_MIN, scenes.S_MAX)
 want = ops.unproject_fwd(params_all, cams_all, muls, *cfg)
 nccl = parallel.gather_gaussians(lambda slots: ops.unproject_fwd(params, cams, muls, *cfg, out=slots), n_local, dev)
-pg = parallel.PeerGather(n_local, dev)
-for it in range(3):  # repeated use of the same buffer
-    got = pg.gather(lambda n, ptrs: ops.unproject_fwd_multi(params, cams, muls, *cfg, n, ptrs))
-    torch.cuda.synchronize()
-    for a, b, c in zip(got, want, nccl):
-        assert torch.equal(a, b) and torch.equal(c, b), "mismatch on rank %d" % rank
+gathers = {}
+for name, mc in (("peer stores", False), ("NVSwitch multicast", True)):
+    pg = parallel.PeerGather(n_local, dev, multicast=mc, force_multicast=mc)
+    if mc and not pg.multicast:
+        continue  # no multicast support on this box
+    gathers[name] = pg
+    for it in range(3):  # repeated use of the same buffer
+        got = pg.gather(lambda n, ptrs: ops.unproject_fwd_multi(params, cams, muls, *cfg, n, ptrs))
+        torch.cuda.synchronize()
+        for a, b, c in zip(got, want, nccl):
+            assert torch.equal(a, b) and torch.equal(c, b), "mismatch on rank %d (%s)" % (rank, name)
 
 
 def timeit(fn, n=20):
@@ -44,9 +49,10 @@ def timeit(fn, n=20):
     return (time.perf_counter() - t0) / n * 1e3
 
 
-t_p2p = timeit(lambda: pg.gather(lambda n, ptrs: ops.unproject_fwd_multi(params, cams, muls, *cfg, n, ptrs)))
+times = {name: timeit(lambda pg=pg: pg.gather(lambda n, ptrs: ops.unproject_fwd_multi(params, cams, muls, *cfg, n, ptrs)))
+         for name, pg in gathers.items()}
 t_nccl = timeit(lambda: parallel.gather_gaussians(lambda slots: ops.unproject_fwd(params, cams, muls, *cfg, out=slots), n_local, dev))
 if rank == 0:
-    print("p2p gather ok on %d GPUs: %d Gaussians/rank; fused unproject+gather %.3f ms, unproject + NCCL all-gather %.3f ms" % (
-        world, n_local, t_p2p, t_nccl))
+    print("p2p gather ok on %d GPUs: %d Gaussians/rank; fused unproject+gather %s; unproject + NCCL all-gather %.3f ms" % (
+        world, n_local, ", ".join("%s %.3f ms" % kv for kv in times.items()), t_nccl))
 dist.destroy_process_group()
