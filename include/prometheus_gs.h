@@ -259,7 +259,7 @@ PM_API int pm_composite_fwd(const float *means2d, const float *conics, const flo
  * pm_tile_sort + pm_composite_fwd; flatten_ids [n] is filled for the first
  * sorted_counts[c,ty,tx] entries of each tile only (all that pm_composite_bwd
  * reads). *overflow_flag (device int32, caller zero-fills) is set if a depth
- * sub-bucket of some tile exceeds the 1024-record group capacity: the caller
+ * second-level sub-bucket of some tile still exceeds the 768-record group capacity (e.g. hundreds of identical depths): the caller
  * must then redo the call with pm_tile_sort + pm_composite_fwd. tile_order (may be NULL): the
  * (camera, tile) index each CTA takes, e.g. heaviest first from pm_tile_scan. */
 PM_API int pm_tile_render_fwd(const uint64_t *records, const int32_t *isect_offsets, int64_t n_isects,

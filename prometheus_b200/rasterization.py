@@ -198,7 +198,7 @@ def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, b
 
 
 # Largest per-tile group the fused kernel sorts at once (tile_render.cu: kTrCap)
-FUSED_GROUP_CAP = 256  # <= the smallest group capacity any build uses, so the overflow flag is always looked at
+FUSED_GROUP_CAP = 256  # tiles at or below this size can never overflow a sort group (kTrCap = 768): no flag read-back
 
 
 def isect_tiles(means2d, radii, depths, tiles_per_gauss, width, height, C, force_generic=False):

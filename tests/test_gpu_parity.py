@@ -584,7 +584,7 @@ def test_fused_module_path_matches_unfused_including_gradients():
 
 
 def test_fused_overflow_falls_back():
-    """3000 splats with identical depth on one tile: one depth sub-bucket exceeds the fused group capacity (1024),
+    """3000 splats with identical depth on one tile: even a second-level depth sub-bucket exceeds the fused group capacity (768),
     the overflow flag is raised and the module falls back to the separate stages — same image either way."""
     import importlib
 
