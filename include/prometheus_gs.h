@@ -59,6 +59,13 @@ enum pm_convert_mode {
   PM_MODE_DIRECTOR3D = 2
 };
 
+/* storage type of the decoder maps handed to the unproject stage (the *_dt entry points) */
+enum pm_dtype {
+  PM_DTYPE_F32 = 0,
+  PM_DTYPE_F16 = 1,
+  PM_DTYPE_BF16 = 2
+};
+
 PM_API int pm_abi_version(void);
 PM_API const char *pm_status_string(int status);
 /* Last CUDA error string recorded by a failing call on this host thread. */
@@ -81,23 +88,41 @@ PM_API int pm_unproject_fwd(const float *params, const float *cameras, const flo
                      float *xyz, float *rgb, float *opacity, float *scales, float *quats,
                      pm_stream_t stream);
 
-/* VJP of pm_unproject_fwd w.r.t. params (cameras carry no gradient in the
- * reference: gs_decoder_system.py:200 feeds dataset cameras). Any v_* input may
- * be NULL (treated as zero). v_params [V,14,h,w] is fully overwritten. */
-/* pm_unproject_fwd with n_dst (1..8) destination sets: dst_ptrs is a HOST array of 5 * n_dst device pointers
+/* pm_unproject_fwd for decoder maps stored as fp32 / fp16 / bf16 (params_dtype = enum pm_dtype): the reference
+ * promotes half-precision maps to fp32 by its `* self.muls` (gaussians_renderer.py:219), so the results are
+ * those of pm_unproject_fwd on the widened maps, bit for bit, without the widening pass. */
+PM_API int pm_unproject_fwd_dt(const void *params, int params_dtype, const float *cameras, const float *muls,
+                     int mode, float z_near, float z_far, float s_min, float s_max,
+                     int n_views, int h, int w,
+                     float *xyz, float *rgb, float *opacity, float *scales, float *quats,
+                     pm_stream_t stream);
+
+/* pm_unproject_fwd_dt with n_dst (1..8) destination sets: dst_ptrs is a HOST array of 5 * n_dst device pointers
  * {xyz, rgb, opacity, scales, quats} per destination. With peer-mapped pointers (NVLink P2P / symmetric memory)
  * this is the fused "unproject + all-gather" of the view-sharded decode: every rank stores its Gaussians straight
  * into its slot of every peer's gather buffer; the caller brackets it with cross-rank barriers. */
-PM_API int pm_unproject_fwd_multi(const float *params, const float *cameras, const float *muls,
+PM_API int pm_unproject_fwd_multi(const void *params, int params_dtype, const float *cameras, const float *muls,
                      int mode, float z_near, float z_far, float s_min, float s_max,
                      int n_views, int h, int w, int n_dst, float *const *dst_ptrs, pm_stream_t stream);
 
+/* VJP of pm_unproject_fwd w.r.t. params (cameras carry no gradient in the
+ * reference: gs_decoder_system.py:200 feeds dataset cameras). Any v_* input may
+ * be NULL (treated as zero). v_params [V,14,h,w] is fully overwritten. */
 PM_API int pm_unproject_bwd(const float *params, const float *cameras, const float *muls,
                      int mode, float z_near, float z_far, float s_min, float s_max,
                      int n_views, int h, int w,
                      const float *v_xyz, const float *v_rgb, const float *v_opacity,
                      const float *v_scales, const float *v_quats,
                      float *v_params, pm_stream_t stream);
+
+/* pm_unproject_bwd for half-precision maps: v_params has the maps' storage type and receives the fp32 gradient
+ * rounded to nearest-even (what autograd's cast back through the reference's promotion produces). */
+PM_API int pm_unproject_bwd_dt(const void *params, int params_dtype, const float *cameras, const float *muls,
+                     int mode, float z_near, float z_far, float s_min, float s_max,
+                     int n_views, int h, int w,
+                     const float *v_xyz, const float *v_rgb, const float *v_opacity,
+                     const float *v_scales, const float *v_quats, void *v_params,
+                     pm_stream_t stream);
 
 /* Camera preparation on the device. Replaces the host round trip of
  * convert_camera_parameters_into_viewpoint_cameras + MiniCam + the K build

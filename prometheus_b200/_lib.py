@@ -28,8 +28,10 @@ SIGNATURES = {
     "pm_status_string": (c_char_p, [c_int]),
     "pm_last_cuda_error": (c_char_p, []),
     "pm_unproject_fwd": (c_int, [_P, _P, _P, _I, _F, _F, _F, _F, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
-    "pm_unproject_fwd_multi": (c_int, [_P, _P, _P, _I, _F, _F, _F, _F, _I, _I, _I, _I, _P, _P]),
+    "pm_unproject_fwd_dt": (c_int, [_P, _I, _P, _P, _I, _F, _F, _F, _F, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "pm_unproject_fwd_multi": (c_int, [_P, _I, _P, _P, _I, _F, _F, _F, _F, _I, _I, _I, _I, _P, _P]),
     "pm_unproject_bwd": (c_int, [_P, _P, _P, _I, _F, _F, _F, _F, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "pm_unproject_bwd_dt": (c_int, [_P, _I, _P, _P, _I, _F, _F, _F, _F, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "pm_camera_prep": (c_int, [_P, _I, _I, _I, _P, _P, _P]),
     "pm_project_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P]),
     "pm_project_count_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P]),

@@ -10,7 +10,30 @@
 // records so every 32-B sector a warp touches is fully used.
 #include "common.cuh"
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 namespace pm {
+
+// The decoder maps may arrive in half precision (the decoder runs under autocast; the reference's
+// `local_gaussian_params * self.muls` promotes them to fp32, gaussians_renderer.py:219): read them in their
+// storage type and widen in registers instead of paying a separate conversion pass over the 14 planes.
+template <typename T> __device__ __forceinline__ float load_param(const T *p);
+template <> __device__ __forceinline__ float load_param<float>(const float *p) { return __ldcs(p); }
+template <> __device__ __forceinline__ float load_param<__half>(const __half *p) {
+  return __half2float(__ushort_as_half(__ldcs(reinterpret_cast<const unsigned short *>(p))));
+}
+template <> __device__ __forceinline__ float load_param<__nv_bfloat16>(const __nv_bfloat16 *p) {
+  return __uint_as_float((unsigned)__ldcs(reinterpret_cast<const unsigned short *>(p)) << 16);
+}
+template <typename T> __device__ __forceinline__ void store_param_grad(T *p, float v);
+template <> __device__ __forceinline__ void store_param_grad<float>(float *p, float v) { __stcs(p, v); }
+template <> __device__ __forceinline__ void store_param_grad<__half>(__half *p, float v) {
+  __stcs(reinterpret_cast<unsigned short *>(p), __half_as_ushort(__float2half_rn(v)));
+}
+template <> __device__ __forceinline__ void store_param_grad<__nv_bfloat16>(__nv_bfloat16 *p, float v) {
+  __stcs(reinterpret_cast<unsigned short *>(p), __bfloat16_as_ushort(__float2bfloat16_rn(v)));
+}
 
 struct UnprojCam {
   float R[9];
@@ -55,8 +78,9 @@ struct UnprojDstSet {
   int n;
 };
 
+template <typename TP>
 __global__ void __launch_bounds__(256)
-unproject_fwd_kernel(const float *__restrict__ params, const float *__restrict__ cameras,
+unproject_fwd_kernel(const TP *__restrict__ params, const float *__restrict__ cameras,
                      const float *__restrict__ muls, int mode, float z_near, float z_far,
                      float s_min, float s_max, int h, int w, const UnprojDstSet dst) {
   const int hw = h * w;
@@ -64,10 +88,10 @@ unproject_fwd_kernel(const float *__restrict__ params, const float *__restrict__
   const int v = blockIdx.y;
   if (pix >= hw) return;
   const UnprojCam c = load_unproj_cam(cameras + (size_t)v * 18, h, w);
-  const float *p = params + (size_t)v * 14 * hw + pix;
+  const TP *p = params + (size_t)v * 14 * hw + pix;
   float ch[14];
 #pragma unroll
-  for (int k = 0; k < 14; ++k) ch[k] = __ldcs(p + (size_t)k * hw) * __ldg(muls + k);
+  for (int k = 0; k < 14; ++k) ch[k] = load_param<TP>(p + (size_t)k * hw) * __ldg(muls + k);
 
   const float i = (float)(pix % w) + 0.5f;
   const float j = (float)(pix / w) + 0.5f;
@@ -125,24 +149,25 @@ unproject_fwd_kernel(const float *__restrict__ params, const float *__restrict__
   }
 }
 
+template <typename TP>
 __global__ void __launch_bounds__(256)
-unproject_bwd_kernel(const float *__restrict__ params, const float *__restrict__ cameras,
+unproject_bwd_kernel(const TP *__restrict__ params, const float *__restrict__ cameras,
                      const float *__restrict__ muls, int mode, float z_near, float z_far,
                      float s_min, float s_max, int h, int w,
                      const float *__restrict__ v_xyz, const float *__restrict__ v_rgb,
                      const float *__restrict__ v_opacity, const float *__restrict__ v_scales,
-                     const float *__restrict__ v_quats, float *__restrict__ v_params) {
+                     const float *__restrict__ v_quats, TP *__restrict__ v_params) {
   const int hw = h * w;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   const int v = blockIdx.y;
   if (pix >= hw) return;
   const UnprojCam c = load_unproj_cam(cameras + (size_t)v * 18, h, w);
-  const float *p = params + (size_t)v * 14 * hw + pix;
+  const TP *p = params + (size_t)v * 14 * hw + pix;
   float mul[14], ch[14];
 #pragma unroll
   for (int k = 0; k < 14; ++k) {
     mul[k] = __ldg(muls + k);
-    ch[k] = __ldcs(p + (size_t)k * hw) * mul[k];
+    ch[k] = load_param<TP>(p + (size_t)k * hw) * mul[k];
   }
   const size_t g = (size_t)v * hw + pix;
   float gx[3] = {0, 0, 0}, gc[3] = {0, 0, 0}, gs[3] = {0, 0, 0}, gq[4] = {0, 0, 0, 0}, go = 0.0f;
@@ -237,9 +262,9 @@ unproject_bwd_kernel(const float *__restrict__ params, const float *__restrict__
   } else {
     out[10] = gq[0] / qn; out[11] = gq[1] / qn; out[12] = gq[2] / qn; out[13] = gq[3] / qn;
   }
-  float *o = v_params + (size_t)v * 14 * hw + pix;
+  TP *o = v_params + (size_t)v * 14 * hw + pix;
 #pragma unroll
-  for (int k = 0; k < 14; ++k) __stcs(o + (size_t)k * hw, out[k] * mul[k]);
+  for (int k = 0; k < 14; ++k) store_param_grad<TP>(o + (size_t)k * hw, out[k] * mul[k]);
 }
 
 // Device-side camera preparation. Reference: host round trip in
@@ -288,36 +313,69 @@ __global__ void camera_prep_kernel(const float *__restrict__ cameras, int n, int
 
 }  // namespace pm
 
+namespace pm {
+
+static int unproject_check(const void *params, const float *cameras, const float *muls, int dtype, int mode,
+                           int n_views, int h, int w) {
+  if (!params || !cameras || !muls) return PM_ERR_BAD_ARG;
+  if (n_views < 0 || h <= 0 || w <= 0) return PM_ERR_BAD_ARG;
+  if (mode < PM_MODE_MVSPLAT || mode > PM_MODE_DIRECTOR3D) return PM_ERR_UNSUPPORTED;
+  if (dtype < PM_DTYPE_F32 || dtype > PM_DTYPE_BF16) return PM_ERR_UNSUPPORTED;
+  if ((int64_t)h * w > (int64_t)1 << 30 || n_views > 65535) return PM_ERR_RANGE;
+  return PM_OK;
+}
+
+static int unproject_fwd_launch(const void *params, int dtype, const float *cameras, const float *muls, int mode,
+                                float z_near, float z_far, float s_min, float s_max, int n_views, int h, int w,
+                                const UnprojDstSet &dst, pm_stream_t stream) {
+  if (n_views == 0) return PM_OK;
+  const int hw = h * w;
+  dim3 grid((hw + 255) / 256, n_views);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == PM_DTYPE_F16)
+    unproject_fwd_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half *>(params), cameras, muls, mode,
+                                                       z_near, z_far, s_min, s_max, h, w, dst);
+  else if (dtype == PM_DTYPE_BF16)
+    unproject_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16 *>(params), cameras,
+                                                              muls, mode, z_near, z_far, s_min, s_max, h, w, dst);
+  else
+    unproject_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float *>(params), cameras, muls, mode,
+                                                      z_near, z_far, s_min, s_max, h, w, dst);
+  return check_launch();
+}
+
+}  // namespace pm
+
 extern "C" {
+
+int pm_unproject_fwd_dt(const void *params, int params_dtype, const float *cameras, const float *muls, int mode,
+                        float z_near, float z_far, float s_min, float s_max, int n_views, int h, int w,
+                        float *xyz, float *rgb, float *opacity, float *scales, float *quats,
+                        pm_stream_t stream) {
+  if (const int rc = pm::unproject_check(params, cameras, muls, params_dtype, mode, n_views, h, w)) return rc;
+  if (!xyz || !rgb || !opacity || !scales || !quats) return PM_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(quats) & 15) != 0) return PM_ERR_BAD_ARG;
+  pm::UnprojDstSet dst;
+  dst.n = 1;
+  dst.d[0] = pm::UnprojDst{xyz, rgb, opacity, scales, quats};
+  return pm::unproject_fwd_launch(params, params_dtype, cameras, muls, mode, z_near, z_far, s_min, s_max, n_views,
+                                  h, w, dst, stream);
+}
 
 int pm_unproject_fwd(const float *params, const float *cameras, const float *muls, int mode,
                      float z_near, float z_far, float s_min, float s_max, int n_views, int h, int w,
                      float *xyz, float *rgb, float *opacity, float *scales, float *quats,
                      pm_stream_t stream) {
-  if (!params || !cameras || !muls || !xyz || !rgb || !opacity || !scales || !quats) return PM_ERR_BAD_ARG;
-  if (n_views < 0 || h <= 0 || w <= 0) return PM_ERR_BAD_ARG;
-  if (mode < PM_MODE_MVSPLAT || mode > PM_MODE_DIRECTOR3D) return PM_ERR_UNSUPPORTED;
-  if ((reinterpret_cast<uintptr_t>(quats) & 15) != 0) return PM_ERR_BAD_ARG;
-  if ((int64_t)h * w > (int64_t)1 << 30 || n_views > 65535) return PM_ERR_RANGE;
-  if (n_views == 0) return PM_OK;
-  const int hw = h * w;
-  dim3 grid((hw + 255) / 256, n_views);
-  pm::UnprojDstSet dst;
-  dst.n = 1;
-  dst.d[0] = pm::UnprojDst{xyz, rgb, opacity, scales, quats};
-  pm::unproject_fwd_kernel<<<grid, 256, 0, pm::as_stream(stream)>>>(
-      params, cameras, muls, mode, z_near, z_far, s_min, s_max, h, w, dst);
-  return pm::check_launch();
+  return pm_unproject_fwd_dt(params, PM_DTYPE_F32, cameras, muls, mode, z_near, z_far, s_min, s_max, n_views, h, w,
+                             xyz, rgb, opacity, scales, quats, stream);
 }
 
-int pm_unproject_fwd_multi(const float *params, const float *cameras, const float *muls, int mode,
+int pm_unproject_fwd_multi(const void *params, int params_dtype, const float *cameras, const float *muls, int mode,
                            float z_near, float z_far, float s_min, float s_max, int n_views, int h, int w,
                            int n_dst, float *const *dst_ptrs, pm_stream_t stream) {
-  if (!params || !cameras || !muls || !dst_ptrs) return PM_ERR_BAD_ARG;
+  if (const int rc = pm::unproject_check(params, cameras, muls, params_dtype, mode, n_views, h, w)) return rc;
+  if (!dst_ptrs) return PM_ERR_BAD_ARG;
   if (n_dst < 1 || n_dst > pm::kMaxUnprojDst) return PM_ERR_RANGE;
-  if (n_views < 0 || h <= 0 || w <= 0) return PM_ERR_BAD_ARG;
-  if (mode < PM_MODE_MVSPLAT || mode > PM_MODE_DIRECTOR3D) return PM_ERR_UNSUPPORTED;
-  if ((int64_t)h * w > (int64_t)1 << 30 || n_views > 65535) return PM_ERR_RANGE;
   pm::UnprojDstSet dst;
   dst.n = n_dst;
   for (int k = 0; k < n_dst; ++k) {
@@ -325,11 +383,34 @@ int pm_unproject_fwd_multi(const float *params, const float *cameras, const floa
     if (!p[0] || !p[1] || !p[2] || !p[3] || !p[4] || (reinterpret_cast<uintptr_t>(p[4]) & 15) != 0) return PM_ERR_BAD_ARG;
     dst.d[k] = pm::UnprojDst{p[0], p[1], p[2], p[3], p[4]};
   }
+  return pm::unproject_fwd_launch(params, params_dtype, cameras, muls, mode, z_near, z_far, s_min, s_max, n_views,
+                                  h, w, dst, stream);
+}
+
+int pm_unproject_bwd_dt(const void *params, int params_dtype, const float *cameras, const float *muls, int mode,
+                        float z_near, float z_far, float s_min, float s_max, int n_views, int h, int w,
+                        const float *v_xyz, const float *v_rgb, const float *v_opacity,
+                        const float *v_scales, const float *v_quats, void *v_params,
+                        pm_stream_t stream) {
+  if (const int rc = pm::unproject_check(params, cameras, muls, params_dtype, mode, n_views, h, w)) return rc;
+  if (!v_params) return PM_ERR_BAD_ARG;
+  if (v_quats && (reinterpret_cast<uintptr_t>(v_quats) & 15) != 0) return PM_ERR_BAD_ARG;
   if (n_views == 0) return PM_OK;
   const int hw = h * w;
   dim3 grid((hw + 255) / 256, n_views);
-  pm::unproject_fwd_kernel<<<grid, 256, 0, pm::as_stream(stream)>>>(
-      params, cameras, muls, mode, z_near, z_far, s_min, s_max, h, w, dst);
+  cudaStream_t st = pm::as_stream(stream);
+  if (params_dtype == PM_DTYPE_F16)
+    pm::unproject_bwd_kernel<__half><<<grid, 256, 0, st>>>(
+        static_cast<const __half *>(params), cameras, muls, mode, z_near, z_far, s_min, s_max, h, w, v_xyz, v_rgb,
+        v_opacity, v_scales, v_quats, static_cast<__half *>(v_params));
+  else if (params_dtype == PM_DTYPE_BF16)
+    pm::unproject_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+        static_cast<const __nv_bfloat16 *>(params), cameras, muls, mode, z_near, z_far, s_min, s_max, h, w, v_xyz,
+        v_rgb, v_opacity, v_scales, v_quats, static_cast<__nv_bfloat16 *>(v_params));
+  else
+    pm::unproject_bwd_kernel<float><<<grid, 256, 0, st>>>(
+        static_cast<const float *>(params), cameras, muls, mode, z_near, z_far, s_min, s_max, h, w, v_xyz, v_rgb,
+        v_opacity, v_scales, v_quats, static_cast<float *>(v_params));
   return pm::check_launch();
 }
 
@@ -338,18 +419,8 @@ int pm_unproject_bwd(const float *params, const float *cameras, const float *mul
                      const float *v_xyz, const float *v_rgb, const float *v_opacity,
                      const float *v_scales, const float *v_quats, float *v_params,
                      pm_stream_t stream) {
-  if (!params || !cameras || !muls || !v_params) return PM_ERR_BAD_ARG;
-  if (n_views < 0 || h <= 0 || w <= 0) return PM_ERR_BAD_ARG;
-  if (mode < PM_MODE_MVSPLAT || mode > PM_MODE_DIRECTOR3D) return PM_ERR_UNSUPPORTED;
-  if (v_quats && (reinterpret_cast<uintptr_t>(v_quats) & 15) != 0) return PM_ERR_BAD_ARG;
-  if ((int64_t)h * w > (int64_t)1 << 30 || n_views > 65535) return PM_ERR_RANGE;
-  if (n_views == 0) return PM_OK;
-  const int hw = h * w;
-  dim3 grid((hw + 255) / 256, n_views);
-  pm::unproject_bwd_kernel<<<grid, 256, 0, pm::as_stream(stream)>>>(
-      params, cameras, muls, mode, z_near, z_far, s_min, s_max, h, w, v_xyz, v_rgb, v_opacity,
-      v_scales, v_quats, v_params);
-  return pm::check_launch();
+  return pm_unproject_bwd_dt(params, PM_DTYPE_F32, cameras, muls, mode, z_near, z_far, s_min, s_max, n_views, h, w,
+                             v_xyz, v_rgb, v_opacity, v_scales, v_quats, v_params, stream);
 }
 
 int pm_camera_prep(const float *cameras, int n, int h, int w, float *viewmats, float *Ks,

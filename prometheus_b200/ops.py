@@ -68,6 +68,18 @@ def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
+PARAM_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}  # enum pm_dtype
+
+
+def _req_params(t: torch.Tensor, name: str = "params") -> torch.Tensor:
+    """Decoder maps: fp32, or fp16 / bf16 as they come out of an autocast decoder (read natively)."""
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (prometheus_b200 has no CPU path)")
+    if t.dtype not in PARAM_DTYPES:
+        t = t.float()
+    return t.contiguous()
+
+
 def _opt(t, dtype, name):
     return None if t is None else _req(t, dtype, name)
 
@@ -87,7 +99,7 @@ def unproject_fwd(params, cameras, muls, mode, z_near, z_far, s_min, s_max, out=
     """params [V,14,h,w], cameras [V,18] -> (xyz [G,3], rgb [G,3], opacity [G], scales [G,3], quats [G,4]).
     `out` may hold five preallocated tensors (e.g. slots of an all-gather buffer)."""
     L = _lib.load()
-    params = _req(params, torch.float32, "params")
+    params = _req_params(params)
     cameras = _req(cameras, torch.float32, "cameras")
     muls = _req(muls, torch.float32, "muls").reshape(-1)
     V, Cc, h, w = params.shape
@@ -100,9 +112,9 @@ def unproject_fwd(params, cameras, muls, mode, z_near, z_far, s_min, s_max, out=
     xyz, rgb, opacity, scales, quats = out
     for t, n in zip(out, (3 * G, 3 * G, G, 3 * G, 4 * G)):
         assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n
-    _lib.check(L.pm_unproject_fwd(_ptr(params), _ptr(cameras), _ptr(muls), MODES[mode], z_near, z_far,
-                                  s_min, s_max, V, h, w, _ptr(xyz), _ptr(rgb), _ptr(opacity), _ptr(scales),
-                                  _ptr(quats), _stream()), "pm_unproject_fwd")
+    _lib.check(L.pm_unproject_fwd_dt(_ptr(params), PARAM_DTYPES[params.dtype], _ptr(cameras), _ptr(muls), MODES[mode],
+                                     z_near, z_far, s_min, s_max, V, h, w, _ptr(xyz), _ptr(rgb), _ptr(opacity),
+                                     _ptr(scales), _ptr(quats), _stream()), "pm_unproject_fwd_dt")
     return xyz, rgb, opacity, scales, quats
 
 
@@ -111,28 +123,29 @@ def unproject_fwd_multi(params, cameras, muls, mode, z_near, z_far, s_min, s_max
     """Unproject this rank's views into n_dst destination sets (pm_unproject_fwd_multi): `dst_ptrs` is a ctypes
     array of 5 * n_dst device pointers {xyz, rgb, opacity, scales, quats} — see parallel.PeerGather."""
     L = _lib.load()
-    params = _req(params, torch.float32, "params")
+    params = _req_params(params)
     cameras = _req(cameras, torch.float32, "cameras")
     muls = _req(muls, torch.float32, "muls").reshape(-1)
     V, Cc, h, w = params.shape
     assert Cc == 14 and cameras.shape == (V, 18) and muls.numel() == 14
-    _lib.check(L.pm_unproject_fwd_multi(_ptr(params), _ptr(cameras), _ptr(muls), MODES[mode], z_near, z_far, s_min, s_max,
+    _lib.check(L.pm_unproject_fwd_multi(_ptr(params), PARAM_DTYPES[params.dtype], _ptr(cameras), _ptr(muls), MODES[mode], z_near, z_far, s_min, s_max,
                                         V, h, w, int(n_dst), dst_ptrs, _stream()), "pm_unproject_fwd_multi")
 
 
 @_instrument("unproject_bwd", 1)
 def unproject_bwd(params, cameras, muls, mode, z_near, z_far, s_min, s_max, v_xyz, v_rgb, v_opacity,
                   v_scales, v_quats):
+    """v_params in the maps' own dtype (fp32 gradient rounded to nearest for fp16 / bf16 maps)."""
     L = _lib.load()
-    params = _req(params, torch.float32, "params")
+    params = _req_params(params)
     cameras = _req(cameras, torch.float32, "cameras")
     muls = _req(muls, torch.float32, "muls").reshape(-1)
     V, _, h, w = params.shape
     vs = [_opt(t, torch.float32, "grad") for t in (v_xyz, v_rgb, v_opacity, v_scales, v_quats)]
     v_params = torch.empty_like(params)
-    _lib.check(L.pm_unproject_bwd(_ptr(params), _ptr(cameras), _ptr(muls), MODES[mode], z_near, z_far,
-                                  s_min, s_max, V, h, w, *[_ptr(t) for t in vs], _ptr(v_params), _stream()),
-               "pm_unproject_bwd")
+    _lib.check(L.pm_unproject_bwd_dt(_ptr(params), PARAM_DTYPES[params.dtype], _ptr(cameras), _ptr(muls), MODES[mode],
+                                     z_near, z_far, s_min, s_max, V, h, w, *[_ptr(t) for t in vs], _ptr(v_params),
+                                     _stream()), "pm_unproject_bwd_dt")
     return v_params
 
 

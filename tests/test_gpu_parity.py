@@ -78,6 +78,48 @@ def test_unproject_fwd_bwd_vs_reference_golden(golden_dir, mode):
     assert grad_close(params.grad.cpu().numpy(), g["v_params"], atol=1e-5, rtol=1e-4)
 
 
+@pytest.mark.parametrize("mode,name", [("mvsplat", "bf16"), ("mvsplat", "f16"), ("director3d", "bf16"), ("gslrm", "f16")])
+def test_unproject_half_precision_maps_vs_reference_golden(golden_dir, mode, name):
+    """Decoder maps that arrive in fp16 / bf16 (autocast decoder) are read natively: same Gaussians as the
+    reference converter on those maps (it widens by `* muls`, gaussians_renderer.py:219), the gradient comes
+    back in the maps' dtype, and both equal the fp32 entry points on the widened maps bit for bit."""
+    from prometheus_b200 import GaussianConverter, ops
+
+    dt = {"bf16": torch.bfloat16, "f16": torch.float16}[name]
+    g = np.load(os.path.join(golden_dir, "converter_half.npz"))
+    base = np.load(os.path.join(golden_dir, f"converter_{mode}.npz"))
+    pre = f"{mode}_{name}_"
+    keys = ("xyz", "features", "opacity", "scales", "rotations")
+    conv = GaussianConverter(gs_convert_mode=mode, z_near=0.01, z_far=100.0, s_min=0.001, s_max=1.0).to(DEV)
+    params = dev(g[pre + "params"]).to(dt)
+    assert torch.equal(params.float().cpu(), torch.from_numpy(g[pre + "params"]))  # the fixture is exact in dt
+    params.requires_grad_(True)
+    cams = dev(base["cameras"])
+    outs = conv(params, cams)
+    for o, k in zip(outs, keys):
+        assert o.dtype == torch.float32 and o.shape == g[pre + k].shape, k
+        assert allclose(o.detach().cpu().numpy(), g[pre + k], atol=1e-5, rtol=1e-4), k
+    loss = sum((o * dev(base["w_" + k])).sum() for o, k in zip(outs, keys))
+    loss.backward()
+    assert params.grad.dtype == dt
+    # one ulp of the half type on top of the fp32 tolerance: a last-bit fp32 difference may flip the rounding
+    ulp = 2.0 ** -7 if dt == torch.bfloat16 else 2.0 ** -10
+    got, want = params.grad.float().cpu().numpy(), g[pre + "v_params"]
+    assert np.all(np.abs(got - want) <= 1e-5 + (ulp + 1e-4) * np.abs(want)), np.abs(got - want).max()
+
+    # bit-exact against the fp32 kernels on the widened maps
+    wide = params.detach().float()
+    B, N = wide.shape[:2]
+    p32, p16 = wide.reshape(B * N, 14, *wide.shape[3:]), params.detach().reshape(B * N, 14, *wide.shape[3:])
+    args = (cams.reshape(B * N, 18), conv.muls.reshape(-1), mode, 0.01, 100.0, 0.001, 1.0)
+    o32, o16 = ops.unproject_fwd(p32, *args), ops.unproject_fwd(p16, *args)
+    for a, b in zip(o32, o16):
+        assert torch.equal(a, b)
+    vs = [dev(base["w_" + k]).reshape(o.shape).contiguous() for o, k in zip(o32, keys)]
+    v32, v16 = ops.unproject_bwd(p32, *args, *vs), ops.unproject_bwd(p16, *args, *vs)
+    assert v16.dtype == dt and torch.equal(v32.to(dt), v16)
+
+
 def test_unproject_vs_oracle_larger(oracle):
     from prometheus_b200 import ops, scenes
 
