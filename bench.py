@@ -193,6 +193,7 @@ def main():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--ref-views", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-half-maps", action="store_true", help="skip the bf16-maps e2e side figure")
     ap.add_argument("--no-bwd", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="C5 exchange step")
     args = ap.parse_args()
@@ -300,6 +301,11 @@ def main():
         launches = ops.LAUNCHES - n0
         prof, ops.PROFILE = ops.PROFILE, None
         total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        if os.environ.get("PM_BENCH_DEBUG"):
+            ms = torch.cuda.memory_stats()
+            print("[debug] step ms:", [round(a.elapsed_time(b), 2) for a, b in evs], "device_alloc/free/retries:",
+                  ms.get("num_device_alloc"), ms.get("num_device_free"), ms.get("num_alloc_retries"),
+                  "hints:", dict(rend._cap_hint), file=sys.stderr)
         if world > 1:
             t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -414,8 +420,8 @@ def main():
     out_h = [torch.empty(B, V_out, c, S, S).pin_memory() for c in (3, 1, 1)]
     pipe = DecodeRenderPipeline(conv, rend, S, S, device=dev)
 
-    def e2e_loop(n):
-        inputs = (params_h, cams_in_h, cams_out_h)
+    def e2e_loop(n, maps_h=None):
+        inputs = (params_h if maps_h is None else maps_h, cams_in_h, cams_out_h)
         pipe.prefetch(*inputs)
         for i in range(n):
             pipe.run(out_h, next_inputs_h=inputs if i + 1 < n else None)
@@ -463,7 +469,7 @@ def main():
         target = (torch.rand(B, V_out, 3, S, S, device=dev) * 2 - 1)
         bsteps = max(3, args.steps // 2)
         rend.defer_checks = True
-        bwd_ms, bl, bprof = timed(lambda: step_fwdbwd(params_d, cams_in_d, cams_out_d, target), bsteps, 3, profile=True)
+        bwd_ms, bl, bprof = timed(lambda: step_fwdbwd(params_d, cams_in_d, cams_out_d, target), bsteps, max(3, args.warmup), profile=True)
         rend.defer_checks = False
         assert invalid["n"] == 0, "a deferred capacity / overflow check failed inside the timed region"
         bwd_ms /= bsteps
@@ -473,6 +479,29 @@ def main():
         extra["fwd_bwd"] = {"value": world * pixels / (bwd_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": round(bwd_ms, 4),
                             "gaussians_per_s": world * B * V_out * G / (bwd_ms * 1e-3),
                             "stages_ms": {k: round(v, 4) for k, v in bst.items()}}
+
+    # side figure (measured last so that its allocations cannot disturb the figures above; not the headline, whose maps are fp32 as BASELINE's config says): the same loop fed with the
+    # maps in bf16, the storage type an autocast decoder hands over; the unproject kernel reads them natively
+    half = None
+    if world == 1 and not args.no_half_maps:
+        maps_bf16 = params_h.to(torch.bfloat16).pin_memory()
+        e2e_loop(3, maps_bf16)
+        barrier()
+        gc.disable()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        e2e_loop(args.steps, maps_bf16)
+        h1.record()
+        barrier()
+        gc.enable()
+        half_ms = h0.elapsed_time(h1) / args.steps
+        half = {"value": pixels / (half_ms * 1e-3) / 1e6, "ms_per_step": round(half_ms, 4),
+                "h2d_bytes_per_step": maps_bf16.numel() * 2 + cams_in_h.numel() * 4 + cams_out_h.numel() * 4,
+                "note": "decoder maps rounded to bf16 on the host; a different input precision, reported beside the "
+                        "fp32 headline only"}
+        del maps_bf16
+    if half is not None:
+        e2e["bf16_maps"] = half
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on all host cores, bounded sample
     cpu_baseline = None

@@ -114,6 +114,9 @@ project_bwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
     if (v_means2d) { gm0 = __ldg(v_means2d + f * 2 + 0); gm1 = __ldg(v_means2d + f * 2 + 1); }
     if (v_depths) gd = __ldg(v_depths + f);
     if (radius <= 0) continue;
+    // a pair no pixel blended (culled by the compositor, or behind the point where its tiles saturated) arrives
+    // with all six cotangents exactly zero and contributes exactly nothing: most pairs of an opaque scene
+    if (gc0 == 0.0f && gc1 == 0.0f && gc2 == 0.0f && gm0 == 0.0f && gm1 == 0.0f && gd == 0.0f) continue;
     const BwdCam &cf = s_cam[cid];  // per-camera constants (incl. the clamp limits: 6 fp64 divisions) once per CTA
     const double *R = cf.R;
     const double *ct = cf.t;
