@@ -193,6 +193,9 @@ def main():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--ref-views", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline", choices=["eager", "graph"], default="graph",
+                    help="e2e leg: DecodeRenderPipeline launching the modules eagerly, or replaying CUDA-graph plans")
+    ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay side figure")
     ap.add_argument("--no-half-maps", action="store_true", help="skip the bf16-maps e2e side figure")
     ap.add_argument("--no-bwd", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="C5 exchange step")
@@ -418,16 +421,25 @@ def main():
     from prometheus_b200 import DecodeRenderPipeline
 
     out_h = [torch.empty(B, V_out, c, S, S).pin_memory() for c in (3, 1, 1)]
-    pipe = DecodeRenderPipeline(conv, rend, S, S, device=dev)
+    pipe = DecodeRenderPipeline(conv, rend, S, S, device=dev, graph=args.pipeline == "graph")
 
     def e2e_loop(n, maps_h=None):
         inputs = (params_h if maps_h is None else maps_h, cams_in_h, cams_out_h)
         pipe.prefetch(*inputs)
+        dbg = [] if os.environ.get("PM_BENCH_DEBUG") else None
         for i in range(n):
+            t0 = time.perf_counter()
             pipe.run(out_h, next_inputs_h=inputs if i + 1 < n else None)
+            if dbg is not None:
+                dbg.append(round((time.perf_counter() - t0) * 1e3, 2))
         pipe.flush()
+        if dbg is not None:
+            ms = torch.cuda.memory_stats()
+            hs = torch.cuda.host_memory_stats() if hasattr(torch.cuda, "host_memory_stats") else {}
+            print("[debug] e2e host ms per run():", dbg, "device_alloc:", ms.get("num_device_alloc"),
+                  "host_alloc:", hs.get("num_host_alloc"), file=sys.stderr)
 
-    e2e_loop(max(3, args.warmup))
+    e2e_loop(max(8, args.warmup))  # long enough for the caching allocator to own every buffer the pipeline rotates through
     barrier()
     flush_buf.fill_(1)
     import gc
@@ -460,7 +472,7 @@ def main():
     h2d = params_h.numel() * 4 + cams_in_h.numel() * 4 + cams_out_h.numel() * 4
     d2h = sum(t.numel() * 4 for t in out_h)
     e2e = {"value": world * pixels / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 4), "api": "DecodeRenderPipeline (3 streams, double buffered)",
+           "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 4), "api": "DecodeRenderPipeline (3 streams, double buffered%s)" % (", CUDA-graph plans" if args.pipeline == "graph" else ""),
            "serial_ms_per_step": round(ser_ms, 4)}
 
     # ---- fwd+bwd (training-style step with the synthetic render loss)
@@ -479,6 +491,22 @@ def main():
         extra["fwd_bwd"] = {"value": world * pixels / (bwd_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": round(bwd_ms, 4),
                             "gaussians_per_s": world * B * V_out * G / (bwd_ms * 1e-3),
                             "stages_ms": {k: round(v, 4) for k, v in bst.items()}}
+
+    # side figure: the same forward step replayed from a CUDA graph (GraphedDecodeRender; inputs resident, checks
+    # deferred and validated after the loop like the headline loop)
+    if not args.no_graph:
+        from prometheus_b200 import GraphedDecodeRender
+
+        gr = GraphedDecodeRender(conv, rend, S, S)
+        ins = (params_d, cams_in_d, cams_out_d)
+        gr.run(*ins)
+        g_ms, g_launches, _ = timed(lambda: gr.run(*ins, check=False), args.steps, max(3, args.warmup))
+        assert gr.validate(), "the graphed replay overflowed its captured buffers"
+        g_ms /= args.steps
+        extra["graph_replay"] = {"value": world * pixels / (g_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": round(g_ms, 4),
+                                 "gpu_launches": g_launches,
+                                 "note": "decode+render captured once, replayed as one CUDA graph (fwd, inputs resident)"}
+        del gr
 
     # side figure (measured last so that its allocations cannot disturb the figures above; not the headline, whose maps are fp32 as BASELINE's config says): the same loop fed with the
     # maps in bf16, the storage type an autocast decoder hands over; the unproject kernel reads them natively

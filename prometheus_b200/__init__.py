@@ -7,13 +7,15 @@ Public surface (mirrors the reference, see DESIGN.md / INTEGRATION.md):
   GaussianConverter, GaussianRenderer   module-level mirrors
   install_as_gsplat()           plug the operator under the unmodified reference
   DecodeRenderPipeline          streaming host->device->host decode+render (copies overlap compute)
+  GraphedDecodeRender           the same launch set captured once per shape and replayed as a CUDA graph
   TrajectoryRenderer, sample_from_dense_cameras, export_video   novel-view video along a camera path
 """
 from .rasterization import rasterization  # noqa: F401
 from .renderer import GaussianConverter, GaussianRenderer, install_as_gsplat  # noqa: F401
 from .pipeline import DecodeRenderPipeline  # noqa: F401
+from .graphed import GraphedDecodeRender  # noqa: F401
 from .trajectory import (TrajectoryRenderer, export_ply_for_gaussians, export_video,  # noqa: F401
                          sample_from_dense_cameras)
 
-__all__ = ["rasterization", "GaussianConverter", "GaussianRenderer", "install_as_gsplat", "DecodeRenderPipeline",
+__all__ = ["rasterization", "GaussianConverter", "GaussianRenderer", "install_as_gsplat", "DecodeRenderPipeline", "GraphedDecodeRender",
            "TrajectoryRenderer", "sample_from_dense_cameras", "export_video", "export_ply_for_gaussians"]

@@ -93,6 +93,7 @@ class GaussianRenderer(nn.Module):
     # chunk and the per-scene Gaussian count is a multiple of 256 (always, for pixel-aligned maps)
     scene_batch = True
     scene_chunk = 8  # scenes per launch set
+    STATS_RING = 4096  # pinned {n_isects, max tile count, overflow} rows for the deferred checks
 
     def __init__(self, sh_degree=0, background=[1, 1, 1]):
         super().__init__()
@@ -102,6 +103,9 @@ class GaussianRenderer(nn.Module):
         self.viewspace_points: List[torch.Tensor] = []
         self._cap_hint = {}
         self._pending = []
+        self._static_stats = None
+        self._stats_ring = None
+        self._stats_next = 0
         self._stat_sources = []
         self._stat_scenes = 0
 
@@ -139,7 +143,8 @@ class GaussianRenderer(nn.Module):
     def _check(self, job) -> bool:
         """True if the fused render of `job` is valid; updates the capacity hint."""
         key = job["key"]
-        job["event"].synchronize()  # fires when the render kernel is done; later work (a backward pass) keeps running
+        if job["event"] is not None:
+            job["event"].synchronize()  # fires when the render kernel is done; later work (a backward pass) keeps running
         n_isects, max_count, overflow = (int(v) for v in job["stats_host"])
         self._update_hint(key, n_isects)
         if n_isects > job["capacity"]:
@@ -164,11 +169,28 @@ class GaussianRenderer(nn.Module):
     def _job_for(self, args, out, info, key):
         """Queue the device-side counts of a fused render for the later check: {n_isects, max tile count, overflow
         flag} travel to pinned memory behind the render kernel."""
-        stats_host = torch.empty(3, dtype=torch.int32, pin_memory=True)
+        if self._static_stats is not None:
+            # under CUDA-graph capture (graphed.py): a preallocated pinned row per job, no event — the two copies
+            # become nodes of the graph and the caller synchronises on its own event before looking at the row
+            rows, used = self._static_stats
+            stats_host, ev = rows[used[0]], None
+            used[0] += 1
+        else:
+            # a ring of pinned rows instead of one pinned allocation per job: the host allocator would otherwise
+            # fall back to cudaHostAlloc (milliseconds, and it serialises with the device) whenever its free blocks
+            # are still waiting for their events
+            if self._stats_ring is None:
+                self._stats_ring = torch.zeros(self.STATS_RING, 3, dtype=torch.int32).pin_memory()
+            if len(self._pending) < self.STATS_RING - 64:
+                stats_host = self._stats_ring[self._stats_next]
+                self._stats_next = (self._stats_next + 1) % self.STATS_RING
+            else:  # thousands of unchecked jobs outstanding: never overwrite a row that has not been looked at
+                stats_host = torch.empty(3, dtype=torch.int32, pin_memory=True)
+            ev = torch.cuda.Event()
         stats_host[:2].copy_(info["stats"], non_blocking=True)
         stats_host[2:].copy_(info["overflow_flag"], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
+        if ev is not None:
+            ev.record()
         return dict(args=args, out=out, info=info, key=key, stats_host=stats_host, event=ev, capacity=info["capacity"])
 
     def _forward_batched(self, viewmats, Ks, gaussians, scaling_modifier, bg_color, h, w):

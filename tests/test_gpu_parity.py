@@ -787,6 +787,82 @@ def test_deferred_checks_and_pipeline_recover_from_a_bad_hint():
             assert torch.equal(a, b.cpu())
 
 
+def test_graphed_decode_render_replays_bit_identical_and_recovers_from_overflow():
+    """GraphedDecodeRender: the whole decode+render launch set replayed from a CUDA graph gives the eager modules'
+    bits for every scene of the captured shape (device or pinned-host inputs, several scenes per call), counts its
+    launches, and a scene that overflows the captured intersection buffers is detected, re-rendered and the plan
+    re-captured."""
+    from prometheus_b200 import GaussianConverter, GaussianRenderer, GraphedDecodeRender, ops, scenes
+
+    conv = GaussianConverter("mvsplat", z_near=0.01, z_far=100.0, s_min=0.001, s_max=1.0).to(DEV)
+    rend = GaussianRenderer().to(DEV)
+    eager = GaussianRenderer().to(DEV)
+    gr = GraphedDecodeRender(conv, rend, 80, 80)
+
+    def want_for(sc):
+        with torch.no_grad():
+            return eager(sc.cameras_out.to(DEV), conv(sc.params.to(DEV), sc.cameras_in.to(DEV)), h=80, w=80)[:3]
+
+    for B in (1, 2):  # one scene, and a scene-batched pair
+        scs = [scenes.make_scene("C1", seed=s, scenes=B, views_in=3, size_in=64, views_out=3, size_out=80) for s in (23, 24, 25)]
+        for i, sc in enumerate(scs):
+            ins = (sc.params, sc.cameras_in, sc.cameras_out)
+            ins = tuple(t.pin_memory() for t in ins) if i == 1 else tuple(t.to(DEV) for t in ins)
+            n0 = ops.LAUNCHES
+            got = gr.run(*ins)
+            assert ops.LAUNCHES - n0 >= 6  # unproject, camera prep, project, scan, scatter, render (+ capture's eager pass)
+            for a, b in zip(got, want_for(sc)):
+                assert torch.equal(a, b)
+        assert len(gr._plans) == B  # one capture per shape, replayed for the other scenes
+
+    # a scene with ~4x larger splats needs more intersections than the capture was sized for
+    sc = scenes.make_scene("C1", seed=23, scenes=1, views_in=3, size_in=64, views_out=3, size_out=80)
+    big = sc.params.clone()
+    big[:, :, 7:10] += 1.5
+    key = gr._key(sc.params, sc.cameras_in, sc.cameras_out) + (0,)
+    old_cap = gr._plans[key]["jobs"][0]["capacity"]
+    got = gr.run(big.to(DEV), sc.cameras_in.to(DEV), sc.cameras_out.to(DEV), check=False)
+    assert not gr.validate()
+    got = gr.recover()
+    with torch.no_grad():
+        want = eager(sc.cameras_out.to(DEV), conv(big.to(DEV), sc.cameras_in.to(DEV)), h=80, w=80)[:3]
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    assert gr._plans[key]["stale"]
+    got = gr.run(big.to(DEV), sc.cameras_in.to(DEV), sc.cameras_out.to(DEV))  # re-captured, larger buffers
+    assert not gr._plans[key]["stale"] and gr._plans[key]["jobs"][0]["capacity"] > old_cap
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+
+
+def test_pipeline_graph_mode_streams_scenes_and_recovers_from_overflow():
+    """DecodeRenderPipeline(graph=True): pinned host scenes in, pinned host images out, every scene replayed from
+    one of two alternating CUDA-graph plans; same bits as the eager modules, including for a scene in the middle of
+    the stream that overflows the captured buffers (re-rendered, plans re-captured) and the scenes after it."""
+    from prometheus_b200 import DecodeRenderPipeline, GaussianConverter, GaussianRenderer, scenes
+
+    conv = GaussianConverter("mvsplat", z_near=0.01, z_far=100.0, s_min=0.001, s_max=1.0).to(DEV)
+    eager = GaussianRenderer().to(DEV)
+    scs = [scenes.make_scene("C1", seed=40 + i, scenes=1, views_in=3, size_in=64, views_out=3, size_out=80) for i in range(7)]
+    scs[3].params[:, :, 7:10] += 1.5  # ~4x larger splats: more intersections than the plans were captured for
+    ins = [tuple(t.clone().pin_memory() for t in (sc.params, sc.cameras_in, sc.cameras_out)) for sc in scs]
+    want = []
+    with torch.no_grad():
+        for sc in scs:
+            want.append(eager(sc.cameras_out.to(DEV), conv(sc.params.to(DEV), sc.cameras_in.to(DEV)), h=80, w=80)[:3])
+    pipe = DecodeRenderPipeline(conv, GaussianRenderer().to(DEV), 80, 80, device=DEV, graph=True)
+    outs = [[torch.empty_like(w.cpu()).pin_memory() for w in ws] for ws in want]
+    pipe.prefetch(*ins[0])
+    for i in range(len(scs)):
+        pipe.run(outs[i], next_inputs_h=ins[i + 1] if i + 1 < len(scs) else None)
+    pipe.flush()
+    torch.cuda.synchronize()
+    for i, (o, ws) in enumerate(zip(outs, want)):
+        for a, b in zip(o, ws):
+            assert torch.equal(a, b.cpu()), i
+    assert len(pipe.graphed._plans) == 2
+
+
 # --------------------------------------------------------------------------- trajectory row (SURVEY §8f rank 3)
 @pytest.mark.parametrize("name", ["orbit_big", "smooth", "repeat", "video120"])
 def test_sample_cameras_vs_reference_golden(golden_dir, name):

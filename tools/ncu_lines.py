@@ -46,6 +46,9 @@ def main():
     print("---- by stall samples")
     for a in sorted(agg, key=lambda a: -a[1])[:top]:
         print("%5.1f%% smp %5.1f%% inst  %s:%s  %s   [%s]" % (100 * a[1] / tot_s, 100 * a[0] / tot_i, a[2], a[3], a[4], a[5]))
+    print("---- by executed instructions")
+    for a in sorted(agg, key=lambda a: -a[0])[:top]:
+        print("%5.1f%% inst %5.1f%% smp  %s:%s  %s   [%s]" % (100 * a[0] / tot_i, 100 * a[1] / tot_s, a[2], a[3], a[4], a[5]))
 
 
 if __name__ == "__main__":

@@ -41,7 +41,9 @@ def main():
             continue
         if hdr is None or len(r) < 10 or r[0] == "":
             continue
-        num = lambda k: float((r[hdr[k]] or "0").replace(",", "")) if r[hdr[k]] not in ("", "-") else 0.0
+        # the source-text column may itself contain commas / quotes (inline asm): index the numeric columns from the end
+        off = len(r) - len(hl)
+        num = lambda k: float((r[hdr[k] + off] or "0").replace(",", "")) if r[hdr[k] + off] not in ("", "-") else 0.0
         ln = int(r[0])
         reg = regions[cur][ln - 1] if regions[cur] and ln - 1 < len(regions[cur]) and regions[cur][ln - 1] else cur
         a = agg.setdefault(reg, [0.0, 0.0, {}])
