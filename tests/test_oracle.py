@@ -27,6 +27,18 @@ def test_unproject_matches_reference_converter(oracle, golden_dir, mode):
         assert allclose(o[k], g[k], atol=1e-5, rtol=1e-4), k
 
 
+@pytest.mark.parametrize("mode,name", [("mvsplat", "bf16"), ("mvsplat", "f16"), ("director3d", "bf16"), ("gslrm", "f16")])
+def test_unproject_on_half_precision_maps_matches_reference_converter(oracle, golden_dir, mode, name):
+    """fp16 / bf16 maps: the reference widens them by `* muls` (gaussians_renderer.py:219), i.e. the restatement
+    applied to the widened maps (stored exactly, as fp32, in the fixture)."""
+    g = np.load(os.path.join(golden_dir, "converter_half.npz"))
+    base = np.load(os.path.join(golden_dir, f"converter_{mode}.npz"))
+    pre = f"{mode}_{name}_"
+    o = oracle.unproject(g[pre + "params"], base["cameras"], base["muls"], mode, 0.01, 100.0, 0.001, 1.0)
+    for k in ("xyz", "features", "opacity", "scales", "rotations"):
+        assert allclose(o[k], g[pre + k], atol=1e-5, rtol=1e-4), k
+
+
 def test_camera_prep_matches_reference(oracle, golden_dir):
     d = np.load(os.path.join(golden_dir, "cameras.npz"))
     vm, K = oracle.camera_prep(d["cameras"], int(d["h"]), int(d["w"]))
