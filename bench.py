@@ -511,7 +511,7 @@ def main():
     # side figure (measured last so that its allocations cannot disturb the figures above; not the headline, whose maps are fp32 as BASELINE's config says): the same loop fed with the
     # maps in bf16, the storage type an autocast decoder hands over; the unproject kernel reads them natively
     half = None
-    if world == 1 and not args.no_half_maps:
+    if world == 1 and not args.no_half_maps and params_h.numel() * 4 <= (1 << 30):  # bounded extra pinned memory
         maps_bf16 = params_h.to(torch.bfloat16).pin_memory()
         e2e_loop(3, maps_bf16)
         barrier()
