@@ -149,8 +149,11 @@ unproject_fwd_kernel(const TP *__restrict__ params, const float *__restrict__ ca
   }
 }
 
+#ifndef PM_UBWD_MINBLOCKS
+#define PM_UBWD_MINBLOCKS 4
+#endif
 template <typename TP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, PM_UBWD_MINBLOCKS)
 unproject_bwd_kernel(const TP *__restrict__ params, const float *__restrict__ cameras,
                      const float *__restrict__ muls, int mode, float z_near, float z_far,
                      float s_min, float s_max, int h, int w,
