@@ -644,33 +644,53 @@ def run_c5(args, rank, world, dev):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     ms = total_ms / args.steps
-    # e2e of this config = the trajectory video API (prometheus_b200.TrajectoryRenderer): poses sampled on the
-    # device along a path through the target cameras, frames rendered in chunks, packed to uint8 and copied to
-    # pinned host memory on a side stream. Rank 0's share of the frames; Gaussians already gathered.
-    e2e = None
-    if rank == 0:
-        from prometheus_b200 import TrajectoryRenderer
+    # e2e of this config = the trajectory video API (prometheus_b200.TrajectoryRenderer) behind the decode: every rank
+    # unprojects its input views into the gathered scene (the exchange step), samples the poses of the video schedule
+    # on the device along a path through the target cameras, renders ITS share of the frames in chunks, packs them to
+    # uint8 and copies them (+ fp32 depth) to pinned host memory on a side stream. Wall clock around the whole
+    # call between barriers, max over ranks.
+    from prometheus_b200 import TrajectoryRenderer
 
+    tr = TrajectoryRenderer(rend)
+    path = cams_out[::15].contiguous()  # 8 key poses of the arc
+    frames_h = torch.empty(f1 - f0, S, S, 3, dtype=torch.uint8).pin_memory()
+    depths_h = torch.empty(f1 - f0, S, S, 1).pin_memory()
+
+    def e2e_step():
         with torch.no_grad():
-            full = parallel.gather_gaussians(
-                lambda slots: ops.unproject_fwd(params, cams_in, muls, "mvsplat", scenes.Z_NEAR, scenes.Z_FAR,
-                                                scenes.S_MIN, scenes.S_MAX, out=slots), n_local, dev) if world == 1 else None
-        if full is not None:
+            if peer is not None:
+                full = peer.gather(lambda n, ptrs: ops.unproject_fwd_multi(params, cams_in, muls, *ucfg, n, ptrs))
+            else:
+                full = parallel.gather_gaussians(
+                    lambda slots: ops.unproject_fwd(params, cams_in, muls, *ucfg, out=slots), n_local, dev)
             xyz, rgb, opac, scl, quat = full
             g = (xyz[None], rgb[None, :, None, :], opac[None, :, None], scl[None], quat[None])
-            tr = TrajectoryRenderer(rend)
-            path = cams_out[::15].contiguous()  # 8 key poses of the arc
-            frames_h = torch.empty(V_out, S, S, 3, dtype=torch.uint8).pin_memory()
-            depths_h = torch.empty(V_out, S, S, 1).pin_memory()
-            tr.render(g, path, num_frames=V_out, render_size=S, frames_out=frames_h, depths_out=depths_h)
+            tr.render(g, path, num_frames=V_out, render_size=S, frames_out=frames_h, depths_out=depths_h,
+                      frame_range=(f0, f1))
+
+    e2e_step()
+    e2e_step()
+    barrier()
+    n_e2e = max(2, args.steps)
+    t0 = time.perf_counter()
+    laps = []
+    for _ in range(n_e2e):
+        e2e_step()
+        if os.environ.get("PM_BENCH_DEBUG"):
             torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            tr.render(g, path, num_frames=V_out, render_size=S, frames_out=frames_h, depths_out=depths_h)
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            e2e = {"value": V_out * S * S / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(path.numel() * 4),
-                   "d2h_bytes_per_step": int(frames_h.numel() + depths_h.numel() * 4), "ms_per_step": round(dt * 1e3, 3),
-                   "api": "TrajectoryRenderer.render (device-side pose sampling, uint8 frames + fp32 depth to pinned host)"}
+            laps.append(round((time.perf_counter() - t0) * 1e3, 1))
+    barrier()
+    dt = (time.perf_counter() - t0) / n_e2e
+    if laps:
+        print("[debug] rank %d e2e laps (cumulative ms): %s" % (rank, laps), file=sys.stderr)
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e = {"value": V_out * S * S / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(path.numel() * 4),
+           "d2h_bytes_per_step": int(frames_h.numel() + depths_h.numel() * 4), "ms_per_step": round(dt * 1e3, 3),
+           "api": "unproject + exchange + TrajectoryRenderer.render(frame_range = this rank's frames): device-side pose "
+                  "sampling, uint8 frames + fp32 depth to pinned host; d2h bytes are per rank"}
     if rank == 0:
         print(json.dumps({
             "e2e": e2e,

@@ -61,16 +61,21 @@ class TrajectoryRenderer:
         return ops.sample_cameras(dense, _video_schedule(num_frames, dense.device))[0]
 
     def render(self, gaussians, dense_cameras: torch.Tensor, num_frames: int = 720, render_size: int = 512,
-               bg_color=None, frames_out: Optional[torch.Tensor] = None, depths_out: Optional[torch.Tensor] = None
-               ) -> Tuple[torch.Tensor, torch.Tensor]:
+               bg_color=None, frames_out: Optional[torch.Tensor] = None, depths_out: Optional[torch.Tensor] = None,
+               frame_range: Optional[Tuple[int, int]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """`frame_range = (a, b)`: render only frames a..b-1 of the `num_frames` schedule (one rank's share when the
+        frames of a video are sharded over GPUs); the outputs then hold b - a frames."""
         dev = gaussians[0].device
         H = W = int(render_size)
+        fa, fb = (0, num_frames) if frame_range is None else (int(frame_range[0]), int(frame_range[1]))
+        assert 0 <= fa <= fb <= num_frames
         if self._side is None:
             self._side = torch.cuda.Stream(dev)
         if frames_out is None:
-            frames_out = torch.empty(num_frames, H, W, 3, dtype=torch.uint8, pin_memory=True)
+            frames_out = torch.empty(fb - fa, H, W, 3, dtype=torch.uint8, pin_memory=True)
         if depths_out is None:
-            depths_out = torch.empty(num_frames, H, W, 1, dtype=torch.float32, pin_memory=True)
+            depths_out = torch.empty(fb - fa, H, W, 1, dtype=torch.float32, pin_memory=True)
+        assert frames_out.shape[0] == fb - fa and depths_out.shape[0] == fb - fa
         cams = self.cameras(dense_cameras.to(dev), num_frames)
         cur = torch.cuda.current_stream(dev)
         prev_defer = self.rend.defer_checks
@@ -78,21 +83,21 @@ class TrajectoryRenderer:
         pending = []
         try:
             with torch.no_grad():
-                for f0 in range(0, num_frames, self.chunk):
-                    f1 = min(num_frames, f0 + self.chunk)
-                    self._render_chunk(gaussians, cams, f0, f1, H, W, bg_color, frames_out, depths_out, cur)
+                for f0 in range(fa, fb, self.chunk):
+                    f1 = min(fb, f0 + self.chunk)
+                    self._render_chunk(gaussians, cams, f0, f1, H, W, bg_color, frames_out, depths_out, cur, fa)
                     pending.append((f0, f1, self.rend.take_pending()))
                 # the renders are queued: look at their deferred checks, redo a chunk in the rare failing case
                 self.rend.defer_checks = False
                 for f0, f1, jobs in pending:
                     if not self.rend.check_jobs(jobs):
-                        self._render_chunk(gaussians, cams, f0, f1, H, W, bg_color, frames_out, depths_out, cur)
+                        self._render_chunk(gaussians, cams, f0, f1, H, W, bg_color, frames_out, depths_out, cur, fa)
         finally:
             self.rend.defer_checks = prev_defer
         cur.wait_stream(self._side)
         return frames_out, depths_out
 
-    def _render_chunk(self, gaussians, cams, f0, f1, H, W, bg_color, frames_out, depths_out, cur):
+    def _render_chunk(self, gaussians, cams, f0, f1, H, W, bg_color, frames_out, depths_out, cur, base=0):
         images, depths, _, _, _ = self.rend(cams[None, f0:f1], gaussians, bg_color=bg_color, h=H, w=W)
         u8 = ops.pack_frames_u8(images[0])
         d = depths[0]  # [n,1,H,W] is bit-for-bit [n,H,W,1]
@@ -102,8 +107,8 @@ class TrajectoryRenderer:
             self._side.wait_event(done)
             u8.record_stream(self._side)
             d.record_stream(self._side)
-            frames_out[f0:f1].copy_(u8, non_blocking=True)
-            depths_out[f0:f1].view(f1 - f0, 1, H, W).copy_(d, non_blocking=True)
+            frames_out[f0 - base:f1 - base].copy_(u8, non_blocking=True)
+            depths_out[f0 - base:f1 - base].view(f1 - f0, 1, H, W).copy_(d, non_blocking=True)
 
 
 def export_video(render_fn, save_path, name, dense_cameras, fps=60, num_frames=720, render_size=512, device="cuda:0"):

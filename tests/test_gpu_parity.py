@@ -936,6 +936,11 @@ def test_trajectory_renderer_matches_the_per_frame_loop(golden_dir):
             assert np.array_equal(frames[i].numpy(), want), i
             assert np.array_equal(depths[i].numpy(), de.reshape(1, S, S).permute(1, 2, 0).cpu().numpy()), i
     assert frames.shape == (n_frames, S, S, 3) and frames.numpy().std() > 5
+    # one rank's share of the frames (view-sharded video): same bits as the corresponding slice
+    with torch.no_grad():
+        part_f, part_d = TrajectoryRenderer(rend).render(g, dense.to(DEV), num_frames=n_frames, render_size=S, frame_range=(3, 9))
+        torch.cuda.synchronize()
+    assert part_f.shape[0] == 6 and torch.equal(part_f, frames[3:9]) and torch.equal(part_d, depths[3:9])
 
 
 # --------------------------------------------------------------------------- densification statistics
