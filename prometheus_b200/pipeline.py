@@ -9,6 +9,8 @@ buffered. This is the public end-to-end API that bench.py's `e2e` number goes th
 With `graph=True` the per-scene launch set is replayed from CUDA graphs (graphed.GraphedDecodeRender): two plans
 with their own static inputs and outputs alternate, so the same three-stream overlap holds while the host only
 issues a handful of calls per scene — what small scenes need, whose step is launch-bound rather than PCIe-bound.
+In both modes a scene's pinned inputs must stay untouched until the scene after the next one has been submitted (or
+flush() has returned): the copies are asynchronous, and a scene whose deferred check fails is rendered again from them.
 """
 from __future__ import annotations
 
