@@ -127,6 +127,9 @@ def run_reference(args):
     from prometheus_b200 import scenes
 
     O.build()
+    # all the host threads this process may use — torchrun exports OMP_NUM_THREADS=1 to every rank, which would
+    # otherwise turn the N > 1 reference runs into single-thread runs
+    O.set_num_threads(len(os.sched_getaffinity(0)))
     cores = O.num_threads()
     scene = scenes.make_scene(args.config)
     S, V = scene.size_out, scene.cameras_out.shape[1]
