@@ -198,6 +198,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipeline", choices=["eager", "graph"], default="graph",
                     help="e2e leg: DecodeRenderPipeline launching the modules eagerly, or replaying CUDA-graph plans")
+    ap.add_argument("--loss", choices=["fused", "eager"], default="fused",
+                    help="fwd+bwd leg: per-pixel loss glue through render_loss_terms (one kernel each way) or plain ATen ops")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay side figure")
     ap.add_argument("--no-half-maps", action="store_true", help="skip the bf16-maps e2e side figure")
     ap.add_argument("--no-bwd", action="store_true")
@@ -264,11 +266,13 @@ def main():
             g = conv(params, cin)
             return rend(cout, g, bg_color=None, h=S, w=S)
 
+    loss_fn = scenes.render_loss_fused if args.loss == "fused" else scenes.render_loss
+
     def step_fwdbwd(params, cin, cout, target):
         p = params.detach().requires_grad_(True)
         g = conv(p, cin)
         images, depths, masks, _, _ = rend(cout, g, bg_color=None, h=S, w=S)
-        loss = scenes.render_loss(images, depths, masks, target)
+        loss = loss_fn(images, depths, masks, target)
         loss.backward()
         if not rend.validate():
             invalid["n"] += 1
@@ -493,7 +497,9 @@ def main():
             bst[name] = bst.get(name, 0.0) + e0.elapsed_time(e1) / bsteps
         extra["fwd_bwd"] = {"value": world * pixels / (bwd_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": round(bwd_ms, 4),
                             "gaussians_per_s": world * B * V_out * G / (bwd_ms * 1e-3),
-                            "stages_ms": {k: round(v, 4) for k, v in bst.items()}}
+                            "stages_ms": {k: round(v, 4) for k, v in bst.items()},
+                            "loss": "mse(images) + mean(1 / clip(depth, 0.1, 100)) + mean(1 - mask); per-pixel glue: %s"
+                                    % ("prometheus_b200.render_loss_terms" if args.loss == "fused" else "ATen ops")}
 
     # side figure: the same forward step replayed from a CUDA graph (GraphedDecodeRender; inputs resident, checks
     # deferred and validated after the loop like the headline loop)

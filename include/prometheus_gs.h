@@ -378,6 +378,22 @@ PM_API int pm_splat_pack(const float *xyz, const float *rgb, const float *opacit
                   const float *rots, const int32_t *order, int64_t n, int compatible,
                   uint8_t *out, pm_stream_t stream);
 
+/* Loss-side glue of the stage-1 rendering loss (prometheus/systems/gs_decoder_system.py:214-239) on the packed
+ * renderer outputs, one pass: images / target [V,3,H,W], depths / masks [V,1,H,W] ->
+ *   disparity [V,1,H,W] = 1 / clamp(depth, 0.1, 100)     (:218, input of the scale-and-shift-invariant loss)
+ *   valid     [V,1,H,W] = depth <= 0.1 ? 0 : 1           (:216-217)
+ *   sums[0] = sum (images - target)^2  (F.mse_loss numerator, :221),  sums[1] = sum (1 - masks)  (:233)
+ * sums is 2 doubles on the device, overwritten. */
+PM_API int pm_loss_terms_fwd(const float *images, const float *target, const float *depths, const float *masks,
+                      int64_t n_views, int height, int width, float *disparity, float *valid, double *sums,
+                      pm_stream_t stream);
+/* Its VJP, straight into the packed cotangents pm_composite_bwd_packed takes: g_mse / g_entropy are the (device,
+ * scalar) cotangents of mean((images - target)^2) and mean(1 - masks), v_disparity [V,1,H,W] that of disparity;
+ * any of the three may be NULL (zero). v_images / v_depths / v_masks are fully overwritten. */
+PM_API int pm_loss_terms_bwd(const float *images, const float *target, const float *depths, int64_t n_views,
+                      int height, int width, const float *g_mse, const float *g_entropy, const float *v_disparity,
+                      float *v_images, float *v_depths, float *v_masks, pm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

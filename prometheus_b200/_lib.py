@@ -54,6 +54,8 @@ SIGNATURES = {
                                         _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "pm_splat_keys": (c_int, [_P, _P, _L, _I, _P, _P, _P]),
     "pm_splat_pack": (c_int, [_P, _P, _P, _P, _P, _P, _L, _I, _P, _P]),
+    "pm_loss_terms_fwd": (c_int, [_P, _P, _P, _P, _L, _I, _I, _P, _P, _P, _P]),
+    "pm_loss_terms_bwd": (c_int, [_P, _P, _P, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "pm_densify_stats": (c_int, [_P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "pm_sample_cameras": (c_int, [_P, _P, _I, _I, _I, _P, _P]),
     "pm_pack_frames_u8": (c_int, [_P, _L, _I, _I, _P, _P]),

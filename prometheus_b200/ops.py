@@ -533,3 +533,34 @@ def splat_pack(xyz, rgb, opacity, scales, rots, compatible=True):
     _lib.check(L.pm_splat_pack(_ptr(xyz), _ptr(rgb), _ptr(opacity), _ptr(scales), _ptr(rots), _ptr(order), n,
                                int(bool(compatible)), _ptr(out), _stream()), "pm_splat_pack")
     return out
+
+
+# --------------------------------------------------------------------------- loss-side glue
+@_instrument("loss_terms_fwd", 1)
+def loss_terms_fwd(images, target, depths, masks):
+    """images / target [V,3,H,W], depths / masks [V,1,H,W] -> (disparity [V,1,H,W], valid [V,1,H,W],
+    sums = {sum (images - target)^2, sum (1 - masks)} as 2 doubles on the device)."""
+    L = _lib.load()
+    images, target = _req(images, torch.float32, "images"), _req(target, torch.float32, "target")
+    depths, masks = _req(depths, torch.float32, "depths"), _req(masks, torch.float32, "masks")
+    V, three, H, W = images.shape
+    assert three == 3 and target.shape == images.shape and depths.shape == (V, 1, H, W) and masks.shape == (V, 1, H, W)
+    disparity, valid = torch.empty_like(depths), torch.empty_like(depths)
+    sums = torch.empty(2, dtype=torch.float64, device=images.device)
+    _lib.check(L.pm_loss_terms_fwd(_ptr(images), _ptr(target), _ptr(depths), _ptr(masks), V, H, W, _ptr(disparity),
+                                   _ptr(valid), _ptr(sums), _stream()), "pm_loss_terms_fwd")
+    return disparity, valid, sums
+
+
+@_instrument("loss_terms_bwd", 1)
+def loss_terms_bwd(images, target, depths, g_mse, g_entropy, v_disparity):
+    """-> (v_images, v_depths, v_masks); g_mse / g_entropy: 0-dim device tensors or None, v_disparity [V,1,H,W] or None."""
+    L = _lib.load()
+    V, _, H, W = images.shape
+    g_mse, g_entropy = _opt(g_mse, torch.float32, "g_mse"), _opt(g_entropy, torch.float32, "g_entropy")
+    v_disparity = _opt(v_disparity, torch.float32, "v_disparity")
+    v_images, v_depths, v_masks = torch.empty_like(images), torch.empty_like(depths), torch.empty_like(depths)
+    _lib.check(L.pm_loss_terms_bwd(_ptr(images), _ptr(target), _ptr(depths), V, H, W, _ptr(g_mse), _ptr(g_entropy),
+                                   _ptr(v_disparity), _ptr(v_images), _ptr(v_depths), _ptr(v_masks), _stream()),
+               "pm_loss_terms_bwd")
+    return v_images, v_depths, v_masks

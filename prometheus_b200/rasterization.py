@@ -152,6 +152,9 @@ class _TileRenderPacked(torch.autograd.Function):
             last_ids, v_images, v_depth_out, v_masks, d_n=stats, tile_order=order, views_per_scene=ctx.views_per_scene)
         if ctx.grad_sink is not None:
             ctx.grad_sink["v_means2d"] = v_means2d
+            for j, view in enumerate(ctx.grad_sink.get("views", ())):  # the reference's viewspace_points[j].grad
+                g = v_means2d[j:j + 1]
+                view.grad = g if view.grad is None else view.grad + g
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[5] and v_images is not None:
             v_bg = (2.0 * v_images * (1.0 - masks)).sum(dim=(2, 3))
@@ -177,19 +180,23 @@ def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, b
     means, quats, scales, opacities, colors, viewmats, Ks = map(f32, (means, quats, scales, opacities, colors, viewmats, Ks))
     means2d, depths, conics, radii, counts = _Project.apply(means, quats, scales, viewmats, Ks, width, height, eps2d,
                                                              near_plane, far_plane, radius_clip, True, views_per_scene)
-    means2d_views = [v.unsqueeze(0) for v in means2d.unbind(0)]
-    means2d_in = means2d
+    # The reference keeps one [1,N,2] screen-space tensor per rendered view and reads its .grad after backward
+    # (`viewspace_points`, gaussians_renderer.py:428-445). Routing autograd through per-view tensors costs a cat and a
+    # stack of the whole [C,N,2] array each way; instead the per-view tensors are leaf views of the projected means
+    # and the compositing backward hands each its slice of the contiguous gradient (no copy).
+    grad_sink = {}
     if means2d.requires_grad:
-        for v in means2d_views:
-            v.retain_grad()
-        means2d_in = torch.cat(means2d_views, dim=0)
+        base = means2d.detach()
+        means2d_views = [base[j:j + 1].requires_grad_(True) for j in range(C)]
+        grad_sink["views"] = means2d_views
+    else:
+        means2d_views = [v.unsqueeze(0) for v in means2d.unbind(0)]
     isect_offsets, stats, tile_order = ops.tile_scan(counts, want_order=True)
     if capacity is None:
         capacity = int(stats[0].item())
     records = ops.bin_scatter(means2d.detach(), radii, depths.detach(), isect_offsets, width, height, int(capacity))
-    grad_sink = {}
     images, depth_out, masks, flag, flatten_ids, sorted_counts = _TileRenderPacked.apply(
-        means2d_in, conics, opacities, colors, depths, backgrounds, records, isect_offsets, stats, width, height, grad_sink,
+        means2d, conics, opacities, colors, depths, backgrounds, records, isect_offsets, stats, width, height, grad_sink,
         tile_order, views_per_scene)
     info = {"radii": radii, "means2d": means2d, "means2d_views": means2d_views, "depths": depths, "conics": conics,
             "isect_offsets": isect_offsets, "flatten_ids": flatten_ids, "sorted_counts": sorted_counts,

@@ -100,3 +100,12 @@ def render_loss(images: torch.Tensor, depths: torch.Tensor, masks: torch.Tensor,
     """Synthetic stand-in for the stage-1 loss (gs_decoder_system.py:214-239; LPIPS weights are
     not available offline): every one of the three outputs receives a gradient."""
     return ((images - target) ** 2).mean() + (1.0 / depths.clamp(0.1, 100.0)).mean() + (1.0 - masks).mean()
+
+
+def render_loss_fused(images: torch.Tensor, depths: torch.Tensor, masks: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """`render_loss` with its per-pixel glue done by losses.render_loss_terms (one kernel each way instead of a dozen
+    ATen passes); same value and gradients up to the summation order."""
+    from .losses import render_loss_terms
+
+    mse, disparity, _valid, entropy = render_loss_terms(images, depths, masks, target)
+    return mse + disparity.mean() + entropy

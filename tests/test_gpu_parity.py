@@ -943,6 +943,61 @@ def test_trajectory_renderer_matches_the_per_frame_loop(golden_dir):
     assert part_f.shape[0] == 6 and torch.equal(part_f, frames[3:9]) and torch.equal(part_d, depths[3:9])
 
 
+# --------------------------------------------------------------------------- loss-side glue
+@pytest.mark.parametrize("shape", [(2, 3, 40, 56), (1, 1, 17, 9)])
+def test_render_loss_terms_match_the_reference_expressions(shape):
+    """render_loss_terms vs the expressions of gs_decoder_system.py:214-239 written with ATen ops, values and
+    gradients (depths straddle both clip bounds; validity mask bit-exact)."""
+    from prometheus_b200 import render_loss_terms
+
+    B, N, H, W = shape
+    g = torch.Generator().manual_seed(5)
+    images = (torch.rand(B, N, 3, H, W, generator=g) * 2 - 1).to(DEV).requires_grad_(True)
+    target = (torch.rand(B, N, 3, H, W, generator=g) * 2 - 1).to(DEV)
+    depths = torch.exp(torch.randn(B, N, 1, H, W, generator=g) * 3.0)
+    depths.view(-1)[:7] = torch.tensor([0.1, 100.0, 0.0, 0.05, 150.0, 0.1000001, 99.99999])
+    depths = depths.to(DEV).requires_grad_(True)
+    masks = torch.rand(B, N, 1, H, W, generator=g).to(DEV).requires_grad_(True)
+    w_disp = torch.randn(B, N, 1, H, W, generator=g).to(DEV)
+
+    def reference(images, depths, masks):
+        mask = torch.ones_like(depths)
+        mask[depths <= 0.1] = 0
+        disp = 1 / depths.clip(0.1, 100)
+        return torch.nn.functional.mse_loss(images, target), disp, mask, (1 - masks).mean()
+
+    want = reference(images, depths, masks)
+    (0.7 * want[0] + (want[1] * w_disp).sum() + 1.3 * want[3]).backward()
+    want_g = [t.grad.clone() for t in (images, depths, masks)]
+    for t in (images, depths, masks):
+        t.grad = None
+    got = render_loss_terms(images, depths, masks, target)
+    (0.7 * got[0] + (got[1] * w_disp).sum() + 1.3 * got[3]).backward()
+    assert torch.allclose(got[0], want[0], rtol=1e-6, atol=0) and torch.allclose(got[3], want[3], rtol=1e-6, atol=0)
+    assert torch.equal(got[1], want[1].detach()) and torch.equal(got[2], want[2])
+    for a, b in zip((images.grad, depths.grad, masks.grad), want_g):
+        assert torch.allclose(a, b, rtol=2e-6, atol=1e-12), (a - b).abs().max()
+
+
+def test_fused_loss_glue_through_the_renderer():
+    """The training-style step with render_loss_fused equals the one with the ATen loss: loss and map gradients."""
+    from prometheus_b200 import GaussianRenderer, scenes
+
+    sc, conv = _module_scene()
+    rend = GaussianRenderer().to(DEV)
+    target = (torch.rand(1, 3, 3, 80, 80, generator=torch.Generator().manual_seed(2)) * 2 - 1).to(DEV)
+    res = []
+    for fn in (scenes.render_loss, scenes.render_loss_fused):
+        p = sc.params.to(DEV).requires_grad_(True)
+        im, de, ma, _, _ = rend(sc.cameras_out.to(DEV), conv(p, sc.cameras_in.to(DEV)), h=80, w=80)
+        loss = fn(im, de, ma, target) * im.numel()  # O(1) cotangents per pixel
+        loss.backward()
+        res.append((loss.detach(), p.grad.clone()))
+    assert torch.allclose(res[0][0], res[1][0], rtol=1e-6)
+    assert float(res[0][1].abs().max()) > 1.0
+    assert grad_close(res[1][1].cpu().numpy(), res[0][1].cpu().numpy(), atol=1e-6, rtol=1e-4)
+
+
 # --------------------------------------------------------------------------- densification statistics (SURVEY §8f rank 2)
 @pytest.mark.parametrize("fused", [True, False])
 def test_densification_stats_match_the_refiner_loop(fused):
