@@ -43,6 +43,8 @@ class GraphedDecodeRender:
         self.h, self.w, self.bg = int(h), int(w), bg_color
         self._plans = {}
         self._last = None
+        self.n_captures = 0     # telemetry: graphs captured (first use of a shape / slot, and re-captures)
+        self.n_failed_checks = 0  # replays whose deferred checks failed (each is re-rendered eagerly by the caller)
 
     # ------------------------------------------------------------------ capture
     def _eager(self, params, cin, cout):
@@ -62,6 +64,7 @@ class GraphedDecodeRender:
         # one eager pass with blocking checks: sets the capacity hints the captured buffers are sized from (and
         # takes the slow path now if this scene needs it)
         self._eager(*static_in)
+        self.n_captures += 1
         rows = torch.zeros(self.MAX_JOBS, 3, dtype=torch.int32).pin_memory()
         used = [0]
         rend = self.rend
@@ -117,6 +120,7 @@ class GraphedDecodeRender:
         plan["done"].synchronize()
         ok = self.rend.check_jobs(plan["jobs"])
         if not ok:
+            self.n_failed_checks += 1
             for k, p in self._plans.items():
                 if k[:-1] == plan["key"][:-1]:
                     p["stale"] = True

@@ -120,6 +120,20 @@ class DecodeRenderPipeline:
         while len(self._unchecked) > self.max_in_flight:
             self._settle(self._unchecked.pop(0))
 
+    def run_batch(self, inputs_h: Tuple[torch.Tensor, ...], out_h: Sequence[torch.Tensor], chunk: Optional[int] = None) -> None:
+        """A large host-resident batch of scenes (config C4: 64 scenes) as a stream of `chunk`-scene slices (default:
+        the renderer's scene_chunk): the host->device copy of slice k+1 and the device->host copy of slice k-1 overlap
+        the render of slice k, instead of the whole batch being copied, then rendered, then copied back.
+        inputs_h = (params [B,N,14,h,w], cameras_in [B,N,18], cameras_out [B,M,18]) pinned; out_h = pinned
+        (images [B,M,3,H,W], depths [B,M,1,H,W], masks [B,M,1,H,W]). Call flush() before reading out_h."""
+        B = inputs_h[0].shape[0]
+        c = int(chunk or self.rend.scene_chunk)
+        slices = [slice(b, min(B, b + c)) for b in range(0, B, c)]
+        self.prefetch(*(t[slices[0]] for t in inputs_h))
+        for i, sl in enumerate(slices):
+            nxt = tuple(t[slices[i + 1]] for t in inputs_h) if i + 1 < len(slices) else None
+            self.run([o[sl] for o in out_h], next_inputs_h=nxt)
+
     def _render(self, params, cin, cout, deferred: bool):
         prev = self.rend.defer_checks
         self.rend.defer_checks = deferred

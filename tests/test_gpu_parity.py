@@ -863,6 +863,25 @@ def test_pipeline_graph_mode_streams_scenes_and_recovers_from_overflow():
     assert len(pipe.graphed._plans) == 2
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_pipeline_run_batch_streams_a_large_batch_in_slices(graph):
+    """run_batch: a host batch of 5 scenes in slices of 2 (2 + 2 + 1) equals the one-shot render of the batch."""
+    from prometheus_b200 import DecodeRenderPipeline, GaussianConverter, GaussianRenderer, scenes
+
+    conv = GaussianConverter("mvsplat", z_near=0.01, z_far=100.0, s_min=0.001, s_max=1.0).to(DEV)
+    sc = scenes.make_scene("C1", seed=61, scenes=5, views_in=2, size_in=64, views_out=3, size_out=72)
+    with torch.no_grad():
+        want = GaussianRenderer().to(DEV)(sc.cameras_out.to(DEV), conv(sc.params.to(DEV), sc.cameras_in.to(DEV)), h=72, w=72)[:3]
+    pipe = DecodeRenderPipeline(conv, GaussianRenderer().to(DEV), 72, 72, device=DEV, graph=graph)
+    ins = tuple(t.pin_memory() for t in (sc.params, sc.cameras_in, sc.cameras_out))
+    outs = [torch.empty_like(w.cpu()).pin_memory() for w in want]
+    pipe.run_batch(ins, outs, chunk=2)
+    pipe.flush()
+    torch.cuda.synchronize()
+    for a, b in zip(outs, want):
+        assert torch.equal(a, b.cpu())
+
+
 # --------------------------------------------------------------------------- trajectory row (SURVEY §8f rank 3)
 @pytest.mark.parametrize("name", ["orbit_big", "smooth", "repeat", "video120"])
 def test_sample_cameras_vs_reference_golden(golden_dir, name):
