@@ -81,3 +81,38 @@ def test_ops_refuse_cpu_tensors():
     with pytest.raises(AssertionError):
         pb.rasterization(torch.zeros(N, 2), torch.ones(N, 4), torch.ones(N, 3), torch.ones(N), torch.ones(N, 3),
                          torch.eye(4)[None], torch.eye(3)[None], 32, 32, packed=False)
+
+
+def test_widened_entry_points_refuse_cpu_tensors_and_bad_configurations():
+    """The rows added around the path keep the rule: CPU tensors are an error, and configurations a CUDA-graph
+    capture cannot hold are rejected up front."""
+    import torch
+
+    import prometheus_b200 as pb
+
+    with pytest.raises(RuntimeError, match="no CPU"):
+        pb.render_loss_terms(torch.zeros(1, 1, 3, 8, 8), torch.ones(1, 1, 1, 8, 8), torch.ones(1, 1, 1, 8, 8),
+                             torch.zeros(1, 1, 3, 8, 8))
+    conv, rend = pb.GaussianConverter(), pb.GaussianRenderer()
+    with pytest.raises(RuntimeError, match="no CPU"):
+        conv(torch.zeros(1, 1, 14, 8, 8, dtype=torch.bfloat16), torch.zeros(1, 1, 18))
+    with pytest.raises(ValueError, match="random background"):
+        pb.GraphedDecodeRender(conv, rend, 64, 64, bg_color="random")
+    rend.fused = False
+    with pytest.raises(ValueError, match="fused path"):
+        pb.GraphedDecodeRender(conv, rend, 64, 64)
+
+
+def test_param_dtype_codes_match_the_header():
+    """ops.PARAM_DTYPES (torch dtype -> enum pm_dtype) against include/prometheus_gs.h."""
+    import re
+
+    import torch
+
+    from prometheus_b200 import ops
+
+    text = open(os.path.join(ROOT, "include", "prometheus_gs.h")).read()
+    enum = dict((k, int(v)) for k, v in re.findall(r"(PM_DTYPE_\w+)\s*=\s*(\d+)", text))
+    assert enum == {"PM_DTYPE_F32": 0, "PM_DTYPE_F16": 1, "PM_DTYPE_BF16": 2}
+    assert ops.PARAM_DTYPES == {torch.float32: enum["PM_DTYPE_F32"], torch.float16: enum["PM_DTYPE_F16"],
+                                torch.bfloat16: enum["PM_DTYPE_BF16"]}
