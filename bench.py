@@ -175,8 +175,20 @@ def torch_cpu_baseline(O):
         torch_ref.rasterization(*args, torch.from_numpy(vm), torch.from_numpy(K), 256, 256,
                                 backgrounds=torch.ones(1, 3), render_mode="RGB+ED")
     dt = time.perf_counter() - t0
+    # forward + backward of the same view (torch autograd through the restatement = the oracle of the backward
+    # kernels), with the synthetic render loss on all three outputs
+    leaves = [a.clone().requires_grad_(True) for a in args]
+    t0 = time.perf_counter()
+    out = torch_ref.rasterization(*leaves, torch.from_numpy(vm), torch.from_numpy(K), 256, 256,
+                                  backgrounds=torch.ones(1, 3), render_mode="RGB+ED")
+    render, alpha = out[0], out[1]
+    loss = (render[..., :3] ** 2).mean() + (1.0 / render[..., 3:].clamp(0.1, 100.0)).mean() + (1.0 - alpha).mean()
+    loss.backward()
+    dt_b = time.perf_counter() - t0
     return {"value": 256 * 256 / dt / 1e6, "unit": UNIT, "cores": os.cpu_count(),
-            "sample": "oracle/torch_ref.py, 1 target view of C1 (262144 Gaussians -> 256^2) in %.2fs" % dt}
+            "sample": "oracle/torch_ref.py, 1 target view of C1 (262144 Gaussians -> 256^2) in %.2fs" % dt,
+            "fwd_bwd": {"value": 256 * 256 / dt_b / 1e6, "unit": UNIT,
+                        "sample": "the same view forward + autograd backward in %.2fs" % dt_b}}
 
 
 def workload_name(cfg, scene):
