@@ -300,3 +300,59 @@ def test_splat_oracle_matches_reference_golden(tag, thr):
                              g["rotations"][0][keep])
     assert np.all(np.diff(keys) >= 0)
     check_splat_against_reference(got, g["splat_" + tag], int(keep.sum()))
+
+
+# --------------------------------------------------------------------------- size-independent properties of the oracle
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_oracle_compositing_properties(oracle, seed):
+    """Properties any correct restatement of the path has, whatever the scene: compositing is linear in the colours
+    (no background), the result does not depend on the order the Gaussians are listed in (distinct depths), alpha
+    and transmittance stay in range, expected depth lies between the nearest and farthest visible splat, and every
+    pixel's last contributing entry lies inside its tile's range."""
+    s = random_blobs(n=1500, C=2, W=72, H=40, seed=30 + seed)
+    a = oracle.forward_pipeline(**s, want_fragile=False)
+    # ranges
+    assert a["alphas"].min() >= 0.0 and a["alphas"].max() <= 1.0
+    vis_depth = a["depths"][a["radii"] > 0]
+    hit = a["alphas"] > 0.5
+    ed = a["render"][..., 3] / np.maximum(a["alphas"], 1e-10)
+    assert ed[hit].min() >= vis_depth.min() * (1 - 1e-5) and ed[hit].max() <= vis_depth.max() * (1 + 1e-5)
+    # last_ids inside the tile's range of the sorted list
+    off = a["isect_offsets"].reshape(-1)
+    C, H, W = a["last_ids"].shape
+    tw = a["tile_width"]
+    ends = np.append(off[1:], a["flatten_ids"].shape[0])
+    for c in range(C):
+        for (y, x) in ((0, 0), (H - 1, W - 1), (H // 2, W // 3)):
+            t = (c * a["tile_height"] + y // 16) * tw + x // 16
+            last = a["last_ids"][c, y, x]
+            assert (off[t] <= last < ends[t]) or a["alphas"][c, y, x] == 0.0
+    # linearity in the colours
+    rng = np.random.default_rng(seed)
+    col2 = rng.random(s["colors"].shape, dtype=np.float32)
+    s2 = dict(s, colors=col2)
+    s3 = dict(s, colors=(0.25 * s["colors"] + 0.5 * col2).astype(np.float32))
+    b, c3 = oracle.forward_pipeline(**s2, want_fragile=False), oracle.forward_pipeline(**s3, want_fragile=False)
+    assert np.array_equal(a["alphas"], b["alphas"]) and np.array_equal(a["last_ids"], b["last_ids"])
+    assert allclose(c3["render"][..., :3], 0.25 * a["render"][..., :3] + 0.5 * b["render"][..., :3], atol=2e-6, rtol=1e-5)
+    # permutation invariance (depths are distinct with probability 1; ties would be ordered by index)
+    d0 = a["depths"][0][a["radii"][0] > 0]
+    assert np.unique(d0).size == d0.size
+    perm = rng.permutation(s["means"].shape[0])
+    sp = dict(s, **{k: s[k][perm] for k in ("means", "quats", "scales", "opacities", "colors")})
+    p = oracle.forward_pipeline(**sp, want_fragile=False)
+    assert np.array_equal(p["render"], a["render"]) and np.array_equal(p["alphas"], a["alphas"])
+    assert np.array_equal(p["radii"], a["radii"][:, perm])
+
+
+def test_oracle_background_and_opacity_limits(oracle):
+    """Zero opacity renders pure background with alpha 0; the background enters as T * bg exactly."""
+    s = random_blobs(n=400, C=1, W=48, H=32, seed=77)
+    bg = np.array([[0.2, 0.5, 0.9]], np.float32)
+    z = oracle.forward_pipeline(**dict(s, opacities=np.zeros_like(s["opacities"])), backgrounds=bg, want_fragile=False)
+    assert np.all(z["alphas"] == 0.0) and np.all(z["render"][..., :3] == bg[0]) and np.all(z["render"][..., 3] == 0.0)
+    a = oracle.forward_pipeline(**s, want_fragile=False)
+    b = oracle.forward_pipeline(**s, backgrounds=bg, want_fragile=False)
+    T = 1.0 - a["alphas"]
+    assert allclose(b["render"][..., :3], a["render"][..., :3] + T[..., None] * bg[0], atol=1e-6, rtol=1e-6)
+    assert np.array_equal(b["render"][..., 3], a["render"][..., 3])  # the depth channel has no background
