@@ -79,7 +79,7 @@ struct UnprojDstSet {
 };
 
 template <typename TP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)  // 48 registers: 5 CTAs/SM, as before the kernel was templated on the map type
 unproject_fwd_kernel(const TP *__restrict__ params, const float *__restrict__ cameras,
                      const float *__restrict__ muls, int mode, float z_near, float z_far,
                      float s_min, float s_max, int h, int w, const UnprojDstSet dst) {
