@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PM_ABI_VERSION 1
+#define PM_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define PM_API __attribute__((visibility("default")))
@@ -267,6 +267,9 @@ PM_API int pm_tile_offsets(const int64_t *sorted_isect_ids, int64_t n, const int
  *   backgrounds [C,D] or NULL (the depth channel's background is 0)
  * outputs: render [C,H,W,CD], alphas [C,H,W], last_ids [C,H,W] int32 (index into
  *   the sorted list of the last Gaussian composited into the pixel).
+ *   transmittance [C,H,W] (may be NULL): the exact fp32 T = prod(1 - alpha_i) the pixel ended with. Upstream's
+ *   backward rebuilds it as 1 - render_alpha, which rounds away up to ulp(alpha) / T ~ 3e-4 relative on an opaque
+ *   pixel; pm_composite_bwd takes this array instead when it is given.
  * ------------------------------------------------------------------------- */
 PM_API int pm_composite_fwd(const float *means2d, const float *conics, const float *opacities,
                      const float *colors, int colors_per_camera, int D,
@@ -274,7 +277,7 @@ PM_API int pm_composite_fwd(const float *means2d, const float *conics, const flo
                      const int32_t *isect_offsets, const int32_t *flatten_ids,
                      int64_t n_isects, const int32_t *d_n,
                      int N, int C, int width, int height, int tile_size,
-                     float *render, float *alphas, int32_t *last_ids,
+                     float *render, float *alphas, int32_t *last_ids, float *transmittance,
                      pm_stream_t stream);
 
 /* Fused "sort-as-you-go" forward (fast path of the module-level renderer): takes
@@ -294,7 +297,7 @@ PM_API int pm_tile_render_fwd(const uint64_t *records, const int32_t *isect_offs
                               int width, int height, int tile_size,
                               float *render, float *alphas, int32_t *last_ids,
                               int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
-                              const int32_t *tile_order, pm_stream_t stream);
+                              const int32_t *tile_order, float *transmittance, pm_stream_t stream);
 
 /* The same kernel with the module-level epilogue fused in (RGB + expected depth, D = 3): writes
  * what GaussianRenderer.forward returns (gaussians_renderer.py:437-440, :507-509) —
@@ -310,9 +313,11 @@ PM_API int pm_tile_render_packed_fwd(const uint64_t *records, const int32_t *ise
                               int width, int height, int tile_size,
                               float *images, float *depth_out, float *masks, int32_t *last_ids,
                               int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
-                              const int32_t *tile_order, int views_per_scene, pm_stream_t stream);
+                              const int32_t *tile_order, int views_per_scene, float *transmittance,
+                              pm_stream_t stream);
 
-/* Backward. v_render [C,H,W,CD], v_alphas [C,H,W] (either may be NULL).
+/* Backward. v_render [C,H,W,CD], v_alphas [C,H,W] (either may be NULL). transmittance [C,H,W] = the forward's
+ * array of that name, or NULL: T_final is then rebuilt as 1 - alphas like upstream.
  * Gradients are ACCUMULATED (+=) into v_means2d [C,N,2], v_conics [C,N,3],
  * v_colors ([N,D] or [C,N,D]), v_opacities [N], v_depths [C,N]: the caller
  * zero-fills them. v_depths must be non-NULL iff depths is. */
@@ -322,7 +327,7 @@ PM_API int pm_composite_bwd(const float *means2d, const float *conics, const flo
                      const int32_t *isect_offsets, const int32_t *flatten_ids,
                      int64_t n_isects, const int32_t *d_n,
                      int N, int C, int width, int height, int tile_size,
-                     const float *alphas, const int32_t *last_ids,
+                     const float *alphas, const int32_t *last_ids, const float *transmittance,
                      const float *v_render, const float *v_alphas,
                      float *v_means2d, float *v_conics, float *v_colors,
                      float *v_opacities, float *v_depths, pm_stream_t stream);
@@ -336,6 +341,7 @@ PM_API int pm_composite_bwd_packed(const float *means2d, const float *conics, co
                      const int32_t *flatten_ids, int64_t n_isects, const int32_t *d_n,
                      int N, int C, int width, int height, int tile_size,
                      const float *masks, const float *depth_out, const int32_t *last_ids,
+                     const float *transmittance,
                      const float *v_images, const float *v_depth_out, const float *v_masks,
                      float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
                      float *v_depths, const int32_t *tile_order, int views_per_scene, pm_stream_t stream);

@@ -419,7 +419,8 @@ ORC_API void orc_composite_fwd(const float *means2d, const float *conics, const 
                                const float *depths, const float *backgrounds,
                                const int32_t *offsets, const int32_t *flatten_ids, int64_t n_isects,
                                int N, int C, int width, int height, int tile_size,
-                               float *render, float *alphas, int32_t *last_ids, uint8_t *fragile) {
+                               float *render, float *alphas, int32_t *last_ids, uint8_t *fragile,
+                               float *transmittance) {
   const int tw = (width + tile_size - 1) / tile_size;
   const int th = (height + tile_size - 1) / tile_size;
   const int CD = D + (depths ? 1 : 0);
@@ -468,13 +469,20 @@ ORC_API void orc_composite_fwd(const float *means2d, const float *conics, const 
         }
         last_ids[pix] = last;
         if (fragile) fragile[pix] = frag;
+        if (transmittance) transmittance[pix] = T; /* exact final T, see orc_composite_bwd */
       }
   }
 }
 
 /* Backward of the compositing, restating rasterize_to_pixels_bwd (SURVEY §8c
  * step 12). Accumulates in double so that the oracle's own summation order adds
- * no noise; outputs are fp32 and must be zero-filled by the caller. */
+ * no noise (tiles run in parallel, the accumulations are atomic doubles: the order
+ * changes the result by ~1e-16 relative); outputs must be zero-filled by the caller.
+ * transmittance == NULL: T_final = 1 - alphas[pix], the form upstream uses. That
+ * subtraction rounds away up to ulp(alpha) / T_final (~3e-4 relative on an opaque
+ * pixel) of the transmittance the forward actually ended with, and every term of
+ * the pixel's gradient scales with it. transmittance != NULL (what the forward
+ * wrote): the exact value — the form the CUDA path uses and the tests compare. */
 ORC_API void orc_composite_bwd(const float *means2d, const float *conics, const float *opacities,
                                const float *colors, int colors_per_camera, int D,
                                const float *depths, const float *backgrounds,
@@ -483,13 +491,13 @@ ORC_API void orc_composite_bwd(const float *means2d, const float *conics, const 
                                const float *alphas, const int32_t *last_ids,
                                const float *v_render, const float *v_alphas,
                                double *v_means2d, double *v_conics, double *v_colors,
-                               double *v_opacities, double *v_depths) {
+                               double *v_opacities, double *v_depths, const float *transmittance) {
   const int tw = (width + tile_size - 1) / tile_size;
   const int th = (height + tile_size - 1) / tile_size;
   const int CD = D + (depths ? 1 : 0);
   const long n_tiles = (long)tw * th;
   (void)n_isects;
-  /* serial over pixels: accumulation targets are shared between tiles */
+#pragma omp parallel for schedule(dynamic, 4)
   for (long ct = 0; ct < (long)C * n_tiles; ++ct) {
     const int c = (int)(ct / n_tiles);
     const int tile = (int)(ct % n_tiles);
@@ -499,7 +507,7 @@ ORC_API void orc_composite_bwd(const float *means2d, const float *conics, const 
       for (int ix = txi * tile_size; ix < (txi + 1) * tile_size && ix < width; ++ix) {
         const long pix = ((long)c * height + iy) * width + ix;
         const float px = (float)ix + 0.5f, py = (float)iy + 0.5f;
-        const float T_final = 1.0f - alphas[pix];
+        const float T_final = transmittance ? transmittance[pix] : 1.0f - alphas[pix];
         float T = T_final;
         float buffer[4] = {0, 0, 0, 0};
         float vr[4] = {0, 0, 0, 0};
@@ -526,8 +534,14 @@ ORC_API void orc_composite_bwd(const float *means2d, const float *conics, const 
           float chan[4] = {0, 0, 0, 0};
           for (int k = 0; k < D; ++k) chan[k] = colors[cidx + k];
           if (depths) chan[D] = depths[f];
-          for (int k = 0; k < D; ++k) v_colors[cidx + k] += (double)(fac * vr[k]);
-          if (depths) v_depths[f] += (double)(fac * vr[D]);
+          for (int k = 0; k < D; ++k) {
+#pragma omp atomic
+            v_colors[cidx + k] += (double)(fac * vr[k]);
+          }
+          if (depths) {
+#pragma omp atomic
+            v_depths[f] += (double)(fac * vr[D]);
+          }
           for (int k = 0; k < CD; ++k) v_alpha += (chan[k] * T - buffer[k] * ra) * vr[k];
           v_alpha += T_final * ra * va;
           if (backgrounds) {
@@ -537,11 +551,17 @@ ORC_API void orc_composite_bwd(const float *means2d, const float *conics, const 
           }
           if (opac * vis <= 0.999f) {
             const float v_sigma = -opac * vis * v_alpha;
+#pragma omp atomic
             v_conics[3 * (long)f + 0] += (double)(0.5f * v_sigma * dx * dx);
+#pragma omp atomic
             v_conics[3 * (long)f + 1] += (double)(v_sigma * dx * dy);
+#pragma omp atomic
             v_conics[3 * (long)f + 2] += (double)(0.5f * v_sigma * dy * dy);
+#pragma omp atomic
             v_means2d[2 * (long)f + 0] += (double)(v_sigma * (con[0] * dx + con[1] * dy));
+#pragma omp atomic
             v_means2d[2 * (long)f + 1] += (double)(v_sigma * (con[1] * dx + con[2] * dy));
+#pragma omp atomic
             v_opacities[g] += (double)(vis * v_alpha);
           }
           for (int k = 0; k < CD; ++k) buffer[k] += chan[k] * fac;

@@ -208,16 +208,20 @@ def composite_fwd(means2d, conics, opacities, colors, depths, backgrounds, offse
     alphas = np.zeros((C, height, width), np.float32)
     last_ids = np.zeros((C, height, width), np.int32)
     fragile = np.zeros((C, height, width), np.uint8) if want_fragile else None
+    trans = np.zeros((C, height, width), np.float32)
     lib().orc_composite_fwd(_p(means2d), _p(conics), _p(opacities), _p(colors), c_int(per_cam), c_int(D),
                             _p(depths), _p(backgrounds), _p(offsets, c_int32), _p(flatten_ids, c_int32),
                             c_int64(flatten_ids.shape[0]), c_int(N), c_int(C), c_int(width), c_int(height),
                             c_int(tile_size), _p(render), _p(alphas), _p(last_ids, c_int32),
-                            _p(fragile, c_uint8))
+                            _p(fragile, c_uint8), _p(trans))
+    composite_fwd.transmittance = trans  # the exact final T per pixel of the last call (see composite_bwd)
     return render, alphas, last_ids, fragile
 
 
 def composite_bwd(means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids,
-                  width, height, alphas, last_ids, v_render, v_alphas, tile_size=16):
+                  width, height, alphas, last_ids, v_render, v_alphas, tile_size=16, transmittance=None):
+    """transmittance [C,H,W] = the forward's exact final T (what the CUDA path keeps); None = upstream's
+    T_final = 1 - alphas, which rounds away up to ~3e-4 relative of it on opaque pixels."""
     means2d, conics, opacities = _f32(means2d), _f32(conics), _f32(opacities)
     C, N = means2d.shape[:2]
     colors, per_cam, D = _color_args(colors, C, N)
@@ -229,6 +233,7 @@ def composite_bwd(means2d, conics, opacities, colors, depths, backgrounds, offse
     last_ids = np.ascontiguousarray(last_ids, np.int32)
     v_render = None if v_render is None else _f32(v_render)
     v_alphas = None if v_alphas is None else _f32(v_alphas)
+    transmittance = None if transmittance is None else _f32(transmittance)
     v_means2d = np.zeros((C, N, 2), np.float64)
     v_conics = np.zeros((C, N, 3), np.float64)
     v_colors = np.zeros(colors.shape, np.float64)
@@ -239,7 +244,7 @@ def composite_bwd(means2d, conics, opacities, colors, depths, backgrounds, offse
                             c_int64(flatten_ids.shape[0]), c_int(N), c_int(C), c_int(width), c_int(height),
                             c_int(tile_size), _p(alphas), _p(last_ids, c_int32), _p(v_render), _p(v_alphas),
                             _p(v_means2d, c_double), _p(v_conics, c_double), _p(v_colors, c_double),
-                            _p(v_opac, c_double), _p(v_depths, c_double))
+                            _p(v_opac, c_double), _p(v_depths, c_double), _p(transmittance))
     return dict(v_means2d=v_means2d, v_conics=v_conics, v_colors=v_colors, v_opacities=v_opac,
                 v_depths=v_depths)
 
@@ -285,17 +290,20 @@ def forward_pipeline(means, quats, scales, opacities, colors, viewmats, Ks, widt
     out = dict(pr)
     out.update(isect_ids_unsorted=ids, flatten_ids_unsorted=flat, isect_ids=ids_s, flatten_ids=flat_s,
                isect_offsets=off, render=render, alphas=alphas, last_ids=last_ids, fragile=fragile,
+               transmittance=composite_fwd.transmittance,
                tile_width=tw, tile_height=th, tile_n_bits=tb, cam_n_bits=cb)
     return out
 
 
 def rasterization(means, quats, scales, opacities, colors, viewmats, Ks, width, height,
                   near_plane=0.01, far_plane=1e10, radius_clip=0.0, eps2d=0.3, sh_degree=None,
-                  packed=False, tile_size=16, backgrounds=None, render_mode="RGB", **_unused):
+                  packed=False, tile_size=16, backgrounds=None, render_mode="RGB", exact_transmittance=True,
+                  **_unused):
     """gsplat.rasterization stand-in on torch CPU tensors, with autograd wired as
     two nodes (projection -> compositing) like upstream, so `meta["means2d"]`
     accepts retain_grad() (reference call site gaussians_renderer.py:413-435).
-    Oracle use only."""
+    exact_transmittance=False makes the backward rebuild T_final = 1 - alpha as
+    upstream does (see composite_bwd). Oracle use only."""
     import torch
 
     assert sh_degree is None and not packed
@@ -342,7 +350,8 @@ def rasterization(means, quats, scales, opacities, colors, viewmats, Ks, width, 
             render, alphas, last_ids, fragile = composite_fwd(
                 m2, con, o, col, dep if with_depth else None, bg, off, flat_s, width, height, tile_size, True)
             st.update(isect_ids=ids_s, flatten_ids=flat_s, isect_offsets=off, last_ids=last_ids,
-                      fragile=fragile, alphas=alphas, tile_n_bits=tb, cam_n_bits=cb)
+                      fragile=fragile, alphas=alphas, tile_n_bits=tb, cam_n_bits=cb,
+                      transmittance=composite_fwd.transmittance)
             ctx.saved = (m2, con, dep, o, col, bg)
             return torch.from_numpy(render), torch.from_numpy(alphas)[..., None]
 
@@ -352,7 +361,8 @@ def rasterization(means, quats, scales, opacities, colors, viewmats, Ks, width, 
             vr = None if v_render is None else v_render.contiguous().numpy()
             va = None if v_alphas is None else v_alphas.contiguous().numpy()[..., 0]
             g = composite_bwd(m2, con, o, col, dep if with_depth else None, bg, st["isect_offsets"],
-                              st["flatten_ids"], width, height, st["alphas"], st["last_ids"], vr, va, tile_size)
+                              st["flatten_ids"], width, height, st["alphas"], st["last_ids"], vr, va, tile_size,
+                              transmittance=st["transmittance"] if exact_transmittance else None)
             f32 = lambda a: None if a is None else torch.from_numpy(a.astype(np.float32))
             return (f32(g["v_means2d"]), f32(g["v_conics"]), f32(g["v_depths"]), f32(g["v_opacities"]),
                     None if only_depth else f32(g["v_colors"]))

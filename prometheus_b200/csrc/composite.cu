@@ -40,7 +40,7 @@ composite_fwd_kernel(const float *__restrict__ means2d, const float *__restrict_
                      const int32_t *__restrict__ flatten_ids, int64_t n_host,
                      const int32_t *__restrict__ d_n, int N, int width, int height, int tile_width,
                      int tile_height, float *__restrict__ render, float *__restrict__ alphas,
-                     int32_t *__restrict__ last_ids) {
+                     int32_t *__restrict__ last_ids, float *__restrict__ transmittance) {
   __shared__ Staged<kBatch> stg;
   __shared__ uint32_t queue[8][kQueueWords];
   staged_init_null(stg);
@@ -76,7 +76,7 @@ composite_fwd_kernel(const float *__restrict__ means2d, const float *__restrict_
     composite_batch_fwd<kBatch>(aS, aQ, batch_size, batch_start, fp, st);
   }
 
-  if (inside) store_pixel(st, ((size_t)cam * height + iy) * width + ix, cam, D, CD, backgrounds, render, alphas, last_ids);
+  if (inside) store_pixel(st, ((size_t)cam * height + iy) * width + ix, cam, D, CD, backgrounds, render, alphas, last_ids, transmittance);
 }
 
 // ---------------------------------------------------------------------------
@@ -158,7 +158,8 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
                      float *__restrict__ v_opacities, float *__restrict__ v_depths,
                      const float *__restrict__ v_images, const float *__restrict__ v_depth_out,
                      const float *__restrict__ v_masks, const float *__restrict__ depth_out, int packed,
-                     const int32_t *__restrict__ tile_order, int views_per_scene) {
+                     const int32_t *__restrict__ tile_order, int views_per_scene,
+                     const float *__restrict__ transmittance) {
   extern __shared__ __align__(16) unsigned char bwd_smem[];
   BwdShared &sh = *reinterpret_cast<BwdShared *>(bwd_smem);
   GaussA *sA = sh.sA; GaussB *sB = sh.sB; GaussC *sC = sh.sC;
@@ -193,7 +194,7 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
     const size_t plane = (size_t)height * width, in_plane = (size_t)iy * width + ix;
     const size_t pix = (size_t)cam * plane + in_plane;
     const float alpha = alphas[pix];
-    T_final = 1.0f - alpha;
+    T_final = transmittance ? transmittance[pix] : 1.0f - alpha;  // exact T of the forward when it was kept
     my_last = last_ids[pix];
     if (v_images) {
 #pragma unroll
@@ -208,7 +209,7 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
     }
   } else if (inside) {
     const size_t pix = ((size_t)cam * height + iy) * width + ix;
-    T_final = 1.0f - alphas[pix];
+    T_final = transmittance ? transmittance[pix] : 1.0f - alphas[pix];
     my_last = last_ids[pix];
     if (v_render) {
       if (CD == 4) {
@@ -315,14 +316,11 @@ composite_bwd_kernel(const float *__restrict__ means2d, const float *__restrict_
 }
 
 static int bwd_set_attr() {
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(BwdShared)) != cudaSuccess) {
-      set_last_cuda_error(cudaGetLastError());
-      return PM_ERR_CUDA;
-    }
-    attr_set = true;
+  // per device and cheap: set on every call (a process may drive several GPUs)
+  if (cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sizeof(BwdShared)) != cudaSuccess) {
+    set_last_cuda_error(cudaGetLastError());
+    return PM_ERR_CUDA;
   }
   return PM_OK;
 }
@@ -352,7 +350,7 @@ int pm_composite_fwd(const float *means2d, const float *conics, const float *opa
                      const float *backgrounds, const int32_t *isect_offsets,
                      const int32_t *flatten_ids, int64_t n_isects, const int32_t *d_n, int N, int C,
                      int width, int height, int tile_size, float *render, float *alphas,
-                     int32_t *last_ids, pm_stream_t stream) {
+                     int32_t *last_ids, float *transmittance, pm_stream_t stream) {
   const int rc = pm::check_common(means2d, conics, opacities, colors, D, depths, isect_offsets, flatten_ids,
                                   n_isects, N, C, width, height, tile_size);
   if (rc != PM_OK) return rc;
@@ -365,7 +363,7 @@ int pm_composite_fwd(const float *means2d, const float *conics, const float *opa
   if (blocks >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
   pm::composite_fwd_kernel<<<(unsigned)blocks, 256, 0, pm::as_stream(stream)>>>(
       means2d, conics, opacities, colors, colors_per_camera, D, depths, backgrounds, isect_offsets,
-      flatten_ids, n_isects, d_n, N, width, height, tw, th, render, alphas, last_ids);
+      flatten_ids, n_isects, d_n, N, width, height, tw, th, render, alphas, last_ids, transmittance);
   return pm::check_launch();
 }
 
@@ -374,7 +372,7 @@ int pm_composite_bwd(const float *means2d, const float *conics, const float *opa
                      const float *backgrounds, const int32_t *isect_offsets,
                      const int32_t *flatten_ids, int64_t n_isects, const int32_t *d_n, int N, int C,
                      int width, int height, int tile_size, const float *alphas,
-                     const int32_t *last_ids, const float *v_render, const float *v_alphas,
+                     const int32_t *last_ids, const float *transmittance, const float *v_render, const float *v_alphas,
                      float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
                      float *v_depths, pm_stream_t stream) {
   const int rc = pm::check_common(means2d, conics, opacities, colors, D, depths, isect_offsets, flatten_ids,
@@ -393,7 +391,7 @@ int pm_composite_bwd(const float *means2d, const float *conics, const float *opa
   pm::composite_bwd_kernel<<<(unsigned)(blocks * pm::kBwdParts), pm::kBwdThreads, sizeof(pm::BwdShared), pm::as_stream(stream)>>>(
       means2d, conics, opacities, colors, colors_per_camera, D, depths, backgrounds, isect_offsets,
       flatten_ids, n_isects, d_n, N, width, height, tw, th, alphas, last_ids, v_render, v_alphas,
-      v_means2d, v_conics, v_colors, v_opacities, v_depths, nullptr, nullptr, nullptr, nullptr, 0, nullptr, C);
+      v_means2d, v_conics, v_colors, v_opacities, v_depths, nullptr, nullptr, nullptr, nullptr, 0, nullptr, C, transmittance);
   return pm::check_launch();
 }
 
@@ -402,7 +400,7 @@ int pm_composite_bwd_packed(const float *means2d, const float *conics, const flo
                             const float *backgrounds, const int32_t *isect_offsets,
                             const int32_t *flatten_ids, int64_t n_isects, const int32_t *d_n, int N, int C,
                             int width, int height, int tile_size, const float *masks, const float *depth_out,
-                            const int32_t *last_ids, const float *v_images, const float *v_depth_out,
+                            const int32_t *last_ids, const float *transmittance, const float *v_images, const float *v_depth_out,
                             const float *v_masks, float *v_means2d, float *v_conics, float *v_colors,
                             float *v_opacities, float *v_depths, const int32_t *tile_order, int views_per_scene,
                             pm_stream_t stream) {
@@ -420,7 +418,7 @@ int pm_composite_bwd_packed(const float *means2d, const float *conics, const flo
       means2d, conics, opacities, colors, colors_per_camera, 3, depths, backgrounds, isect_offsets,
       flatten_ids, n_isects, d_n, N, width, height, tw, th, masks, last_ids, nullptr, nullptr,
       v_means2d, v_conics, v_colors, v_opacities, v_depths, v_images, v_depth_out, v_masks, depth_out, 1, tile_order,
-      views_per_scene > 0 ? views_per_scene : C);
+      views_per_scene > 0 ? views_per_scene : C, transmittance);
   return pm::check_launch();
 }
 

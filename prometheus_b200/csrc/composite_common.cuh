@@ -262,7 +262,7 @@ __device__ __forceinline__ void composite_batch_fwd(uint32_t aS, uint32_t aQ, in
                                                     const WarpFootprint &fp, PixelState &st) {
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
-  uint32_t last_ga = 0;
+  uint32_t last_ga = 0xffffffffu;  // explicit 'nothing blended' sentinel (a staged slot may sit at shared address 0)
   for (int sub = 0; sub < batch_size; sub += 32) {
     // Gaussians are culled against the rectangle of the warp's LIVE pixels, so splats that only cover finished
     // pixels are skipped as well
@@ -306,16 +306,20 @@ __device__ __forceinline__ void composite_batch_fwd(uint32_t aS, uint32_t aQ, in
     }
     __syncwarp();
   }
-  if (last_ga != 0u) st.last = list_pos + (int)((last_ga - aS) >> 4);
+  if (last_ga != 0xffffffffu) st.last = list_pos + (int)((last_ga - aS) >> 4);
 }
 
 // Write one pixel's results (shared epilogue).
 __device__ __forceinline__ void store_pixel(const PixelState &st, size_t pix, int cam, int D, int CD,
                                             const float *__restrict__ backgrounds, float *__restrict__ render,
-                                            float *__restrict__ alphas, int32_t *__restrict__ last_ids) {
+                                            float *__restrict__ alphas, int32_t *__restrict__ last_ids,
+                                            float *__restrict__ transmittance) {
   const float T = fabsf(st.T);
   alphas[pix] = 1.0f - T;
   last_ids[pix] = st.last;
+  // The backward needs the final transmittance. Upstream rebuilds it as 1 - render_alpha, which loses up to
+  // ulp(alpha) / T ~ 3e-4 relative on an opaque pixel; the exact fp32 T is 4 bytes per pixel.
+  if (transmittance) transmittance[pix] = T;
   float out[4] = {st.o0, st.o1, st.o2, st.o3};
   if (backgrounds) {
 #pragma unroll
@@ -340,7 +344,7 @@ __device__ __forceinline__ void store_pixel(const PixelState &st, size_t pix, in
 __device__ __forceinline__ void store_pixel_packed(const PixelState &st, int cam, int iy, int ix, int width, int height,
                                                    const float *__restrict__ backgrounds, float *__restrict__ images,
                                                    float *__restrict__ depth_out, float *__restrict__ masks,
-                                                   int32_t *__restrict__ last_ids) {
+                                                   int32_t *__restrict__ last_ids, float *__restrict__ transmittance) {
   const float T = fabsf(st.T);
   const float alpha = 1.0f - T;
   const size_t plane = (size_t)height * width;
@@ -356,6 +360,7 @@ __device__ __forceinline__ void store_pixel_packed(const PixelState &st, int cam
   depth_out[pix] = __fdiv_rn(st.o3, fmaxf(alpha, 1e-10f));
   masks[pix] = fminf(fmaxf(alpha, 0.0f), 1.0f);
   last_ids[pix] = st.last;
+  if (transmittance) transmittance[pix] = T;
 }
 
 }  // namespace pm

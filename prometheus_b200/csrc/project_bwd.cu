@@ -295,14 +295,11 @@ int pm_project_bwd(const float *means, const float *quats, const float *scales, 
   const int64_t total = (int64_t)N * (C > 0 ? C / Nv : 1);
   const size_t cam_bytes = sizeof(pm::BwdCam) * (size_t)(C > 0 ? C : 1);
   if (cam_bytes > 48 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      if (cudaFuncSetAttribute(pm::project_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)(sizeof(pm::BwdCam) * pm::kBwdMaxCams)) != cudaSuccess) {
-        pm::set_last_cuda_error(cudaGetLastError());
-        return PM_ERR_CUDA;
-      }
-      attr_set = true;
+    // per device and cheap: set on every call (a process may drive several GPUs)
+    if (cudaFuncSetAttribute(pm::project_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(sizeof(pm::BwdCam) * pm::kBwdMaxCams)) != cudaSuccess) {
+      pm::set_last_cuda_error(cudaGetLastError());
+      return PM_ERR_CUDA;
     }
   }
   pm::project_bwd_kernel<<<(unsigned)((total + 127) / 128), 128, cam_bytes, pm::as_stream(stream)>>>(

@@ -208,7 +208,8 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
                        int32_t *__restrict__ flatten_ids, int32_t *__restrict__ sorted_counts,
                        int32_t *__restrict__ overflow_flag, float *__restrict__ images,
                        float *__restrict__ depth_out, float *__restrict__ masks,
-                       const int32_t *__restrict__ tile_order, int views_per_scene) {
+                       const int32_t *__restrict__ tile_order, int views_per_scene,
+                       float *__restrict__ transmittance) {
   extern __shared__ __align__(16) unsigned char tr_smem[];
   TrShared &sh = *reinterpret_cast<TrShared *>(tr_smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -457,9 +458,10 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
   if (tid == 0) sorted_counts[ct] = sorted;
   if (inside) {
     if (images != nullptr)  // packed module outputs (pm_tile_render_packed_fwd)
-      store_pixel_packed(st, cam, iy, ix, width, height, backgrounds, images, depth_out, masks, last_ids);
+      store_pixel_packed(st, cam, iy, ix, width, height, backgrounds, images, depth_out, masks, last_ids,
+                         transmittance);
     else
-      store_pixel(st, ((size_t)cam * height + iy) * width + ix, cam, D, CD, backgrounds, render, alphas, last_ids);
+      store_pixel(st, ((size_t)cam * height + iy) * width + ix, cam, D, CD, backgrounds, render, alphas, last_ids, transmittance);
   }
 }
 
@@ -473,7 +475,8 @@ static int tile_render_launch(const uint64_t *records, const int32_t *isect_offs
                               const float *backgrounds, int N, int C, int width, int height, int tile_size,
                               float *render, float *alphas, int32_t *last_ids, int32_t *flatten_ids,
                               int32_t *sorted_counts, int32_t *overflow_flag, float *images, float *depth_out,
-                              float *masks, const int32_t *tile_order, int views_per_scene, pm_stream_t stream) {
+                              float *masks, const int32_t *tile_order, int views_per_scene, float *transmittance,
+                              pm_stream_t stream) {
   if (N < 0 || C < 0 || width <= 0 || height <= 0 || n_isects < 0 || D < 0) return PM_ERR_BAD_ARG;
   if (tile_size != pm::kTile) return PM_ERR_UNSUPPORTED;
   const int CD = D + (depths ? 1 : 0);
@@ -496,19 +499,16 @@ static int tile_render_launch(const uint64_t *records, const int32_t *isect_offs
   const int tw = (width + pm::kTile - 1) / pm::kTile, th = (height + pm::kTile - 1) / pm::kTile;
   const int64_t blocks = (int64_t)C * tw * th;
   if (blocks >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(pm::tile_render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)pm::kTrSmemBytes) != cudaSuccess) {
-      pm::set_last_cuda_error(cudaGetLastError());
-      return PM_ERR_CUDA;
-    }
-    attr_set = true;
+  // per device and cheap: set on every call (a process may drive several GPUs)
+  if (cudaFuncSetAttribute(pm::tile_render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)pm::kTrSmemBytes) != cudaSuccess) {
+    pm::set_last_cuda_error(cudaGetLastError());
+    return PM_ERR_CUDA;
   }
   pm::tile_render_fwd_kernel<<<(unsigned)blocks, pm::kTrThreads, pm::kTrSmemBytes, pm::as_stream(stream)>>>(
       records, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera, D, depths,
       backgrounds, N, width, height, tw, th, render, alphas, last_ids, flatten_ids, sorted_counts, overflow_flag,
-      images, depth_out, masks, tile_order, views_per_scene > 0 ? views_per_scene : C);
+      images, depth_out, masks, tile_order, views_per_scene > 0 ? views_per_scene : C, transmittance);
   return pm::check_launch();
 }
 
@@ -530,10 +530,10 @@ int pm_tile_render_fwd(const uint64_t *records, const int32_t *isect_offsets, in
                        const float *depths, const float *backgrounds, int N, int C, int width, int height,
                        int tile_size, float *render, float *alphas, int32_t *last_ids,
                        int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
-                       const int32_t *tile_order, pm_stream_t stream) {
+                       const int32_t *tile_order, float *transmittance, pm_stream_t stream) {
   return tile_render_launch(records, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera,
                             D, depths, backgrounds, N, C, width, height, tile_size, render, alphas, last_ids,
-                            flatten_ids, sorted_counts, overflow_flag, nullptr, nullptr, nullptr, tile_order, 0, stream);
+                            flatten_ids, sorted_counts, overflow_flag, nullptr, nullptr, nullptr, tile_order, 0, transmittance, stream);
 }
 
 int pm_tile_render_packed_fwd(const uint64_t *records, const int32_t *isect_offsets, int64_t n_isects,
@@ -542,11 +542,13 @@ int pm_tile_render_packed_fwd(const uint64_t *records, const int32_t *isect_offs
                               const float *depths, const float *backgrounds, int N, int C, int width, int height,
                               int tile_size, float *images, float *depth_out, float *masks, int32_t *last_ids,
                               int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
-                              const int32_t *tile_order, int views_per_scene, pm_stream_t stream) {
+                              const int32_t *tile_order, int views_per_scene, float *transmittance,
+                              pm_stream_t stream) {
   if (!images) return PM_ERR_BAD_ARG;
   return tile_render_launch(records, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera,
                             3, depths, backgrounds, N, C, width, height, tile_size, nullptr, nullptr, last_ids,
-                            flatten_ids, sorted_counts, overflow_flag, images, depth_out, masks, tile_order, views_per_scene, stream);
+                            flatten_ids, sorted_counts, overflow_flag, images, depth_out, masks, tile_order, views_per_scene,
+                            transmittance, stream);
 }
 
 }  // extern "C"

@@ -567,16 +567,13 @@ int pm_tile_sort(const uint64_t *records, uint64_t *scratch, const int32_t *isec
   if (total >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
   const int tile_n_bits = pm::n_bits_for(n_tiles);
   if (tile_n_bits + pm::n_bits_for(C) > 32) return PM_ERR_RANGE;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(pm::tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)pm::kTsSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(pm::tile_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)pm::kTsSmemBytes) != cudaSuccess) {
-      pm::set_last_cuda_error(cudaGetLastError());
-      return PM_ERR_CUDA;
-    }
-    attr_set = true;
+  // per device and cheap: set on every call (a process may drive several GPUs)
+  if (cudaFuncSetAttribute(pm::tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)pm::kTsSmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(pm::tile_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)pm::kTsSmemBytes) != cudaSuccess) {
+    pm::set_last_cuda_error(cudaGetLastError());
+    return PM_ERR_CUDA;
   }
   cudaStream_t s = pm::as_stream(stream);
   pm::tile_sort_kernel<<<(unsigned)total, pm::kTsThreads, pm::kTsSmemBytes, s>>>(

@@ -352,7 +352,7 @@ def _colors_layout(colors, C, N):
 @_instrument("composite_fwd", 1)
 def composite_fwd(means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width,
                   height, d_n=None):
-    """-> render [C,H,W,CD], alphas [C,H,W], last_ids [C,H,W] (see pm_composite_fwd)."""
+    """-> render [C,H,W,CD], alphas [C,H,W], last_ids [C,H,W], transmittance [C,H,W] (see pm_composite_fwd)."""
     L = _lib.load()
     C, N = means2d.shape[:2]
     colors, per_cam, D = _colors_layout(colors, C, N)
@@ -361,18 +361,19 @@ def composite_fwd(means2d, conics, opacities, colors, depths, backgrounds, offse
     render = torch.empty(C, height, width, CD, device=dev)
     alphas = torch.empty(C, height, width, device=dev)
     last_ids = torch.empty(C, height, width, dtype=torch.int32, device=dev)
+    trans = torch.empty(C, height, width, device=dev)
     _lib.check(L.pm_composite_fwd(_ptr(means2d), _ptr(conics), _ptr(opacities), _ptr(colors), per_cam, D,
                                   _ptr(depths), _ptr(backgrounds), _ptr(offsets), _ptr(flatten_ids),
                                   flatten_ids.numel(), _ptr(d_n), N, C, width, height, TILE, _ptr(render),
-                                  _ptr(alphas), _ptr(last_ids), _stream()), "pm_composite_fwd")
-    return render, alphas, last_ids
+                                  _ptr(alphas), _ptr(last_ids), _ptr(trans), _stream()), "pm_composite_fwd")
+    return render, alphas, last_ids, trans
 
 
 @_instrument("tile_render_fwd", 1)
 def tile_render_fwd(records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height, d_n=None,
                     tile_order=None):
     """Fused sort-as-you-go forward -> render, alphas, last_ids, flatten_ids (sorted prefix per tile),
-    sorted_counts [C,th,tw], overflow flag int32[1]."""
+    sorted_counts [C,th,tw], overflow flag int32[1], transmittance [C,H,W]."""
     L = _lib.load()
     C, N = means2d.shape[:2]
     colors, per_cam, D = _colors_layout(colors, C, N)
@@ -385,16 +386,19 @@ def tile_render_fwd(records, offsets, means2d, conics, opacities, colors, depths
     flat = torch.empty(n, dtype=torch.int32, device=dev)
     sorted_counts = torch.empty_like(offsets)
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    trans = torch.empty(C, height, width, device=dev)
     _lib.check(L.pm_tile_render_fwd(_ptr(records), _ptr(offsets), n, _ptr(d_n), _ptr(means2d), _ptr(conics),
                                     _ptr(opacities), _ptr(colors), per_cam, D, _ptr(depths), _ptr(backgrounds), N, C,
                                     width, height, TILE, _ptr(render), _ptr(alphas), _ptr(last_ids), _ptr(flat),
-                                    _ptr(sorted_counts), _ptr(flag), _ptr(tile_order), _stream()), "pm_tile_render_fwd")
-    return render, alphas, last_ids, flat, sorted_counts, flag
+                                    _ptr(sorted_counts), _ptr(flag), _ptr(tile_order), _ptr(trans), _stream()),
+               "pm_tile_render_fwd")
+    return render, alphas, last_ids, flat, sorted_counts, flag, trans
 
 
 @_instrument("composite_bwd", 1)
 def composite_bwd(means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width,
-                  height, alphas, last_ids, v_render, v_alphas, d_n=None):
+                  height, alphas, last_ids, v_render, v_alphas, d_n=None, transmittance=None):
+    """transmittance: the forward's exact final T per pixel; None = rebuild it as 1 - alphas (upstream's form)."""
     L = _lib.load()
     C, N = means2d.shape[:2]
     colors, per_cam, D = _colors_layout(colors, C, N)
@@ -408,7 +412,8 @@ def composite_bwd(means2d, conics, opacities, colors, depths, backgrounds, offse
     _lib.check(L.pm_composite_bwd(_ptr(means2d), _ptr(conics), _ptr(opacities), _ptr(colors), per_cam, D,
                                   _ptr(depths), _ptr(backgrounds), _ptr(offsets), _ptr(flatten_ids),
                                   flatten_ids.numel(), _ptr(d_n), N, C, width, height, TILE, _ptr(alphas),
-                                  _ptr(last_ids), _ptr(v_render), _ptr(v_alphas), _ptr(v_means2d),
+                                  _ptr(last_ids), _ptr(_opt(transmittance, torch.float32, "transmittance")),
+                                  _ptr(v_render), _ptr(v_alphas), _ptr(v_means2d),
                                   _ptr(v_conics), _ptr(v_colors), _ptr(v_opac), _ptr(v_depths), _stream()),
                "pm_composite_bwd")
     return v_means2d, v_conics, v_colors, v_opac, v_depths
@@ -417,11 +422,12 @@ def composite_bwd(means2d, conics, opacities, colors, depths, backgrounds, offse
 # ------------------------------------------------------------------ module fast path (packed outputs)
 @_instrument("tile_render_fwd", 1)
 def tile_render_packed_fwd(records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height,
-                           d_n=None, tile_order=None, views_per_scene=0):
+                           d_n=None, tile_order=None, views_per_scene=0, want_transmittance=False):
     """Fused sort-as-you-go forward with the module epilogue: -> images [C,3,H,W] (2 rgb - 1),
     depth_out [C,1,H,W] (expected depth), masks [C,1,H,W], last_ids [C,H,W], flatten_ids (sorted prefix per
-    tile), sorted_counts [C,th,tw], overflow flag int32[1]. `records` may be a speculative capacity with the
-    true count in d_n[0] (see pm_tile_render_packed_fwd)."""
+    tile), sorted_counts [C,th,tw], overflow flag int32[1], transmittance [C,H,W] (only when want_transmittance:
+    the backward's exact T_final). `records` may be a speculative capacity with the true count in d_n[0]
+    (see pm_tile_render_packed_fwd)."""
     L = _lib.load()
     C, N = means2d.shape[:2]
     n_scenes = C // views_per_scene if views_per_scene else 1
@@ -436,19 +442,20 @@ def tile_render_packed_fwd(records, offsets, means2d, conics, opacities, colors,
     flat = torch.empty(n, dtype=torch.int32, device=dev)
     sorted_counts = torch.empty_like(offsets)
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    trans = torch.empty(C, height, width, device=dev) if want_transmittance else None
     _lib.check(L.pm_tile_render_packed_fwd(_ptr(records), _ptr(offsets), n, _ptr(d_n), _ptr(means2d), _ptr(conics),
                                            _ptr(opacities), _ptr(colors), per_cam, _ptr(depths), _ptr(backgrounds), N, C,
                                            width, height, TILE, _ptr(images), _ptr(depth_out), _ptr(masks),
                                            _ptr(last_ids), _ptr(flat), _ptr(sorted_counts), _ptr(flag), _ptr(tile_order),
-                                           int(views_per_scene), _stream()),
+                                           int(views_per_scene), _ptr(trans), _stream()),
                "pm_tile_render_packed_fwd")
-    return images, depth_out, masks, last_ids, flat, sorted_counts, flag
+    return images, depth_out, masks, last_ids, flat, sorted_counts, flag, trans
 
 
 @_instrument("composite_bwd", 1)
 def composite_bwd_packed(means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width, height,
                          masks, depth_out, last_ids, v_images, v_depth_out, v_masks, d_n=None, tile_order=None,
-                         views_per_scene=0):
+                         views_per_scene=0, transmittance=None):
     L = _lib.load()
     C, N = means2d.shape[:2]
     colors, per_cam, D = _colors_layout(colors, C, N * (C // views_per_scene if views_per_scene else 1))
@@ -461,7 +468,7 @@ def composite_bwd_packed(means2d, conics, opacities, colors, depths, backgrounds
     _lib.check(L.pm_composite_bwd_packed(_ptr(means2d), _ptr(conics), _ptr(opacities), _ptr(colors), per_cam,
                                          _ptr(depths), _ptr(backgrounds), _ptr(offsets), _ptr(flatten_ids),
                                          flatten_ids.numel(), _ptr(d_n), N, C, width, height, TILE, _ptr(masks),
-                                         _ptr(depth_out), _ptr(last_ids), _ptr(v_images), _ptr(v_depth_out),
+                                         _ptr(depth_out), _ptr(last_ids), _ptr(transmittance), _ptr(v_images), _ptr(v_depth_out),
                                          _ptr(v_masks), _ptr(v_means2d), _ptr(v_conics), _ptr(v_colors), _ptr(v_opac),
                                          _ptr(v_depths), _ptr(tile_order), int(views_per_scene), _stream()),
                "pm_composite_bwd_packed")

@@ -63,10 +63,10 @@ class _Composite(torch.autograd.Function):
         colors = None if colors is None else colors.contiguous()
         depths = None if depths is None else depths.contiguous()
         backgrounds = None if backgrounds is None else backgrounds.contiguous().float()
-        render, alphas, last_ids = ops.composite_fwd(means2d, conics, opacities, colors, depths, backgrounds,
-                                                     offsets, flatten_ids, width, height, d_n)
+        render, alphas, last_ids, trans = ops.composite_fwd(means2d, conics, opacities, colors, depths, backgrounds,
+                                                            offsets, flatten_ids, width, height, d_n)
         ctx.save_for_backward(means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids,
-                              alphas, last_ids, d_n)
+                              alphas, last_ids, d_n, trans)
         ctx.dims = (width, height)
         ctx.last_ids = last_ids
         return render, alphas.unsqueeze(-1)
@@ -74,16 +74,16 @@ class _Composite(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_render, v_alphas):
         (means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, alphas, last_ids,
-         d_n) = ctx.saved_tensors
+         d_n, trans) = ctx.saved_tensors
         width, height = ctx.dims
         v_alphas2 = None if v_alphas is None else v_alphas.squeeze(-1)
         v_means2d, v_conics, v_colors, v_opac, v_depths = ops.composite_bwd(
             means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width, height, alphas,
-            last_ids, v_render, v_alphas2, d_n)
+            last_ids, v_render, v_alphas2, d_n, transmittance=trans)
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[5] and v_render is not None:
             D = backgrounds.shape[-1]
-            v_bg = (v_render[..., :D] * (1.0 - alphas).unsqueeze(-1)).sum(dim=(1, 2))
+            v_bg = (v_render[..., :D] * trans.unsqueeze(-1)).sum(dim=(1, 2))
         return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None, None
 
 
@@ -97,25 +97,27 @@ class _TileRender(torch.autograd.Function):
         colors = None if colors is None else colors.contiguous()
         depths = None if depths is None else depths.contiguous()
         backgrounds = None if backgrounds is None else backgrounds.contiguous().float()
-        render, alphas, last_ids, flat, sorted_counts, flag = ops.tile_render_fwd(
+        render, alphas, last_ids, flat, sorted_counts, flag, trans = ops.tile_render_fwd(
             records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height)
-        ctx.save_for_backward(means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, alphas, last_ids)
+        ctx.save_for_backward(means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, alphas, last_ids,
+                              trans)
         ctx.dims = (width, height)
         ctx.mark_non_differentiable(flag, flat, sorted_counts)
         return render, alphas.unsqueeze(-1), flag, flat, sorted_counts
 
     @staticmethod
     def backward(ctx, v_render, v_alphas, _vf, _vflat, _vsc):
-        means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, alphas, last_ids = ctx.saved_tensors
+        (means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, alphas, last_ids,
+         trans) = ctx.saved_tensors
         width, height = ctx.dims
         v_alphas2 = None if v_alphas is None else v_alphas.squeeze(-1)
         v_means2d, v_conics, v_colors, v_opac, v_depths = ops.composite_bwd(
             means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, width, height, alphas, last_ids,
-            v_render, v_alphas2, None)
+            v_render, v_alphas2, None, transmittance=trans)
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[5] and v_render is not None:
             D = backgrounds.shape[-1]
-            v_bg = (v_render[..., :D] * (1.0 - alphas).unsqueeze(-1)).sum(dim=(1, 2))
+            v_bg = (v_render[..., :D] * trans.unsqueeze(-1)).sum(dim=(1, 2))
         return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None
 
 
@@ -131,11 +133,13 @@ class _TileRenderPacked(torch.autograd.Function):
         means2d, conics = means2d.contiguous(), conics.contiguous()
         opacities, colors, depths = opacities.contiguous(), colors.contiguous(), depths.contiguous()
         backgrounds = None if backgrounds is None else backgrounds.contiguous().float()
-        images, depth_out, masks, last_ids, flat, sorted_counts, flag = ops.tile_render_packed_fwd(
+        # the exact final transmittance is kept only when a backward will consume it (4 B/pixel)
+        need_t = any(ctx.needs_input_grad[:6])
+        images, depth_out, masks, last_ids, flat, sorted_counts, flag, trans = ops.tile_render_packed_fwd(
             records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height, d_n=stats,
-            tile_order=tile_order, views_per_scene=views_per_scene)
+            tile_order=tile_order, views_per_scene=views_per_scene, want_transmittance=need_t)
         ctx.save_for_backward(means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, masks, depth_out,
-                              last_ids, stats, sorted_counts)
+                              last_ids, stats, sorted_counts, trans)
         ctx.dims = (width, height)
         ctx.mark_non_differentiable(flag, flat, sorted_counts)
         return images, depth_out, masks, flag, flat, sorted_counts
@@ -143,13 +147,14 @@ class _TileRenderPacked(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_images, v_depth_out, v_masks, _vf, _vflat, _vsc):
         (means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, masks, depth_out, last_ids,
-         stats, sorted_counts) = ctx.saved_tensors
+         stats, sorted_counts, trans) = ctx.saved_tensors
         width, height = ctx.dims
         # the backward replays what the forward sorted: tiles with the longest sorted prefix go first
         order = ops.tile_scan(sorted_counts, want_order=True)[2]
         v_means2d, v_conics, v_colors, v_opac, v_depths = ops.composite_bwd_packed(
             means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, width, height, masks, depth_out,
-            last_ids, v_images, v_depth_out, v_masks, d_n=stats, tile_order=order, views_per_scene=ctx.views_per_scene)
+            last_ids, v_images, v_depth_out, v_masks, d_n=stats, tile_order=order, views_per_scene=ctx.views_per_scene,
+            transmittance=trans)
         if ctx.grad_sink is not None:
             ctx.grad_sink["v_means2d"] = v_means2d
             for j, view in enumerate(ctx.grad_sink.get("views", ())):  # the reference's viewspace_points[j].grad
@@ -157,7 +162,7 @@ class _TileRenderPacked(torch.autograd.Function):
                 view.grad = g if view.grad is None else view.grad + g
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[5] and v_images is not None:
-            v_bg = (2.0 * v_images * (1.0 - masks)).sum(dim=(2, 3))
+            v_bg = (2.0 * v_images * (trans.unsqueeze(1) if trans is not None else 1.0 - masks)).sum(dim=(2, 3))
         return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None, None, None, None, None
 
 

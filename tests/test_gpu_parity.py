@@ -5,8 +5,8 @@ BASELINE.json's full size — through size-independent properties.
 
 Bars (BASELINE.json north_star): bit-exact radii / tile counts / sort keys / order /
 per-tile ranges; images, depth, alpha and gradients within 1e-5 abs / 1e-4 rel in fp32
-(gradients: relative to the largest gradient entry, see `grad_close`), asserted on
-pixels whose decisions are not within a few ulp of a threshold (oracle's fragile mask).
+(gradients: element-wise, see `grad_close`), asserted on pixels whose decisions are not within
+a few ulp of a threshold (oracle's fragile mask).
 """
 import os
 
@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import allclose, max_violation, random_blobs, small_scene
+from tests.util import allclose, max_violation, random_blobs, small_scene, violations
 
 pytestmark = pytest.mark.gpu
 
@@ -28,12 +28,19 @@ def dev(a, dtype=None):
     return t.to(DEV)
 
 
-def grad_close(a, b, atol=1e-5, rtol=1e-4):
-    """Gradient comparison: tolerances are relative to the gradient's own scale (the upstream
-    gradients in these tests are O(1) per pixel, so sums over hundreds of pixels are O(100))."""
-    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
-    scale = max(1.0, float(np.abs(b).max()) if b.size else 1.0)
-    return allclose(a / scale, b / scale, atol=atol, rtol=rtol)
+def grad_close(a, b, atol=1e-5, rtol=1e-4, max_share=0.0, what=""):
+    """Gradient comparison at the north_star's bar, ELEMENT-WISE: |a - b| <= atol + rtol |b| for every entry
+    (the fp64-accumulating oracle is b). `max_share` = share of entries allowed to violate it (0 unless the
+    test says why); the measured share and the worst ratio are printed so that `-s` shows the margin."""
+    share, worst = violations(a, b, atol, rtol)
+    print("grad_close %s: violating share %.3g (allowed %.3g), worst |a-b| / (atol + rtol |b|) = %.3g" % (what, share, max_share, worst))
+    return share <= max_share
+
+
+# Allowed share of gradient entries outside |a - b| <= 1e-5 + 1e-4 |b| (measured shares are printed by grad_close):
+PROJECT_BWD_SHARE = 1e-3    # fp32 VJP chains vs the oracle's fp64 ones on strongly anisotropic splats
+OPERATOR_GRAD_SHARE = 1e-3  # two correct fp32 forwards differ in the last bit of some alphas (see the test)
+ORDER_SHARE = 1e-3          # same kernels, different fp32 atomic summation order
 
 
 def scenes_for_parity(oracle):
@@ -351,15 +358,19 @@ def test_composite_fwd(cases, name):
     from prometheus_b200 import ops
 
     s, bg, st = cases[name]
-    render, alphas, last_ids = ops.composite_fwd(dev(st["means2d"]), dev(st["conics"]), dev(s["opacities"]), dev(s["colors"]),
-                                                 dev(st["depths"]), dev(bg), dev(st["isect_offsets"]), dev(st["flatten_ids"]),
-                                                 s["width"], s["height"])
+    render, alphas, last_ids, trans = ops.composite_fwd(dev(st["means2d"]), dev(st["conics"]), dev(s["opacities"]), dev(s["colors"]),
+                                                        dev(st["depths"]), dev(bg), dev(st["isect_offsets"]), dev(st["flatten_ids"]),
+                                                        s["width"], s["height"])
     keep = st["fragile"] == 0
     assert keep.mean() > 0.97, keep.mean()
     r, a, l = render.cpu().numpy(), alphas.cpu().numpy(), last_ids.cpu().numpy()
     assert allclose(r[keep], st["render"][keep], atol=1e-5, rtol=1e-4), max_violation(r[keep], st["render"][keep])
     assert allclose(a[keep], st["alphas"][keep], atol=1e-5, rtol=1e-4)
     assert np.array_equal(l[keep], st["last_ids"][keep])
+    # the exact final transmittance (what the backward consumes instead of 1 - alpha): relative bar only, T ~ 1e-4..1
+    t = trans.cpu().numpy()
+    assert np.all(np.abs(t[keep] - st["transmittance"][keep]) <= 1e-9 + 1e-4 * st["transmittance"][keep])
+    assert torch.equal(1.0 - trans, alphas)
     # fragile pixels may flip one decision, never more than one Gaussian's worth of weight
     assert np.abs(a - st["alphas"]).max() < 5e-3
 
@@ -373,7 +384,7 @@ def test_composite_channel_layouts(oracle, D, with_depth, with_bg):
     bg = np.random.default_rng(2).random((2, D)).astype(np.float32) if with_bg else None
     st = oracle.forward_pipeline(s["means"], s["quats"], s["scales"], s["opacities"], colors, s["viewmats"], s["Ks"],
                                  64, 48, backgrounds=bg, with_depth=with_depth)
-    render, alphas, _ = ops.composite_fwd(dev(st["means2d"]), dev(st["conics"]), dev(s["opacities"]),
+    render, alphas, _, _ = ops.composite_fwd(dev(st["means2d"]), dev(st["conics"]), dev(s["opacities"]),
                                           dev(colors) if D else None, dev(st["depths"]) if with_depth else None,
                                           dev(bg) if with_bg else None, dev(st["isect_offsets"]), dev(st["flatten_ids"]), 64, 48)
     keep = st["fragile"] == 0
@@ -391,15 +402,19 @@ def test_composite_bwd(oracle, cases, name):
     keep = (st["fragile"] == 0).astype(np.float32)
     v_render = (rng.standard_normal(st["render"].shape).astype(np.float32)) * keep[..., None]
     v_alphas = (rng.standard_normal(st["alphas"].shape).astype(np.float32)) * keep
-    ref = oracle.composite_bwd(st["means2d"], st["conics"], s["opacities"], s["colors"], st["depths"], bg,
-                               st["isect_offsets"], st["flatten_ids"], s["width"], s["height"], st["alphas"],
-                               st["last_ids"], v_render, v_alphas)
-    # feed the oracle's forward state so this test isolates the backward kernel
-    out = ops.composite_bwd(dev(st["means2d"]), dev(st["conics"]), dev(s["opacities"]), dev(s["colors"]), dev(st["depths"]),
-                            dev(bg), dev(st["isect_offsets"]), dev(st["flatten_ids"]), s["width"], s["height"],
-                            dev(st["alphas"]), dev(st["last_ids"]), dev(v_render), dev(v_alphas))
-    for got, key in zip(out, ("v_means2d", "v_conics", "v_colors", "v_opacities", "v_depths")):
-        assert grad_close(got.cpu().numpy(), ref[key]), (key, np.abs(got.cpu().numpy() - ref[key]).max(), np.abs(ref[key]).max())
+    # feed the oracle's forward state so this test isolates the backward kernel; both forms of T_final:
+    # the exact transmittance the forward kept (the product path) and upstream's 1 - alpha
+    for trans in (st["transmittance"], None):
+        ref = oracle.composite_bwd(st["means2d"], st["conics"], s["opacities"], s["colors"], st["depths"], bg,
+                                   st["isect_offsets"], st["flatten_ids"], s["width"], s["height"], st["alphas"],
+                                   st["last_ids"], v_render, v_alphas, transmittance=trans)
+        out = ops.composite_bwd(dev(st["means2d"]), dev(st["conics"]), dev(s["opacities"]), dev(s["colors"]), dev(st["depths"]),
+                                dev(bg), dev(st["isect_offsets"]), dev(st["flatten_ids"]), s["width"], s["height"],
+                                dev(st["alphas"]), dev(st["last_ids"]), dev(v_render), dev(v_alphas),
+                                transmittance=None if trans is None else dev(trans))
+        for got, key in zip(out, ("v_means2d", "v_conics", "v_colors", "v_opacities", "v_depths")):
+            # fp32 atomics in arbitrary order vs fp64 accumulation: a handful of heavily cancelling sums may miss
+            assert grad_close(got.cpu().numpy(), ref[key], max_share=2e-4, what="%s/%s" % (name, key)), key
 
 
 @pytest.mark.parametrize("name", ["pixel_aligned", "blobs", "big_blobs"])
@@ -417,11 +432,7 @@ def test_project_bwd(oracle, cases, name):
     got = ops.project_bwd(dev(s["means"]), dev(s["quats"]), dev(s["scales"]), dev(s["viewmats"]), dev(s["Ks"]),
                           s["width"], s["height"], dev(st["radii"]), dev(st["conics"]), dev(v_m2), dev(v_d), dev(v_c))
     for g_, key in zip(got, ("v_means", "v_quats", "v_scales")):
-        a, b = g_.cpu().numpy(), ref[key]
-        # per-Gaussian relative check: these gradients span many orders of magnitude
-        err = np.abs(a - b).max(axis=1)
-        tol = 1e-5 + 2e-4 * np.abs(b).max(axis=1)
-        assert (err <= tol).mean() > 0.999, (key, float((err / tol).max()))
+        assert grad_close(g_.cpu().numpy(), ref[key], max_share=PROJECT_BWD_SHARE, what="%s/%s" % (name, key)), key
 
 
 # --------------------------------------------------------------------------- operator level (the drop-in)
@@ -457,17 +468,16 @@ def test_rasterization_operator_fwd_bwd(oracle, cases, name, render_mode):
     m["means2d"].retain_grad()
     ((r_ref * wr).sum() + (a_ref * wa).sum()).backward()
     ((r * wr.to(DEV)).sum() + (a * wa.to(DEV)).sum()).backward()
-    # End-to-end tolerance is 1e-4 (of the gradient scale) / 1e-3 rel, looser than the per-stage bar
-    # (test_composite_bwd / test_project_bwd: 1e-5 / 1e-4 on identical forward state). Reason: like
-    # upstream, the backward reconstructs T_final = 1 - render_alpha from the STORED fp32 alpha; in
-    # these scenes alpha ~ 0.9997, so a 1-ulp (6e-8) difference in alpha between two correct fp32
-    # forwards (expf vs __expf, FMA contraction) is a ~3e-4 RELATIVE change of T_final and hence of
-    # every gradient term of that pixel, which the projection VJP then multiplies by f/z ~ 30-100.
+    # End to end at the north_star's bar, element-wise. Both sides carry the exact final transmittance from
+    # their own forward (round 1 rebuilt it as 1 - alpha like upstream and needed 1e-4 / 1e-3). What is left is
+    # the difference between two correct fp32 forwards (expf vs ex2.approx): a 1-ulp change of an alpha near
+    # 0.99 is a 6e-6 relative change of (1 - alpha) and of everything behind that splat; the share of entries
+    # that miss the bar for that reason is bounded by OPERATOR_GRAD_SHARE and printed.
     for t, t_ref, k in zip(ins, ins_ref, keys):
         assert t.grad is not None, k
-        assert grad_close(t.grad.cpu().numpy(), t_ref.grad.numpy(), atol=1e-4, rtol=1e-3), (k, float((t.grad.cpu() - t_ref.grad).abs().max()), float(t_ref.grad.abs().max()))
+        assert grad_close(t.grad.cpu().numpy(), t_ref.grad.numpy(), max_share=OPERATOR_GRAD_SHARE, what="%s/%s/%s" % (name, render_mode, k)), k
     gm, gm_ref = m["means2d"].grad.cpu().numpy(), m_ref["means2d"].grad.numpy()  # the refiner side-contract
-    assert grad_close(gm, gm_ref, atol=1e-4, rtol=1e-3), (float(np.abs(gm - gm_ref).max()), float(np.abs(gm_ref).max()))
+    assert grad_close(gm, gm_ref, max_share=OPERATOR_GRAD_SHARE, what="%s/%s/means2d" % (name, render_mode))
 
 
 def test_reference_module_runs_unmodified_on_the_operator(golden_dir):
@@ -586,14 +596,14 @@ def test_fused_tile_render_is_bit_identical_to_separate_stages(cases, name):
     s, bg, st = cases[name]
     C = s["viewmats"].shape[0]
     args = (dev(st["means2d"]), dev(st["conics"]), dev(s["opacities"]), dev(s["colors"]), dev(st["depths"]), dev(bg))
-    ref_r, ref_a, ref_l = ops.composite_fwd(*args, dev(st["isect_offsets"]), dev(st["flatten_ids"]), s["width"], s["height"])
+    ref_r, ref_a, ref_l, ref_t = ops.composite_fwd(*args, dev(st["isect_offsets"]), dev(st["flatten_ids"]), s["width"], s["height"])
     counts = ops.bin_count(dev(st["means2d"]), dev(st["radii"]), s["width"], s["height"])
     offsets, stats = ops.tile_scan(counts)
     n, _ = stats.tolist()
     records = ops.bin_scatter(dev(st["means2d"]), dev(st["radii"]), dev(st["depths"]), offsets, s["width"], s["height"], n)
-    r, a, l, flat, sorted_counts, flag = ops.tile_render_fwd(records, offsets, *args, s["width"], s["height"])
+    r, a, l, flat, sorted_counts, flag, t = ops.tile_render_fwd(records, offsets, *args, s["width"], s["height"])
     assert int(flag.item()) == 0
-    assert torch.equal(r, ref_r) and torch.equal(a, ref_a) and torch.equal(l, ref_l)
+    assert torch.equal(r, ref_r) and torch.equal(a, ref_a) and torch.equal(l, ref_l) and torch.equal(t, ref_t)
     off = st["isect_offsets"].reshape(-1)
     sc = sorted_counts.cpu().numpy().reshape(-1)
     cnt = np.diff(np.append(off, len(st["flatten_ids"])))
@@ -622,7 +632,7 @@ def test_fused_module_path_matches_unfused_including_gradients():
         outs.append((images.detach(), depths.detach(), masks.detach(), params.grad.clone(), torch.stack(rend.radii)))
     a, b = outs
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[4], b[4])
-    assert grad_close(a[3].cpu().numpy(), b[3].cpu().numpy(), atol=1e-5, rtol=1e-4)
+    assert grad_close(a[3].cpu().numpy(), b[3].cpu().numpy(), max_share=ORDER_SHARE, what="fused vs unfused")
 
 
 def test_fused_overflow_falls_back():
@@ -1014,7 +1024,7 @@ def test_fused_loss_glue_through_the_renderer():
         res.append((loss.detach(), p.grad.clone()))
     assert torch.allclose(res[0][0], res[1][0], rtol=1e-6)
     assert float(res[0][1].abs().max()) > 1.0
-    assert grad_close(res[1][1].cpu().numpy(), res[0][1].cpu().numpy(), atol=1e-6, rtol=1e-4)
+    assert grad_close(res[1][1].cpu().numpy(), res[0][1].cpu().numpy(), max_share=ORDER_SHARE, what="fused loss glue")
 
 
 # --------------------------------------------------------------------------- densification statistics
@@ -1172,8 +1182,8 @@ def test_scene_batched_forward_backward_equals_per_scene():
     assert a[0].shape == (3, 3, 3, 56, 56)
     for x, y in zip(a[:4], b[:4]):
         assert torch.equal(x, y)
-    assert grad_close(a[4].cpu().numpy(), b[4].cpu().numpy(), atol=1e-5, rtol=1e-4)
-    assert grad_close(a[5].cpu().numpy(), b[5].cpu().numpy(), atol=1e-5, rtol=1e-4)
+    assert grad_close(a[4].cpu().numpy(), b[4].cpu().numpy(), max_share=ORDER_SHARE, what="scene batched params")
+    assert grad_close(a[5].cpu().numpy(), b[5].cpu().numpy(), max_share=ORDER_SHARE, what="scene batched means2d")
 
 
 def test_scene_batched_bad_hint_falls_back_to_per_scene():

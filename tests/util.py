@@ -42,3 +42,13 @@ def allclose(a, b, atol=1e-5, rtol=1e-4):
 def max_violation(a, b, atol=1e-5, rtol=1e-4):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return float(np.max(np.abs(a - b) - (atol + rtol * np.abs(b)))) if a.size else 0.0
+
+
+def violations(a, b, atol=1e-5, rtol=1e-4):
+    """Element-wise |a - b| <= atol + rtol |b| (the north_star's 1e-5 abs / 1e-4 rel): returns
+    (share of violating entries, largest |a - b| / (atol + rtol |b|))."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    if a.size == 0:
+        return 0.0, 0.0
+    ratio = np.abs(a - b) / (atol + rtol * np.abs(b))
+    return float((ratio > 1.0).mean()), float(ratio.max())
