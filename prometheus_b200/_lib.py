@@ -68,6 +68,20 @@ def library_path() -> str:
     return _SO
 
 
+def kernel_source_sha() -> str:
+    """sha256 (first 16 hex digits) over csrc/*.cu, *.cuh and the header: stamps profiler captures with the
+    kernel sources they describe (profiles/traffic.json), so a stale capture is never quoted for newer code."""
+    import hashlib
+
+    h = hashlib.sha256()
+    files = sorted(f for f in os.listdir(_CSRC) if f.endswith((".cu", ".cuh")))
+    for f in files:
+        h.update(f.encode())
+        h.update(open(os.path.join(_CSRC, f), "rb").read())
+    h.update(open(os.path.join(os.path.dirname(_PKG), "include", "prometheus_gs.h"), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def build(verbose: bool = False) -> str:
     """Compile csrc/*.cu for sm_100a into libprometheus_gs.so (in-tree)."""
     if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):

@@ -536,9 +536,11 @@ def splat_pack(xyz, rgb, opacity, scales, rots, compatible=True):
         return out
     _lib.check(L.pm_splat_keys(_ptr(opacity), _ptr(scales), n, int(bool(compatible)), _ptr(keys), _ptr(vals), _stream()),
                "pm_splat_keys")
-    _, order = sort_pairs(keys, vals, 32)
+    _, order, ws = sort_pairs(keys, vals, 32, return_workspace=True)
     _lib.check(L.pm_splat_pack(_ptr(xyz), _ptr(rgb), _ptr(opacity), _ptr(scales), _ptr(rots), _ptr(order), n,
                                int(bool(compatible)), _ptr(out), _stream()), "pm_splat_pack")
+    if sort_error_flag(ws):  # (the exporter copies `out` to the host next: this sync is not an extra one)
+        raise RuntimeError("pm_sort_pairs: decoupled look-back timed out; the .splat order is invalid")
     return out
 
 

@@ -171,7 +171,9 @@ class DecodeRenderPipeline:
         self._copy_out(out_h, outs, cur)
 
     def flush(self) -> None:
-        """Make the current stream wait for every outstanding copy (call before reading `out_h`)."""
+        """Wait — on the HOST — for every outstanding render and device->host copy: when flush() returns, every
+        `out_h` handed to run() / run_batch() holds its final content and may be read on the CPU. (The current
+        stream is ordered behind the copies as well.)"""
         cur = torch.cuda.current_stream(self.device)
         while self._unchecked:
             self._settle(self._unchecked.pop(0))
@@ -180,5 +182,6 @@ class DecodeRenderPipeline:
                 self._settle_graph(plan)
         for ev in self._pending_out:
             cur.wait_event(ev)
+            ev.synchronize()  # the host reads out_h next: ordering streams does not block the CPU
         self._pending_out = []
         cur.wait_stream(self.s_in)

@@ -234,8 +234,12 @@ def isect_tiles(means2d, radii, depths, tiles_per_gauss, width, height, C, force
     tw, th = ops.tile_grid(width, height)
     ids, flat = ops.bin_emit(means2d, radii, depths, cum, width, height, n_isects)
     tb, cb = ops.key_bits(tw, th, C)
-    ids, flat = ops.sort_pairs(ids, flat, 32 + tb + cb)
+    ids, flat, ws = ops.sort_pairs(ids, flat, 32 + tb + cb, return_workspace=True)
     offsets = ops.tile_offsets(ids, C, width, height)
+    # the onesweep look-back gives up after a bounded spin and raises a flag instead of hanging; a timed-out sort
+    # must never be returned as if it were sorted (this generic path already synchronises on n_isects)
+    if ops.sort_error_flag(ws):
+        raise RuntimeError("pm_sort_pairs: decoupled look-back timed out; the sorted arrays are invalid")
     return ids, flat, offsets
 
 

@@ -114,8 +114,16 @@ class GaussianRenderer(nn.Module):
         if isinstance(bg_color, str) and bg_color == "random":
             return torch.rand(n_views, 3, device=device)
         if bg_color is None:
-            return self.bg_color.to(device).expand(n_views, 3).contiguous()
-        return torch.as_tensor(bg_color, dtype=torch.float32, device=device).reshape(1, 3).expand(n_views, 3).contiguous()
+            return self.bg_color.to(device=device, dtype=torch.float32).expand(n_views, 3).contiguous()
+        if torch.is_tensor(bg_color):
+            return bg_color.to(device=device, dtype=torch.float32).reshape(1, 3).expand(n_views, 3).contiguous()
+        # a tuple / list: materialised on the device ONCE per colour — a pageable host->device copy per call would
+        # synchronise, and is illegal inside a CUDA-graph capture (graphed.py replays this path)
+        key = (tuple(float(v) for v in bg_color), str(device))
+        cache = self.__dict__.setdefault("_bg_cache", {})
+        if key not in cache:
+            cache[key] = torch.tensor(key[0], dtype=torch.float32, device=device).reshape(1, 3)
+        return cache[key].expand(n_views, 3).contiguous()
 
     # ---------------------------------------------------------------- separate-stage path (fused = False)
     def _render_chunk_unfused(self, xyz, rot, sc, opac, feat, viewmats, Ks, bgs, h, w):
@@ -200,7 +208,7 @@ class GaussianRenderer(nn.Module):
         B, N = viewmats.shape[:2]
         xyz, features, opacity, scales, rotations = gaussians
         G = xyz.shape[1]
-        sc = scales if scaling_modifier == 1.0 else scales * scaling_modifier
+        sc = scales  # scaling_modifier: see forward()
         args = (xyz.reshape(B * G, 3), rotations.reshape(B * G, 4), sc.reshape(B * G, 3), opacity.reshape(B * G),
                 features[:, :, 0].reshape(B * G, 3), viewmats.reshape(B * N, 4, 4), Ks.reshape(B * N, 3, 3),
                 self._backgrounds(bg_color, B * N, xyz.device))
@@ -220,6 +228,9 @@ class GaussianRenderer(nn.Module):
         return (im.reshape(B, N, 3, h, w), de.reshape(B, N, 1, h, w), ma.reshape(B, N, 1, h, w), None, None)
 
     def forward(self, cameras, gaussians, scaling_modifier=1.0, bg_color=None, h=256, w=256):
+        """`scaling_modifier` is accepted for signature parity and IGNORED, exactly like the reference's gsplat
+        branch (gaussians_renderer.py:377-440 never reads it; only the diff_gaussian_rasterization fallback
+        branch, :337, which is out of scope, does)."""
         B, N = cameras.shape[:2]
         xyz, features, opacity, scales, rotations = gaussians
         device = xyz.device
@@ -246,7 +257,7 @@ class GaussianRenderer(nn.Module):
         jobs = []
         for i in range(B):
             bgs = self._backgrounds(bg_color, N, device)
-            sc = scales[i] if scaling_modifier == 1.0 else scales[i] * scaling_modifier
+            sc = scales[i]
             for c0 in range(0, N, self.view_chunk):
                 c1 = min(N, c0 + self.view_chunk)
                 args = (xyz[i], rotations[i], sc, opacity[i].squeeze(-1), features[i][:, 0], viewmats[i, c0:c1],

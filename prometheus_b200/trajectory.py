@@ -95,6 +95,9 @@ class TrajectoryRenderer:
         finally:
             self.rend.defer_checks = prev_defer
         cur.wait_stream(self._side)
+        # the outputs are pinned HOST tensors a caller reads on the CPU: block the host until the side-stream
+        # device->host copies have landed (ordering the current stream behind them is not enough for that)
+        self._side.synchronize()
         return frames_out, depths_out
 
     def _render_chunk(self, gaussians, cams, f0, f1, H, W, bg_color, frames_out, depths_out, cur, base=0):

@@ -167,7 +167,7 @@ def check_backward(oracle, name, gauss, vm, K, S, bg, st, max_share):
 
 # share of gradient entries allowed outside the bar at full size: fp32 atomics in arbitrary order (the composite
 # gradients are sums of up to thousands of signed terms) and fp32 VJP chains vs the oracle's fp64 accumulation
-FULL_GRAD_SHARE = 1e-3
+FULL_GRAD_SHARE = 1e-4  # measured on the B200: <= 6.4e-6 (v_conics, C1); everything else 0 .. 3e-6
 
 
 def test_c1_all_views_forward_and_backward(oracle):
@@ -249,4 +249,4 @@ def test_c2_module_training_step_vs_oracle_autograd(oracle):
     for k in KEYS:
         share, worst = violations(leaves[k].grad.cpu().numpy(), cpu[k].grad.numpy())
         print("C2 module step grad %-9s violating share %.3g, worst ratio %.3g" % (k, share, worst))
-        assert share <= 2e-3, (k, share, worst)
+        assert share <= 5e-4, (k, share, worst)  # measured: means 8e-5, scales 1.3e-4, others <= 1e-7

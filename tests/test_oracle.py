@@ -46,6 +46,21 @@ def test_camera_prep_matches_reference(oracle, golden_dir):
     assert allclose(K, d["Ks"], atol=0, rtol=1e-6)    # torch.atan vs numpy arctan: <= 1 ulp
 
 
+def test_camera_prep_matches_reference_non_square(oracle, golden_dir):
+    """h != w and H != W: the reference pairs fovx with h and fovy with w (gaussians_renderer.py:469-470) and the K
+    build un-pairs them again (:405-412); for square images the swaps cancel, here they do not."""
+    d = np.load(os.path.join(golden_dir, "cameras_nonsquare.npz"))
+    h, w = int(d["h"]), int(d["w"])
+    assert h != w and d["cameras"][0, 16] != d["cameras"][0, 17]
+    vm, K = oracle.camera_prep(d["cameras"], h, w)
+    assert np.array_equal(vm, d["viewmats"])
+    assert allclose(K, d["Ks"], atol=0, rtol=1e-6)
+    # what the two swaps amount to: fx' = w fx / H, fy' = h fy / W, principal point at the image centre
+    cam = d["cameras"][0]
+    assert allclose(K[0, 0, 0], w * cam[12] / cam[16], atol=0, rtol=1e-5) and allclose(K[0, 1, 1], h * cam[13] / cam[17], atol=0, rtol=1e-5)
+    assert K[0, 0, 2] == w / 2 and K[0, 1, 2] == h / 2
+
+
 # --------------------------------------------------------------------------- known answers
 def test_single_isotropic_gaussian_closed_form(oracle):
     """One isotropic Gaussian on the optical axis: cov2d = (f s / z)^2 + 0.3, closed-form alpha(r)."""
