@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PM_ABI_VERSION 2
+#define PM_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define PM_API __attribute__((visibility("default")))
@@ -278,7 +278,20 @@ PM_API int pm_composite_fwd(const float *means2d, const float *conics, const flo
                      int64_t n_isects, const int32_t *d_n,
                      int N, int C, int width, int height, int tile_size,
                      float *render, float *alphas, int32_t *last_ids, float *transmittance,
-                     pm_stream_t stream);
+                     float *splat_stream, pm_stream_t stream);
+
+/* The SPLAT STREAM: what the compositing backward replays. splat_stream [n_isects, 12] fp32 (16-byte aligned, may be
+ * NULL when no backward follows): the forward kernels write every Gaussian they stage, at its position in the sorted
+ * list, as one 48-byte record {mean x, mean y, half extents of alpha >= 1/255 (2 x fp16, rounded up), flatten id |
+ * conic scaled to base-2 exponent units, opacity | colour channels, depth}. Only the prefix of each tile's list that
+ * the compositor consumed is written — all the backward reads. A tile's records are contiguous, so the backward
+ * moves 32 of them into shared memory with one cp.async.bulk (TMA) + mbarrier instead of 32 x 7 scattered loads.
+ * pm_splat_stream_build gathers the WHOLE sorted list into a stream (for a forward state that did not come from these
+ * kernels, e.g. in tests, or a forward that ran with splat_stream = NULL). */
+PM_API int pm_splat_stream_build(const float *means2d, const float *conics, const float *opacities,
+                     const float *colors, int colors_per_camera, int D, const float *depths,
+                     const int32_t *flatten_ids, int64_t n_isects, const int32_t *d_n,
+                     int N, int C, int views_per_scene, float *splat_stream, pm_stream_t stream);
 
 /* Fused "sort-as-you-go" forward (fast path of the module-level renderer): takes
  * the UNSORTED per-tile records of pm_bin_scatter and, per tile, sorts only as
@@ -297,7 +310,8 @@ PM_API int pm_tile_render_fwd(const uint64_t *records, const int32_t *isect_offs
                               int width, int height, int tile_size,
                               float *render, float *alphas, int32_t *last_ids,
                               int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
-                              const int32_t *tile_order, float *transmittance, pm_stream_t stream);
+                              const int32_t *tile_order, float *transmittance, float *splat_stream,
+                              pm_stream_t stream);
 
 /* The same kernel with the module-level epilogue fused in (RGB + expected depth, D = 3): writes
  * what GaussianRenderer.forward returns (gaussians_renderer.py:437-440, :507-509) —
@@ -314,17 +328,15 @@ PM_API int pm_tile_render_packed_fwd(const uint64_t *records, const int32_t *ise
                               float *images, float *depth_out, float *masks, int32_t *last_ids,
                               int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
                               const int32_t *tile_order, int views_per_scene, float *transmittance,
-                              pm_stream_t stream);
+                              float *splat_stream, pm_stream_t stream);
 
-/* Backward. v_render [C,H,W,CD], v_alphas [C,H,W] (either may be NULL). transmittance [C,H,W] = the forward's
- * array of that name, or NULL: T_final is then rebuilt as 1 - alphas like upstream.
- * Gradients are ACCUMULATED (+=) into v_means2d [C,N,2], v_conics [C,N,3],
- * v_colors ([N,D] or [C,N,D]), v_opacities [N], v_depths [C,N]: the caller
- * zero-fills them. v_depths must be non-NULL iff depths is. */
-PM_API int pm_composite_bwd(const float *means2d, const float *conics, const float *opacities,
-                     const float *colors, int colors_per_camera, int D,
-                     const float *depths, const float *backgrounds,
-                     const int32_t *isect_offsets, const int32_t *flatten_ids,
+/* Backward. Replays splat_stream (see above; colours [N,D] or [C,N,D] per colors_per_camera, has_depth = the forward
+ * rendered a depth channel, CD = D + has_depth). v_render [C,H,W,CD], v_alphas [C,H,W] (either may be NULL).
+ * transmittance [C,H,W] = the forward's array of that name, or NULL: T_final is then rebuilt as 1 - alphas like
+ * upstream. Gradients are ACCUMULATED (+=) into v_means2d [C,N,2], v_conics [C,N,3], v_colors ([N,D] or [C,N,D]),
+ * v_opacities [N], v_depths [C,N]: the caller zero-fills them. v_depths must be non-NULL iff has_depth. */
+PM_API int pm_composite_bwd(const float *splat_stream, int colors_per_camera, int D, int has_depth,
+                     const float *backgrounds, const int32_t *isect_offsets,
                      int64_t n_isects, const int32_t *d_n,
                      int N, int C, int width, int height, int tile_size,
                      const float *alphas, const int32_t *last_ids, const float *transmittance,
@@ -335,10 +347,9 @@ PM_API int pm_composite_bwd(const float *means2d, const float *conics, const flo
 /* Backward of pm_tile_render_packed_fwd: cotangents of the packed outputs (any may be NULL) in,
  * the same accumulated per-Gaussian gradients out. masks / depth_out are the forward's outputs.
  * tile_order (may be NULL): launch order of the tiles, e.g. pm_tile_scan over the forward's sorted_counts. */
-PM_API int pm_composite_bwd_packed(const float *means2d, const float *conics, const float *opacities,
-                     const float *colors, int colors_per_camera, const float *depths,
+PM_API int pm_composite_bwd_packed(const float *splat_stream, int colors_per_camera,
                      const float *backgrounds, const int32_t *isect_offsets,
-                     const int32_t *flatten_ids, int64_t n_isects, const int32_t *d_n,
+                     int64_t n_isects, const int32_t *d_n,
                      int N, int C, int width, int height, int tile_size,
                      const float *masks, const float *depth_out, const int32_t *last_ids,
                      const float *transmittance,

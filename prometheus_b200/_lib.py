@@ -19,7 +19,7 @@ _CSRC = os.path.join(_PKG, "csrc")
 _lib = None
 
 PM_OK = 0
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # name -> (restype, argtypes); mirrors include/prometheus_gs.h one to one
 _F, _I, _L, _P, _S = c_float, c_int, c_int64, c_void_p, c_size_t
@@ -47,10 +47,11 @@ SIGNATURES = {
     "pm_sort_workspace_bytes": (c_size_t, [_L]),
     "pm_sort_pairs": (c_int, [_P, _P, _P, _P, _L, _P, _I, _P, _S, POINTER(c_int), _P]),
     "pm_tile_offsets": (c_int, [_P, _L, _P, _I, _I, _I, _P, _P]),
-    "pm_composite_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
-    "pm_tile_render_fwd": (c_int, [_P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "pm_tile_render_packed_fwd": (c_int, [_P, _P, _L, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
-    "pm_composite_bwd_packed": (c_int, [_P, _P, _P, _P, _I, _P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I,
+    "pm_composite_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "pm_splat_stream_build": (c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _L, _P, _I, _I, _I, _P, _P]),
+    "pm_tile_render_fwd": (c_int, [_P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pm_tile_render_packed_fwd": (c_int, [_P, _P, _L, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
+    "pm_composite_bwd_packed": (c_int, [_P, _I, _P, _P, _L, _P, _I, _I, _I, _I, _I,
                                         _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "pm_splat_keys": (c_int, [_P, _P, _L, _I, _P, _P, _P]),
     "pm_splat_pack": (c_int, [_P, _P, _P, _P, _P, _P, _L, _I, _P, _P]),
@@ -59,7 +60,7 @@ SIGNATURES = {
     "pm_densify_stats": (c_int, [_P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "pm_sample_cameras": (c_int, [_P, _P, _I, _I, _I, _P, _P]),
     "pm_pack_frames_u8": (c_int, [_P, _L, _I, _I, _P, _P]),
-    "pm_composite_bwd": (c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I,
+    "pm_composite_bwd": (c_int, [_P, _I, _I, _I, _P, _P, _L, _P, _I, _I, _I, _I, _I,
                                  _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 

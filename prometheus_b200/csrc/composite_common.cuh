@@ -3,6 +3,8 @@
 // the explicitly rounded alpha evaluation and the per-batch forward loop. Keeping ONE copy of the
 // arithmetic is what makes the fused path's images bit-identical to the separate-stage path.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace pm {
@@ -112,6 +114,35 @@ __device__ __forceinline__ void gather(int32_t f, int32_t g, const float *__rest
                                        const float *__restrict__ colors, int colors_per_camera, int D,
                                        const float *__restrict__ depths, GaussA &a, GaussB &b, GaussC &c) {
   gather_finish(gather_load(f, g, means2d, conics, opacities, colors, colors_per_camera, D, depths), a, b, c);
+}
+
+// ---- the splat stream: what the backward replays -------------------------------------------------------------
+// When a backward will follow, the forward kernels write every Gaussian they stage — in the tile's sorted order, at
+// its list position — as one 48-byte record {mean x, mean y, half extents (2 x fp16, rounded up), flatten id |
+// scaled conic, opacity | colour, depth}. A tile's records are contiguous, so the backward streams a chunk of 32 of
+// them (1536 bytes) into shared memory with ONE cp.async.bulk (TMA) and an mbarrier instead of 32 lanes x 7
+// scattered loads through the L1 data pipe (which ran at 74 % of its peak doing that, profiles/r2d_*), and never
+// recomputes log / sqrt / div for the extents.
+constexpr int kStreamFloats = 12;
+__device__ __forceinline__ float pack_extents(float hx, float hy) {
+  // conservative: rounded towards +inf; 3e38 ("no culling") becomes +inf, -1e30 ("never visible") becomes -inf
+  const unsigned lo = __half_as_ushort(__float2half_ru(hx)), hi = __half_as_ushort(__float2half_ru(hy));
+  return __uint_as_float(lo | (hi << 16));
+}
+__device__ __forceinline__ float2 unpack_extents(float packed) {
+  const unsigned u = __float_as_uint(packed);
+  return make_float2(__half2float(__ushort_as_half((unsigned short)(u & 0xffffu))),
+                     __half2float(__ushort_as_half((unsigned short)(u >> 16))));
+}
+__device__ __forceinline__ void stream_store(float *__restrict__ stream, size_t pos, int32_t f, const struct GaussA &a,
+                                             const struct GaussB &b, const struct GaussC &c);
+
+__device__ __forceinline__ void stream_store(float *__restrict__ stream, size_t pos, int32_t f, const GaussA &a,
+                                             const GaussB &b, const GaussC &c) {
+  float4 *dst = reinterpret_cast<float4 *>(stream) + pos * 3;
+  dst[0] = make_float4(a.mx, a.my, pack_extents(a.hx, a.hy), __int_as_float(f));
+  dst[1] = make_float4(b.cx, b.cy, b.cz, b.opac);
+  dst[2] = make_float4(c.c0, c.c1, c.c2, c.c3);
 }
 
 // Per-pixel forward state of one lane. The sign of T carries the "done" flag: T > 0 while the pixel
@@ -227,14 +258,15 @@ __device__ __forceinline__ LiveRect live_rect(unsigned live, float wcx, float wc
 // not contain the mean it peaks on the edge(s) facing the mean; the splat can contribute only if that peak is
 // >= -log2(255 opacity). The margins make rounding err on the side of keeping a splat, so culling never changes
 // a result.
-__device__ __forceinline__ bool cull_hit(const float4 &a, uint32_t aB_j, const LiveRect &r) {
+template <typename LoadB>
+__device__ __forceinline__ bool cull_hit_impl(const float4 &a, LoadB load_b, const LiveRect &r) {
   const float dx0 = r.x0 - a.x, dx1 = r.x1 - a.x, dy0 = r.y0 - a.y, dy1 = r.y1 - a.y;
   bool hit = dx0 <= a.z && dx1 >= -a.z && dy0 <= a.w && dy1 >= -a.w;
 #if PM_EXACT_CULL
   if (hit && a.z < 1e37f) {
     const float ax = fminf(fmaxf(0.0f, dx0), dx1), by = fminf(fmaxf(0.0f, dy0), dy1);
     if (ax != 0.0f || by != 0.0f) {
-      const float4 b = lds128(aB_j);
+      const float4 b = load_b();
       // (slack = a relative bound on the rounding of the three products: strongly anisotropic conics cancel)
       float pmax = -3e38f, slack = 0.0f;
       if (ax != 0.0f) {
@@ -255,6 +287,13 @@ __device__ __forceinline__ bool cull_hit(const float4 &a, uint32_t aB_j, const L
   }
 #endif
   return hit;
+}
+// B record in shared memory (forward: the whole group is staged) or already in registers (backward: staged only if hit)
+__device__ __forceinline__ bool cull_hit(const float4 &a, uint32_t aB_j, const LiveRect &r) {
+  return cull_hit_impl(a, [aB_j] { return lds128(aB_j); }, r);
+}
+__device__ __forceinline__ bool cull_hit_reg(const float4 &a, const float4 &b, const LiveRect &r) {
+  return cull_hit_impl(a, [&b] { return b; }, r);
 }
 
 template <int CAP>

@@ -209,7 +209,7 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
                        int32_t *__restrict__ overflow_flag, float *__restrict__ images,
                        float *__restrict__ depth_out, float *__restrict__ masks,
                        const int32_t *__restrict__ tile_order, int views_per_scene,
-                       float *__restrict__ transmittance) {
+                       float *__restrict__ transmittance, float *__restrict__ stream) {
   extern __shared__ __align__(16) unsigned char tr_smem[];
   TrShared &sh = *reinterpret_cast<TrShared *>(tr_smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -341,9 +341,13 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
 #pragma unroll
     for (int k = 0; k < kTrItems; ++k) {
       const int slot = k * kTrThreads + tid;
-      if (slot < m)
-        gather(ids[k], ids[k] - cam_base, means2d, conics, opacities, colors, colors_per_camera, D, depths, sh.stg.sA[slot],
-               sh.stg.sB[slot], sh.stg.sC[slot]);
+      if (slot < m) {
+        GaussA ga; GaussB gb; GaussC gc;
+        gather(ids[k], ids[k] - cam_base, means2d, conics, opacities, colors, colors_per_camera, D, depths, ga, gb, gc);
+        sh.stg.sA[slot] = ga; sh.stg.sB[slot] = gb; sh.stg.sC[slot] = gc;
+        // what the backward replays: the staged record, at its position in the tile's sorted list
+        if (stream) stream_store(stream, (size_t)start + list_base + gs + slot, ids[k], ga, gb, gc);
+      }
     }
     __syncthreads();
     // composite the whole group; warps do not wait for each other — same arithmetic as composite_fwd_kernel
@@ -476,7 +480,7 @@ static int tile_render_launch(const uint64_t *records, const int32_t *isect_offs
                               float *render, float *alphas, int32_t *last_ids, int32_t *flatten_ids,
                               int32_t *sorted_counts, int32_t *overflow_flag, float *images, float *depth_out,
                               float *masks, const int32_t *tile_order, int views_per_scene, float *transmittance,
-                              pm_stream_t stream) {
+                              float *splat_stream, pm_stream_t stream) {
   if (N < 0 || C < 0 || width <= 0 || height <= 0 || n_isects < 0 || D < 0) return PM_ERR_BAD_ARG;
   if (tile_size != pm::kTile) return PM_ERR_UNSUPPORTED;
   const int CD = D + (depths ? 1 : 0);
@@ -493,6 +497,7 @@ static int tile_render_launch(const uint64_t *records, const int32_t *isect_offs
   if (D > 0 && !colors) return PM_ERR_BAD_ARG;
   if (n_isects > 0 && (!records || !flatten_ids)) return PM_ERR_BAD_ARG;
   if ((reinterpret_cast<uintptr_t>(means2d) & 7) != 0) return PM_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(splat_stream) & 15) != 0) return PM_ERR_BAD_ARG;
   if (n_isects >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
   if (C == 0) return PM_OK;
   if (views_per_scene > 0 && C % views_per_scene != 0) return PM_ERR_BAD_ARG;
@@ -508,7 +513,7 @@ static int tile_render_launch(const uint64_t *records, const int32_t *isect_offs
   pm::tile_render_fwd_kernel<<<(unsigned)blocks, pm::kTrThreads, pm::kTrSmemBytes, pm::as_stream(stream)>>>(
       records, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera, D, depths,
       backgrounds, N, width, height, tw, th, render, alphas, last_ids, flatten_ids, sorted_counts, overflow_flag,
-      images, depth_out, masks, tile_order, views_per_scene > 0 ? views_per_scene : C, transmittance);
+      images, depth_out, masks, tile_order, views_per_scene > 0 ? views_per_scene : C, transmittance, splat_stream);
   return pm::check_launch();
 }
 
@@ -530,10 +535,11 @@ int pm_tile_render_fwd(const uint64_t *records, const int32_t *isect_offsets, in
                        const float *depths, const float *backgrounds, int N, int C, int width, int height,
                        int tile_size, float *render, float *alphas, int32_t *last_ids,
                        int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
-                       const int32_t *tile_order, float *transmittance, pm_stream_t stream) {
+                       const int32_t *tile_order, float *transmittance, float *splat_stream, pm_stream_t stream) {
   return tile_render_launch(records, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera,
                             D, depths, backgrounds, N, C, width, height, tile_size, render, alphas, last_ids,
-                            flatten_ids, sorted_counts, overflow_flag, nullptr, nullptr, nullptr, tile_order, 0, transmittance, stream);
+                            flatten_ids, sorted_counts, overflow_flag, nullptr, nullptr, nullptr, tile_order, 0, transmittance,
+                            splat_stream, stream);
 }
 
 int pm_tile_render_packed_fwd(const uint64_t *records, const int32_t *isect_offsets, int64_t n_isects,
@@ -543,12 +549,12 @@ int pm_tile_render_packed_fwd(const uint64_t *records, const int32_t *isect_offs
                               int tile_size, float *images, float *depth_out, float *masks, int32_t *last_ids,
                               int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
                               const int32_t *tile_order, int views_per_scene, float *transmittance,
-                              pm_stream_t stream) {
+                              float *splat_stream, pm_stream_t stream) {
   if (!images) return PM_ERR_BAD_ARG;
   return tile_render_launch(records, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera,
                             3, depths, backgrounds, N, C, width, height, tile_size, nullptr, nullptr, last_ids,
                             flatten_ids, sorted_counts, overflow_flag, images, depth_out, masks, tile_order, views_per_scene,
-                            transmittance, stream);
+                            transmittance, splat_stream, stream);
 }
 
 }  // extern "C"

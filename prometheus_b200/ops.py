@@ -351,8 +351,9 @@ def _colors_layout(colors, C, N):
 
 @_instrument("composite_fwd", 1)
 def composite_fwd(means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width,
-                  height, d_n=None):
-    """-> render [C,H,W,CD], alphas [C,H,W], last_ids [C,H,W], transmittance [C,H,W] (see pm_composite_fwd)."""
+                  height, d_n=None, want_stream=False):
+    """-> render [C,H,W,CD], alphas [C,H,W], last_ids [C,H,W], transmittance [C,H,W] (see pm_composite_fwd)
+    [, splat_stream [n,12] when want_stream: what composite_bwd replays]."""
     L = _lib.load()
     C, N = means2d.shape[:2]
     colors, per_cam, D = _colors_layout(colors, C, N)
@@ -362,16 +363,36 @@ def composite_fwd(means2d, conics, opacities, colors, depths, backgrounds, offse
     alphas = torch.empty(C, height, width, device=dev)
     last_ids = torch.empty(C, height, width, dtype=torch.int32, device=dev)
     trans = torch.empty(C, height, width, device=dev)
+    stream = torch.empty(flatten_ids.numel(), STREAM_FLOATS, device=dev) if want_stream else None
     _lib.check(L.pm_composite_fwd(_ptr(means2d), _ptr(conics), _ptr(opacities), _ptr(colors), per_cam, D,
                                   _ptr(depths), _ptr(backgrounds), _ptr(offsets), _ptr(flatten_ids),
                                   flatten_ids.numel(), _ptr(d_n), N, C, width, height, TILE, _ptr(render),
-                                  _ptr(alphas), _ptr(last_ids), _ptr(trans), _stream()), "pm_composite_fwd")
-    return render, alphas, last_ids, trans
+                                  _ptr(alphas), _ptr(last_ids), _ptr(trans), _ptr(stream), _stream()), "pm_composite_fwd")
+    return (render, alphas, last_ids, trans, stream) if want_stream else (render, alphas, last_ids, trans)
+
+
+STREAM_FLOATS = 12  # floats per splat-stream record (include/prometheus_gs.h)
+
+
+@_instrument("splat_stream_build", 1)
+def splat_stream_build(means2d, conics, opacities, colors, depths, flatten_ids, d_n=None, views_per_scene=0):
+    """Gather the whole sorted list into a splat stream [n,12] (pm_splat_stream_build): for a backward on a forward
+    state that did not come from our forward kernels."""
+    L = _lib.load()
+    C, N = means2d.shape[:2]
+    n_scenes = C // views_per_scene if views_per_scene else 1
+    colors, per_cam, D = _colors_layout(colors, C, N * n_scenes)
+    n = flatten_ids.numel()
+    stream = torch.empty(n, STREAM_FLOATS, device=means2d.device)
+    _lib.check(L.pm_splat_stream_build(_ptr(means2d), _ptr(conics), _ptr(opacities), _ptr(colors), per_cam, D, _ptr(depths),
+                                       _ptr(flatten_ids), n, _ptr(d_n), N, C, int(views_per_scene), _ptr(stream), _stream()),
+               "pm_splat_stream_build")
+    return stream
 
 
 @_instrument("tile_render_fwd", 1)
 def tile_render_fwd(records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height, d_n=None,
-                    tile_order=None):
+                    tile_order=None, want_stream=False):
     """Fused sort-as-you-go forward -> render, alphas, last_ids, flatten_ids (sorted prefix per tile),
     sorted_counts [C,th,tw], overflow flag int32[1], transmittance [C,H,W]."""
     L = _lib.load()
@@ -387,21 +408,26 @@ def tile_render_fwd(records, offsets, means2d, conics, opacities, colors, depths
     sorted_counts = torch.empty_like(offsets)
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
     trans = torch.empty(C, height, width, device=dev)
+    stream = torch.empty(n, STREAM_FLOATS, device=dev) if want_stream else None
     _lib.check(L.pm_tile_render_fwd(_ptr(records), _ptr(offsets), n, _ptr(d_n), _ptr(means2d), _ptr(conics),
                                     _ptr(opacities), _ptr(colors), per_cam, D, _ptr(depths), _ptr(backgrounds), N, C,
                                     width, height, TILE, _ptr(render), _ptr(alphas), _ptr(last_ids), _ptr(flat),
-                                    _ptr(sorted_counts), _ptr(flag), _ptr(tile_order), _ptr(trans), _stream()),
+                                    _ptr(sorted_counts), _ptr(flag), _ptr(tile_order), _ptr(trans), _ptr(stream), _stream()),
                "pm_tile_render_fwd")
-    return render, alphas, last_ids, flat, sorted_counts, flag, trans
+    out = (render, alphas, last_ids, flat, sorted_counts, flag, trans)
+    return out + (stream,) if want_stream else out
 
 
 @_instrument("composite_bwd", 1)
 def composite_bwd(means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width,
-                  height, alphas, last_ids, v_render, v_alphas, d_n=None, transmittance=None):
-    """transmittance: the forward's exact final T per pixel; None = rebuild it as 1 - alphas (upstream's form)."""
+                  height, alphas, last_ids, v_render, v_alphas, d_n=None, transmittance=None, stream=None):
+    """transmittance: the forward's exact final T per pixel; None = rebuild it as 1 - alphas (upstream's form).
+    stream: the forward's splat stream; None = gather it from the sorted list first (pm_splat_stream_build)."""
     L = _lib.load()
     C, N = means2d.shape[:2]
     colors, per_cam, D = _colors_layout(colors, C, N)
+    if stream is None:
+        stream = splat_stream_build(means2d, conics, opacities, colors, depths, flatten_ids, d_n)
     v_render = _opt(v_render, torch.float32, "v_render")
     v_alphas = _opt(v_alphas, torch.float32, "v_alphas")
     v_means2d = torch.zeros_like(means2d)
@@ -409,9 +435,8 @@ def composite_bwd(means2d, conics, opacities, colors, depths, backgrounds, offse
     v_colors = torch.zeros_like(colors) if colors is not None else None
     v_opac = torch.zeros_like(opacities)
     v_depths = torch.zeros_like(depths) if depths is not None else None
-    _lib.check(L.pm_composite_bwd(_ptr(means2d), _ptr(conics), _ptr(opacities), _ptr(colors), per_cam, D,
-                                  _ptr(depths), _ptr(backgrounds), _ptr(offsets), _ptr(flatten_ids),
-                                  flatten_ids.numel(), _ptr(d_n), N, C, width, height, TILE, _ptr(alphas),
+    _lib.check(L.pm_composite_bwd(_ptr(stream), per_cam, D, int(depths is not None), _ptr(backgrounds), _ptr(offsets),
+                                  stream.shape[0], _ptr(d_n), N, C, width, height, TILE, _ptr(alphas),
                                   _ptr(last_ids), _ptr(_opt(transmittance, torch.float32, "transmittance")),
                                   _ptr(v_render), _ptr(v_alphas), _ptr(v_means2d),
                                   _ptr(v_conics), _ptr(v_colors), _ptr(v_opac), _ptr(v_depths), _stream()),
@@ -422,12 +447,12 @@ def composite_bwd(means2d, conics, opacities, colors, depths, backgrounds, offse
 # ------------------------------------------------------------------ module fast path (packed outputs)
 @_instrument("tile_render_fwd", 1)
 def tile_render_packed_fwd(records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height,
-                           d_n=None, tile_order=None, views_per_scene=0, want_transmittance=False):
+                           d_n=None, tile_order=None, views_per_scene=0, for_backward=False):
     """Fused sort-as-you-go forward with the module epilogue: -> images [C,3,H,W] (2 rgb - 1),
     depth_out [C,1,H,W] (expected depth), masks [C,1,H,W], last_ids [C,H,W], flatten_ids (sorted prefix per
-    tile), sorted_counts [C,th,tw], overflow flag int32[1], transmittance [C,H,W] (only when want_transmittance:
-    the backward's exact T_final). `records` may be a speculative capacity with the true count in d_n[0]
-    (see pm_tile_render_packed_fwd)."""
+    tile), sorted_counts [C,th,tw], overflow flag int32[1], transmittance [C,H,W] and splat_stream [n,12] (both None
+    unless for_backward: the backward's exact T_final and the records it replays). `records` may be a speculative
+    capacity with the true count in d_n[0] (see pm_tile_render_packed_fwd)."""
     L = _lib.load()
     C, N = means2d.shape[:2]
     n_scenes = C // views_per_scene if views_per_scene else 1
@@ -442,35 +467,37 @@ def tile_render_packed_fwd(records, offsets, means2d, conics, opacities, colors,
     flat = torch.empty(n, dtype=torch.int32, device=dev)
     sorted_counts = torch.empty_like(offsets)
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
-    trans = torch.empty(C, height, width, device=dev) if want_transmittance else None
+    trans = torch.empty(C, height, width, device=dev) if for_backward else None
+    stream = torch.empty(n, STREAM_FLOATS, device=dev) if for_backward else None
     _lib.check(L.pm_tile_render_packed_fwd(_ptr(records), _ptr(offsets), n, _ptr(d_n), _ptr(means2d), _ptr(conics),
                                            _ptr(opacities), _ptr(colors), per_cam, _ptr(depths), _ptr(backgrounds), N, C,
                                            width, height, TILE, _ptr(images), _ptr(depth_out), _ptr(masks),
                                            _ptr(last_ids), _ptr(flat), _ptr(sorted_counts), _ptr(flag), _ptr(tile_order),
-                                           int(views_per_scene), _ptr(trans), _stream()),
+                                           int(views_per_scene), _ptr(trans), _ptr(stream), _stream()),
                "pm_tile_render_packed_fwd")
-    return images, depth_out, masks, last_ids, flat, sorted_counts, flag, trans
+    return images, depth_out, masks, last_ids, flat, sorted_counts, flag, trans, stream
 
 
 @_instrument("composite_bwd", 1)
 def composite_bwd_packed(means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width, height,
                          masks, depth_out, last_ids, v_images, v_depth_out, v_masks, d_n=None, tile_order=None,
-                         views_per_scene=0, transmittance=None):
+                         views_per_scene=0, transmittance=None, stream=None):
     L = _lib.load()
     C, N = means2d.shape[:2]
     colors, per_cam, D = _colors_layout(colors, C, N * (C // views_per_scene if views_per_scene else 1))
+    if stream is None:
+        stream = splat_stream_build(means2d, conics, opacities, colors, depths, flatten_ids, d_n, views_per_scene)
     v_images, v_depth_out, v_masks = (_opt(t, torch.float32, "grad") for t in (v_images, v_depth_out, v_masks))
     v_means2d = torch.zeros_like(means2d)
     v_conics = torch.zeros_like(conics)
     v_colors = torch.zeros_like(colors)
     v_opac = torch.zeros_like(opacities)
     v_depths = torch.zeros_like(depths)
-    _lib.check(L.pm_composite_bwd_packed(_ptr(means2d), _ptr(conics), _ptr(opacities), _ptr(colors), per_cam,
-                                         _ptr(depths), _ptr(backgrounds), _ptr(offsets), _ptr(flatten_ids),
-                                         flatten_ids.numel(), _ptr(d_n), N, C, width, height, TILE, _ptr(masks),
-                                         _ptr(depth_out), _ptr(last_ids), _ptr(transmittance), _ptr(v_images), _ptr(v_depth_out),
-                                         _ptr(v_masks), _ptr(v_means2d), _ptr(v_conics), _ptr(v_colors), _ptr(v_opac),
-                                         _ptr(v_depths), _ptr(tile_order), int(views_per_scene), _stream()),
+    _lib.check(L.pm_composite_bwd_packed(_ptr(stream), per_cam, _ptr(backgrounds), _ptr(offsets), stream.shape[0], _ptr(d_n),
+                                         N, C, width, height, TILE, _ptr(masks), _ptr(depth_out), _ptr(last_ids),
+                                         _ptr(transmittance), _ptr(v_images), _ptr(v_depth_out), _ptr(v_masks),
+                                         _ptr(v_means2d), _ptr(v_conics), _ptr(v_colors), _ptr(v_opac), _ptr(v_depths),
+                                         _ptr(tile_order), int(views_per_scene), _stream()),
                "pm_composite_bwd_packed")
     return v_means2d, v_conics, v_colors, v_opac, v_depths
 

@@ -63,10 +63,12 @@ class _Composite(torch.autograd.Function):
         colors = None if colors is None else colors.contiguous()
         depths = None if depths is None else depths.contiguous()
         backgrounds = None if backgrounds is None else backgrounds.contiguous().float()
-        render, alphas, last_ids, trans = ops.composite_fwd(means2d, conics, opacities, colors, depths, backgrounds,
-                                                            offsets, flatten_ids, width, height, d_n)
+        need_bwd = any(ctx.needs_input_grad[:6])  # then the forward also writes the splat stream the backward replays
+        out = ops.composite_fwd(means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width,
+                                height, d_n, want_stream=need_bwd)
+        render, alphas, last_ids, trans = out[:4]
         ctx.save_for_backward(means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids,
-                              alphas, last_ids, d_n, trans)
+                              alphas, last_ids, d_n, trans, out[4] if need_bwd else None)
         ctx.dims = (width, height)
         ctx.last_ids = last_ids
         return render, alphas.unsqueeze(-1)
@@ -74,12 +76,12 @@ class _Composite(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_render, v_alphas):
         (means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, alphas, last_ids,
-         d_n, trans) = ctx.saved_tensors
+         d_n, trans, stream) = ctx.saved_tensors
         width, height = ctx.dims
         v_alphas2 = None if v_alphas is None else v_alphas.squeeze(-1)
         v_means2d, v_conics, v_colors, v_opac, v_depths = ops.composite_bwd(
             means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width, height, alphas,
-            last_ids, v_render, v_alphas2, d_n, transmittance=trans)
+            last_ids, v_render, v_alphas2, d_n, transmittance=trans, stream=stream)
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[5] and v_render is not None:
             D = backgrounds.shape[-1]
@@ -97,10 +99,12 @@ class _TileRender(torch.autograd.Function):
         colors = None if colors is None else colors.contiguous()
         depths = None if depths is None else depths.contiguous()
         backgrounds = None if backgrounds is None else backgrounds.contiguous().float()
-        render, alphas, last_ids, flat, sorted_counts, flag, trans = ops.tile_render_fwd(
-            records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height)
+        need_bwd = any(ctx.needs_input_grad[:6])
+        out = ops.tile_render_fwd(records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height,
+                                  want_stream=need_bwd)
+        render, alphas, last_ids, flat, sorted_counts, flag, trans = out[:7]
         ctx.save_for_backward(means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, alphas, last_ids,
-                              trans)
+                              trans, out[7] if need_bwd else None)
         ctx.dims = (width, height)
         ctx.mark_non_differentiable(flag, flat, sorted_counts)
         return render, alphas.unsqueeze(-1), flag, flat, sorted_counts
@@ -108,12 +112,12 @@ class _TileRender(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_render, v_alphas, _vf, _vflat, _vsc):
         (means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, alphas, last_ids,
-         trans) = ctx.saved_tensors
+         trans, stream) = ctx.saved_tensors
         width, height = ctx.dims
         v_alphas2 = None if v_alphas is None else v_alphas.squeeze(-1)
         v_means2d, v_conics, v_colors, v_opac, v_depths = ops.composite_bwd(
             means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, width, height, alphas, last_ids,
-            v_render, v_alphas2, None, transmittance=trans)
+            v_render, v_alphas2, None, transmittance=trans, stream=stream)
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[5] and v_render is not None:
             D = backgrounds.shape[-1]
@@ -133,13 +137,14 @@ class _TileRenderPacked(torch.autograd.Function):
         means2d, conics = means2d.contiguous(), conics.contiguous()
         opacities, colors, depths = opacities.contiguous(), colors.contiguous(), depths.contiguous()
         backgrounds = None if backgrounds is None else backgrounds.contiguous().float()
-        # the exact final transmittance is kept only when a backward will consume it (4 B/pixel)
-        need_t = any(ctx.needs_input_grad[:6])
-        images, depth_out, masks, last_ids, flat, sorted_counts, flag, trans = ops.tile_render_packed_fwd(
+        # the exact final transmittance (4 B/pixel) and the splat stream the backward replays (48 B per staged
+        # Gaussian) are written only when a backward will consume them
+        need_bwd = any(ctx.needs_input_grad[:6])
+        images, depth_out, masks, last_ids, flat, sorted_counts, flag, trans, stream = ops.tile_render_packed_fwd(
             records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height, d_n=stats,
-            tile_order=tile_order, views_per_scene=views_per_scene, want_transmittance=need_t)
+            tile_order=tile_order, views_per_scene=views_per_scene, for_backward=need_bwd)
         ctx.save_for_backward(means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, masks, depth_out,
-                              last_ids, stats, sorted_counts, trans)
+                              last_ids, stats, sorted_counts, trans, stream)
         ctx.dims = (width, height)
         ctx.mark_non_differentiable(flag, flat, sorted_counts)
         return images, depth_out, masks, flag, flat, sorted_counts
@@ -147,14 +152,14 @@ class _TileRenderPacked(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_images, v_depth_out, v_masks, _vf, _vflat, _vsc):
         (means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, masks, depth_out, last_ids,
-         stats, sorted_counts, trans) = ctx.saved_tensors
+         stats, sorted_counts, trans, stream) = ctx.saved_tensors
         width, height = ctx.dims
         # the backward replays what the forward sorted: tiles with the longest sorted prefix go first
         order = ops.tile_scan(sorted_counts, want_order=True)[2]
         v_means2d, v_conics, v_colors, v_opac, v_depths = ops.composite_bwd_packed(
             means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, width, height, masks, depth_out,
             last_ids, v_images, v_depth_out, v_masks, d_n=stats, tile_order=order, views_per_scene=ctx.views_per_scene,
-            transmittance=trans)
+            transmittance=trans, stream=stream)
         if ctx.grad_sink is not None:
             ctx.grad_sink["v_means2d"] = v_means2d
             for j, view in enumerate(ctx.grad_sink.get("views", ())):  # the reference's viewspace_points[j].grad

@@ -32,7 +32,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert os.path.exists(_lib.library_path())
     for s in declared_symbols():
         assert hasattr(lib, s), s
-    assert lib.pm_abi_version() == 2
+    assert lib.pm_abi_version() == 3
     assert lib.pm_status_string(0) == b"ok"
     assert b"workspace" in lib.pm_status_string(-3)
 
@@ -57,7 +57,7 @@ def test_argument_errors_are_reported_before_launch():
     assert lib.pm_sort_pairs(one, one, one, one, 100, null, 40, one, 8, ctypes.byref(sel), null) == -3  # workspace too small
     assert lib.pm_sort_pairs(one, one, one, one, 1 << 31, null, 40, one, 1 << 40, ctypes.byref(sel), null) == -5
     assert lib.pm_sort_pairs(null, null, null, null, 0, null, 44, null, 0, ctypes.byref(sel), null) == 0 and sel.value == 0
-    assert lib.pm_composite_fwd(one, one, one, one, 0, 5, null, null, one, one, 10, null, 4, 1, 32, 32, 16, one, one, one, null, null) == -2
+    assert lib.pm_composite_fwd(one, one, one, one, 0, 5, null, null, one, one, 10, null, 4, 1, 32, 32, 16, one, one, one, null, null, null) == -2
     assert lib.pm_tile_sort_capacity() == 8192
     assert lib.pm_tile_sort(one, null, one, 10, null, 1, 2, 2, -1, one, one, null, null) == -1  # overflow flag is mandatory
     assert lib.pm_bin_scatter(one, one, one, one, one, 4, 1, 8, 2, 2, one, 10, null) == -2  # tile_size 8
