@@ -163,13 +163,16 @@ PM_API int pm_project_count_fwd(const float *means, const float *quats, const fl
 
 /* VJP of the projection. v_means2d [C,N,2], v_depths [C,N], v_conics [C,N,3]
  * (any may be NULL) -> v_means [N,3], v_quats [N,4], v_scales [N,3], summed over
- * cameras, fully overwritten. viewmats/Ks carry no gradient on this path. */
+ * cameras, fully overwritten. viewmats/Ks carry no gradient on this path.
+ * touched [C,N] uint8 (may be NULL): the array pm_composite_bwd* marked — nonzero for every pair whose cotangents
+ * may be nonzero; pairs with a zero byte are skipped unread (most pairs of an opaque scene). */
 PM_API int pm_project_bwd(const float *means, const float *quats, const float *scales,
                    const float *viewmats, const float *Ks,
                    int N, int C, int views_per_scene, int width, int height, float eps2d,
                    const int32_t *radii, const float *conics,
                    const float *v_means2d, const float *v_depths, const float *v_conics,
-                   float *v_means, float *v_quats, float *v_scales, pm_stream_t stream);
+                   float *v_means, float *v_quats, float *v_scales, const uint8_t *touched,
+                   pm_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
  * Stage 3 — tile binning and depth sort. Replaces gsplat isect_tiles (cumsum +
@@ -334,7 +337,9 @@ PM_API int pm_tile_render_packed_fwd(const uint64_t *records, const int32_t *ise
  * rendered a depth channel, CD = D + has_depth). v_render [C,H,W,CD], v_alphas [C,H,W] (either may be NULL).
  * transmittance [C,H,W] = the forward's array of that name, or NULL: T_final is then rebuilt as 1 - alphas like
  * upstream. Gradients are ACCUMULATED (+=) into v_means2d [C,N,2], v_conics [C,N,3], v_colors ([N,D] or [C,N,D]),
- * v_opacities [N], v_depths [C,N]: the caller zero-fills them. v_depths must be non-NULL iff has_depth. */
+ * v_opacities [N], v_depths [C,N]: the caller zero-fills them. v_depths must be non-NULL iff has_depth.
+ * touched [C,N] uint8 (may be NULL; caller zero-fills): set to 1 for every pair that received a gradient, for
+ * pm_project_bwd. */
 PM_API int pm_composite_bwd(const float *splat_stream, int colors_per_camera, int D, int has_depth,
                      const float *backgrounds, const int32_t *isect_offsets,
                      int64_t n_isects, const int32_t *d_n,
@@ -342,7 +347,7 @@ PM_API int pm_composite_bwd(const float *splat_stream, int colors_per_camera, in
                      const float *alphas, const int32_t *last_ids, const float *transmittance,
                      const float *v_render, const float *v_alphas,
                      float *v_means2d, float *v_conics, float *v_colors,
-                     float *v_opacities, float *v_depths, pm_stream_t stream);
+                     float *v_opacities, float *v_depths, uint8_t *touched, pm_stream_t stream);
 
 /* Backward of pm_tile_render_packed_fwd: cotangents of the packed outputs (any may be NULL) in,
  * the same accumulated per-Gaussian gradients out. masks / depth_out are the forward's outputs.
@@ -355,7 +360,8 @@ PM_API int pm_composite_bwd_packed(const float *splat_stream, int colors_per_cam
                      const float *transmittance,
                      const float *v_images, const float *v_depth_out, const float *v_masks,
                      float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
-                     float *v_depths, const int32_t *tile_order, int views_per_scene, pm_stream_t stream);
+                     float *v_depths, const int32_t *tile_order, int views_per_scene, uint8_t *touched,
+                     pm_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
  * Trajectory rendering: pose sampling along a camera path and

@@ -40,7 +40,7 @@ SIGNATURES = {
     "pm_bin_scatter": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _L, _P]),
     "pm_tile_sort_capacity": (c_int, []),
     "pm_tile_sort": (c_int, [_P, _P, _P, _L, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
-    "pm_project_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pm_project_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pm_scan_workspace_bytes": (c_size_t, [_L]),
     "pm_scan_tiles": (c_int, [_P, _L, _P, _P, _P, _S, _P]),
     "pm_bin_emit": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _L, _P]),
@@ -52,7 +52,7 @@ SIGNATURES = {
     "pm_tile_render_fwd": (c_int, [_P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pm_tile_render_packed_fwd": (c_int, [_P, _P, _L, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
     "pm_composite_bwd_packed": (c_int, [_P, _I, _P, _P, _L, _P, _I, _I, _I, _I, _I,
-                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "pm_splat_keys": (c_int, [_P, _P, _L, _I, _P, _P, _P]),
     "pm_splat_pack": (c_int, [_P, _P, _P, _P, _P, _P, _L, _I, _P, _P]),
     "pm_loss_terms_fwd": (c_int, [_P, _P, _P, _P, _L, _I, _I, _P, _P, _P, _P]),
@@ -61,7 +61,7 @@ SIGNATURES = {
     "pm_sample_cameras": (c_int, [_P, _P, _I, _I, _I, _P, _P]),
     "pm_pack_frames_u8": (c_int, [_P, _L, _I, _I, _P, _P]),
     "pm_composite_bwd": (c_int, [_P, _I, _I, _I, _P, _P, _L, _P, _I, _I, _I, _I, _I,
-                                 _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+                                 _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 
 

@@ -37,6 +37,33 @@ __device__ __forceinline__ int hash_find(const TileHash &h, int t) {
 
 constexpr int kWinCells = 2048;  // dense per-CTA window of tiles (covers e.g. 64 x 32 tiles)
 
+// Visit every tile of the AABB [x0,x1) x [y0,y1). Pixel-aligned splats cover 1-2 tiles per axis (radius ~6 px on a
+// 16 px grid: ~3 tiles per Gaussian), so the first 2 x 2 block is straight-line predicated code — the nested loops
+// with their one- or two-trip counts were 40 % of bin_scatter's instructions, most of it loop control replayed
+// under divergence (profiles/r2h_*) — and only larger splats enter the loop for the rest.
+template <typename F>
+__device__ __forceinline__ void for_each_tile(int x0, int x1, int y0, int y1, F fn) {
+  const int nx = x1 - x0, ny = y1 - y0;
+  if (nx <= 0 || ny <= 0) return;
+  fn(x0, y0);
+  if (nx >= 2) fn(x0 + 1, y0);
+  if (ny >= 2) {
+    fn(x0, y0 + 1);
+    if (nx >= 2) fn(x0 + 1, y0 + 1);
+  }
+  if (nx > 2 || ny > 2) {
+    for (int y = y0; y < y1; ++y)
+      for (int x = (y < y0 + 2 ? x0 + 2 : x0); x < x1; ++x) fn(x, y);
+  }
+}
+
+// Strided CTA order chunk = (block * stride) % n_blocks in 32-bit arithmetic when the product fits (the 64-bit
+// remainder is ~100 instructions per thread).
+__device__ __forceinline__ int strided_chunk(unsigned block, int stride, unsigned n_blocks) {
+  if ((unsigned long long)n_blocks * (unsigned)stride <= 0xffffffffull) return (int)((block * (unsigned)stride) % n_blocks);
+  return (int)(((unsigned long long)block * (unsigned)stride) % n_blocks);
+}
+
 // Shared-memory state of one CTA-wide histogram round.
 struct TileCountSmem {
   TileHash h;
@@ -71,8 +98,7 @@ __device__ __forceinline__ void cta_tile_count(TileCountSmem &s, int x0, int x1,
     const int cells = ww * wh;
     for (int i = threadIdx.x; i < cells; i += blockDim.x) s.win[i] = 0;
     __syncthreads();
-    for (int y = y0; y < y1; ++y)
-      for (int x = x0; x < x1; ++x) atomicAdd(&s.win[(y - wy0) * ww + (x - wx0)], 1);
+    for_each_tile(x0, x1, y0, y1, [&](int x, int y) { atomicAdd(&s.win[(y - wy0) * ww + (x - wx0)], 1); });
     __syncthreads();
     for (int i = threadIdx.x; i < cells; i += blockDim.x) {
       const int c = s.win[i];

@@ -148,7 +148,7 @@ composite_bwd_kernel(const float *__restrict__ stream, int colors_per_camera, in
                      const float *__restrict__ v_images, const float *__restrict__ v_depth_out,
                      const float *__restrict__ v_masks, const float *__restrict__ depth_out, int packed,
                      const int32_t *__restrict__ tile_order, int views_per_scene,
-                     const float *__restrict__ transmittance) {
+                     const float *__restrict__ transmittance, uint8_t *__restrict__ touched) {
   extern __shared__ __align__(16) unsigned char bwd_smem[];
   BwdWarpShared &sh = reinterpret_cast<BwdShared *>(bwd_smem)->w[threadIdx.x >> 5];
 
@@ -305,6 +305,9 @@ composite_bwd_kernel(const float *__restrict__ stream, int colors_per_camera, in
       const int32_t f = __float_as_int(ha.w);
       const int32_t g = f - g_base;
       if (half == 0) {
+        // one byte per (camera, Gaussian) pair that received a gradient: pm_project_bwd then finds its work from
+        // 1 byte per pair instead of 28 (a plain idempotent store; the bit-mask + atomicOr form cost more than it saved)
+        if (touched) touched[f] = 1;
         const size_t ci = (size_t)(colors_per_camera ? f : g) * D;
         const float cs[4] = {c0, c1, c2, c3};
 #pragma unroll
@@ -471,7 +474,7 @@ static int bwd_launch(const float *splat_stream, int colors_per_camera, int D, i
                       const float *v_render, const float *v_alphas, float *v_means2d, float *v_conics, float *v_colors,
                       float *v_opacities, float *v_depths, const float *v_images, const float *v_depth_out,
                       const float *v_masks, const float *depth_out, int packed, const int32_t *tile_order,
-                      int views_per_scene, pm_stream_t stream) {
+                      int views_per_scene, uint8_t *touched, pm_stream_t stream) {
   if (N < 0 || C < 0 || width <= 0 || height <= 0 || n_isects < 0 || D < 0) return PM_ERR_BAD_ARG;
   if (tile_size != kTile) return PM_ERR_UNSUPPORTED;
   const int CD = D + (has_depth ? 1 : 0);
@@ -492,7 +495,7 @@ static int bwd_launch(const float *splat_stream, int colors_per_camera, int D, i
   composite_bwd_kernel<<<(unsigned)(blocks * kBwdParts), kBwdThreads, sizeof(BwdShared), as_stream(stream)>>>(
       splat_stream, colors_per_camera, D, has_depth ? 1 : 0, backgrounds, isect_offsets, n_isects, d_n, N, width, height,
       tw, th, alphas, last_ids, v_render, v_alphas, v_means2d, v_conics, v_colors, v_opacities, v_depths, v_images,
-      v_depth_out, v_masks, depth_out, packed, tile_order, views_per_scene > 0 ? views_per_scene : C, transmittance);
+      v_depth_out, v_masks, depth_out, packed, tile_order, views_per_scene > 0 ? views_per_scene : C, transmittance, touched);
   return check_launch();
 }
 
@@ -545,10 +548,10 @@ int pm_composite_bwd(const float *splat_stream, int colors_per_camera, int D, in
                      int N, int C, int width, int height, int tile_size, const float *alphas,
                      const int32_t *last_ids, const float *transmittance, const float *v_render, const float *v_alphas,
                      float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
-                     float *v_depths, pm_stream_t stream) {
+                     float *v_depths, uint8_t *touched, pm_stream_t stream) {
   return pm::bwd_launch(splat_stream, colors_per_camera, D, has_depth, backgrounds, isect_offsets, n_isects, d_n, N, C,
                         width, height, tile_size, alphas, last_ids, transmittance, v_render, v_alphas, v_means2d, v_conics,
-                        v_colors, v_opacities, v_depths, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, stream);
+                        v_colors, v_opacities, v_depths, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, touched, stream);
 }
 
 int pm_composite_bwd_packed(const float *splat_stream, int colors_per_camera, const float *backgrounds,
@@ -557,12 +560,12 @@ int pm_composite_bwd_packed(const float *splat_stream, int colors_per_camera, co
                             const int32_t *last_ids, const float *transmittance, const float *v_images,
                             const float *v_depth_out, const float *v_masks, float *v_means2d, float *v_conics,
                             float *v_colors, float *v_opacities, float *v_depths, const int32_t *tile_order,
-                            int views_per_scene, pm_stream_t stream) {
+                            int views_per_scene, uint8_t *touched, pm_stream_t stream) {
   if (!masks || !depth_out || !v_colors || !v_depths) return PM_ERR_BAD_ARG;
   return pm::bwd_launch(splat_stream, colors_per_camera, 3, 1, backgrounds, isect_offsets, n_isects, d_n, N, C, width,
                         height, tile_size, masks, last_ids, transmittance, nullptr, nullptr, v_means2d, v_conics, v_colors,
                         v_opacities, v_depths, v_images, v_depth_out, v_masks, depth_out, 1, tile_order, views_per_scene,
-                        stream);
+                        touched, stream);
 }
 
 }  // extern "C"

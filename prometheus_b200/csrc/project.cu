@@ -93,7 +93,7 @@ project_fwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
   __shared__ ProjCamS s_cam[kProjCamChunk];
   __shared__ TileCountSmem s_cnt[1];  // (unused and optimised away when !COUNT)
   // strided CTA order (see binning_common.cuh): concurrently resident CTAs touch far-apart tiles
-  const int chunk = (int)(((int64_t)blockIdx.x * chunk_stride) % gridDim.x);
+  const int chunk = strided_chunk(blockIdx.x, chunk_stride, gridDim.x);
   // scene batching: the Gaussian arrays hold S scenes of N Gaussians, camera c belongs to scene c / views_per_scene
   // and sees only that scene. With S > 1 the launcher guarantees N % 256 == 0, so a CTA never straddles two scenes.
   const int chunks_per_scene = (N + 255) / 256;

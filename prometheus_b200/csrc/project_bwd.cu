@@ -63,7 +63,7 @@ project_bwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
                    const int32_t *__restrict__ radii, const float *__restrict__ conics,
                    const float *__restrict__ v_means2d, const float *__restrict__ v_depths,
                    const float *__restrict__ v_conics, float *__restrict__ v_means,
-                   float *__restrict__ v_quats, float *__restrict__ v_scales) {
+                   float *__restrict__ v_quats, float *__restrict__ v_scales, const uint8_t *__restrict__ touched) {
   extern __shared__ __align__(16) unsigned char bwd_cam_smem[];
   BwdCam *s_cam = reinterpret_cast<BwdCam *>(bwd_cam_smem);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -121,6 +121,12 @@ project_bwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
   const int cam_begin = scene * views_per_scene, cam_end = min(C, (scene + 1) * views_per_scene);
   for (int c0 = cam_begin; c0 < cam_end; c0 += 8) {
     unsigned active = 0u;
+    if (touched) {
+      // the compositing backward left one byte per pair that received a gradient: 1 byte per pair instead of 28
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (c0 + u < cam_end && __ldg(touched + (size_t)(c0 + u) * N + g) != 0) active |= 1u << u;
+    } else {
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       if (c0 + u < cam_end) {
@@ -132,6 +138,7 @@ project_bwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
         if (v_depths) bits |= __float_as_uint(__ldg(v_depths + f));
         if (__ldg(radii + f) > 0 && (bits & 0x7fffffffu) != 0u) active |= 1u << u;
       }
+    }
     }
     while (active) {
       const int cid = c0 + __ffs(active) - 1;
@@ -280,7 +287,7 @@ int pm_project_bwd(const float *means, const float *quats, const float *scales, 
                    const float *Ks, int N, int C, int views_per_scene, int width, int height, float eps2d,
                    const int32_t *radii, const float *conics, const float *v_means2d,
                    const float *v_depths, const float *v_conics, float *v_means, float *v_quats,
-                   float *v_scales, pm_stream_t stream) {
+                   float *v_scales, const uint8_t *touched, pm_stream_t stream) {
   (void)eps2d;  // the blur is an additive constant: no gradient term
   if (!means || !quats || !scales || !viewmats || !Ks || !radii || !conics || !v_means || !v_quats || !v_scales)
     return PM_ERR_BAD_ARG;
@@ -304,7 +311,7 @@ int pm_project_bwd(const float *means, const float *quats, const float *scales, 
   }
   pm::project_bwd_kernel<<<(unsigned)((total + 127) / 128), 128, cam_bytes, pm::as_stream(stream)>>>(
       means, quats, scales, viewmats, Ks, N, C, Nv, width, height, radii, conics, v_means2d, v_depths,
-      v_conics, v_means, v_quats, v_scales);
+      v_conics, v_means, v_quats, v_scales, touched);
   return pm::check_launch();
 }
 

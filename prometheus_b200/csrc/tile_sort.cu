@@ -55,7 +55,7 @@ bin_kernel(const float *__restrict__ means2d, const int32_t *__restrict__ radii,
   if (threadIdx.x == 0) { box[0] = 0x7fffffff; box[1] = 0x7fffffff; box[2] = 0; box[3] = 0; }
   __syncthreads();
   // strided CTA order: consecutive (= concurrently resident) CTAs touch far-apart chunks
-  const int chunk = (int)(((int64_t)blockIdx.x * chunk_stride) % gridDim.x);
+  const int chunk = strided_chunk(blockIdx.x, chunk_stride, gridDim.x);
   const int g = chunk * blockDim.x + threadIdx.x;
   const int cid = blockIdx.y;
   const size_t f = (size_t)cid * N + (g < N ? g : 0);
@@ -92,8 +92,7 @@ bin_kernel(const float *__restrict__ means2d, const int32_t *__restrict__ radii,
     const int cells = ww * wh;
     for (int i = threadIdx.x; i < cells; i += blockDim.x) win[i] = 0;
     __syncthreads();
-    for (int y = y0; y < y1; ++y)
-      for (int x = x0; x < x1; ++x) atomicAdd(&win[(y - wy0) * ww + (x - wx0)], 1);
+    for_each_tile(x0, x1, y0, y1, [&](int x, int y) { atomicAdd(&win[(y - wy0) * ww + (x - wx0)], 1); });
     __syncthreads();
     for (int i = threadIdx.x; i < cells; i += blockDim.x) {
       const int c = win[i];
@@ -105,12 +104,11 @@ bin_kernel(const float *__restrict__ means2d, const int32_t *__restrict__ radii,
     }
     if (!SCATTER) return;
     __syncthreads();
-    for (int y = y0; y < y1; ++y)
-      for (int x = x0; x < x1; ++x) {
-        const int cell = (y - wy0) * ww + (x - wx0);
-        const int64_t slot = (int64_t)win_base[cell] + atomicAdd(&win[cell], 1);
-        if (slot < capacity) records[slot] = rec;
-      }
+    for_each_tile(x0, x1, y0, y1, [&](int x, int y) {
+      const int cell = (y - wy0) * ww + (x - wx0);
+      const int64_t slot = (int64_t)win_base[cell] + atomicAdd(&win[cell], 1);
+      if (slot < capacity) records[slot] = rec;
+    });
     return;
   }
 

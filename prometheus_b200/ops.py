@@ -199,7 +199,9 @@ def project_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d=0.3, ne
 
 @_instrument("project_bwd", 1)
 def project_bwd(means, quats, scales, viewmats, Ks, width, height, radii, conics, v_means2d, v_depths,
-                v_conics, eps2d=0.3, views_per_scene=0):
+                v_conics, eps2d=0.3, views_per_scene=0, touched=None):
+    """touched [C,N] uint8: the pair map composite_bwd* marked for exactly these cotangents (pairs with a zero byte
+    are skipped unread); None = look at the cotangents themselves."""
     L = _lib.load()
     means, quats, scales = (_req(t, torch.float32, "in") for t in (means, quats, scales))
     viewmats, Ks = _req(viewmats, torch.float32, "viewmats"), _req(Ks, torch.float32, "Ks")
@@ -209,7 +211,7 @@ def project_bwd(means, quats, scales, viewmats, Ks, width, height, radii, conics
     v_means, v_quats, v_scales = torch.empty_like(means), torch.empty_like(quats), torch.empty_like(scales)
     _lib.check(L.pm_project_bwd(_ptr(means), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks), N, C,
                                 int(views_per_scene), width, height, eps2d, _ptr(radii), _ptr(conics), _ptr(v_means2d), _ptr(v_depths),
-                                _ptr(v_conics), _ptr(v_means), _ptr(v_quats), _ptr(v_scales), _stream()),
+                                _ptr(v_conics), _ptr(v_means), _ptr(v_quats), _ptr(v_scales), _ptr(touched), _stream()),
                "pm_project_bwd")
     return v_means, v_quats, v_scales
 
@@ -420,9 +422,10 @@ def tile_render_fwd(records, offsets, means2d, conics, opacities, colors, depths
 
 @_instrument("composite_bwd", 1)
 def composite_bwd(means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width,
-                  height, alphas, last_ids, v_render, v_alphas, d_n=None, transmittance=None, stream=None):
+                  height, alphas, last_ids, v_render, v_alphas, d_n=None, transmittance=None, stream=None, touched=None):
     """transmittance: the forward's exact final T per pixel; None = rebuild it as 1 - alphas (upstream's form).
-    stream: the forward's splat stream; None = gather it from the sorted list first (pm_splat_stream_build)."""
+    stream: the forward's splat stream; None = gather it from the sorted list first (pm_splat_stream_build).
+    touched: zero-filled uint8 [C,N] that receives 1 for every pair with a gradient (for project_bwd), or None."""
     L = _lib.load()
     C, N = means2d.shape[:2]
     colors, per_cam, D = _colors_layout(colors, C, N)
@@ -439,7 +442,7 @@ def composite_bwd(means2d, conics, opacities, colors, depths, backgrounds, offse
                                   stream.shape[0], _ptr(d_n), N, C, width, height, TILE, _ptr(alphas),
                                   _ptr(last_ids), _ptr(_opt(transmittance, torch.float32, "transmittance")),
                                   _ptr(v_render), _ptr(v_alphas), _ptr(v_means2d),
-                                  _ptr(v_conics), _ptr(v_colors), _ptr(v_opac), _ptr(v_depths), _stream()),
+                                  _ptr(v_conics), _ptr(v_colors), _ptr(v_opac), _ptr(v_depths), _ptr(touched), _stream()),
                "pm_composite_bwd")
     return v_means2d, v_conics, v_colors, v_opac, v_depths
 
@@ -481,7 +484,7 @@ def tile_render_packed_fwd(records, offsets, means2d, conics, opacities, colors,
 @_instrument("composite_bwd", 1)
 def composite_bwd_packed(means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width, height,
                          masks, depth_out, last_ids, v_images, v_depth_out, v_masks, d_n=None, tile_order=None,
-                         views_per_scene=0, transmittance=None, stream=None):
+                         views_per_scene=0, transmittance=None, stream=None, touched=None):
     L = _lib.load()
     C, N = means2d.shape[:2]
     colors, per_cam, D = _colors_layout(colors, C, N * (C // views_per_scene if views_per_scene else 1))
@@ -497,7 +500,7 @@ def composite_bwd_packed(means2d, conics, opacities, colors, depths, backgrounds
                                          N, C, width, height, TILE, _ptr(masks), _ptr(depth_out), _ptr(last_ids),
                                          _ptr(transmittance), _ptr(v_images), _ptr(v_depth_out), _ptr(v_masks),
                                          _ptr(v_means2d), _ptr(v_conics), _ptr(v_colors), _ptr(v_opac), _ptr(v_depths),
-                                         _ptr(tile_order), int(views_per_scene), _stream()),
+                                         _ptr(tile_order), int(views_per_scene), _ptr(touched), _stream()),
                "pm_composite_bwd_packed")
     return v_means2d, v_conics, v_colors, v_opac, v_depths
 

@@ -28,11 +28,38 @@ _RENDER_MODES = ("RGB", "D", "ED", "RGB+D", "RGB+ED")
 FORCE_GENERIC_SORT = False
 
 
+def _new_touched(link, means2d):
+    """Zero-filled pair map for the compositing backward, only when a projection node will consume it."""
+    if link is None:
+        return None
+    C, N = means2d.shape[:2]
+    return torch.zeros(C, N, dtype=torch.uint8, device=means2d.device)
+
+
+def _leave_touched(link, touched, v_means2d, v_conics, v_depths):
+    if link is not None and touched is not None:
+        # valid only for exactly these gradient tensors (autograd may hand the projection node a SUM with other
+        # contributions, e.g. a loss on meta["means2d"]; then the cotangents themselves are scanned)
+        link["touched"] = (touched, v_means2d.data_ptr(), v_conics.data_ptr(), None if v_depths is None else v_depths.data_ptr())
+
+
+def _take_touched(link, v_means2d, v_depths, v_conics):
+    if not link or "touched" not in link:
+        return None
+    touched, p_m, p_c, p_d = link.pop("touched")
+    same = (v_means2d is not None and v_means2d.data_ptr() == p_m and v_conics is not None and v_conics.data_ptr() == p_c
+            and (None if v_depths is None else v_depths.data_ptr()) == p_d)
+    return touched if same else None
+
+
 class _Project(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
-                radius_clip, fused_count=False, views_per_scene=0):
-        """fused_count (module fast path): skip tiles_per_gauss, return the per-tile histogram instead."""
+                radius_clip, fused_count=False, views_per_scene=0, link=None):
+        """fused_count (module fast path): skip tiles_per_gauss, return the per-tile histogram instead.
+        link: dict shared with the compositing node of the same render — its backward leaves the map of pairs that
+        received a gradient there (`touched`), so that this node's backward reads 1 byte per pair to find its work."""
+        ctx.link = link
         out = ops.project_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
                               radius_clip, count_tiles=not fused_count, tile_histogram=fused_count,
                               views_per_scene=views_per_scene)
@@ -48,16 +75,18 @@ class _Project(torch.autograd.Function):
     def backward(ctx, v_means2d, v_depths, v_conics, _v_radii, _v_aux):
         means, quats, scales, viewmats, Ks, radii, conics = ctx.saved_tensors
         width, height, eps2d = ctx.dims
+        touched = _take_touched(ctx.link, v_means2d, v_depths, v_conics)
         v_means, v_quats, v_scales = ops.project_bwd(means, quats, scales, viewmats, Ks, width, height, radii,
                                                      conics, v_means2d, v_depths, v_conics, eps2d,
-                                                     views_per_scene=ctx.views_per_scene)
-        return (v_means, v_quats, v_scales) + (None,) * 10
+                                                     views_per_scene=ctx.views_per_scene, touched=touched)
+        return (v_means, v_quats, v_scales) + (None,) * 11
 
 
 class _Composite(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width,
-                height, d_n):
+                height, d_n, link=None):
+        ctx.link = link
         means2d, conics = means2d.contiguous(), conics.contiguous()
         opacities = opacities.contiguous()
         colors = None if colors is None else colors.contiguous()
@@ -79,21 +108,24 @@ class _Composite(torch.autograd.Function):
          d_n, trans, stream) = ctx.saved_tensors
         width, height = ctx.dims
         v_alphas2 = None if v_alphas is None else v_alphas.squeeze(-1)
+        touched = _new_touched(ctx.link, means2d)
         v_means2d, v_conics, v_colors, v_opac, v_depths = ops.composite_bwd(
             means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width, height, alphas,
-            last_ids, v_render, v_alphas2, d_n, transmittance=trans, stream=stream)
+            last_ids, v_render, v_alphas2, d_n, transmittance=trans, stream=stream, touched=touched)
+        _leave_touched(ctx.link, touched, v_means2d, v_conics, v_depths)
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[5] and v_render is not None:
             D = backgrounds.shape[-1]
             v_bg = (v_render[..., :D] * trans.unsqueeze(-1)).sum(dim=(1, 2))
-        return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None, None
+        return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None, None, None
 
 
 class _TileRender(torch.autograd.Function):
     """Fused sort-as-you-go forward (ops.tile_render_fwd) + the ordinary compositing backward."""
 
     @staticmethod
-    def forward(ctx, means2d, conics, opacities, colors, depths, backgrounds, records, offsets, width, height):
+    def forward(ctx, means2d, conics, opacities, colors, depths, backgrounds, records, offsets, width, height, link=None):
+        ctx.link = link
         means2d, conics = means2d.contiguous(), conics.contiguous()
         opacities = opacities.contiguous()
         colors = None if colors is None else colors.contiguous()
@@ -115,14 +147,16 @@ class _TileRender(torch.autograd.Function):
          trans, stream) = ctx.saved_tensors
         width, height = ctx.dims
         v_alphas2 = None if v_alphas is None else v_alphas.squeeze(-1)
+        touched = _new_touched(ctx.link, means2d)
         v_means2d, v_conics, v_colors, v_opac, v_depths = ops.composite_bwd(
             means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, width, height, alphas, last_ids,
-            v_render, v_alphas2, None, transmittance=trans, stream=stream)
+            v_render, v_alphas2, None, transmittance=trans, stream=stream, touched=touched)
+        _leave_touched(ctx.link, touched, v_means2d, v_conics, v_depths)
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[5] and v_render is not None:
             D = backgrounds.shape[-1]
             v_bg = (v_render[..., :D] * trans.unsqueeze(-1)).sum(dim=(1, 2))
-        return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None
+        return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None, None
 
 
 class _TileRenderPacked(torch.autograd.Function):
@@ -131,7 +165,8 @@ class _TileRenderPacked(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means2d, conics, opacities, colors, depths, backgrounds, records, offsets, stats, width, height,
-                grad_sink=None, tile_order=None, views_per_scene=0):
+                grad_sink=None, tile_order=None, views_per_scene=0, link=None):
+        ctx.link = link
         ctx.views_per_scene = views_per_scene
         ctx.grad_sink = grad_sink  # dict that receives the contiguous [C,N,2] means2d gradient (densification statistics)
         means2d, conics = means2d.contiguous(), conics.contiguous()
@@ -156,10 +191,12 @@ class _TileRenderPacked(torch.autograd.Function):
         width, height = ctx.dims
         # the backward replays what the forward sorted: tiles with the longest sorted prefix go first
         order = ops.tile_scan(sorted_counts, want_order=True)[2]
+        touched = _new_touched(ctx.link, means2d)
         v_means2d, v_conics, v_colors, v_opac, v_depths = ops.composite_bwd_packed(
             means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, width, height, masks, depth_out,
             last_ids, v_images, v_depth_out, v_masks, d_n=stats, tile_order=order, views_per_scene=ctx.views_per_scene,
-            transmittance=trans, stream=stream)
+            transmittance=trans, stream=stream, touched=touched)
+        _leave_touched(ctx.link, touched, v_means2d, v_conics, v_depths)
         if ctx.grad_sink is not None:
             ctx.grad_sink["v_means2d"] = v_means2d
             for j, view in enumerate(ctx.grad_sink.get("views", ())):  # the reference's viewspace_points[j].grad
@@ -168,7 +205,7 @@ class _TileRenderPacked(torch.autograd.Function):
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[5] and v_images is not None:
             v_bg = (2.0 * v_images * (trans.unsqueeze(1) if trans is not None else 1.0 - masks)).sum(dim=(2, 3))
-        return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None, None, None, None, None
+        return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None, None, None, None, None, None
 
 
 def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, backgrounds, width, height,
@@ -188,8 +225,9 @@ def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, b
         raise RuntimeError("prometheus_b200 needs CUDA tensors: there is no CPU fallback")
     f32 = lambda t: (t if t.dtype == torch.float32 else t.float()).contiguous()
     means, quats, scales, opacities, colors, viewmats, Ks = map(f32, (means, quats, scales, opacities, colors, viewmats, Ks))
+    link = {}  # compositing backward -> projection backward: the map of pairs that received a gradient
     means2d, depths, conics, radii, counts = _Project.apply(means, quats, scales, viewmats, Ks, width, height, eps2d,
-                                                             near_plane, far_plane, radius_clip, True, views_per_scene)
+                                                             near_plane, far_plane, radius_clip, True, views_per_scene, link)
     # The reference keeps one [1,N,2] screen-space tensor per rendered view and reads its .grad after backward
     # (`viewspace_points`, gaussians_renderer.py:428-445). Routing autograd through per-view tensors costs a cat and a
     # stack of the whole [C,N,2] array each way; instead the per-view tensors are leaf views of the projected means
@@ -207,7 +245,7 @@ def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, b
     records = ops.bin_scatter(means2d.detach(), radii, depths.detach(), isect_offsets, width, height, int(capacity))
     images, depth_out, masks, flag, flatten_ids, sorted_counts = _TileRenderPacked.apply(
         means2d, conics, opacities, colors, depths, backgrounds, records, isect_offsets, stats, width, height, grad_sink,
-        tile_order, views_per_scene)
+        tile_order, views_per_scene, link)
     info = {"radii": radii, "means2d": means2d, "means2d_views": means2d_views, "depths": depths, "conics": conics,
             "isect_offsets": isect_offsets, "flatten_ids": flatten_ids, "sorted_counts": sorted_counts,
             "stats": stats, "overflow_flag": flag, "capacity": int(capacity), "means2d_grad_sink": grad_sink}
@@ -322,9 +360,12 @@ def _rasterize_core(means, quats, scales, opacities, colors, viewmats, Ks, width
     viewmats, Ks = f32(viewmats).contiguous(), f32(Ks).contiguous()
 
     use_fused = fused and not FORCE_GENERIC_SORT
+    # compositing backward -> projection backward: the map of pairs that received a gradient. Not with per-view
+    # means2d tensors (their gradients reach the projection node through a cat, as new tensors).
+    link = None if per_view_means2d else {}
     means2d, depths, conics, radii, aux = _Project.apply(
         means.contiguous(), quats.contiguous(), scales.contiguous(), viewmats, Ks, width, height, eps2d,
-        near_plane, far_plane, radius_clip, use_fused)
+        near_plane, far_plane, radius_clip, use_fused, 0, link)
     tpg = None if use_fused else aux
     with_depth = render_mode in ("D", "ED", "RGB+D", "RGB+ED")
     only_depth = render_mode in ("D", "ED")
@@ -350,7 +391,7 @@ def _rasterize_core(means, quats, scales, opacities, colors, viewmats, Ks, width
         isect_offsets, stats = ops.tile_scan(aux)  # aux = per-tile histogram, counted inside the projection
         n_isects, max_count = stats.tolist()
         records = ops.bin_scatter(m2d, radii, dep, isect_offsets, width, height, n_isects)
-        render, alphas, flag, flatten_ids, sorted_counts = _TileRender.apply(*comp_args, records, isect_offsets, width, height)
+        render, alphas, flag, flatten_ids, sorted_counts = _TileRender.apply(*comp_args, records, isect_offsets, width, height, link)
         isect_ids = None
         # a depth sub-bucket larger than the group capacity can only exist if some tile is larger than it
         if max_count > FUSED_GROUP_CAP and int(flag.item()) != 0:
@@ -359,7 +400,7 @@ def _rasterize_core(means, quats, scales, opacities, colors, viewmats, Ks, width
         isect_ids, flatten_ids, isect_offsets = isect_tiles(means2d.detach(), radii, depths.detach(), tpg, width,
                                                             height, C, force_generic=FORCE_GENERIC_SORT)
         sorted_counts = None
-        render, alphas = _Composite.apply(*comp_args, isect_offsets, flatten_ids, width, height, None)
+        render, alphas = _Composite.apply(*comp_args, isect_offsets, flatten_ids, width, height, None, link)
     if render_mode in ("ED", "RGB+ED"):
         render = torch.cat([render[..., :-1], render[..., -1:] / alphas.clamp(min=1e-10)], dim=-1)
 

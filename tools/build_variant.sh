@@ -9,6 +9,6 @@ mkdir -p "$ROOT/gpurun_variants" "$TMP/prometheus_b200" "$TMP/include"
 cp -r "$ROOT/prometheus_b200/csrc" "$TMP/prometheus_b200/csrc"
 cp "$ROOT/include/"*.h "$TMP/include/"
 rm -f "$TMP/prometheus_b200/csrc/"*.o
-PATH=/usr/local/cuda/bin:$PATH make -C "$TMP/prometheus_b200/csrc" -j8 EXTRA="$*" OUT="$ROOT/gpurun_variants/$NAME.so" >/dev/null
+PATH=/usr/local/cuda/bin:$PATH make -C "$TMP/prometheus_b200/csrc" -j8 $MAKEVARS EXTRA="$*" OUT="$ROOT/gpurun_variants/$NAME.so" >/dev/null
 rm -rf "$TMP"
 echo "built gpurun_variants/$NAME.so"
