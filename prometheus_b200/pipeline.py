@@ -26,7 +26,12 @@ class DecodeRenderPipeline:
     max_in_flight = 2  # scenes whose deferred checks have not been looked at yet (eager mode)
 
     def __init__(self, converter: GaussianConverter, renderer: GaussianRenderer, h: int, w: int, device=None,
-                 bg_color=None, graph: bool = False):
+                 bg_color=None, graph: bool = False, compact_outputs: bool = False):
+        """compact_outputs: hand the host uint8 frames [B,M,H,W,3] (the conversion of export_video, io.py:181, done on
+        the device by pm_pack_frames_u8) and fp16 depths / masks [B,M,1,H,W] instead of three fp32 tensors — 7 instead
+        of 20 bytes per pixel over PCIe, for consumers that write videos / previews. `out_h` must then hold pinned
+        tensors of those dtypes and shapes."""
+        self.compact = bool(compact_outputs)
         self.conv, self.rend = converter, renderer
         self.graphed = GraphedDecodeRender(converter, renderer, h, w, bg_color) if graph else None
         self._n_staged = 0
@@ -145,6 +150,13 @@ class DecodeRenderPipeline:
             self.rend.defer_checks = prev
 
     def _copy_out(self, out_h, outs, cur, record_stream: bool = True):
+        if self.compact:
+            from . import ops
+
+            images, depths, masks = outs[:3]
+            B, M, _, H, W = images.shape
+            outs = (ops.pack_frames_u8(images.reshape(B * M, 3, H, W)).reshape(B, M, H, W, 3), depths.half(), masks.half())
+            record_stream = True  # fresh allocator blocks, also in graph mode
         done = torch.cuda.Event()
         done.record(cur)
         with torch.cuda.stream(self.s_out):

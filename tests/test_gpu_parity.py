@@ -961,6 +961,28 @@ def test_pipeline_run_batch_streams_a_large_batch_in_slices(graph):
         assert torch.equal(a, b.cpu())
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_pipeline_compact_outputs(graph):
+    """DecodeRenderPipeline(compact_outputs=True): uint8 frames (export_video's conversion, io.py:181) and fp16
+    depth / mask instead of fp32 — the same pixels, converted on the device before the copy."""
+    from prometheus_b200 import DecodeRenderPipeline, GaussianConverter, GaussianRenderer, scenes
+
+    conv = GaussianConverter("mvsplat", z_near=0.01, z_far=100.0, s_min=0.001, s_max=1.0).to(DEV)
+    sc = scenes.make_scene("C1", seed=71, scenes=2, views_in=2, size_in=48, views_out=3, size_out=64)
+    with torch.no_grad():
+        im, de, ma = GaussianRenderer().to(DEV)(sc.cameras_out.to(DEV), conv(sc.params.to(DEV), sc.cameras_in.to(DEV)), h=64, w=64)[:3]
+    pipe = DecodeRenderPipeline(conv, GaussianRenderer().to(DEV), 64, 64, device=DEV, graph=graph, compact_outputs=True)
+    ins = tuple(t.pin_memory() for t in (sc.params, sc.cameras_in, sc.cameras_out))
+    outs = [torch.empty(2, 3, 64, 64, 3, dtype=torch.uint8).pin_memory(), torch.empty(2, 3, 1, 64, 64, dtype=torch.float16).pin_memory(),
+            torch.empty(2, 3, 1, 64, 64, dtype=torch.float16).pin_memory()]
+    pipe.prefetch(*ins)
+    pipe.run(outs)
+    pipe.flush()
+    want_u8 = im.cpu().permute(0, 1, 3, 4, 2).mul(1 / 2).add(1 / 2).clamp(0, 1).mul(255).to(torch.uint8)
+    assert torch.equal(outs[0], want_u8) and float(outs[0].float().std()) > 5
+    assert torch.equal(outs[1], de.half().cpu()) and torch.equal(outs[2], ma.half().cpu())
+
+
 # --------------------------------------------------------------------------- trajectory row (SURVEY §8f rank 3)
 @pytest.mark.parametrize("name", ["orbit_big", "smooth", "repeat", "video120"])
 def test_sample_cameras_vs_reference_golden(golden_dir, name):
