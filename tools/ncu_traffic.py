@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Regenerate profiles/traffic.json from `ncu --set full` captures, stamped with the kernel sources they describe.
 
-    python tools/ncu_traffic.py gpurun_out/a.ncu-rep [gpurun_out/b.ncu-rep ...]
+    python tools/ncu_traffic.py gpurun_out/a.ncu-rep[::suffix] [gpurun_out/b.ncu-rep ...]
+
+`::suffix` is appended to the kernel names of that report (e.g. the training-mode capture of a kernel that also has an
+inference-mode entry).
 
 For every kernel name in the reports (last launch wins): dram__bytes_read.sum + dram__bytes_write.sum and
 smsp__inst_executed.sum per launch. `src_sha` = prometheus_b200.kernel_source_sha() of the tree the capture was made
@@ -34,15 +37,16 @@ def main():
 
     out = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum and smsp__inst_executed.sum per launch from `ncu --set full` "
                        "(tools/ncu_traffic.py); bench.py uses an entry only while src_sha matches the kernel sources it runs",
-           "src_sha": kernel_source_sha(), "reports": [os.path.basename(p) for p in sys.argv[1:]],
+           "src_sha": kernel_source_sha(), "reports": [os.path.basename(p.split("::")[0]) for p in sys.argv[1:]],
            "_warp_instructions": {}}
-    for rep in sys.argv[1:]:
+    for arg in sys.argv[1:]:
+        rep, _, suffix = arg.partition("::")
         txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(txt.splitlines()))
         hdr, data = rows[0], rows[2:]
         idx = {h: i for i, h in enumerate(hdr)}
         for r in data:
-            k = short(r[idx["Kernel Name"]])
+            k = short(r[idx["Kernel Name"]]) + ("[%s]" % suffix if suffix else "")
             out[k] = int(num(r[idx["dram__bytes_read.sum"]]) + num(r[idx["dram__bytes_write.sum"]]))
             if "smsp__inst_executed.sum" in idx:
                 out["_warp_instructions"][k] = int(num(r[idx["smsp__inst_executed.sum"]]))
