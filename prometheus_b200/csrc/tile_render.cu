@@ -36,7 +36,12 @@ constexpr int kTrWarps = kTrThreads / 32;
 #endif
 constexpr int kTrCap = PM_TR_CAP;                                   // records per group
 constexpr int kTrItems = (kTrCap + kTrThreads - 1) / kTrThreads;   // records per thread in the sort / staging loops
-constexpr int kTrRadix = 256;
+constexpr int kTrRadix = 256;   // digits of the in-group radix sort
+#ifndef PM_TR_BUCKET_BITS
+#define PM_TR_BUCKET_BITS 9
+#endif
+constexpr int kTrBucketBits = PM_TR_BUCKET_BITS;
+constexpr int kTrBuckets = 1 << kTrBucketBits;  // depth-ordered buckets per level: shorter runs = cheaper all-pairs ranking (256: runs of ~23 on C2, 9 % of the kernel's instructions)
 #ifndef PM_TR_MLP
 #define PM_TR_MLP 8  // record loads in flight per thread in the passes over a tile's segment
 #endif
@@ -45,7 +50,7 @@ constexpr int kTrRankMax = 128;  // longest bucket run ordered by all-pairs rank
 
 // depth sub-bucket of a key: monotone in the key for any kmin / shift
 __device__ __forceinline__ int tr_bucket(uint32_t k, uint32_t kmin, int shift) {
-  return k <= kmin ? 0 : (int)min((k - kmin) >> shift, 255u);
+  return k <= kmin ? 0 : (int)min((k - kmin) >> shift, (uint32_t)(kTrBuckets - 1));
 }
 
 __device__ __forceinline__ unsigned tr_match_digit8(uint32_t d) {
@@ -69,8 +74,9 @@ struct TrShared {
   };
   uint32_t queue[kTrWarps][kQueueWords];     // per-warp hit queues of composite_batch_fwd
   uint32_t red[64];
-  int bucket[kTrRadix + 1];                  // start of each depth sub-bucket inside the tile's list
-  int bucket2[kTrRadix + 1];                 // second level: sub-buckets of one level-1 bucket that exceeds a group
+  int bucket[kTrBuckets + 1];                // start of each depth sub-bucket inside the tile's list
+  int bucket2[kTrBuckets + 1];               // second level: sub-buckets of one level-1 bucket that exceeds a group
+  uint32_t cursor[kTrBuckets];               // per-bucket cursors of the counting-sort placement
   int cnt;
   uint32_t kmin, kmax;
 };
@@ -179,11 +185,16 @@ __device__ __forceinline__ void sort_group(TrShared &sh, int m, uint32_t gmin, u
   __syncthreads();
 }
 
-// Exclusive scan of tbl[1..256] in place (tbl[0] = 0 on entry): tbl[d] = start of bucket d, tbl[256] = total.
+// Exclusive scan of tbl[1..kTrBuckets] in place (tbl[0] = 0 on entry): tbl[d] = start of bucket d, tbl[kTrBuckets] = total.
+// Thread t owns the kTrBuckets / kTrThreads consecutive entries behind tbl[1 + t * per].
 __device__ __forceinline__ void tr_scan_buckets(int *tbl, uint32_t *red) {
+  constexpr int per = kTrBuckets / kTrThreads;
+  static_assert(per >= 1 && per * kTrThreads == kTrBuckets, "bucket count must be a multiple of the CTA size");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int v = tbl[tid + 1];
-  int inc = v;
+  int v[per], sum = 0;
+#pragma unroll
+  for (int i = 0; i < per; ++i) { v[i] = tbl[1 + tid * per + i]; sum += v[i]; }
+  int inc = sum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const int t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -191,9 +202,10 @@ __device__ __forceinline__ void tr_scan_buckets(int *tbl, uint32_t *red) {
   }
   if (lane == 31) red[warp] = (uint32_t)inc;
   __syncthreads();
-  int wbase = 0;
-  for (int w = 0; w < warp; ++w) wbase += (int)red[w];
-  tbl[tid + 1] = wbase + inc;
+  int run = inc - sum;
+  for (int w = 0; w < warp; ++w) run += (int)red[w];
+#pragma unroll
+  for (int i = 0; i < per; ++i) { run += v[i]; tbl[1 + tid * per + i] = run; }
   __syncthreads();
 }
 
@@ -239,7 +251,7 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
   // Histogram of the tile's records with key in [flo, fhi] over the 256 buckets of (kmin_c, shift_c) into tbl,
   // then the exclusive scan. (Every pass over the tile's records keeps kTrMlp loads per thread in flight.)
   auto build_table = [&](int *tbl, uint32_t kmin_c, int shift_c, uint32_t flo, uint32_t fhi) {
-    for (int i = tid; i <= kTrRadix; i += kTrThreads) tbl[i] = 0;
+    for (int i = tid; i <= kTrBuckets; i += kTrThreads) tbl[i] = 0;
     __syncthreads();
     for (int i0 = 0; i0 < cnt; i0 += kTrMlp * kTrThreads) {
       uint32_t k[kTrMlp];
@@ -264,7 +276,7 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
     const int gs = tbl[b0], m = tbl[b1] - gs;
     // collect the group straight into bucket order (a counting-sort placement: the position of a record is
     // its bucket's start + a per-bucket cursor), so that only the short runs of equal bucket remain to be ordered
-    uint32_t *cur = sh.digit_start;
+    uint32_t *cur = sh.cursor;
     for (int bb = b0 + tid; bb < b1; bb += kTrThreads) cur[bb] = 0u;
     if (tid == 0) { sh.kmin = 0xffffffffu; sh.kmax = 0u; }
     __syncthreads();
@@ -358,7 +370,7 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
   // largest b1 in (b0, 256] with tbl[b1] - tbl[b0] <= capacity (binary search; tbl[] is monotone), b0 + 1 if none
   auto group_end = [&](const int *tbl, int b0) {
     const int gs = tbl[b0];
-    int b1 = b0 + 1, hi = kTrRadix;
+    int b1 = b0 + 1, hi = kTrBuckets;
     while (b1 < hi) {
       const int mid = (b1 + hi + 1) >> 1;
       if (tbl[mid] - gs <= kTrCap) b1 = mid; else hi = mid - 1;
@@ -395,14 +407,14 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
     kmin = sh.kmin;
     const uint32_t range = sh.kmax - kmin;
     const int bits = 32 - __clz(range | 1u);
-    const int shift = bits > 8 ? bits - 8 : 0;
+    const int shift = bits > kTrBucketBits ? bits - kTrBucketBits : 0;
     __syncthreads();  // sh.kmin / sh.kmax are reused below
     build_table(sh.bucket, kmin, shift, 0u, 0xffffffffu);
 
     // ---- 2. groups of buckets, front to back, until every pixel is done
     bool stop = false;
     int g0 = 0;
-    while (g0 < kTrRadix && !stop) {
+    while (g0 < kTrBuckets && !stop) {
       // group boundary barrier: the staged group of the previous round is dead after it
       if (__syncthreads_count(pixel_done(st)) == kTrThreads) break;
       const int g1 = group_end(sh.bucket, g0);
@@ -417,7 +429,7 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
       // kTrCap records within 1/65536 of the tile's depth range, e.g. identical depths — the caller re-renders
       // with the separate stages.
       const uint32_t flo = g0 == 0 ? 0u : kmin + ((uint32_t)g0 << shift);
-      const uint32_t fhi = g0 == kTrRadix - 1 ? 0xffffffffu : kmin + (((uint32_t)g0 + 1u) << shift) - 1u;
+      const uint32_t fhi = g0 == kTrBuckets - 1 ? 0xffffffffu : kmin + (((uint32_t)g0 + 1u) << shift) - 1u;
       if (tid == 0) { sh.kmin = 0xffffffffu; sh.kmax = 0u; }
       __syncthreads();
       uint32_t lo2 = 0xffffffffu, hi2 = 0u;
@@ -439,12 +451,12 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
       const uint32_t kmin2 = sh.kmin;
       const uint32_t range2 = sh.kmax - kmin2;
       const int bits2 = 32 - __clz(range2 | 1u);
-      const int shift2 = bits2 > 8 ? bits2 - 8 : 0;
+      const int shift2 = bits2 > kTrBucketBits ? bits2 - kTrBucketBits : 0;
       __syncthreads();
       build_table(sh.bucket2, kmin2, shift2, flo, fhi);
       const int base2 = sh.bucket[g0];
       int s0 = 0;
-      while (s0 < kTrRadix) {
+      while (s0 < kTrBuckets) {
         if (s0 > 0 && __syncthreads_count(pixel_done(st)) == kTrThreads) { stop = true; break; }
         const int s1 = group_end(sh.bucket2, s0);
         const int m2 = sh.bucket2[s1] - sh.bucket2[s0];
