@@ -251,8 +251,7 @@ composite_bwd_kernel(const float *__restrict__ stream, int colors_per_camera, in
         an = lds128(aA + (s0 + i + 1) * 16);
         bn = lds128(aB + (s0 + i + 1) * 16);
       }
-      const float dx = a.x - px, dy = a.y - py;
-      const float p = power2(b.x, b.y, b.z, dx, dy);
+      const float p = power2_at(b.x, b.y, b.z, make_float2(a.x, a.y), make_float2(-px, -py));
       const float vis = ex2_approx(p);
       const float a_raw = b.w * vis;
       const float alpha = fminf(0.999f, a_raw);
@@ -282,16 +281,25 @@ composite_bwd_kernel(const float *__restrict__ stream, int colors_per_camera, in
     const float4 ha = lds128(aA + (s0 + h) * 16);
     const float4 hb = lds128(aB + (s0 + h) * 16);
     const float dx0 = ha.x - px_base, dy0 = ha.y - py_base;
-    float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f, sxx = 0.0f, sxy = 0.0f, syy = 0.0f, sx = 0.0f, sy = 0.0f, s00 = 0.0f;
+    float c0, c1, c2, c3, sxx, sxy = 0.0f, syy, sx, sy, s00 = 0.0f;
+    {
+      // two-wide fp32 (FFMA2 / FMUL2 / FADD2): the ten sums as three pairs + two scalars
+      float2 c01 = make_float2(0.0f, 0.0f), c23 = c01, sq = c01, sl = c01;
 #pragma unroll kBwdP2Unroll
-    for (int j = 0; j < 16; ++j) {
-      const float2 fv = lds64(aM + (h * kBwdRow + 2 * (16 * half + j)) * 4);
-      const float4 v = lds128(aV + (16 * half + j) * 16);
-      const float dx = dx0 - (float)(j & 7), dy = dy0 - (float)(j >> 3);
-      c0 = fmaf(fv.x, v.x, c0); c1 = fmaf(fv.x, v.y, c1); c2 = fmaf(fv.x, v.z, c2); c3 = fmaf(fv.x, v.w, c3);
-      const float tx = fv.y * dx, ty = fv.y * dy;
-      sxx = fmaf(tx, dx, sxx); sxy = fmaf(tx, dy, sxy); syy = fmaf(ty, dy, syy);
-      sx += tx; sy += ty; s00 += fv.y;
+      for (int j = 0; j < 16; ++j) {
+        const float2 fv = lds64(aM + (h * kBwdRow + 2 * (16 * half + j)) * 4);
+        const float4 v = lds128(aV + (16 * half + j) * 16);
+        const float2 d = make_float2(dx0 - (float)(j & 7), dy0 - (float)(j >> 3));
+        const float2 ff = make_float2(fv.x, fv.x);
+        c01 = __ffma2_rn(ff, make_float2(v.x, v.y), c01);
+        c23 = __ffma2_rn(ff, make_float2(v.z, v.w), c23);
+        const float2 t = __fmul2_rn(make_float2(fv.y, fv.y), d);  // (vsig dx, vsig dy)
+        sq = __ffma2_rn(t, d, sq);                                // (sum vsig dx^2, sum vsig dy^2)
+        sxy = fmaf(t.x, d.y, sxy);
+        sl = __fadd2_rn(sl, t);
+        s00 += fv.y;
+      }
+      c0 = c01.x; c1 = c01.y; c2 = c23.x; c3 = c23.y; sxx = sq.x; syy = sq.y; sx = sl.x; sy = sl.y;
     }
     // fold the two halves (lanes h and h + 16 hold the same hit): afterwards the lower half owns colours, depth
     // and opacity, the upper half conic and mean

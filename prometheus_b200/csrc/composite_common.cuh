@@ -55,6 +55,22 @@ __device__ __forceinline__ float power2(float Q0, float Q1, float Q2, float dx, 
   return __fmaf_rn(Q0, __fmul_rn(dx, dx), __fmaf_rn(Q2, __fmul_rn(dy, dy), __fmul_rn(Q1, __fmul_rn(dx, dy))));
 }
 
+// The same value from the packed pair (mean - pixel): sm_100's two-wide fp32 instructions (FADD2 / FMUL2) form
+// (dx, dy) and (dx^2, dy^2) in one issue slot each; every lane of the pair is an individually rounded IEEE operation,
+// so the result is bit-identical to power2() — forward and backward both go through this one helper.
+#ifndef PM_F32X2
+#define PM_F32X2 1
+#endif
+__device__ __forceinline__ float power2_at(float Q0, float Q1, float Q2, float2 mean, float2 neg_pixel) {
+#if PM_F32X2
+  const float2 d = __fadd2_rn(mean, neg_pixel);
+  const float2 sq = __fmul2_rn(d, d);
+  return __fmaf_rn(Q0, sq.x, __fmaf_rn(Q2, sq.y, __fmul_rn(Q1, __fmul_rn(d.x, d.y))));
+#else
+  return power2(Q0, Q1, Q2, mean.x + neg_pixel.x, mean.y + neg_pixel.y);
+#endif
+}
+
 // Gather one Gaussian of the sorted list into the staging records, in two halves so that callers can
 // put the global loads of several Gaussians in flight before the first use (gather_load) and do the
 // arithmetic afterwards (gather_finish). f = flatten id (camera * N + g), g = Gaussian id.
@@ -197,8 +213,7 @@ template <int CAP>
 __device__ __forceinline__ void eval_alpha(uint32_t ga, const WarpFootprint &fp, float &alpha, bool &contrib) {
   const float2 m = lds64(ga);
   const float4 b = lds128(ga + (CAP + 1) * 16);
-  const float dx = m.x - fp.px, dy = m.y - fp.py;
-  const float p = power2(b.x, b.y, b.z, dx, dy);  // = -sigma * log2e
+  const float p = power2_at(b.x, b.y, b.z, m, make_float2(-fp.px, -fp.py));  // = -sigma * log2e
   alpha = fminf(0.999f, b.w * ex2_approx(p));
   contrib = !(p > 0.0f) && alpha >= kAlphaMin;  // p > 0 <=> sigma < 0
 }
