@@ -16,4 +16,4 @@ ncu --set full --clock-control none --import-source on -k regex:"unproject_|came
     python tools/stage_bench.py --bwd --steps 2 > $O/${TAG}_ncu_full.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"tile_render" --launch-skip 5 --launch-count 1 -o $O/${TAG}_fwd -f \
     python tools/stage_bench.py --steps 2 > $O/${TAG}_ncu_fwd.log 2>&1
-tail -2 $O/${TAG}_ncu_full.log $O/${TAG}_ncu_fwd.log
+tail -n 2 $O/${TAG}_ncu_full.log $O/${TAG}_ncu_fwd.log
