@@ -12,8 +12,13 @@ namespace pm {
 #ifdef PM_STATS
 // developer build (tools/build_variant.sh stats -DPM_STATS): culling statistics of the forward compositor:
 // [0] warp-chunks with >= 1 hit, [1] warp-level hits, [2] lane evaluations above the alpha threshold,
-// [3] those on a live pixel, [4] hits with >= 1 such lane, [5] hits with >= 1 live such lane
-__device__ unsigned long long g_pm_stats[8];
+// [3] those on a live pixel, [4] hits with >= 1 such lane, [5] hits with >= 1 live such lane; fused renderer:
+// [6] full passes over a tile's records, [7] groups, [8] level-2 refinements, [9] radix-sorted ("fat") groups,
+// [10] staged Gaussians, [11] footprint candidates, [12] dense cull rounds, [13] non-empty tiles, [14] records
+__device__ unsigned long long g_pm_stats[16];
+#define PM_STAT_ADD(i, v) do { atomicAdd(&g_pm_stats[i], (unsigned long long)(v)); } while (0)
+#else
+#define PM_STAT_ADD(i, v) do { } while (0)
 #endif
 
 constexpr int kBatch = 256;
@@ -71,6 +76,7 @@ __device__ __forceinline__ float power2_at(float Q0, float Q1, float Q2, float2 
 #endif
 }
 
+// @region cc_gather
 // Gather one Gaussian of the sorted list into the staging records, in two halves so that callers can
 // put the global loads of several Gaussians in flight before the first use (gather_load) and do the
 // arithmetic afterwards (gather_finish). f = flatten id (camera * N + g), g = Gaussian id.
@@ -132,6 +138,7 @@ __device__ __forceinline__ void gather(int32_t f, int32_t g, const float *__rest
   gather_finish(gather_load(f, g, means2d, conics, opacities, colors, colors_per_camera, D, depths), a, b, c);
 }
 
+// @region cc_stream
 // ---- the splat stream: what the backward replays -------------------------------------------------------------
 // When a backward will follow, the forward kernels write every Gaussian they stage — in the tile's sorted order, at
 // its list position — as one 48-byte record {mean x, mean y, half extents (2 x fp16, rounded up), flatten id |
@@ -161,6 +168,7 @@ __device__ __forceinline__ void stream_store(float *__restrict__ stream, size_t 
   dst[2] = make_float4(c.c0, c.c1, c.c2, c.c3);
 }
 
+// @region cc_eval_blend
 // Per-pixel forward state of one lane. The sign of T carries the "done" flag: T > 0 while the pixel
 // is live (the stop rule keeps a live T above 1e-4), T < 0 once it stopped or if it lies outside the
 // image; |T| is the transmittance the epilogue writes. A done pixel can never add again because
@@ -231,6 +239,7 @@ __device__ __forceinline__ void blend(const float4 &c, float alpha, bool contrib
   last_ga = add ? ga : last_ga;
 }
 
+// @region cc_cull
 // Composite one staged run (`batch_size` valid entries of the Staged<CAP> block at shared address aS,
 // whose position in the tile's sorted list starts at `list_pos`) into the lane's pixel.
 //   * warp-level culling: 32 lanes test 32 Gaussians against the rectangle of the warp's LIVE pixels — first the
@@ -311,6 +320,7 @@ __device__ __forceinline__ bool cull_hit_reg(const float4 &a, const float4 &b, c
   return cull_hit_impl(a, [&b] { return b; }, r);
 }
 
+// @region cc_batch_loop
 template <int CAP>
 __device__ __forceinline__ void composite_batch_fwd(uint32_t aS, uint32_t aQ, int batch_size, int list_pos,
                                                     const WarpFootprint &fp, PixelState &st) {
@@ -363,6 +373,99 @@ __device__ __forceinline__ void composite_batch_fwd(uint32_t aS, uint32_t aQ, in
   if (last_ga != 0xffffffffu) st.last = list_pos + (int)((last_ga - aS) >> 4);
 }
 
+// @region cc_footprint_mask
+// ---- footprint masks (fused renderer) ------------------------------------------------------------------------
+// composite_batch_fwd makes every warp test every staged Gaussian: 8 warps x ~120 instructions per 32 entries, of
+// which ~20 % survive (the splats of these scenes are a few pixels wide, a warp's footprint is 8 x 4). The fused
+// renderer's staging threads hold each Gaussian's extent in registers anyway, so ONE thread tests it against the 8
+// static warp footprints of the tile (footprint_mask: two column and four row intervals) and the staging warp
+// publishes a 32-bit word per (footprint, 32 staged entries) with 8 ballots. A compositing warp then only walks the
+// non-zero words of ITS footprint, gathers the candidates into a ring of 64 shared-memory addresses and runs the
+// live-rectangle test (AABB + exact) on 32 DENSE candidates at a time — same decisions, same order, same arithmetic
+// as composite_batch_fwd (culling never changes a result), ~3x fewer instructions outside the evaluation itself.
+constexpr int kCandWords = 64;  // per-warp candidate ring
+
+// bit w (= 2 * row + column, the warp index) set when the axis-aligned extent of {alpha >= 1/255} overlaps the pixel
+// centres of warp w's 8 x 4 footprint; tx0 / ty0 = first pixel centre of the tile
+__device__ __forceinline__ unsigned footprint_mask(float mx, float my, float hx, float hy, float tx0, float ty0) {
+  unsigned cols = 0u, fm = 0u;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const float x0 = tx0 + (float)(8 * c), x1 = x0 + 7.0f;
+    if (x0 - mx <= hx && x1 - mx >= -hx) cols |= 1u << c;
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float y0 = ty0 + (float)(4 * r), y1 = y0 + 3.0f;
+    if (y0 - my <= hy && y1 - my >= -hy) fm |= cols << (2 * r);
+  }
+  return fm;
+}
+
+// @region cc_masked_loop
+// Composite one staged group through the warp's footprint words (aM: ceil(batch_size / 32) words, bit = staged slot).
+template <int CAP>
+__device__ __forceinline__ void composite_group_masked_fwd(uint32_t aS, uint32_t aQ, uint32_t aCQ, uint32_t aM,
+                                                           int batch_size, int list_pos, const WarpFootprint &fp,
+                                                           PixelState &st) {
+  static_assert(CAP <= 1024, "one footprint word per lane");
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const int nch = (batch_size + 31) >> 5;
+  const uint32_t words = lane < nch ? lds32u(aM + lane * 4) : 0u;
+  unsigned nz = __ballot_sync(0xffffffffu, words != 0u);
+  uint32_t last_ga = 0xffffffffu;
+  int head = 0, q = 0;  // the ring holds candidates head .. head + q - 1 (mod kCandWords), in list order
+  while (nz != 0u || q > 0) {
+    // refill: append whole words while fewer than 32 candidates wait (q < 32 before, <= 63 after)
+    while (q < 32 && nz != 0u) {
+      const int c = __ffs(nz) - 1;
+      nz &= nz - 1u;
+      const uint32_t word = __shfl_sync(0xffffffffu, words, c);
+      if ((word >> lane) & 1u)
+        sts32(aCQ + ((head + q + __popc(word & lt)) & (kCandWords - 1)) * 4, aS + (c * 32 + lane) * 16);
+      q += __popc(word);
+    }
+    __syncwarp();
+    const unsigned live = __ballot_sync(0xffffffffu, !pixel_done(st));
+    if (live == 0u) break;
+    const LiveRect rect = live_rect(live, fp.wcx, fp.wcy);
+    const int nb = min(q, 32);
+    if (lane == 0) { PM_STAT_ADD(11, nb); PM_STAT_ADD(12, 1); }
+    bool hit = false;
+    uint32_t ga = 0u;
+    if (lane < nb) {
+      ga = lds32u(aCQ + ((head + lane) & (kCandWords - 1)) * 4);
+      hit = cull_hit(lds128(ga), ga + (CAP + 1) * 16, rect);
+    }
+    head = (head + nb) & (kCandWords - 1);
+    q -= nb;
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if (bal == 0u) continue;
+    const int n = __popc(bal);
+#ifdef PM_STATS
+    if (lane == 0) { atomicAdd(&g_pm_stats[0], 1ull); atomicAdd(&g_pm_stats[1], (unsigned long long)n); }
+#endif
+    if (hit) sts32(aQ + __popc(bal & lt) * 4, ga);
+    if (lane == 0) sts32(aQ + n * 4, aS + CAP * 16);
+    __syncwarp();
+    for (int i = 0; i < n; i += 2) {
+      const uint2 g2 = lds64u(aQ + i * 4);
+      float alpha0, alpha1;
+      bool c0, c1;
+      eval_alpha<CAP>(g2.x, fp, alpha0, c0);
+      eval_alpha<CAP>(g2.y, fp, alpha1, c1);
+      const float4 col0 = lds128(g2.x + 2 * (CAP + 1) * 16);
+      const float4 col1 = lds128(g2.y + 2 * (CAP + 1) * 16);
+      blend(col0, alpha0, c0, g2.x, last_ga, st);
+      blend(col1, alpha1, c1, g2.y, last_ga, st);
+    }
+    __syncwarp();
+  }
+  if (last_ga != 0xffffffffu) st.last = list_pos + (int)((last_ga - aS) >> 4);
+}
+
+// @region cc_epilogue
 // Write one pixel's results (shared epilogue).
 __device__ __forceinline__ void store_pixel(const PixelState &st, size_t pix, int cam, int D, int CD,
                                             const float *__restrict__ backgrounds, float *__restrict__ render,

@@ -72,7 +72,9 @@ struct TrShared {
     };
     Staged<kTrCap> stg;                      // (its null slot lies beyond the sort buffers)
   };
-  uint32_t queue[kTrWarps][kQueueWords];     // per-warp hit queues of composite_batch_fwd
+  uint32_t queue[kTrWarps][kQueueWords];     // per-warp hit queues of the compositing loop
+  uint32_t cand[kTrWarps][kCandWords];       // per-warp candidate rings (composite_group_masked_fwd)
+  uint32_t fmask[kTrWarps][kTrItems * kTrWarps];  // footprint words: [compositing warp][32 staged slots]
   uint32_t red[64];
   int bucket[kTrBuckets + 1];                // start of each depth sub-bucket inside the tile's list
   int bucket2[kTrBuckets + 1];               // second level: sub-buckets of one level-1 bucket that exceeds a group
@@ -83,6 +85,7 @@ struct TrShared {
 constexpr size_t kTrSmemBytes = sizeof(TrShared);
 
 // Sort sh.gbuf[0..m) by (key, flatten id); gmin/gmax = key range of the group. All threads call it.
+// @region tr_radix_sort_group
 __device__ __forceinline__ void sort_group(TrShared &sh, int m, uint32_t gmin, uint32_t gmax) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int chunk0 = warp * (kTrItems * 32);
@@ -185,6 +188,7 @@ __device__ __forceinline__ void sort_group(TrShared &sh, int m, uint32_t gmin, u
   __syncthreads();
 }
 
+// @region tr_scan
 // Exclusive scan of tbl[1..kTrBuckets] in place (tbl[0] = 0 on entry): tbl[d] = start of bucket d, tbl[kTrBuckets] = total.
 // Thread t owns the kTrBuckets / kTrThreads consecutive entries behind tbl[1 + t * per].
 __device__ __forceinline__ void tr_scan_buckets(int *tbl, uint32_t *red) {
@@ -209,6 +213,7 @@ __device__ __forceinline__ void tr_scan_buckets(int *tbl, uint32_t *red) {
   __syncthreads();
 }
 
+// @region tr_prologue
 __global__ void __launch_bounds__(kTrThreads, PM_TR_MINBLOCKS)
 tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__restrict__ offsets,
                        int64_t n_host, const int32_t *__restrict__ d_n, const float *__restrict__ means2d,
@@ -238,6 +243,8 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
   const WarpFootprint fp{(float)ix + 0.5f, (float)iy + 0.5f, (float)wx0 + 4.0f, (float)wy0 + 2.0f};
   PixelState st{inside ? 1.0f : -1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0};
   const uint32_t aS = smem_u32(&sh.stg), aQ = smem_u32(sh.queue[warp]);
+  const uint32_t aCQ = smem_u32(sh.cand[warp]), aM = smem_u32(sh.fmask[warp]);
+  const float tile_px0 = (float)(tile_x * kTile) + 0.5f, tile_py0 = (float)(tile_y * kTile) + 0.5f;
 
   const int64_t n_isects = effective_n(n_host, d_n);
   // (clamped: with a speculative record capacity smaller than the device-side count the result is
@@ -248,10 +255,12 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
   const unsigned long long *src = reinterpret_cast<const unsigned long long *>(records) + start;
   int sorted = 0;
 
+  // @region tr_histogram_pass
   // Histogram of the tile's records with key in [flo, fhi] over the 256 buckets of (kmin_c, shift_c) into tbl,
   // then the exclusive scan. (Every pass over the tile's records keeps kTrMlp loads per thread in flight.)
   auto build_table = [&](int *tbl, uint32_t kmin_c, int shift_c, uint32_t flo, uint32_t fhi) {
     for (int i = tid; i <= kTrBuckets; i += kTrThreads) tbl[i] = 0;
+    if (tid == 0) PM_STAT_ADD(6, 1);
     __syncthreads();
     for (int i0 = 0; i0 < cnt; i0 += kTrMlp * kTrThreads) {
       uint32_t k[kTrMlp];
@@ -269,6 +278,7 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
     tr_scan_buckets(tbl, sh.red);
   };
 
+  // @region tr_collect_pass
   // One group: the records with key in [flo, fhi] whose bucket under (kmin_c, shift_c) lies in [b0, b1) — at most
   // kTrCap of them, occupying list positions list_base + tbl[b0] .. list_base + tbl[b1] of the tile.
   auto process_group = [&](const int *tbl, uint32_t kmin_c, int shift_c, uint32_t flo, uint32_t fhi, int b0, int b1,
@@ -278,7 +288,7 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
     // its bucket's start + a per-bucket cursor), so that only the short runs of equal bucket remain to be ordered
     uint32_t *cur = sh.cursor;
     for (int bb = b0 + tid; bb < b1; bb += kTrThreads) cur[bb] = 0u;
-    if (tid == 0) { sh.kmin = 0xffffffffu; sh.kmax = 0u; }
+    if (tid == 0) { sh.kmin = 0xffffffffu; sh.kmax = 0u; PM_STAT_ADD(6, 1); PM_STAT_ADD(7, 1); PM_STAT_ADD(10, m); }
     __syncthreads();
     uint32_t gmin = 0xffffffffu, gmax = 0u;
     for (int i0 = 0; i0 < cnt; i0 += kTrMlp * kTrThreads) {
@@ -300,6 +310,7 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
         }
       }
     }
+    // @region tr_rank
     bool fat = false;  // a run too long for the all-pairs ranking below
     for (int bb = b0 + tid; bb < b1; bb += kTrThreads) fat |= tbl[bb + 1] - tbl[bb] > kTrRankMax;
     gmin = __reduce_min_sync(0xffffffffu, gmin);
@@ -308,6 +319,7 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
     fat = __syncthreads_or(fat);
     int32_t ids[kTrItems];
     if (fat) {
+      if (tid == 0) PM_STAT_ADD(9, 1);
       sort_group(sh, m, sh.kmin, sh.kmax);  // LSD radix sort of the whole group
 #pragma unroll
       for (int k = 0; k < kTrItems; ++k) {
@@ -341,6 +353,7 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
         ids[k] = slot < m ? (int32_t)sorted_ids[slot] : -1;
       }
     }
+    // @region tr_ids_gather_stage
     // sorted flatten ids go to their final positions (read again by the backward pass)
 #pragma unroll
     for (int k = 0; k < kTrItems; ++k) {
@@ -353,20 +366,32 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
 #pragma unroll
     for (int k = 0; k < kTrItems; ++k) {
       const int slot = k * kTrThreads + tid;
+      unsigned fm = 0u;  // warp footprints of the tile this Gaussian's extent overlaps
       if (slot < m) {
         GaussA ga; GaussB gb; GaussC gc;
         gather(ids[k], ids[k] - cam_base, means2d, conics, opacities, colors, colors_per_camera, D, depths, ga, gb, gc);
         sh.stg.sA[slot] = ga; sh.stg.sB[slot] = gb; sh.stg.sC[slot] = gc;
         // what the backward replays: the staged record, at its position in the tile's sorted list
         if (stream) stream_store(stream, (size_t)start + list_base + gs + slot, ids[k], ga, gb, gc);
+        fm = footprint_mask(ga.mx, ga.my, ga.hx, ga.hy, tile_px0, tile_py0);
       }
+      // one word per (compositing warp, these 32 slots): lane w keeps the ballot of footprint w
+      uint32_t word = 0u;
+#pragma unroll
+      for (int w = 0; w < kTrWarps; ++w) {
+        const uint32_t b = __ballot_sync(0xffffffffu, (fm >> w) & 1u);
+        if (lane == w) word = b;
+      }
+      if (lane < kTrWarps) sh.fmask[lane][k * kTrWarps + warp] = word;
     }
     __syncthreads();
+    // @region tr_composite_call
     // composite the whole group; warps do not wait for each other — same arithmetic as composite_fwd_kernel
     if (!__all_sync(0xffffffffu, pixel_done(st)))
-      composite_batch_fwd<kTrCap>(aS, aQ, m, start + list_base + gs, fp, st);
+      composite_group_masked_fwd<kTrCap>(aS, aQ, aCQ, aM, m, start + list_base + gs, fp, st);
   };
 
+  // @region tr_group_walk
   // largest b1 in (b0, 256] with tbl[b1] - tbl[b0] <= capacity (binary search; tbl[] is monotone), b0 + 1 if none
   auto group_end = [&](const int *tbl, int b0) {
     const int gs = tbl[b0];
@@ -384,7 +409,7 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
     // value; they only steer the bucket sizes. kmin / kmax therefore come from a strided sample of <= 1024
     // records (one round of 4 independent loads per thread, exact when the tile has <= 1024 records) instead of
     // a full pass; the few keys outside the sampled range land in buckets 0 / 255.
-    if (tid == 0) { sh.kmin = 0xffffffffu; sh.kmax = 0u; }
+    if (tid == 0) { sh.kmin = 0xffffffffu; sh.kmax = 0u; PM_STAT_ADD(13, 1); PM_STAT_ADD(14, cnt); }
     __syncthreads();
     uint32_t kmin = 0xffffffffu, kmax = 0u;
     {
@@ -424,13 +449,14 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
         g0 = g1;
         continue;
       }
+      // @region tr_level2
       // ---- 3. bucket g0 alone exceeds a group (a thin, dense depth shell): give it its own 256 sub-buckets
       // over the key range it actually holds and walk those. Only if a sub-bucket still does not fit — more than
       // kTrCap records within 1/65536 of the tile's depth range, e.g. identical depths — the caller re-renders
       // with the separate stages.
       const uint32_t flo = g0 == 0 ? 0u : kmin + ((uint32_t)g0 << shift);
       const uint32_t fhi = g0 == kTrBuckets - 1 ? 0xffffffffu : kmin + (((uint32_t)g0 + 1u) << shift) - 1u;
-      if (tid == 0) { sh.kmin = 0xffffffffu; sh.kmax = 0u; }
+      if (tid == 0) { sh.kmin = 0xffffffffu; sh.kmax = 0u; PM_STAT_ADD(6, 1); PM_STAT_ADD(8, 1); }
       __syncthreads();
       uint32_t lo2 = 0xffffffffu, hi2 = 0u;
       for (int i0 = 0; i0 < cnt; i0 += kTrMlp * kTrThreads) {
@@ -471,6 +497,7 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
       g0 = g0 + 1;
     }
   }
+  // @region tr_epilogue
   if (tid == 0) sorted_counts[ct] = sorted;
   if (inside) {
     if (images != nullptr)  // packed module outputs (pm_tile_render_packed_fwd)
@@ -532,9 +559,9 @@ static int tile_render_launch(const uint64_t *records, const int32_t *isect_offs
 #ifdef PM_STATS
 __attribute__((visibility("default"))) int pm_debug_stats(unsigned long long *out, int reset) {
   cudaDeviceSynchronize();
-  if (cudaMemcpyFromSymbol(out, pm::g_pm_stats, sizeof(unsigned long long) * 8) != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(out, pm::g_pm_stats, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
   if (reset) {
-    unsigned long long z[8] = {0};
+    unsigned long long z[16] = {0};
     cudaMemcpyToSymbol(pm::g_pm_stats, z, sizeof(z));
   }
   return 0;
