@@ -392,6 +392,8 @@ def main():
         "unproject_fwd": 112 * G * B,
         # module fast path: projection with the per-tile histogram fused in, no tiles_per_gauss array
         "project_fwd": (40 * G + 28 * P) * B,
+        # single-pass binning: the projection also writes the 8-byte intersection records (no bin_scatter)
+        "project_scatter_fwd": (40 * G + 28 * P + 8 * I) * B,
         "scan_tiles": 12 * P * B,
         "bin_emit": (20 * P + 12 * I) * B,
         "sort_pairs": (passes * 24 + 8) * I * B,

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PM_ABI_VERSION 3
+#define PM_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define PM_API __attribute__((visibility("default")))
@@ -160,6 +160,21 @@ PM_API int pm_project_count_fwd(const float *means, const float *quats, const fl
                    float eps2d, float near_plane, float far_plane, float radius_clip,
                    int32_t *radii, float *means2d, float *depths, float *conics,
                    int32_t *tiles_per_gauss, int32_t *tile_counts, pm_stream_t stream);
+
+/* Projection + SINGLE-PASS binning (module fast path; replaces pm_project_count_fwd + pm_bin_scatter, i.e. both
+ * passes of gsplat's isect_tiles, for callers that do not need the compact record array): besides the pair arrays
+ * and the histogram tile_counts [C, tile_height, tile_width] (caller zero-fills) every intersection record
+ * {depth bits, flatten id} is written straight into its tile's fixed-capacity region,
+ * records[(c * tiles + t) * tile_cap + rank], rank = arrival order < tile_cap. A tile that receives more than
+ * tile_cap intersections only keeps the first tile_cap: the caller compares pm_tile_scan's max count with tile_cap
+ * afterwards and, if it is larger, renders again (larger capacity, or pm_project_count_fwd + pm_bin_scatter).
+ * pm_tile_render_packed_fwd reads this layout with record_stride = tile_cap. */
+PM_API int pm_project_scatter_fwd(const float *means, const float *quats, const float *scales,
+                   const float *viewmats, const float *Ks,
+                   int N, int C, int views_per_scene, int width, int height, int tile_size,
+                   float eps2d, float near_plane, float far_plane, float radius_clip,
+                   int32_t *radii, float *means2d, float *depths, float *conics,
+                   int32_t *tile_counts, uint64_t *records, int tile_cap, pm_stream_t stream);
 
 /* VJP of the projection. v_means2d [C,N,2], v_depths [C,N], v_conics [C,N,3]
  * (any may be NULL) -> v_means [N,3], v_quats [N,4], v_scales [N,3], summed over
@@ -322,8 +337,13 @@ PM_API int pm_tile_render_fwd(const uint64_t *records, const int32_t *isect_offs
  * masks [C,1,H,W] = alpha in [0,1] — instead of the interleaved render / alphas tensors.
  * n_isects may be a speculative CAPACITY of records / flatten_ids with the true count in *d_n:
  * nothing is accessed beyond min(n_isects, *d_n); if *d_n > n_isects the outputs are invalid and
- * the caller must retry with a larger capacity. */
-PM_API int pm_tile_render_packed_fwd(const uint64_t *records, const int32_t *isect_offsets, int64_t n_isects,
+ * the caller must retry with a larger capacity.
+ * record_stride = 0: records is the compact array of pm_bin_scatter (tile segments back to back at isect_offsets).
+ * record_stride = S > 0: the fixed-capacity layout of pm_project_scatter_fwd — tile (c, t) owns records[(c * tiles +
+ * t) * S ...], of which min(count, S) are valid; isect_offsets / n_isects then only position flatten_ids and the
+ * splat stream. */
+PM_API int pm_tile_render_packed_fwd(const uint64_t *records, int64_t record_stride,
+                              const int32_t *isect_offsets, int64_t n_isects,
                               const int32_t *d_n, const float *means2d, const float *conics,
                               const float *opacities, const float *colors, int colors_per_camera,
                               const float *depths, const float *backgrounds, int N, int C,

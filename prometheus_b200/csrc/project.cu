@@ -80,7 +80,9 @@ constexpr int kProjCamChunk = 32;  // cameras per launch (shared-memory table); 
 #ifndef PM_PROJ_MINBLOCKS
 #define PM_PROJ_MINBLOCKS 5  // 48 registers: 0.320 -> 0.316 ms on C2 (6: 0.318)
 #endif
-template <bool COUNT>
+// MODE 0: projection only; 1: + per-(camera, tile) histogram; 2: + single-pass binning (histogram and the
+// intersection records, each written into its tile's fixed-capacity region — binning_common.cuh)
+template <int MODE>
 __global__ void __launch_bounds__(256, PM_PROJ_MINBLOCKS)
 project_fwd_kernel(const float *__restrict__ means, const float *__restrict__ quats,
                    const float *__restrict__ scales, const float *__restrict__ viewmats,
@@ -89,9 +91,11 @@ project_fwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
                    int tile_width, int tile_height, float eps2d, float near_plane, float far_plane,
                    float radius_clip, int32_t *__restrict__ radii, float *__restrict__ means2d,
                    float *__restrict__ depths, float *__restrict__ conics,
-                   int32_t *__restrict__ tiles_per_gauss, int32_t *__restrict__ tile_counts) {
+                   int32_t *__restrict__ tiles_per_gauss, int32_t *__restrict__ tile_counts,
+                   uint64_t *__restrict__ records, int tile_cap) {
   __shared__ ProjCamS s_cam[kProjCamChunk];
-  __shared__ TileCountSmem s_cnt[1];  // (unused and optimised away when !COUNT)
+  __shared__ TileCountSmem s_cnt[1];     // MODE 1 (unused shared arrays are optimised away)
+  __shared__ TileScatterSmem s_sct[1];   // MODE 2
   // strided CTA order (see binning_common.cuh): concurrently resident CTAs touch far-apart tiles
   const int chunk = strided_chunk(blockIdx.x, chunk_stride, gridDim.x);
   // scene batching: the Gaussian arrays hold S scenes of N Gaussians, camera c belongs to scene c / views_per_scene
@@ -205,8 +209,14 @@ project_fwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
       conics[f * 3 + 0] = q0; conics[f * 3 + 1] = q1; conics[f * 3 + 2] = q2;
       if (tiles_per_gauss != nullptr) tiles_per_gauss[f] = (x1 - x0) * (y1 - y0);
     }
-    if (COUNT)
+    if (MODE == 1)
       cta_tile_count(s_cnt[0], x0, x1, y0, y1, tile_counts + (size_t)(cam_first + ci) * tile_width * tile_height, tile_width);
+    if (MODE == 2) {
+      const size_t tile0 = (size_t)(cam_first + ci) * tile_width * tile_height;
+      cta_tile_count_scatter(s_sct[0], x0, x1, y0, y1, tile_counts + tile0, tile_width,
+                             ((uint64_t)(uint32_t)f << 32) | (uint64_t)__float_as_uint(depth), records + tile0 * (size_t)tile_cap,
+                             tile_cap);
+    }
   }
 }
 
@@ -219,7 +229,7 @@ static int project_fwd_launch(const float *means, const float *quats, const floa
                               float eps2d,
                               float near_plane, float far_plane, float radius_clip, int32_t *radii, float *means2d,
                               float *depths, float *conics, int32_t *tiles_per_gauss, int32_t *tile_counts,
-                              pm_stream_t stream) {
+                              uint64_t *records, int tile_cap, pm_stream_t stream) {
   if (!means || !quats || !scales || !viewmats || !Ks || !radii || !means2d || !depths || !conics)
     return PM_ERR_BAD_ARG;
   if (N < 0 || C < 0 || width <= 0 || height <= 0) return PM_ERR_BAD_ARG;
@@ -237,14 +247,18 @@ static int project_fwd_launch(const float *means, const float *quats, const floa
   const int stride = pm::coprime_stride(nb);
   for (int cam0 = 0; cam0 < Nv; cam0 += pm::kProjCamChunk) {
     const int n_cams = Nv - cam0 < pm::kProjCamChunk ? Nv - cam0 : pm::kProjCamChunk;
-    if (tile_counts)
-      pm::project_fwd_kernel<true><<<nb, 256, 0, pm::as_stream(stream)>>>(
+    if (tile_counts && records)
+      pm::project_fwd_kernel<2><<<nb, 256, 0, pm::as_stream(stream)>>>(
           means, quats, scales, viewmats, Ks, N, Nv, cam0, n_cams, stride, width, height, tw, th, eps2d, near_plane,
-          far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, tile_counts);
+          far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, tile_counts, records, tile_cap);
+    else if (tile_counts)
+      pm::project_fwd_kernel<1><<<nb, 256, 0, pm::as_stream(stream)>>>(
+          means, quats, scales, viewmats, Ks, N, Nv, cam0, n_cams, stride, width, height, tw, th, eps2d, near_plane,
+          far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, tile_counts, nullptr, 0);
     else
-      pm::project_fwd_kernel<false><<<nb, 256, 0, pm::as_stream(stream)>>>(
+      pm::project_fwd_kernel<0><<<nb, 256, 0, pm::as_stream(stream)>>>(
           means, quats, scales, viewmats, Ks, N, Nv, cam0, n_cams, stride, width, height, tw, th, eps2d, near_plane,
-          far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, nullptr);
+          far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, nullptr, nullptr, 0);
   }
   return pm::check_launch();
 }
@@ -254,7 +268,8 @@ int pm_project_fwd(const float *means, const float *quats, const float *scales, 
                    float near_plane, float far_plane, float radius_clip, int32_t *radii, float *means2d,
                    float *depths, float *conics, int32_t *tiles_per_gauss, pm_stream_t stream) {
   return project_fwd_launch(means, quats, scales, viewmats, Ks, N, C, C, width, height, tile_size, eps2d, near_plane,
-                            far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, nullptr, stream);
+                            far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, nullptr, nullptr, 0,
+                            stream);
 }
 
 int pm_project_count_fwd(const float *means, const float *quats, const float *scales, const float *viewmats,
@@ -265,7 +280,18 @@ int pm_project_count_fwd(const float *means, const float *quats, const float *sc
   if (!tile_counts) return PM_ERR_BAD_ARG;
   return project_fwd_launch(means, quats, scales, viewmats, Ks, N, C, views_per_scene, width, height, tile_size, eps2d, near_plane,
                             far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, tile_counts,
-                            stream);
+                            nullptr, 0, stream);
+}
+
+int pm_project_scatter_fwd(const float *means, const float *quats, const float *scales, const float *viewmats,
+                           const float *Ks, int N, int C, int views_per_scene, int width, int height, int tile_size,
+                           float eps2d, float near_plane, float far_plane, float radius_clip, int32_t *radii,
+                           float *means2d, float *depths, float *conics, int32_t *tile_counts, uint64_t *records,
+                           int tile_cap, pm_stream_t stream) {
+  if (!tile_counts || !records || tile_cap <= 0) return PM_ERR_BAD_ARG;
+  return project_fwd_launch(means, quats, scales, viewmats, Ks, N, C, views_per_scene, width, height, tile_size, eps2d,
+                            near_plane, far_plane, radius_clip, radii, means2d, depths, conics, nullptr, tile_counts,
+                            records, tile_cap, stream);
 }
 
 }  // extern "C"

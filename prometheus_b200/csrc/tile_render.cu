@@ -215,8 +215,8 @@ __device__ __forceinline__ void tr_scan_buckets(int *tbl, uint32_t *red) {
 
 // @region tr_prologue
 __global__ void __launch_bounds__(kTrThreads, PM_TR_MINBLOCKS)
-tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__restrict__ offsets,
-                       int64_t n_host, const int32_t *__restrict__ d_n, const float *__restrict__ means2d,
+tile_render_fwd_kernel(const uint64_t *__restrict__ records, int64_t record_stride,
+                       const int32_t *__restrict__ offsets, int64_t n_host, const int32_t *__restrict__ d_n, const float *__restrict__ means2d,
                        const float *__restrict__ conics, const float *__restrict__ opacities,
                        const float *__restrict__ colors, int colors_per_camera, int D,
                        const float *__restrict__ depths, const float *__restrict__ backgrounds, int N,
@@ -251,8 +251,10 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
   //  discarded by the caller, but nothing may be read or written out of bounds)
   const int start = min(offsets[ct], (int)n_isects);
   const int end = (ct == (int)gridDim.x - 1) ? (int)n_isects : min(offsets[ct + 1], (int)n_isects);
-  const int cnt = end - start;
-  const unsigned long long *src = reinterpret_cast<const unsigned long long *>(records) + start;
+  // fixed-capacity tile regions (single-pass binning): the tile's records sit at ct * stride, at most `stride` of them
+  const int cnt = record_stride > 0 ? min(end - start, (int)record_stride) : end - start;
+  const unsigned long long *src =
+      reinterpret_cast<const unsigned long long *>(records) + (record_stride > 0 ? (size_t)ct * (size_t)record_stride : (size_t)start);
   int sorted = 0;
 
   // @region tr_histogram_pass
@@ -512,7 +514,7 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, const int32_t *__re
 
 extern "C" {
 
-static int tile_render_launch(const uint64_t *records, const int32_t *isect_offsets, int64_t n_isects,
+static int tile_render_launch(const uint64_t *records, int64_t record_stride, const int32_t *isect_offsets, int64_t n_isects,
                               const int32_t *d_n, const float *means2d, const float *conics, const float *opacities,
                               const float *colors, int colors_per_camera, int D, const float *depths,
                               const float *backgrounds, int N, int C, int width, int height, int tile_size,
@@ -520,7 +522,8 @@ static int tile_render_launch(const uint64_t *records, const int32_t *isect_offs
                               int32_t *sorted_counts, int32_t *overflow_flag, float *images, float *depth_out,
                               float *masks, const int32_t *tile_order, int views_per_scene, float *transmittance,
                               float *splat_stream, pm_stream_t stream) {
-  if (N < 0 || C < 0 || width <= 0 || height <= 0 || n_isects < 0 || D < 0) return PM_ERR_BAD_ARG;
+  if (N < 0 || C < 0 || width <= 0 || height <= 0 || n_isects < 0 || D < 0 || record_stride < 0) return PM_ERR_BAD_ARG;
+  if (record_stride >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
   if (tile_size != pm::kTile) return PM_ERR_UNSUPPORTED;
   const int CD = D + (depths ? 1 : 0);
   if (CD < 1 || CD > 4) return PM_ERR_UNSUPPORTED;
@@ -550,7 +553,7 @@ static int tile_render_launch(const uint64_t *records, const int32_t *isect_offs
     return PM_ERR_CUDA;
   }
   pm::tile_render_fwd_kernel<<<(unsigned)blocks, pm::kTrThreads, pm::kTrSmemBytes, pm::as_stream(stream)>>>(
-      records, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera, D, depths,
+      records, record_stride, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera, D, depths,
       backgrounds, N, width, height, tw, th, render, alphas, last_ids, flatten_ids, sorted_counts, overflow_flag,
       images, depth_out, masks, tile_order, views_per_scene > 0 ? views_per_scene : C, transmittance, splat_stream);
   return pm::check_launch();
@@ -575,13 +578,13 @@ int pm_tile_render_fwd(const uint64_t *records, const int32_t *isect_offsets, in
                        int tile_size, float *render, float *alphas, int32_t *last_ids,
                        int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
                        const int32_t *tile_order, float *transmittance, float *splat_stream, pm_stream_t stream) {
-  return tile_render_launch(records, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera,
+  return tile_render_launch(records, 0, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera,
                             D, depths, backgrounds, N, C, width, height, tile_size, render, alphas, last_ids,
                             flatten_ids, sorted_counts, overflow_flag, nullptr, nullptr, nullptr, tile_order, 0, transmittance,
                             splat_stream, stream);
 }
 
-int pm_tile_render_packed_fwd(const uint64_t *records, const int32_t *isect_offsets, int64_t n_isects,
+int pm_tile_render_packed_fwd(const uint64_t *records, int64_t record_stride, const int32_t *isect_offsets, int64_t n_isects,
                               const int32_t *d_n, const float *means2d, const float *conics,
                               const float *opacities, const float *colors, int colors_per_camera,
                               const float *depths, const float *backgrounds, int N, int C, int width, int height,
@@ -590,7 +593,7 @@ int pm_tile_render_packed_fwd(const uint64_t *records, const int32_t *isect_offs
                               const int32_t *tile_order, int views_per_scene, float *transmittance,
                               float *splat_stream, pm_stream_t stream) {
   if (!images) return PM_ERR_BAD_ARG;
-  return tile_render_launch(records, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera,
+  return tile_render_launch(records, record_stride, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera,
                             3, depths, backgrounds, N, C, width, height, tile_size, nullptr, nullptr, last_ids,
                             flatten_ids, sorted_counts, overflow_flag, images, depth_out, masks, tile_order, views_per_scene,
                             transmittance, splat_stream, stream);

@@ -38,7 +38,7 @@ def _instrument(name, n_launches):
             e0.record()
             out = fn(*a, **k)
             e1.record()
-            PROFILE.append((name, e0, e1))
+            PROFILE.append((name(*a, **k) if callable(name) else name, e0, e1))
             return out
 
         return wrapper
@@ -162,11 +162,14 @@ def camera_prep(cameras, h: int, w: int):
 
 
 # ------------------------------------------------------------------ stage 2
-@_instrument("project_fwd", lambda means, quats, scales, viewmats, *a, **k: (viewmats.shape[0] + 31) // 32)
+@_instrument(lambda *a, **k: "project_scatter_fwd" if k.get("tile_capacity") else "project_fwd",
+             lambda means, quats, scales, viewmats, *a, **k: (viewmats.shape[0] + 31) // 32)
 def project_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d=0.3, near_plane=0.01,
-                far_plane=1e10, radius_clip=0.0, count_tiles=True, tile_histogram=False, views_per_scene=0):
+                far_plane=1e10, radius_clip=0.0, count_tiles=True, tile_histogram=False, views_per_scene=0,
+                tile_capacity=0):
     """-> radii, means2d, depths, conics, tiles_per_gauss (None unless count_tiles)
-    [, tile_counts [C,th,tw] int32 when tile_histogram: the fused pm_bin_count].
+    [, tile_counts [C,th,tw] int32 when tile_histogram: the fused pm_bin_count]
+    [, records [C*th*tw, tile_capacity] int64 when tile_capacity > 0: single-pass binning, pm_project_scatter_fwd].
     views_per_scene = V > 0 (tile_histogram only): scene batching — means / quats / scales hold C / V blocks of
     N Gaussians and camera c sees block c / V; the pair outputs are [C, N]."""
     L = _lib.load()
@@ -185,6 +188,15 @@ def project_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d=0.3, ne
     if tile_histogram:
         tw, th = tile_grid(width, height)
         counts = torch.zeros(C, th, tw, dtype=torch.int32, device=dev)
+        if tile_capacity:
+            assert not count_tiles
+            records = torch.empty(C * th * tw, int(tile_capacity), dtype=torch.int64, device=dev)
+            _lib.check(L.pm_project_scatter_fwd(_ptr(means), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks), N, C,
+                                                int(views_per_scene), width, height, TILE, eps2d, near_plane, far_plane,
+                                                radius_clip, _ptr(radii), _ptr(means2d), _ptr(depths), _ptr(conics),
+                                                _ptr(counts), _ptr(records), int(tile_capacity), _stream()),
+                       "pm_project_scatter_fwd")
+            return radii, means2d, depths, conics, None, counts, records
         _lib.check(L.pm_project_count_fwd(_ptr(means), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks), N, C,
                                           int(views_per_scene), width, height, TILE, eps2d, near_plane, far_plane, radius_clip, _ptr(radii),
                                           _ptr(means2d), _ptr(depths), _ptr(conics), _ptr(tpg), _ptr(counts), _stream()),
@@ -450,19 +462,21 @@ def composite_bwd(means2d, conics, opacities, colors, depths, backgrounds, offse
 # ------------------------------------------------------------------ module fast path (packed outputs)
 @_instrument("tile_render_fwd", 1)
 def tile_render_packed_fwd(records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height,
-                           d_n=None, tile_order=None, views_per_scene=0, for_backward=False):
+                           d_n=None, tile_order=None, views_per_scene=0, for_backward=False, record_stride=0,
+                           capacity=None):
     """Fused sort-as-you-go forward with the module epilogue: -> images [C,3,H,W] (2 rgb - 1),
     depth_out [C,1,H,W] (expected depth), masks [C,1,H,W], last_ids [C,H,W], flatten_ids (sorted prefix per
     tile), sorted_counts [C,th,tw], overflow flag int32[1], transmittance [C,H,W] and splat_stream [n,12] (both None
     unless for_backward: the backward's exact T_final and the records it replays). `records` may be a speculative
-    capacity with the true count in d_n[0] (see pm_tile_render_packed_fwd)."""
+    capacity with the true count in d_n[0] (see pm_tile_render_packed_fwd). record_stride > 0: `records` is the
+    fixed-capacity tile layout of project_fwd(tile_capacity=...) and `capacity` sizes flatten_ids / the stream."""
     L = _lib.load()
     C, N = means2d.shape[:2]
     n_scenes = C // views_per_scene if views_per_scene else 1
     colors, per_cam, D = _colors_layout(colors, C, N * n_scenes)
     assert D == 3 and depths is not None and opacities.numel() == N * n_scenes
     dev = means2d.device
-    n = records.numel()
+    n = int(capacity) if record_stride else records.numel()
     images = torch.empty(C, 3, height, width, device=dev)
     depth_out = torch.empty(C, 1, height, width, device=dev)
     masks = torch.empty(C, 1, height, width, device=dev)
@@ -472,7 +486,7 @@ def tile_render_packed_fwd(records, offsets, means2d, conics, opacities, colors,
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
     trans = torch.empty(C, height, width, device=dev) if for_backward else None
     stream = torch.empty(n, STREAM_FLOATS, device=dev) if for_backward else None
-    _lib.check(L.pm_tile_render_packed_fwd(_ptr(records), _ptr(offsets), n, _ptr(d_n), _ptr(means2d), _ptr(conics),
+    _lib.check(L.pm_tile_render_packed_fwd(_ptr(records), int(record_stride), _ptr(offsets), n, _ptr(d_n), _ptr(means2d), _ptr(conics),
                                            _ptr(opacities), _ptr(colors), per_cam, _ptr(depths), _ptr(backgrounds), N, C,
                                            width, height, TILE, _ptr(images), _ptr(depth_out), _ptr(masks),
                                            _ptr(last_ids), _ptr(flat), _ptr(sorted_counts), _ptr(flag), _ptr(tile_order),

@@ -55,31 +55,36 @@ def _take_touched(link, v_means2d, v_depths, v_conics):
 class _Project(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
-                radius_clip, fused_count=False, views_per_scene=0, link=None):
+                radius_clip, fused_count=False, views_per_scene=0, link=None, tile_capacity=0):
         """fused_count (module fast path): skip tiles_per_gauss, return the per-tile histogram instead.
+        tile_capacity > 0 (with fused_count): single-pass binning — the intersection records are written as well, into
+        fixed-capacity tile regions, and returned after the histogram.
         link: dict shared with the compositing node of the same render — its backward leaves the map of pairs that
         received a gradient there (`touched`), so that this node's backward reads 1 byte per pair to find its work."""
         ctx.link = link
         out = ops.project_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
                               radius_clip, count_tiles=not fused_count, tile_histogram=fused_count,
-                              views_per_scene=views_per_scene)
+                              views_per_scene=views_per_scene, tile_capacity=tile_capacity if fused_count else 0)
         ctx.views_per_scene = views_per_scene
         radii, means2d, depths, conics, tpg = out[:5]
         aux = out[5] if fused_count else tpg
         ctx.save_for_backward(means, quats, scales, viewmats, Ks, radii, conics)
         ctx.dims = (width, height, eps2d)
+        if fused_count and tile_capacity:
+            ctx.mark_non_differentiable(radii, aux, out[6])
+            return means2d, depths, conics, radii, aux, out[6]
         ctx.mark_non_differentiable(radii, aux)
         return means2d, depths, conics, radii, aux
 
     @staticmethod
-    def backward(ctx, v_means2d, v_depths, v_conics, _v_radii, _v_aux):
+    def backward(ctx, v_means2d, v_depths, v_conics, _v_radii, _v_aux, _v_records=None):
         means, quats, scales, viewmats, Ks, radii, conics = ctx.saved_tensors
         width, height, eps2d = ctx.dims
         touched = _take_touched(ctx.link, v_means2d, v_depths, v_conics)
         v_means, v_quats, v_scales = ops.project_bwd(means, quats, scales, viewmats, Ks, width, height, radii,
                                                      conics, v_means2d, v_depths, v_conics, eps2d,
                                                      views_per_scene=ctx.views_per_scene, touched=touched)
-        return (v_means, v_quats, v_scales) + (None,) * 11
+        return (v_means, v_quats, v_scales) + (None,) * 12
 
 
 class _Composite(torch.autograd.Function):
@@ -165,7 +170,7 @@ class _TileRenderPacked(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means2d, conics, opacities, colors, depths, backgrounds, records, offsets, stats, width, height,
-                grad_sink=None, tile_order=None, views_per_scene=0, link=None):
+                grad_sink=None, tile_order=None, views_per_scene=0, link=None, record_stride=0, capacity=None):
         ctx.link = link
         ctx.views_per_scene = views_per_scene
         ctx.grad_sink = grad_sink  # dict that receives the contiguous [C,N,2] means2d gradient (densification statistics)
@@ -177,7 +182,8 @@ class _TileRenderPacked(torch.autograd.Function):
         need_bwd = any(ctx.needs_input_grad[:6])
         images, depth_out, masks, last_ids, flat, sorted_counts, flag, trans, stream = ops.tile_render_packed_fwd(
             records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height, d_n=stats,
-            tile_order=tile_order, views_per_scene=views_per_scene, for_backward=need_bwd)
+            tile_order=tile_order, views_per_scene=views_per_scene, for_backward=need_bwd, record_stride=record_stride,
+            capacity=capacity)
         ctx.save_for_backward(means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, masks, depth_out,
                               last_ids, stats, sorted_counts, trans, stream)
         ctx.dims = (width, height)
@@ -205,11 +211,12 @@ class _TileRenderPacked(torch.autograd.Function):
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[5] and v_images is not None:
             v_bg = (2.0 * v_images * (trans.unsqueeze(1) if trans is not None else 1.0 - masks)).sum(dim=(2, 3))
-        return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None, None, None, None, None, None
+        return (v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg) + (None,) * 11
 
 
 def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, backgrounds, width, height,
-                        capacity=None, near_plane=0.01, far_plane=1e10, radius_clip=0.0, eps2d=0.3, views_per_scene=0):
+                        capacity=None, near_plane=0.01, far_plane=1e10, radius_clip=0.0, eps2d=0.3, views_per_scene=0,
+                        tile_capacity=None):
     """Fast path behind GaussianRenderer: all C views of one scene, RGB + expected depth, outputs already in the
     module's layout. -> images [C,3,H,W] in [-1,1], depths [C,1,H,W], masks [C,1,H,W], info.
 
@@ -217,6 +224,11 @@ def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, b
     (one host sync between the tile scan and the scatter, as gsplat does). An int: no host sync at all — the
     count stays on the device (info["stats"] = {n_isects, max tile count}); the caller must check
     n_isects <= capacity afterwards and re-render otherwise (GaussianRenderer does).
+
+    `tile_capacity` = T (only together with `capacity`): SINGLE-PASS BINNING — the projection kernel writes every
+    intersection record straight into its tile's region of T records (pm_project_scatter_fwd), so the second pass over
+    the pairs (pm_bin_scatter) disappears. Speculative like `capacity`: the caller must also check
+    info["stats"][1] (the largest tile) <= T afterwards and re-render without it otherwise.
 
     `views_per_scene` = V > 0: SCENE BATCHING — the Gaussian tensors hold C / V scenes back to back (N Gaussians
     each, N % 256 == 0) and camera c renders scene c / V: one launch set for a whole training batch."""
@@ -226,8 +238,10 @@ def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, b
     f32 = lambda t: (t if t.dtype == torch.float32 else t.float()).contiguous()
     means, quats, scales, opacities, colors, viewmats, Ks = map(f32, (means, quats, scales, opacities, colors, viewmats, Ks))
     link = {}  # compositing backward -> projection backward: the map of pairs that received a gradient
-    means2d, depths, conics, radii, counts = _Project.apply(means, quats, scales, viewmats, Ks, width, height, eps2d,
-                                                             near_plane, far_plane, radius_clip, True, views_per_scene, link)
+    single_pass = bool(tile_capacity) and capacity is not None
+    proj = _Project.apply(means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
+                          True, views_per_scene, link, int(tile_capacity) if single_pass else 0)
+    means2d, depths, conics, radii, counts = proj[:5]
     # The reference keeps one [1,N,2] screen-space tensor per rendered view and reads its .grad after backward
     # (`viewspace_points`, gaussians_renderer.py:428-445). Routing autograd through per-view tensors costs a cat and a
     # stack of the whole [C,N,2] array each way; instead the per-view tensors are leaf views of the projected means
@@ -242,13 +256,17 @@ def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, b
     isect_offsets, stats, tile_order = ops.tile_scan(counts, want_order=True)
     if capacity is None:
         capacity = int(stats[0].item())
-    records = ops.bin_scatter(means2d.detach(), radii, depths.detach(), isect_offsets, width, height, int(capacity))
+    if single_pass:
+        records = proj[5]
+    else:
+        records = ops.bin_scatter(means2d.detach(), radii, depths.detach(), isect_offsets, width, height, int(capacity))
     images, depth_out, masks, flag, flatten_ids, sorted_counts = _TileRenderPacked.apply(
         means2d, conics, opacities, colors, depths, backgrounds, records, isect_offsets, stats, width, height, grad_sink,
-        tile_order, views_per_scene, link)
+        tile_order, views_per_scene, link, int(tile_capacity) if single_pass else 0, int(capacity))
     info = {"radii": radii, "means2d": means2d, "means2d_views": means2d_views, "depths": depths, "conics": conics,
             "isect_offsets": isect_offsets, "flatten_ids": flatten_ids, "sorted_counts": sorted_counts,
-            "stats": stats, "overflow_flag": flag, "capacity": int(capacity), "means2d_grad_sink": grad_sink}
+            "stats": stats, "overflow_flag": flag, "capacity": int(capacity), "means2d_grad_sink": grad_sink,
+            "tile_capacity": int(tile_capacity) if single_pass else 0}
     return images, depth_out, masks, info
 
 

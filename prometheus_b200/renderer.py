@@ -85,6 +85,13 @@ class GaussianRenderer(nn.Module):
     # reading the count back between two kernels; the count is checked once all launches are queued
     speculative_capacity = True
     capacity_slack = 1.3
+    # fused path, once a shape's counts are known: SINGLE-PASS BINNING — the projection kernel writes each intersection
+    # record into its tile's fixed-capacity region (largest tile of the previous call x slack), so the second pass over
+    # the pairs (bin_scatter) disappears. Checked like the capacity (largest tile <= region size); used only while the
+    # regions stay within `single_pass_max_ratio` x the compact record array (uniformly loaded tiles)
+    single_pass_binning = True
+    tile_capacity_slack = 1.25
+    single_pass_max_ratio = 4.0
     # False: forward() returns only after its checks passed (like the reference, which ends with
     # torch.cuda.synchronize(), :510). True: forward() never blocks; call validate() before trusting the images
     # (DecodeRenderPipeline does, when it hands the host copies out).
@@ -102,6 +109,7 @@ class GaussianRenderer(nn.Module):
         self.radii: List[torch.Tensor] = []
         self.viewspace_points: List[torch.Tensor] = []
         self._cap_hint = {}
+        self._tile_cap_hint = {}
         self._pending = []
         self._static_stats = None
         self._stats_ring = None
@@ -139,14 +147,26 @@ class GaussianRenderer(nn.Module):
         key = (xyz.shape[0], viewmats.shape[0], int(h), int(w))
         cap = self._cap_hint.get(key) if self.speculative_capacity else None
         images, depths, masks, info = render_views_packed(xyz, rot, sc, opac, feat, viewmats, Ks, bgs, int(w), int(h),
-                                                          capacity=cap)
+                                                          capacity=cap, tile_capacity=self._tile_cap_for(key, cap, h, w))
         return images, depths, masks, info, key
 
-    def _update_hint(self, key, n_isects: int) -> None:
+    def _tile_cap_for(self, key, cap, h, w):
+        """Region size for single-pass binning, or None (two passes): needs both hints of the shape."""
+        tcap = self._tile_cap_hint.get(key) if (self.single_pass_binning and cap is not None) else None
+        if tcap is None:
+            return None
+        tiles = key[1] * ((int(h) + 15) // 16) * ((int(w) + 15) // 16)
+        if tiles * tcap > self.single_pass_max_ratio * cap or tcap >= 2 ** 31:
+            return None
+        return tcap
+
+    def _update_hint(self, key, n_isects: int, max_count: int = 0) -> None:
         """Capacity for the next call of this shape: the latest count with slack, but never much below the
         previous hint — along a camera trajectory the count varies from chunk to chunk and must not oscillate."""
         want = int(n_isects * self.capacity_slack) + 4096
         self._cap_hint[key] = max(want, int(self._cap_hint.get(key, 0) * 0.97))
+        want_t = int(max_count * self.tile_capacity_slack) + 64
+        self._tile_cap_hint[key] = max(want_t, int(self._tile_cap_hint.get(key, 0) * 0.97))
 
     def _check(self, job) -> bool:
         """True if the fused render of `job` is valid; updates the capacity hint."""
@@ -154,9 +174,11 @@ class GaussianRenderer(nn.Module):
         if job["event"] is not None:
             job["event"].synchronize()  # fires when the render kernel is done; later work (a backward pass) keeps running
         n_isects, max_count, overflow = (int(v) for v in job["stats_host"])
-        self._update_hint(key, n_isects)
+        self._update_hint(key, n_isects, max_count)
         if n_isects > job["capacity"]:
             return False
+        if job.get("tile_capacity") and max_count > job["tile_capacity"]:
+            return False  # single-pass binning dropped records of an over-full tile
         # a depth sub-bucket larger than the group capacity can only exist if some tile is larger than it
         return max_count <= FUSED_GROUP_CAP or overflow == 0
 
@@ -199,7 +221,8 @@ class GaussianRenderer(nn.Module):
         stats_host[2:].copy_(info["overflow_flag"], non_blocking=True)
         if ev is not None:
             ev.record()
-        return dict(args=args, out=out, info=info, key=key, stats_host=stats_host, event=ev, capacity=info["capacity"])
+        return dict(args=args, out=out, info=info, key=key, stats_host=stats_host, event=ev, capacity=info["capacity"],
+                    tile_capacity=info.get("tile_capacity", 0))
 
     def _forward_batched(self, viewmats, Ks, gaussians, scaling_modifier, bg_color, h, w):
         """All B scenes of a training batch in ONE launch set (scene batching, `views_per_scene`): the B x N cameras
@@ -214,10 +237,12 @@ class GaussianRenderer(nn.Module):
                 self._backgrounds(bg_color, B * N, xyz.device))
         key = (G, B * N, int(h), int(w), B)
         cap = self._cap_hint.get(key) if self.speculative_capacity else None
-        im, de, ma, info = render_views_packed(*args, int(w), int(h), capacity=cap, views_per_scene=N)
+        im, de, ma, info = render_views_packed(*args, int(w), int(h), capacity=cap, views_per_scene=N,
+                                               tile_capacity=self._tile_cap_for(key, cap, h, w))
         job = self._job_for(args, (im, de, ma), info, key)
         if self.defer_checks:
-            self._pending.append(dict(key=key, capacity=job["capacity"], stats_host=job["stats_host"], event=job["event"]))
+            self._pending.append(dict(key=key, capacity=job["capacity"], stats_host=job["stats_host"], event=job["event"],
+                                      tile_capacity=job["tile_capacity"]))
         elif not self._check(job):
             return None
         self._stat_sources = [(info["radii"], info.get("means2d_grad_sink"), info["means2d_views"])]
@@ -270,19 +295,21 @@ class GaussianRenderer(nn.Module):
                     jobs.append(dict(args=args, out=(im, de, ma), info=info, key=None))
         if self.fused and self.defer_checks:
             # only what the check needs: holding the jobs' tensors would pin every step's buffers
-            self._pending.extend(dict(key=j["key"], capacity=j["capacity"], stats_host=j["stats_host"], event=j["event"])
-                                 for j in jobs)
+            self._pending.extend(dict(key=j["key"], capacity=j["capacity"], stats_host=j["stats_host"], event=j["event"],
+                                      tile_capacity=j["tile_capacity"]) for j in jobs)
         elif self.fused:
             # every launch is queued; now look at the counts (the GPU is still busy rendering)
             for job in jobs:
                 if not self._check(job):
                     a = job["args"]
-                    n_isects = int(job["stats_host"][0])
-                    if n_isects > job["capacity"]:  # speculative buffers were too small: exact size this time
+                    n_isects, max_count = int(job["stats_host"][0]), int(job["stats_host"][1])
+                    if n_isects > job["capacity"] or (job["tile_capacity"] and max_count > job["tile_capacity"]):
+                        # speculative buffers were too small: exact sizes (two binning passes) this time
                         self._cap_hint.pop(job["key"], None)
+                        self._tile_cap_hint.pop(job["key"], None)
                         im, de, ma, info, _ = self._render_chunk_fused(a, h, w)
                         ok = int(info["stats"][1].item()) <= FUSED_GROUP_CAP or int(info["overflow_flag"].item()) == 0
-                        self._update_hint(job["key"], n_isects)
+                        self._update_hint(job["key"], n_isects, max_count)
                     else:
                         ok = False
                     if not ok:  # a depth sub-bucket beyond the fused kernel's group capacity: separate stages
