@@ -139,7 +139,12 @@ project_fwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
     S[3] = S[1]; S[6] = S[2]; S[7] = S[5];
   }
 
-  for (int ci = 0; ci < n_cams; ++ci) {
+  // MODE 2 walks the cameras in batches of kWinCams: one window round (count, reserve, place) per batch
+  const int n_tiles = tile_width * tile_height;
+  for (int c0 = 0; c0 < n_cams; c0 += (MODE == 2 ? kWinCams : kProjCamChunk)) {
+  const int c1 = MODE == 2 ? min(n_cams, c0 + kWinCams) : n_cams;
+  if (MODE == 2) scatter_batch_begin(s_sct[0], c1 - c0);
+  for (int ci = c0; ci < c1; ++ci) {
     const ProjCam &c = s_cam[ci].c;
     const float *R = c.R;
     const size_t f = (size_t)(cam_first + ci) * N + (in_range ? g : 0);
@@ -212,11 +217,16 @@ project_fwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
     if (MODE == 1)
       cta_tile_count(s_cnt[0], x0, x1, y0, y1, tile_counts + (size_t)(cam_first + ci) * tile_width * tile_height, tile_width);
     if (MODE == 2) {
-      const size_t tile0 = (size_t)(cam_first + ci) * tile_width * tile_height;
-      cta_tile_count_scatter(s_sct[0], x0, x1, y0, y1, tile_counts + tile0, tile_width,
-                             ((uint64_t)(uint32_t)f << 32) | (uint64_t)__float_as_uint(depth), records + tile0 * (size_t)tile_cap,
-                             tile_cap);
+      const size_t tile0 = (size_t)(cam_first + ci) * n_tiles;
+      scatter_batch_add(s_sct[0], ci - c0, x0, x1, y0, y1, __float_as_uint(depth), (uint32_t)f, tile_counts + tile0,
+                        tile_width, records + tile0 * (size_t)tile_cap, tile_cap);
     }
+  }
+  if (MODE == 2) {
+    const size_t tile0 = (size_t)(cam_first + c0) * n_tiles;
+    scatter_batch_end(s_sct[0], c1 - c0, tile_counts + tile0, tile_width, n_tiles, records + tile0 * (size_t)tile_cap, tile_cap,
+                      (uint32_t)((size_t)(cam_first + c0) * N + (in_range ? g : 0)), (uint32_t)N);
+  }
   }
 }
 
@@ -289,6 +299,10 @@ int pm_project_scatter_fwd(const float *means, const float *quats, const float *
                            float *means2d, float *depths, float *conics, int32_t *tile_counts, uint64_t *records,
                            int tile_cap, pm_stream_t stream) {
   if (!tile_counts || !records || tile_cap <= 0) return PM_ERR_BAD_ARG;
+  {  // record indices inside one camera's regions are formed in 32 bits
+    const int64_t tw = (width + pm::kTile - 1) / pm::kTile, th = (height + pm::kTile - 1) / pm::kTile;
+    if (width > 0 && height > 0 && tw * th * (int64_t)tile_cap >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
+  }
   return project_fwd_launch(means, quats, scales, viewmats, Ks, N, C, views_per_scene, width, height, tile_size, eps2d,
                             near_plane, far_plane, radius_clip, radii, means2d, depths, conics, nullptr, tile_counts,
                             records, tile_cap, stream);

@@ -883,6 +883,29 @@ def test_single_pass_binning_same_bits_and_overflow_recovery():
     torch.testing.assert_close(grads[0], grads[1], rtol=1e-4, atol=1e-7)
 
 
+def test_single_pass_binning_fallback_paths():
+    """Single-pass binning outside its comfort zone: unstructured Gaussians on a 66 x 66 tile grid (a CTA's bounding
+    box exceeds the shared-memory window: records go to global memory one atomic each) with a few splats so large
+    that their tile AABB does not fit the packed form (> 63 tiles on an axis). Same bits as two passes."""
+    from prometheus_b200.rasterization import render_views_packed
+
+    s = random_blobs(n=4096, C=2, W=1056, H=1056, seed=11)
+    s["scales"][:6] = 4.0   # a handful of splats that cover the whole image
+    s["Ks"][:, 0, 0] = s["Ks"][:, 1, 1] = 900.0
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    args = [dev(s[k]) for k in ("means", "quats", "scales", "opacities", "colors", "viewmats", "Ks")]
+    bg = torch.ones(2, 3, device=DEV)
+    with torch.no_grad():
+        im0, de0, ma0, info0 = render_views_packed(*args, bg, 1056, 1056)
+        n_isects, max_count = (int(v) for v in info0["stats"].tolist())
+        assert max_count > 6 and int(info0["overflow_flag"].item()) == 0
+        im1, de1, ma1, info1 = render_views_packed(*args, bg, 1056, 1056, capacity=n_isects + 100, tile_capacity=max_count + 3)
+        assert info1["tile_capacity"] == max_count + 3 and info1["stats"].tolist() == [n_isects, max_count]
+        assert torch.equal(info0["isect_offsets"], info1["isect_offsets"])
+    for a, b in ((im0, im1), (de0, de1), (ma0, ma1)):
+        assert torch.equal(a, b)
+
+
 def test_deferred_checks_and_pipeline_recover_from_a_bad_hint():
     """defer_checks: forward() never blocks and validate() reports the bad hint; DecodeRenderPipeline re-renders
     the affected scene before handing out the host copies."""
