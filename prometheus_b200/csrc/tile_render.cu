@@ -46,6 +46,10 @@ constexpr int kTrBuckets = 1 << kTrBucketBits;  // depth-ordered buckets per lev
 #define PM_TR_MLP 8  // record loads in flight per thread in the passes over a tile's segment
 #endif
 constexpr int kTrMlp = PM_TR_MLP;
+#ifndef PM_TR_MLP_K
+#define PM_TR_MLP_K 8  // key-only (32-bit) loads in flight per thread in the histogram / range passes (16: 1.14, 24: 1.20 ms — L1 thrashes)
+#endif
+constexpr int kTrMlpK = PM_TR_MLP_K;
 constexpr int kTrRankMax = 128;  // longest bucket run ordered by all-pairs ranking (longer: radix sort of the group)
 
 // depth sub-bucket of a key: monotone in the key for any kmin / shift
@@ -255,6 +259,7 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, int64_t record_stri
   const int cnt = record_stride > 0 ? min(end - start, (int)record_stride) : end - start;
   const unsigned long long *src =
       reinterpret_cast<const unsigned long long *>(records) + (record_stride > 0 ? (size_t)ct * (size_t)record_stride : (size_t)start);
+  const uint32_t *keys = reinterpret_cast<const uint32_t *>(src);  // record i: keys[2 i] = depth bits, keys[2 i + 1] = flatten id
   int sorted = 0;
 
   // @region tr_histogram_pass
@@ -264,15 +269,15 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, int64_t record_stri
     for (int i = tid; i <= kTrBuckets; i += kTrThreads) tbl[i] = 0;
     if (tid == 0) PM_STAT_ADD(6, 1);
     __syncthreads();
-    for (int i0 = 0; i0 < cnt; i0 += kTrMlp * kTrThreads) {
-      uint32_t k[kTrMlp];
+    for (int i0 = 0; i0 < cnt; i0 += kTrMlpK * kTrThreads) {
+      uint32_t k[kTrMlpK];
 #pragma unroll
-      for (int u = 0; u < kTrMlp; ++u) {
+      for (int u = 0; u < kTrMlpK; ++u) {
         const int i = i0 + u * kTrThreads + tid;
-        k[u] = i < cnt ? (uint32_t)__ldg(src + i) : 0u;
+        k[u] = i < cnt ? __ldg(keys + 2 * (size_t)i) : 0u;
       }
 #pragma unroll
-      for (int u = 0; u < kTrMlp; ++u)
+      for (int u = 0; u < kTrMlpK; ++u)
         if (i0 + u * kTrThreads + tid < cnt && k[u] >= flo && k[u] <= fhi)
           atomicAdd(&tbl[tr_bucket(k[u], kmin_c, shift_c) + 1], 1);
     }
@@ -329,9 +334,9 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, int64_t record_stri
         ids[k] = slot < m ? (int32_t)sh.gbuf[slot].y : -1;
       }
     } else {
+      uint32_t *sorted_ids = reinterpret_cast<uint32_t *>(sh.warp_hist);
       // rank every record inside its bucket's run by (depth bits, flatten id): runs are ~cnt/256 long,
       // a warp's 32 consecutive records share one or two runs (broadcast reads), no barrier needed
-      uint32_t *sorted_ids = reinterpret_cast<uint32_t *>(sh.warp_hist);
 #pragma unroll
       for (int k = 0; k < kTrItems; ++k) {
         const int e = k * kTrThreads + tid;
@@ -461,15 +466,15 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, int64_t record_stri
       if (tid == 0) { sh.kmin = 0xffffffffu; sh.kmax = 0u; PM_STAT_ADD(6, 1); PM_STAT_ADD(8, 1); }
       __syncthreads();
       uint32_t lo2 = 0xffffffffu, hi2 = 0u;
-      for (int i0 = 0; i0 < cnt; i0 += kTrMlp * kTrThreads) {
-        uint32_t k[kTrMlp];
+      for (int i0 = 0; i0 < cnt; i0 += kTrMlpK * kTrThreads) {
+        uint32_t k[kTrMlpK];
 #pragma unroll
-        for (int u = 0; u < kTrMlp; ++u) {
+        for (int u = 0; u < kTrMlpK; ++u) {
           const int i = i0 + u * kTrThreads + tid;
-          k[u] = i < cnt ? (uint32_t)__ldg(src + i) : 0u;
+          k[u] = i < cnt ? __ldg(keys + 2 * (size_t)i) : 0u;
         }
 #pragma unroll
-        for (int u = 0; u < kTrMlp; ++u)
+        for (int u = 0; u < kTrMlpK; ++u)
           if (i0 + u * kTrThreads + tid < cnt && k[u] >= flo && k[u] <= fhi) { lo2 = min(lo2, k[u]); hi2 = max(hi2, k[u]); }
       }
       lo2 = __reduce_min_sync(0xffffffffu, lo2);
