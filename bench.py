@@ -985,7 +985,7 @@ def run_c4(args, rank, world, dev, steps, warmup):
         "e2e": {"value": pixels / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": round(e2e_ms, 3),
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "DecodeRenderPipeline.run_batch (pinned host batch in %d-scene slices, 3 streams); bytes are per rank; "
-                       "wall clock between barriers, max over ranks" % rend.scene_chunk}}
+                       "wall clock between barriers, max over ranks" % max(1, min(rend.scene_chunk, -(-n_local // 4)))}}
 
 
 def parity_check(outs, conv, ops, params_d, cams_in_d, cams_out_d, S, dev, workload):

@@ -127,12 +127,14 @@ class DecodeRenderPipeline:
 
     def run_batch(self, inputs_h: Tuple[torch.Tensor, ...], out_h: Sequence[torch.Tensor], chunk: Optional[int] = None) -> None:
         """A large host-resident batch of scenes (config C4: 64 scenes) as a stream of `chunk`-scene slices (default:
-        the renderer's scene_chunk): the host->device copy of slice k+1 and the device->host copy of slice k-1 overlap
+        the renderer's scene_chunk, or a quarter of the batch if that is smaller): the host->device copy of slice k+1 and the device->host copy of slice k-1 overlap
         the render of slice k, instead of the whole batch being copied, then rendered, then copied back.
         inputs_h = (params [B,N,14,h,w], cameras_in [B,N,18], cameras_out [B,M,18]) pinned; out_h = pinned
         (images [B,M,3,H,W], depths [B,M,1,H,W], masks [B,M,1,H,W]). Call flush() before reading out_h."""
         B = inputs_h[0].shape[0]
-        c = int(chunk or self.rend.scene_chunk)
+        # default slice: the renderer's scene_chunk, but at least four slices per batch — with one or two slices the
+        # copies cannot overlap the render (8 scenes per rank at N = 8 went host->device, render, device->host in series)
+        c = int(chunk or max(1, min(self.rend.scene_chunk, -(-B // 4))))
         slices = [slice(b, min(B, b + c)) for b in range(0, B, c)]
         self.prefetch(*(t[slices[0]] for t in inputs_h))
         for i, sl in enumerate(slices):
