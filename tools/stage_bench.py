@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--bwd", action="store_true")
     ap.add_argument("--unfused", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--two-pass", action="store_true", help="disable single-pass binning (project_count + bin_scatter)")
     ap.add_argument("--tag", default=os.environ.get("PM_GS_LIB", "default"))
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -29,6 +30,7 @@ def main():
     conv = GaussianConverter("mvsplat", z_near=scenes.Z_NEAR, z_far=scenes.Z_FAR, s_min=scenes.S_MIN, s_max=scenes.S_MAX).to(dev)
     rend = GaussianRenderer(background=[1, 1, 1]).to(dev)
     rend.fused = not a.unfused
+    rend.single_pass_binning = not a.two_pass
     params, cin, cout = sc.params.to(dev), sc.cameras_in.to(dev), sc.cameras_out.to(dev)
     target = torch.rand(*cout.shape[:2], 3, S, S, device=dev) * 2 - 1
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
