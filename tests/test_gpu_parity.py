@@ -1349,6 +1349,36 @@ def test_scene_batched_forward_backward_equals_per_scene():
     assert grad_close(a[5].cpu().numpy(), b[5].cpu().numpy(), max_share=ORDER_SHARE, what="scene batched means2d")
 
 
+def test_scene_batched_single_pass_binning_same_bits():
+    """Scene batching + single-pass binning (second call of the shape): the records of scene b's cameras carry flatten
+    ids of scene b's Gaussians; images bit for bit as the first (two-pass) call and as the unbatched renderer, also
+    when the scene-batched region size is too small (the batch is then rendered scene by scene)."""
+    from prometheus_b200 import GaussianConverter, GaussianRenderer, ops, scenes
+
+    sc = scenes.make_scene("C1", seed=63, views_in=4, size_in=32, views_out=3, size_out=56, scenes=3)
+    conv = GaussianConverter("mvsplat", z_near=0.01, z_far=100.0, s_min=0.001, s_max=1.0).to(DEV)
+    cams = sc.cameras_out.to(DEV)
+    with torch.no_grad():
+        g = conv(sc.params.to(DEV), sc.cameras_in.to(DEV))
+        ref = GaussianRenderer().to(DEV)
+        ref.scene_batch = False
+        ref.single_pass_binning = False
+        want = ref(cams, g, h=56, w=56)[:3]
+        rend = GaussianRenderer().to(DEV)
+        first = rend(cams, g, h=56, w=56)[:3]
+        key = [k for k in rend._tile_cap_hint if len(k) == 5][0]
+        prof, ops.PROFILE = ops.PROFILE, []
+        second = rend(cams, g, h=56, w=56)[:3]
+        names = [n for n, _, _ in ops.PROFILE]
+        ops.PROFILE = prof
+        assert names.count("project_scatter_fwd") == 1 and "bin_scatter" not in names   # one launch set, single pass
+        rend._tile_cap_hint[key] = 8
+        third = rend(cams, g, h=56, w=56)[:3]
+    for got in (first, second, third):
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+
+
 def test_scene_batched_bad_hint_falls_back_to_per_scene():
     """A too-small speculative capacity on the scene-batched launch set is caught and the batch re-rendered scene by
     scene: same images as the unbatched renderer."""
