@@ -33,6 +33,8 @@
 extern "C" {
 #endif
 
+/* 2: exact final transmittance kept for the backward; 3: splat stream (TMA-replayed backward), touched-pair map;
+ * 4: pm_project_scatter_fwd (single-pass binning), record_stride of pm_tile_render_packed_fwd */
 #define PM_ABI_VERSION 4
 
 #if defined(__GNUC__)
