@@ -14,6 +14,8 @@ strict=True in paper/stage1_eval.py:167), return tuples and side attributes
 """
 from __future__ import annotations
 
+import os
+
 from typing import List, Optional, Sequence, Tuple, Union
 
 import torch
@@ -89,7 +91,7 @@ class GaussianRenderer(nn.Module):
     # record into its tile's fixed-capacity region (largest tile of the previous call x slack), so the second pass over
     # the pairs (bin_scatter) disappears. Checked like the capacity (largest tile <= region size); used only while the
     # regions stay within `single_pass_max_ratio` x the compact record array (uniformly loaded tiles)
-    single_pass_binning = True
+    single_pass_binning = os.environ.get("PM_SINGLE_PASS_BINNING", "1") != "0"  # (env: developer knob for A/B runs)
     tile_capacity_slack = 1.25
     single_pass_max_ratio = 4.0
     # False: forward() returns only after its checks passed (like the reference, which ends with
