@@ -41,7 +41,8 @@ def main():
            "_warp_instructions": {}}
     for arg in sys.argv[1:]:
         rep, _, suffix = arg.partition("::")
-        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        # base units: the raw page otherwise scales every column to its own unit (Mbyte here, Gbyte there)
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--print-units", "base"], capture_output=True, text=True).stdout
         rows = list(csv.reader(txt.splitlines()))
         hdr, data = rows[0], rows[2:]
         idx = {h: i for i, h in enumerate(hdr)}
