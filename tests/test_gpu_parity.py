@@ -906,6 +906,24 @@ def test_single_pass_binning_fallback_paths():
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("C", [11, 35])
+def test_single_pass_binning_many_cameras(C):
+    """Camera counts that do not fill the 8-camera window batches (11 = 8 + 3) or the 32-camera launches (35 = 32 + 3)."""
+    from prometheus_b200.rasterization import render_views_packed
+
+    s = random_blobs(n=3000, C=C, W=96, H=64, seed=5)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    args = [dev(s[k]) for k in ("means", "quats", "scales", "opacities", "colors", "viewmats", "Ks")]
+    bg = torch.rand(C, 3, device=DEV)
+    with torch.no_grad():
+        im0, de0, ma0, info0 = render_views_packed(*args, bg, 96, 64)
+        n_isects, max_count = (int(v) for v in info0["stats"].tolist())
+        im1, de1, ma1, info1 = render_views_packed(*args, bg, 96, 64, capacity=n_isects + 7, tile_capacity=max_count)
+        assert info1["stats"].tolist() == [n_isects, max_count] and torch.equal(info0["isect_offsets"], info1["isect_offsets"])
+    for a, b in ((im0, im1), (de0, de1), (ma0, ma1)):
+        assert torch.equal(a, b)
+
+
 def test_deferred_checks_and_pipeline_recover_from_a_bad_hint():
     """defer_checks: forward() never blocks and validate() reports the bad hint; DecodeRenderPipeline re-renders
     the affected scene before handing out the host copies."""
