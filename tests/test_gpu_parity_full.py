@@ -127,6 +127,21 @@ def check_fast_path(name, gauss, vm, K, S, bg, st, r_op, a_op):
     assert torch.equal(images, (2.0 * r[..., :3] - 1.0).permute(0, 3, 1, 2))
     assert torch.equal(masks[:, 0], a.clamp(0, 1))
     assert torch.equal(depth_out[:, 0], r[..., 3] / a.clamp(min=1e-10))
+    # single-pass binning (what the module runs from the second call of a shape on): the projection kernel writes the
+    # records into fixed-capacity tile regions — same counts, same images, same sorted prefixes, at size
+    with torch.no_grad():
+        tcap = (int(max_count * 1.25) + 65) & ~1
+        im1, de1, ma1, info1 = render_views_packed(*[gauss[k] for k in KEYS], vm, K, dev(bg), S, S,
+                                                   capacity=int(n * 1.3) + 4096, tile_capacity=tcap)
+    assert info1["tile_capacity"] == tcap and info1["stats"].tolist() == [n, max_count]
+    assert torch.equal(info1["isect_offsets"], offsets) and int(info1["overflow_flag"].item()) == 0
+    assert torch.equal(im1, images) and torch.equal(de1, depth_out) and torch.equal(ma1, masks)
+    # (the group boundaries follow a strided SAMPLE of the records in their scatter order, so the length of a tile's
+    # sorted prefix may differ between the two layouts; what is sorted is the oracle's order either way)
+    sc1 = info1["sorted_counts"].cpu().numpy().reshape(-1)
+    assert (sc1 <= cnt).all() and np.all((tl - off + 1)[has] <= sc1[has])
+    idx1 = np.repeat(off, sc1) + (np.arange(sc1.sum()) - np.repeat(np.cumsum(sc1) - sc1, sc1))
+    assert np.array_equal(info1["flatten_ids"].cpu().numpy()[idx1], st["flatten_ids"][idx1])
     return trans
 
 
