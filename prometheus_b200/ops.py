@@ -505,11 +505,15 @@ def composite_bwd_packed(means2d, conics, opacities, colors, depths, backgrounds
     if stream is None:
         stream = splat_stream_build(means2d, conics, opacities, colors, depths, flatten_ids, d_n, views_per_scene)
     v_images, v_depth_out, v_masks = (_opt(t, torch.float32, "grad") for t in (v_images, v_depth_out, v_masks))
-    v_means2d = torch.zeros_like(means2d)
-    v_conics = torch.zeros_like(conics)
-    v_colors = torch.zeros_like(colors)
-    v_opac = torch.zeros_like(opacities)
-    v_depths = torch.zeros_like(depths)
+    # the five accumulation targets as views of ONE zero-filled allocation (one fill kernel instead of five)
+    shapes = [means2d.shape, conics.shape, colors.shape, opacities.shape, depths.shape]
+    sizes = [(int(torch.Size(sh).numel()) + 3) & ~3 for sh in shapes]  # 16-byte aligned views
+    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=means2d.device)
+    views, o = [], 0
+    for sh, n in zip(shapes, sizes):
+        views.append(flat[o:o + int(torch.Size(sh).numel())].view(sh))
+        o += n
+    v_means2d, v_conics, v_colors, v_opac, v_depths = views
     _lib.check(L.pm_composite_bwd_packed(_ptr(stream), per_cam, _ptr(backgrounds), _ptr(offsets), stream.shape[0], _ptr(d_n),
                                          N, C, width, height, TILE, _ptr(masks), _ptr(depth_out), _ptr(last_ids),
                                          _ptr(transmittance), _ptr(v_images), _ptr(v_depth_out), _ptr(v_masks),

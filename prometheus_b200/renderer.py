@@ -282,13 +282,19 @@ class GaussianRenderer(nn.Module):
                 return tuple(torch.cat([o[k] for o in outs], 0) for k in range(3)) + (None, None)
             self.radii, self.viewspace_points = [], []  # a check failed: scene by scene below (exact sizes, fallbacks)
         jobs = []
+        G = xyz.shape[1]
         for i in range(B):
             bgs = self._backgrounds(bg_color, N, device)
-            sc = scales[i]
+            if B == 1:
+                # views, not selects: the backward of t[i] materialises a zero tensor and copies the gradient into it
+                # (two kernels per Gaussian tensor and step), the backward of a reshape is free
+                gs_i = (xyz.reshape(G, 3), rotations.reshape(G, 4), scales.reshape(G, 3), opacity.reshape(G),
+                        features.reshape(G, -1, 3)[:, 0] if features.shape[2] != 1 else features.reshape(G, 3))
+            else:
+                gs_i = (xyz[i], rotations[i], scales[i], opacity[i].squeeze(-1), features[i][:, 0])
             for c0 in range(0, N, self.view_chunk):
                 c1 = min(N, c0 + self.view_chunk)
-                args = (xyz[i], rotations[i], sc, opacity[i].squeeze(-1), features[i][:, 0], viewmats[i, c0:c1],
-                        Ks[i, c0:c1], bgs[c0:c1])
+                args = gs_i + (viewmats[i, c0:c1], Ks[i, c0:c1], bgs[c0:c1])
                 if self.fused:
                     im, de, ma, info, key = self._render_chunk_fused(args, h, w)
                     jobs.append(self._job_for(args, (im, de, ma), info, key))
