@@ -18,6 +18,7 @@ from . import ops
 class _LossTerms(torch.autograd.Function):
     @staticmethod
     def forward(ctx, images, depths, masks, target):
+        ctx.set_materialize_grads(False)  # undefined cotangents arrive as None, not as zero tensors the size of the outputs
         shape = images.shape
         im, tg = images.reshape(-1, 3, *shape[-2:]), target.reshape(-1, 3, *shape[-2:])
         de, ma = depths.reshape(-1, 1, *shape[-2:]), masks.reshape(-1, 1, *shape[-2:])

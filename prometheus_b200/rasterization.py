@@ -61,6 +61,7 @@ class _Project(torch.autograd.Function):
         fixed-capacity tile regions, and returned after the histogram.
         link: dict shared with the compositing node of the same render — its backward leaves the map of pairs that
         received a gradient there (`touched`), so that this node's backward reads 1 byte per pair to find its work."""
+        ctx.set_materialize_grads(False)  # undefined cotangents arrive as None, not as zero tensors the size of the outputs
         ctx.link = link
         out = ops.project_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
                               radius_clip, count_tiles=not fused_count, tile_histogram=fused_count,
@@ -91,6 +92,7 @@ class _Composite(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width,
                 height, d_n, link=None):
+        ctx.set_materialize_grads(False)  # undefined cotangents arrive as None, not as zero tensors the size of the outputs
         ctx.link = link
         means2d, conics = means2d.contiguous(), conics.contiguous()
         opacities = opacities.contiguous()
@@ -130,6 +132,7 @@ class _TileRender(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means2d, conics, opacities, colors, depths, backgrounds, records, offsets, width, height, link=None):
+        ctx.set_materialize_grads(False)  # undefined cotangents arrive as None, not as zero tensors the size of the outputs
         ctx.link = link
         means2d, conics = means2d.contiguous(), conics.contiguous()
         opacities = opacities.contiguous()
@@ -171,6 +174,7 @@ class _TileRenderPacked(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means2d, conics, opacities, colors, depths, backgrounds, records, offsets, stats, width, height,
                 grad_sink=None, tile_order=None, views_per_scene=0, link=None, record_stride=0, capacity=None):
+        ctx.set_materialize_grads(False)  # undefined cotangents arrive as None, not as zero tensors the size of the outputs
         ctx.link = link
         ctx.views_per_scene = views_per_scene
         ctx.grad_sink = grad_sink  # dict that receives the contiguous [C,N,2] means2d gradient (densification statistics)

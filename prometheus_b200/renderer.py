@@ -28,6 +28,7 @@ from .rasterization import FUSED_GROUP_CAP, _rasterize_core, rasterization, rend
 class _Unproject(torch.autograd.Function):
     @staticmethod
     def forward(ctx, params, cameras, muls, mode, z_near, z_far, s_min, s_max):
+        ctx.set_materialize_grads(False)  # undefined cotangents arrive as None, not as zero tensors the size of the outputs
         # fp16 / bf16 maps (an autocast decoder) are read in their storage type; the reference widens them to fp32
         # by `* self.muls` (:219), and so does the kernel, in registers
         params = params.contiguous() if params.dtype in ops.PARAM_DTYPES else params.float().contiguous()
