@@ -924,6 +924,34 @@ def test_single_pass_binning_many_cameras(C):
         assert torch.equal(a, b)
 
 
+def test_backward_with_undefined_cotangents():
+    """The autograd nodes do not materialise undefined cotangents (they used to arrive as zero tensors the size of the
+    outputs — hundreds of MB per step for the non-differentiable ones): a loss on the images alone hands the compositing
+    backward None for depths / masks; same gradient as with explicit zero-weight terms."""
+    from prometheus_b200 import GaussianRenderer
+
+    sc, conv = _module_scene()
+    cams = sc.cameras_out.to(DEV)
+    grads = []
+    for explicit in (False, True):
+        rend = GaussianRenderer().to(DEV)
+        p = sc.params.to(DEV).clone().requires_grad_(True)
+        im, de, ma, _, _ = rend(cams, conv(p, sc.cameras_in.to(DEV)), h=80, w=80)
+        loss = im.square().mean()
+        if explicit:
+            loss = loss + 0.0 * de.sum() + 0.0 * ma.sum()
+        loss.backward()
+        assert torch.isfinite(p.grad).all() and float(p.grad.abs().sum()) > 0
+        grads.append(p.grad.clone())
+    torch.testing.assert_close(grads[0], grads[1], rtol=1e-4, atol=1e-7)
+    # and the other way round: only the depth output
+    rend = GaussianRenderer().to(DEV)
+    p = sc.params.to(DEV).clone().requires_grad_(True)
+    im, de, ma, _, _ = rend(cams, conv(p, sc.cameras_in.to(DEV)), h=80, w=80)
+    de.mean().backward()
+    assert torch.isfinite(p.grad).all() and float(p.grad.abs().sum()) > 0
+
+
 def test_deferred_checks_and_pipeline_recover_from_a_bad_hint():
     """defer_checks: forward() never blocks and validate() reports the bad hint; DecodeRenderPipeline re-renders
     the affected scene before handing out the host copies."""
