@@ -357,6 +357,8 @@ def main():
     total_ms, launches, prof = timed(lambda: step_fwd(params_d, cams_in_d, cams_out_d), args.steps, args.warmup, profile=True)
     assert rend.validate(), "a deferred capacity / overflow check failed inside the timed region"
     rend.defer_checks = False
+    # records the fast path binned in the last timed step, all scenes (usable tiles: a subset of gsplat's intersections)
+    binned = rend.last_stats[0] if rend.last_stats else None
     clocks = sampler.stop()
     ms_per_step = total_ms / args.steps
     value = world * pixels / (ms_per_step * 1e-3) / 1e6
@@ -386,14 +388,19 @@ def main():
         nxt = torch.cat([off[1:], torch.tensor([I], device=dev)])
         nonempty = nxt > off
         I_need = int(((tiles_last - off + 1).clamp(min=0) * nonempty).sum().item())
+        # the same two counts for the module fast path's own lists (single-pass binning of the usable tiles)
+        I_bin1, I_need_bin = fast_path_counts(ops, g, vm, K, S, V_out, dev, I, int((nxt - off).max().item()), rend.usable_tiles)
     tb, cb = ops.key_bits(S // 16, S // 16, V_out)
     passes = (32 + tb + cb + 7) // 8
+    # the module fast path bins only the tiles a splat can be seen in: ITS kernels are charged for the records they
+    # really move (I_bin <= I), never for gsplat's larger count
+    I_bin = min(I, -(-binned // B)) if binned else I_bin1
     bytes_alg = {
         "unproject_fwd": 112 * G * B,
         # module fast path: projection with the per-tile histogram fused in, no tiles_per_gauss array
         "project_fwd": (40 * G + 28 * P) * B,
         # single-pass binning: the projection also writes the 8-byte intersection records (no bin_scatter)
-        "project_scatter_fwd": (40 * G + 28 * P + 8 * I) * B,
+        "project_scatter_fwd": (40 * G + 28 * P + 8 * I_bin) * B,
         "scan_tiles": 12 * P * B,
         "bin_emit": (20 * P + 12 * I) * B,
         "sort_pairs": (passes * 24 + 8) * I * B,
@@ -402,7 +409,7 @@ def main():
         "bin_scatter": (16 * P + 8 * I) * B,
         "tile_sort": 20 * I * B,
         # fused sort-as-you-go: one pass over the tile's records at minimum + composite traffic
-        "tile_render_fwd": (8 * I + 4 * I_need + 44 * I_need + 24 * X) * B,
+        "tile_render_fwd": (8 * I_bin + 4 * I_need_bin + 44 * I_need_bin + 24 * X) * B,
         "composite_fwd": (44 * I_need + 24 * X) * B,
     }
     peak, peak_src = read_peaks()
@@ -714,7 +721,7 @@ def main():
             "gaussians_per_s": world * B * V_out * G / (ms_per_step * 1e-3),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "parity": parity, "stages": stages,
-            "n_isects": I, "n_isects_needed": I_need,
+            "n_isects": I, "n_isects_needed": I_need, "n_isects_binned": I_bin, "n_isects_needed_binned": I_need_bin,
         }
         line.update(extra)
     # ---- the other multi-GPU configurations of BASELINE.json ride on the same line: C5 (input views and trajectory
@@ -1037,6 +1044,26 @@ def meta_last_ids(r, meta, ops, g, vm, K, S, V_out, dev):
                                    g[1][0, :, 0].contiguous(), meta["depths"].contiguous(),
                                    torch.ones(V_out, 3, device=dev), meta["isect_offsets"], meta["flatten_ids"], S, S)
     return last
+
+
+def fast_path_counts(ops, g, vm, K, S, V_out, dev, I, max_count, usable):
+    """{records binned, records at or before the last one a pixel of their tile needs} of the module fast path on scene 0:
+    single-pass binning (of the usable tiles when `usable`) + the fused renderer, by hand."""
+    import torch
+
+    opac, col = g[2][0, :, 0].contiguous(), g[1][0, :, 0].contiguous()
+    out = ops.project_fwd(g[0][0], g[4][0], g[3][0], vm, K, S, S, count_tiles=False, tile_histogram=True,
+                          tile_capacity=max_count, opacities=opac if usable else None)
+    means2d, depths, conics, counts, records = out[1], out[2], out[3], out[5], out[6]
+    offs, stats, order = ops.tile_scan(counts, want_order=True)
+    last = ops.tile_render_packed_fwd(records, offs, means2d, conics, opac, col, depths, torch.ones(V_out, 3, device=dev), S, S,
+                                      d_n=stats, tile_order=order, record_stride=max_count, capacity=I)[3]
+    n = int(stats[0].item())
+    off = offs.flatten().long()
+    cnt = counts.flatten().long()
+    tiles_last = last.reshape(V_out, S // 16, 16, S // 16, 16).amax(dim=(2, 4)).flatten().long()
+    need = int(((tiles_last - off + 1).clamp(min=0) * (cnt > 0)).sum().item())
+    return n, need
 
 
 if __name__ == "__main__":

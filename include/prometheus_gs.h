@@ -34,8 +34,9 @@ extern "C" {
 #endif
 
 /* 2: exact final transmittance kept for the backward; 3: splat stream (TMA-replayed backward), touched-pair map;
- * 4: pm_project_scatter_fwd (single-pass binning), record_stride of pm_tile_render_packed_fwd */
-#define PM_ABI_VERSION 4
+ * 4: pm_project_scatter_fwd (single-pass binning), record_stride of pm_tile_render_packed_fwd;
+ * 5: pm_project_scatter_fwd(opacities): bins only the tiles a splat can be seen in; histogram-only form */
+#define PM_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define PM_API __attribute__((visibility("default")))
@@ -170,13 +171,20 @@ PM_API int pm_project_count_fwd(const float *means, const float *quats, const fl
  * records[(c * tiles + t) * tile_cap + rank], rank = arrival order < tile_cap. A tile that receives more than
  * tile_cap intersections only keeps the first tile_cap: the caller compares pm_tile_scan's max count with tile_cap
  * afterwards and, if it is larger, renders again (larger capacity, or pm_project_count_fwd + pm_bin_scatter).
- * pm_tile_render_packed_fwd reads this layout with record_stride = tile_cap. */
+ * pm_tile_render_packed_fwd reads this layout with record_stride = tile_cap.
+ * records == NULL with tile_cap == 0: histogram only (sizes the regions on the first call of a shape).
+ * opacities [S * N] (may be NULL): bin only the tiles a splat can be SEEN in — those of gsplat's AABB whose pixel centres
+ * meet the per-axis extent of {alpha >= 1/255} (conservative: the compositor skips the splat on every pixel of a dropped
+ * tile, so images and gradients are unchanged bit for bit; the histogram and the records are a SUBSET of gsplat's
+ * intersections, ~19 % fewer on the benchmark scenes). NULL: gsplat's AABB exactly. A count-only call and the
+ * scatter call that follows it must agree on this argument. */
 PM_API int pm_project_scatter_fwd(const float *means, const float *quats, const float *scales,
                    const float *viewmats, const float *Ks,
                    int N, int C, int views_per_scene, int width, int height, int tile_size,
                    float eps2d, float near_plane, float far_plane, float radius_clip,
                    int32_t *radii, float *means2d, float *depths, float *conics,
-                   int32_t *tile_counts, uint64_t *records, int tile_cap, pm_stream_t stream);
+                   int32_t *tile_counts, uint64_t *records, int tile_cap, const float *opacities,
+                   pm_stream_t stream);
 
 /* VJP of the projection. v_means2d [C,N,2], v_depths [C,N], v_conics [C,N,3]
  * (any may be NULL) -> v_means [N,3], v_quats [N,4], v_scales [N,3], summed over

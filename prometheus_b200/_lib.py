@@ -19,7 +19,7 @@ _CSRC = os.path.join(_PKG, "csrc")
 _lib = None
 
 PM_OK = 0
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # name -> (restype, argtypes); mirrors include/prometheus_gs.h one to one
 _F, _I, _L, _P, _S = c_float, c_int, c_int64, c_void_p, c_size_t
@@ -35,7 +35,7 @@ SIGNATURES = {
     "pm_camera_prep": (c_int, [_P, _I, _I, _I, _P, _P, _P]),
     "pm_project_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P]),
     "pm_project_count_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
-    "pm_project_scatter_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "pm_project_scatter_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "pm_bin_count": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "pm_tile_scan": (c_int, [_P, _L, _P, _P, _P, _P]),
     "pm_bin_scatter": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _L, _P]),

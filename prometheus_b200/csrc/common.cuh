@@ -62,4 +62,24 @@ __device__ __forceinline__ void tile_aabb(float mx, float my, int radius, int ti
   y1 = clamp_tile(ceilf(__fadd_rn(ty, tr)), tile_height);
 }
 
+// Axis-aligned half extents of {alpha >= 1/255} = {sigma <= tau}, tau = ln(255 o): sqrt(2 tau Sigma_xx),
+// sqrt(2 tau Sigma_yy) with Sigma = conic^-1, inflated so that fp rounding can only over-include. ONE expression for
+// the compositor's culling (composite_common.cuh: gather_finish) and for the fast path's binning (project.cu:
+// usable_tiles). -1e30: alpha < 1/255 everywhere; 3e38: degenerate conic, no culling.
+__device__ __forceinline__ void alpha_extents(float q0, float q1, float q2, float o, float &hx, float &hy) {
+  // det(conic) with Kahan's fma compensation: anisotropic splats cancel badly in q0*q2 - q1*q1
+  const float w = q1 * q1;
+  const float det = fmaf(q0, q2, -w) + fmaf(-q1, q1, w);
+  if (!(o * 255.0f > 1.0f)) {
+    hx = hy = -1e30f;  // never evaluated (as upstream would skip it)
+  } else if (!(det > 0.0f) || !(q0 > 0.0f) || !(q2 > 0.0f)) {
+    hx = hy = 3e38f;
+  } else {
+    const float two_tau = 2.0f * __logf(o * 255.0f) * 1.001f + 1e-3f;
+    hx = sqrtf(two_tau * q2 / det) * 1.005f + 0.05f;
+    hy = sqrtf(two_tau * q0 / det) * 1.005f + 0.05f;
+    if (!(hx == hx) || !(hy == hy)) hx = hy = 3e38f;
+  }
+}
+
 }  // namespace pm

@@ -110,22 +110,8 @@ __device__ __forceinline__ GaussRaw gather_load(int32_t f, int32_t g, const floa
 }
 __device__ __forceinline__ void gather_finish(const GaussRaw &r, GaussA &a, GaussB &b, GaussC &c) {
   const float q0 = r.q0, q1 = r.q1, q2 = r.q2, o = r.o;
-  // extent of {alpha >= 1/255} = {sigma <= tau}, tau = ln(255*o): half widths sqrt(2 tau Sigma_xx),
-  // sqrt(2 tau Sigma_yy) with Sigma = conic^-1. Inflated so fp rounding can only over-include.
-  float hx, hy;
-  // det(conic) with Kahan's fma compensation: anisotropic splats cancel badly in q0*q2 - q1*q1
-  const float w = q1 * q1;
-  const float det = fmaf(q0, q2, -w) + fmaf(-q1, q1, w);
-  if (!(o * 255.0f > 1.0f)) {
-    hx = hy = -1e30f;  // alpha < 1/255 everywhere: never evaluated (as upstream would skip it)
-  } else if (!(det > 0.0f) || !(q0 > 0.0f) || !(q2 > 0.0f)) {
-    hx = hy = 3e38f;   // degenerate conic: no culling
-  } else {
-    const float two_tau = 2.0f * __logf(o * 255.0f) * 1.001f + 1e-3f;
-    hx = sqrtf(two_tau * q2 / det) * 1.005f + 0.05f;
-    hy = sqrtf(two_tau * q0 / det) * 1.005f + 0.05f;
-    if (!(hx == hx) || !(hy == hy)) hx = hy = 3e38f;
-  }
+  float hx, hy;  // extent of {alpha >= 1/255} (common.cuh)
+  alpha_extents(q0, q1, q2, o, hx, hy);
   a = GaussA{r.m.x, r.m.y, hx, hy};
   // exp(-sigma) = 2^(Q0 dx^2 + Q1 dx dy + Q2 dy^2) with Q0 = -q0/2 * log2e, Q1 = -q1 * log2e, Q2 = -q2/2 * log2e
   b = GaussB{q0 * (-0.5f * kLog2e), q1 * (-kLog2e), q2 * (-0.5f * kLog2e), o};

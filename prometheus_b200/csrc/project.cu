@@ -80,6 +80,40 @@ constexpr int kProjCamChunk = 32;  // cameras per launch (shared-memory table); 
 #ifndef PM_PROJ_MINBLOCKS
 #define PM_PROJ_MINBLOCKS 5  // 48 registers: 0.320 -> 0.316 ms on C2 (6: 0.318)
 #endif
+// Fast-path binning bins the tiles a splat can actually be SEEN in: gsplat's tile AABB is the square of 3 sigma of the
+// LARGER axis, but the compositor skips a splat wherever alpha < 1/255, i.e. outside the ellipse sigma <= ln(255 o),
+// whose half extents along x / y are sqrt(2 ln(255 o) Sigma_xx / yy) — 19-20 % fewer (Gaussian, tile) pairs on the
+// anisotropic splats of C2 / C5 (tools/isect_stats.py). A tile is kept iff it lies in gsplat's AABB (never a tile more
+// than upstream) AND the span of its pixel centres meets that extent. The extent is the compositor's OWN culling
+// extent (alpha_extents, common.cuh: the value its footprint / live-rectangle tests use, already inflated against fp
+// rounding), widened once more, so a dropped tile is one where the compositor would have culled the splat on every
+// pixel anyway: images, depths, masks and gradients are unchanged bit for bit (checked at full size on C1 / C2 / C3 /
+// C5, tests/test_gpu_parity_full.py: check_usable_tiles); only the fast path's private intersection lists get shorter.
+__device__ __forceinline__ void usable_tiles(float mx, float my, float q0, float q1, float q2, float o, int &x0, int &x1,
+                                             int &y0, int &y1) {
+  // alpha_extents (common.cuh) with approximate division / square root (a few ulp; this kernel is issue-bound and
+  // the IEEE forms cost 0.04 ms on C2), widened by 1e-4 relative + 0.01 px + the rounding of the closed form below
+  const float o255 = o * 255.0f;
+  if (!(o255 > 1.0f)) { x1 = x0; y1 = y0; return; }   // alpha < 1/255 everywhere
+  const float w = q1 * q1;
+  const float det = fmaf(q0, q2, -w) + fmaf(-q1, q1, w);
+  if (!(det > 0.0f) || !(q0 > 0.0f) || !(q2 > 0.0f)) return;  // degenerate conic: keep gsplat's box
+  const float r = __fdividef(2.0f * __logf(o255) * 1.001f + 1e-3f, det);
+  const float ex = r * q2, ey = r * q0;
+  float hx = ex * rsqrtf(ex) * 1.005f + 0.05f, hy = ey * rsqrtf(ey) * 1.005f + 0.05f;
+  if (!(hx < 1e6f) || !(hy < 1e6f)) return;           // NaN / huge: keep gsplat's box
+  hx = hx * 1.0001f + 0.01f + 1e-6f * fabsf(mx);
+  hy = hy * 1.0001f + 0.01f + 1e-6f * fabsf(my);
+  // tile t holds the pixel centres 16 t + 0.5 .. 16 t + 15.5 (composite_common.cuh: footprint_mask keeps it iff
+  // 16 t + 0.5 - m <= h and 16 t + 15.5 - m >= -h)
+  const float inv_ts = 1.0f / (float)kTile;
+  const float lo_x = fmaxf((mx - hx - ((float)kTile - 0.5f)) * inv_ts, -1.0f), hi_x = fminf((mx + hx - 0.5f) * inv_ts, 1e6f);
+  const float lo_y = fmaxf((my - hy - ((float)kTile - 0.5f)) * inv_ts, -1.0f), hi_y = fminf((my + hy - 0.5f) * inv_ts, 1e6f);
+  x0 = max(x0, (int)ceilf(lo_x)); x1 = min(x1, (int)floorf(hi_x) + 1);
+  y0 = max(y0, (int)ceilf(lo_y)); y1 = min(y1, (int)floorf(hi_y) + 1);
+  if (x1 <= x0 || y1 <= y0) { x1 = x0; y1 = y0; }
+}
+
 // MODE 0: projection only; 1: + per-(camera, tile) histogram; 2: + single-pass binning (histogram and the
 // intersection records, each written into its tile's fixed-capacity region — binning_common.cuh)
 template <int MODE>
@@ -92,7 +126,7 @@ project_fwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
                    float radius_clip, int32_t *__restrict__ radii, float *__restrict__ means2d,
                    float *__restrict__ depths, float *__restrict__ conics,
                    int32_t *__restrict__ tiles_per_gauss, int32_t *__restrict__ tile_counts,
-                   uint64_t *__restrict__ records, int tile_cap) {
+                   uint64_t *__restrict__ records, int tile_cap, const float *__restrict__ opacities) {
   __shared__ ProjCamS s_cam[kProjCamChunk];
   __shared__ TileCountSmem s_cnt[1];     // MODE 1 (unused shared arrays are optimised away)
   __shared__ TileScatterSmem s_sct[1];   // MODE 2
@@ -114,6 +148,8 @@ project_fwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
   }
   __syncthreads();
 
+  // opacities != NULL (binning modes only): USABLE tiles — see usable_tiles() above
+  const float opac = (MODE >= 1 && opacities != nullptr && in_range) ? __ldg(opacities + gg) : 0.0f;
   float mx = 0.0f, my = 0.0f, mz = 0.0f;
   float S[9];
 #pragma unroll
@@ -207,6 +243,7 @@ project_fwd_kernel(const float *__restrict__ means, const float *__restrict__ qu
 
     int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
     if (radius_i > 0) tile_aabb(m2x, m2y, radius_i, tile_width, tile_height, x0, x1, y0, y1);
+    if (MODE >= 1 && opacities != nullptr && radius_i > 0) usable_tiles(m2x, m2y, q0, q1, q2, opac, x0, x1, y0, y1);
     if (in_range) {
       radii[f] = radius_i;
       reinterpret_cast<float2 *>(means2d)[f] = make_float2(m2x, m2y);
@@ -239,7 +276,7 @@ static int project_fwd_launch(const float *means, const float *quats, const floa
                               float eps2d,
                               float near_plane, float far_plane, float radius_clip, int32_t *radii, float *means2d,
                               float *depths, float *conics, int32_t *tiles_per_gauss, int32_t *tile_counts,
-                              uint64_t *records, int tile_cap, pm_stream_t stream) {
+                              uint64_t *records, int tile_cap, const float *opacities, pm_stream_t stream) {
   if (!means || !quats || !scales || !viewmats || !Ks || !radii || !means2d || !depths || !conics)
     return PM_ERR_BAD_ARG;
   if (N < 0 || C < 0 || width <= 0 || height <= 0) return PM_ERR_BAD_ARG;
@@ -260,15 +297,15 @@ static int project_fwd_launch(const float *means, const float *quats, const floa
     if (tile_counts && records)
       pm::project_fwd_kernel<2><<<nb, 256, 0, pm::as_stream(stream)>>>(
           means, quats, scales, viewmats, Ks, N, Nv, cam0, n_cams, stride, width, height, tw, th, eps2d, near_plane,
-          far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, tile_counts, records, tile_cap);
+          far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, tile_counts, records, tile_cap, opacities);
     else if (tile_counts)
       pm::project_fwd_kernel<1><<<nb, 256, 0, pm::as_stream(stream)>>>(
           means, quats, scales, viewmats, Ks, N, Nv, cam0, n_cams, stride, width, height, tw, th, eps2d, near_plane,
-          far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, tile_counts, nullptr, 0);
+          far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, tile_counts, nullptr, 0, opacities);
     else
       pm::project_fwd_kernel<0><<<nb, 256, 0, pm::as_stream(stream)>>>(
           means, quats, scales, viewmats, Ks, N, Nv, cam0, n_cams, stride, width, height, tw, th, eps2d, near_plane,
-          far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, nullptr, nullptr, 0);
+          far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, nullptr, nullptr, 0, nullptr);
   }
   return pm::check_launch();
 }
@@ -279,7 +316,7 @@ int pm_project_fwd(const float *means, const float *quats, const float *scales, 
                    float *depths, float *conics, int32_t *tiles_per_gauss, pm_stream_t stream) {
   return project_fwd_launch(means, quats, scales, viewmats, Ks, N, C, C, width, height, tile_size, eps2d, near_plane,
                             far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, nullptr, nullptr, 0,
-                            stream);
+                            nullptr, stream);
 }
 
 int pm_project_count_fwd(const float *means, const float *quats, const float *scales, const float *viewmats,
@@ -290,22 +327,23 @@ int pm_project_count_fwd(const float *means, const float *quats, const float *sc
   if (!tile_counts) return PM_ERR_BAD_ARG;
   return project_fwd_launch(means, quats, scales, viewmats, Ks, N, C, views_per_scene, width, height, tile_size, eps2d, near_plane,
                             far_plane, radius_clip, radii, means2d, depths, conics, tiles_per_gauss, tile_counts,
-                            nullptr, 0, stream);
+                            nullptr, 0, nullptr, stream);
 }
 
 int pm_project_scatter_fwd(const float *means, const float *quats, const float *scales, const float *viewmats,
                            const float *Ks, int N, int C, int views_per_scene, int width, int height, int tile_size,
                            float eps2d, float near_plane, float far_plane, float radius_clip, int32_t *radii,
                            float *means2d, float *depths, float *conics, int32_t *tile_counts, uint64_t *records,
-                           int tile_cap, pm_stream_t stream) {
-  if (!tile_counts || !records || tile_cap <= 0) return PM_ERR_BAD_ARG;
+                           int tile_cap, const float *opacities, pm_stream_t stream) {
+  if (!tile_counts) return PM_ERR_BAD_ARG;
+  if (records ? tile_cap <= 0 : tile_cap != 0) return PM_ERR_BAD_ARG;  // records == NULL, tile_cap == 0: histogram only
   {  // record indices inside one camera's regions are formed in 32 bits
     const int64_t tw = (width + pm::kTile - 1) / pm::kTile, th = (height + pm::kTile - 1) / pm::kTile;
     if (width > 0 && height > 0 && tw * th * (int64_t)tile_cap >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
   }
   return project_fwd_launch(means, quats, scales, viewmats, Ks, N, C, views_per_scene, width, height, tile_size, eps2d,
                             near_plane, far_plane, radius_clip, radii, means2d, depths, conics, nullptr, tile_counts,
-                            records, tile_cap, stream);
+                            records, tile_cap, opacities, stream);
 }
 
 }  // extern "C"

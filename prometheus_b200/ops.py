@@ -166,10 +166,12 @@ def camera_prep(cameras, h: int, w: int):
              lambda means, quats, scales, viewmats, *a, **k: (viewmats.shape[0] + 31) // 32)
 def project_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d=0.3, near_plane=0.01,
                 far_plane=1e10, radius_clip=0.0, count_tiles=True, tile_histogram=False, views_per_scene=0,
-                tile_capacity=0):
+                tile_capacity=0, opacities=None):
     """-> radii, means2d, depths, conics, tiles_per_gauss (None unless count_tiles)
     [, tile_counts [C,th,tw] int32 when tile_histogram: the fused pm_bin_count]
     [, records [C*th*tw, tile_capacity] int64 when tile_capacity > 0: single-pass binning, pm_project_scatter_fwd].
+    opacities [n_scenes * N] (single-pass binning only): bin only the tiles a splat can be seen in (alpha >= 1/255
+    somewhere) instead of gsplat's whole AABB — the counts and records are then a subset of gsplat's intersections.
     views_per_scene = V > 0 (tile_histogram only): scene batching — means / quats / scales hold C / V blocks of
     N Gaussians and camera c sees block c / V; the pair outputs are [C, N]."""
     L = _lib.load()
@@ -190,13 +192,27 @@ def project_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d=0.3, ne
         counts = torch.zeros(C, th, tw, dtype=torch.int32, device=dev)
         if tile_capacity:
             assert not count_tiles
+            if opacities is not None:
+                opacities = _req(opacities, torch.float32, "opacities")
+                assert opacities.numel() == means.shape[0]
             records = torch.empty(C * th * tw, int(tile_capacity), dtype=torch.int64, device=dev)
             _lib.check(L.pm_project_scatter_fwd(_ptr(means), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks), N, C,
                                                 int(views_per_scene), width, height, TILE, eps2d, near_plane, far_plane,
                                                 radius_clip, _ptr(radii), _ptr(means2d), _ptr(depths), _ptr(conics),
-                                                _ptr(counts), _ptr(records), int(tile_capacity), _stream()),
+                                                _ptr(counts), _ptr(records), int(tile_capacity), _ptr(opacities),
+                                                _stream()),
                        "pm_project_scatter_fwd")
             return radii, means2d, depths, conics, None, counts, records
+        if opacities is not None:  # histogram of the USABLE tiles only (what a scatter call with `opacities` will bin)
+            assert not count_tiles
+            opacities = _req(opacities, torch.float32, "opacities")
+            assert opacities.numel() == means.shape[0]
+            _lib.check(L.pm_project_scatter_fwd(_ptr(means), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks), N, C,
+                                                int(views_per_scene), width, height, TILE, eps2d, near_plane, far_plane,
+                                                radius_clip, _ptr(radii), _ptr(means2d), _ptr(depths), _ptr(conics),
+                                                _ptr(counts), None, 0, _ptr(opacities), _stream()),
+                       "pm_project_scatter_fwd")
+            return radii, means2d, depths, conics, None, counts
         _lib.check(L.pm_project_count_fwd(_ptr(means), _ptr(quats), _ptr(scales), _ptr(viewmats), _ptr(Ks), N, C,
                                           int(views_per_scene), width, height, TILE, eps2d, near_plane, far_plane, radius_clip, _ptr(radii),
                                           _ptr(means2d), _ptr(depths), _ptr(conics), _ptr(tpg), _ptr(counts), _stream()),

@@ -55,17 +55,19 @@ def _take_touched(link, v_means2d, v_depths, v_conics):
 class _Project(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
-                radius_clip, fused_count=False, views_per_scene=0, link=None, tile_capacity=0):
+                radius_clip, fused_count=False, views_per_scene=0, link=None, tile_capacity=0, bin_opacities=None):
         """fused_count (module fast path): skip tiles_per_gauss, return the per-tile histogram instead.
         tile_capacity > 0 (with fused_count): single-pass binning — the intersection records are written as well, into
-        fixed-capacity tile regions, and returned after the histogram.
+        fixed-capacity tile regions, and returned after the histogram. bin_opacities (not differentiated): bin only the
+        tiles a splat can be seen in (ops.project_fwd).
         link: dict shared with the compositing node of the same render — its backward leaves the map of pairs that
         received a gradient there (`touched`), so that this node's backward reads 1 byte per pair to find its work."""
         ctx.set_materialize_grads(False)  # undefined cotangents arrive as None, not as zero tensors the size of the outputs
         ctx.link = link
         out = ops.project_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
                               radius_clip, count_tiles=not fused_count, tile_histogram=fused_count,
-                              views_per_scene=views_per_scene, tile_capacity=tile_capacity if fused_count else 0)
+                              views_per_scene=views_per_scene, tile_capacity=tile_capacity if fused_count else 0,
+                              opacities=bin_opacities if (fused_count and tile_capacity) else None)
         ctx.views_per_scene = views_per_scene
         radii, means2d, depths, conics, tpg = out[:5]
         aux = out[5] if fused_count else tpg
@@ -85,7 +87,7 @@ class _Project(torch.autograd.Function):
         v_means, v_quats, v_scales = ops.project_bwd(means, quats, scales, viewmats, Ks, width, height, radii,
                                                      conics, v_means2d, v_depths, v_conics, eps2d,
                                                      views_per_scene=ctx.views_per_scene, touched=touched)
-        return (v_means, v_quats, v_scales) + (None,) * 12
+        return (v_means, v_quats, v_scales) + (None,) * 13
 
 
 class _Composite(torch.autograd.Function):
@@ -220,7 +222,7 @@ class _TileRenderPacked(torch.autograd.Function):
 
 def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, backgrounds, width, height,
                         capacity=None, near_plane=0.01, far_plane=1e10, radius_clip=0.0, eps2d=0.3, views_per_scene=0,
-                        tile_capacity=None):
+                        tile_capacity=None, usable_tiles=True):
     """Fast path behind GaussianRenderer: all C views of one scene, RGB + expected depth, outputs already in the
     module's layout. -> images [C,3,H,W] in [-1,1], depths [C,1,H,W], masks [C,1,H,W], info.
 
@@ -233,6 +235,10 @@ def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, b
     intersection record straight into its tile's region of T records (pm_project_scatter_fwd), so the second pass over
     the pairs (pm_bin_scatter) disappears. Speculative like `capacity`: the caller must also check
     info["stats"][1] (the largest tile) <= T afterwards and re-render without it otherwise.
+    `usable_tiles` (single-pass binning only): bin a splat only into the tiles of gsplat's AABB where it can reach
+    alpha >= 1/255 (project.cu: usable_tiles) — same images / gradients bit for bit; the private lists
+    (info["stats"], "isect_offsets", "flatten_ids", "sorted_counts") then describe a SUBSET of gsplat's intersections,
+    in the same order. False: gsplat's intersections exactly.
 
     `views_per_scene` = V > 0: SCENE BATCHING — the Gaussian tensors hold C / V scenes back to back (N Gaussians
     each, N % 256 == 0) and camera c renders scene c / V: one launch set for a whole training batch."""
@@ -244,7 +250,8 @@ def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, b
     link = {}  # compositing backward -> projection backward: the map of pairs that received a gradient
     single_pass = bool(tile_capacity) and capacity is not None
     proj = _Project.apply(means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
-                          True, views_per_scene, link, int(tile_capacity) if single_pass else 0)
+                          True, views_per_scene, link, int(tile_capacity) if single_pass else 0,
+                          opacities.detach() if (single_pass and usable_tiles) else None)
     means2d, depths, conics, radii, counts = proj[:5]
     # The reference keeps one [1,N,2] screen-space tensor per rendered view and reads its .grad after backward
     # (`viewspace_points`, gaussians_renderer.py:428-445). Routing autograd through per-view tensors costs a cat and a
@@ -270,7 +277,7 @@ def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, b
     info = {"radii": radii, "means2d": means2d, "means2d_views": means2d_views, "depths": depths, "conics": conics,
             "isect_offsets": isect_offsets, "flatten_ids": flatten_ids, "sorted_counts": sorted_counts,
             "stats": stats, "overflow_flag": flag, "capacity": int(capacity), "means2d_grad_sink": grad_sink,
-            "tile_capacity": int(tile_capacity) if single_pass else 0}
+            "tile_capacity": int(tile_capacity) if single_pass else 0, "usable_tiles": bool(single_pass and usable_tiles)}
     return images, depth_out, masks, info
 
 

@@ -32,7 +32,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert os.path.exists(_lib.library_path())
     for s in declared_symbols():
         assert hasattr(lib, s), s
-    assert lib.pm_abi_version() == 4
+    assert lib.pm_abi_version() == 5
     assert lib.pm_status_string(0) == b"ok"
     assert b"workspace" in lib.pm_status_string(-3)
 
@@ -53,8 +53,8 @@ def test_argument_errors_are_reported_before_launch():
     assert lib.pm_unproject_fwd(one, one, one, 7, 0.01, 100.0, 0.001, 1.0, 1, 4, 4, one, one, one, one, one, null) == -2
     assert lib.pm_project_fwd(one, one, one, one, one, 4, 1, 32, 32, 8, 0.3, 0.01, 1e10, 0.0, one, one, one, one, null, null, null) == -2  # tile_size 8
     assert lib.pm_project_fwd(one, one, one, one, one, -1, 1, 32, 32, 16, 0.3, 0.01, 1e10, 0.0, one, one, one, one, null, null, null) == -1
-    assert lib.pm_project_scatter_fwd(one, one, one, one, one, 4, 1, 0, 32, 32, 16, 0.3, 0.01, 1e10, 0.0, one, one, one, one, one, null, 64, null) == -1  # no records
-    assert lib.pm_project_scatter_fwd(one, one, one, one, one, 4, 1, 0, 32, 32, 16, 0.3, 0.01, 1e10, 0.0, one, one, one, one, one, one, 0, null) == -1  # tile_cap 0
+    assert lib.pm_project_scatter_fwd(one, one, one, one, one, 4, 1, 0, 32, 32, 16, 0.3, 0.01, 1e10, 0.0, one, one, one, one, one, null, 64, null, null) == -1  # no records but a capacity
+    assert lib.pm_project_scatter_fwd(one, one, one, one, one, 4, 1, 0, 32, 32, 16, 0.3, 0.01, 1e10, 0.0, one, one, one, one, one, one, 0, null, null) == -1  # records but tile_cap 0
     sel = ctypes.c_int(-1)
     assert lib.pm_sort_pairs(one, one, one, one, 100, null, 40, one, 8, ctypes.byref(sel), null) == -3  # workspace too small
     assert lib.pm_sort_pairs(one, one, one, one, 1 << 31, null, 40, one, 1 << 40, ctypes.byref(sel), null) == -5

@@ -860,7 +860,7 @@ def test_single_pass_binning_same_bits_and_overflow_recovery():
         assert "project_scatter_fwd" in names and "bin_scatter" not in names
         rend._tile_cap_hint[key] = 16                          # far too small: records of full tiles are dropped
         third = rend(cams, g, h=80, w=80)[:3]
-        assert rend._tile_cap_hint[key] == tcap
+        assert 64 < rend._tile_cap_hint[key] <= tcap           # re-rendered, hint restored (from the usable-tile counts)
         rend.defer_checks = True
         rend._tile_cap_hint[key] = 16
         rend(cams, g, h=80, w=80)
@@ -899,11 +899,15 @@ def test_single_pass_binning_fallback_paths():
         im0, de0, ma0, info0 = render_views_packed(*args, bg, 1056, 1056)
         n_isects, max_count = (int(v) for v in info0["stats"].tolist())
         assert max_count > 6 and int(info0["overflow_flag"].item()) == 0
-        im1, de1, ma1, info1 = render_views_packed(*args, bg, 1056, 1056, capacity=n_isects + 100, tile_capacity=max_count + 3)
+        im1, de1, ma1, info1 = render_views_packed(*args, bg, 1056, 1056, capacity=n_isects + 100, tile_capacity=max_count + 3,
+                                                   usable_tiles=False)
         assert info1["tile_capacity"] == max_count + 3 and info1["stats"].tolist() == [n_isects, max_count]
         assert torch.equal(info0["isect_offsets"], info1["isect_offsets"])
-    for a, b in ((im0, im1), (de0, de1), (ma0, ma1)):
-        assert torch.equal(a, b)
+        # the module's default: only the tiles a splat can be seen in — fewer records, same pixels
+        im2, de2, ma2, info2 = render_views_packed(*args, bg, 1056, 1056, capacity=n_isects + 100, tile_capacity=max_count + 3)
+        assert info2["usable_tiles"] and info2["stats"][0].item() < n_isects and info2["stats"][1].item() <= max_count
+    for a, b, c in ((im0, im1, im2), (de0, de1, de2), (ma0, ma1, ma2)):
+        assert torch.equal(a, b) and torch.equal(a, c)
 
 
 @pytest.mark.parametrize("C", [11, 35])
@@ -918,10 +922,17 @@ def test_single_pass_binning_many_cameras(C):
     with torch.no_grad():
         im0, de0, ma0, info0 = render_views_packed(*args, bg, 96, 64)
         n_isects, max_count = (int(v) for v in info0["stats"].tolist())
-        im1, de1, ma1, info1 = render_views_packed(*args, bg, 96, 64, capacity=n_isects + 7, tile_capacity=max_count)
+        im1, de1, ma1, info1 = render_views_packed(*args, bg, 96, 64, capacity=n_isects + 7, tile_capacity=max_count,
+                                                   usable_tiles=False)
         assert info1["stats"].tolist() == [n_isects, max_count] and torch.equal(info0["isect_offsets"], info1["isect_offsets"])
-    for a, b in ((im0, im1), (de0, de1), (ma0, ma1)):
-        assert torch.equal(a, b)
+        im2, de2, ma2, info2 = render_views_packed(*args, bg, 96, 64, capacity=n_isects + 7, tile_capacity=max_count)
+        assert info2["stats"][0].item() <= n_isects and bool((info2["isect_offsets"] <= info0["isect_offsets"]).all())
+        # histogram-only form of the same call (records = NULL): the counts the scatter call bins
+        from prometheus_b200 import ops
+        counts = ops.project_fwd(*args[:3], *args[5:7], 96, 64, count_tiles=False, tile_histogram=True, opacities=args[3])[5]
+        assert torch.equal(ops.tile_scan(counts)[0], info2["isect_offsets"])
+    for a, b, c in ((im0, im1, im2), (de0, de1, de2), (ma0, ma1, ma2)):
+        assert torch.equal(a, b) and torch.equal(a, c)
 
 
 def test_backward_with_undefined_cotangents():

@@ -90,7 +90,8 @@ def check_operator_forward(name, gauss, vm, K, S, bg, st):
 
 def check_fast_path(name, gauss, vm, K, S, bg, st, r_op, a_op):
     """Fused sort-as-you-go renderer (project + histogram, scan, scatter, tile_render_fwd): same bits as the operator path,
-    last_ids equal to the oracle's on non-fragile pixels, sorted prefixes equal to the oracle's order."""
+    last_ids equal to the oracle's on non-fragile pixels, sorted prefixes equal to the oracle's order (a subsequence of it
+    when only the usable tiles are binned: check_usable_tiles)."""
     from prometheus_b200 import ops
     from prometheus_b200.rasterization import render_views_packed
 
@@ -132,7 +133,7 @@ def check_fast_path(name, gauss, vm, K, S, bg, st, r_op, a_op):
     with torch.no_grad():
         tcap = (int(max_count * 1.25) + 65) & ~1
         im1, de1, ma1, info1 = render_views_packed(*[gauss[k] for k in KEYS], vm, K, dev(bg), S, S,
-                                                   capacity=int(n * 1.3) + 4096, tile_capacity=tcap)
+                                                   capacity=int(n * 1.3) + 4096, tile_capacity=tcap, usable_tiles=False)
     assert info1["tile_capacity"] == tcap and info1["stats"].tolist() == [n, max_count]
     assert torch.equal(info1["isect_offsets"], offsets) and int(info1["overflow_flag"].item()) == 0
     assert torch.equal(im1, images) and torch.equal(de1, depth_out) and torch.equal(ma1, masks)
@@ -142,7 +143,49 @@ def check_fast_path(name, gauss, vm, K, S, bg, st, r_op, a_op):
     assert (sc1 <= cnt).all() and np.all((tl - off + 1)[has] <= sc1[has])
     idx1 = np.repeat(off, sc1) + (np.arange(sc1.sum()) - np.repeat(np.cumsum(sc1) - sc1, sc1))
     assert np.array_equal(info1["flatten_ids"].cpu().numpy()[idx1], st["flatten_ids"][idx1])
+    check_usable_tiles(name, gauss, vm, K, S, bg, st, (images, depth_out, masks), n, tcap, off, cnt, tl, has)
     return trans
+
+
+def check_usable_tiles(name, gauss, vm, K, S, bg, st, want, n, tcap, off, cnt, tl, has):
+    """The module's default: single-pass binning of the USABLE tiles only (a splat is binned where it can reach
+    alpha >= 1/255). Same images bit for bit; every tile's list is a SUBSET of the oracle's, its sorted prefix a
+    SUBSEQUENCE of the oracle's order, and it still holds the last contributor of every non-fragile pixel."""
+    from prometheus_b200.rasterization import render_views_packed
+
+    with torch.no_grad():
+        im, de, ma, info = render_views_packed(*[gauss[k] for k in KEYS], vm, K, dev(bg), S, S,
+                                               capacity=int(n * 1.3) + 4096, tile_capacity=tcap)
+    assert info["usable_tiles"] and int(info["overflow_flag"].item()) == 0
+    for a, b in zip((im, de, ma), want):
+        assert torch.equal(a, b), name
+    n_u, max_u = info["stats"].tolist()
+    off_u = info["isect_offsets"].reshape(-1).cpu().numpy().astype(np.int64)
+    cnt_u = np.diff(np.append(off_u, n_u))
+    assert n_u <= n and (cnt_u <= cnt).all() and (cnt_u >= 0).all()
+    sc = info["sorted_counts"].cpu().numpy().reshape(-1).astype(np.int64)
+    assert (sc <= cnt_u).all() and (sc >= 0).all()
+    # position of every sorted fast-path entry in the oracle's list of the same tile (flatten ids are unique in a tile)
+    pairs = int(vm.shape[0]) * int(gauss["means"].shape[0])
+    tiles = torch.repeat_interleave(torch.arange(len(cnt), device=DEV), torch.from_numpy(cnt).to(DEV))
+    okey, opos = torch.sort(tiles * pairs + torch.from_numpy(st["flatten_ids"].astype(np.int64)).to(DEV))
+    del tiles
+    idx = np.repeat(off_u, sc) + (np.arange(sc.sum()) - np.repeat(np.cumsum(sc) - sc, sc))
+    ftile = torch.from_numpy(np.repeat(np.arange(len(sc)), sc)).to(DEV)
+    fkey = ftile * pairs + info["flatten_ids"].long()[torch.from_numpy(idx).to(DEV)]
+    at = torch.searchsorted(okey, fkey).clamp(max=len(okey) - 1)
+    assert bool((okey[at] == fkey).all()), name                     # subset
+    pos = opos[at]
+    same_tile = ftile[1:] == ftile[:-1]
+    assert bool((pos[1:] > pos[:-1])[same_tile].all()), name        # oracle's order
+    # the last contributor of every non-fragile pixel (oracle position tl in its tile) is in the tile's sorted prefix
+    need = np.nonzero(has & (tl - off >= 0) & (tl > 0))[0]  # (0 = the oracle's 'nothing blended')
+    lkey = torch.from_numpy(need * pairs + st["flatten_ids"][tl[need]].astype(np.int64)).to(DEV)
+    fsorted = torch.sort(fkey)[0]
+    at = torch.searchsorted(fsorted, lkey).clamp(max=len(fsorted) - 1)
+    assert bool((fsorted[at] == lkey).all()), name
+    print("%s usable tiles: %d of %d intersections binned (%.1f %% fewer), max tile %d, sorted %d" % (
+        name, n_u, n, 100.0 * (1 - n_u / n), max_u, sc.sum()))
 
 
 def check_backward(oracle, name, gauss, vm, K, S, bg, st, max_share):
