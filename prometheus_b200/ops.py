@@ -21,6 +21,9 @@ MODES = {"mvsplat": 0, "gslrm": 1, "director3d": 2}
 # events on the launching stream.
 LAUNCHES = 0
 PROFILE = None
+# PM_NVTX=1: every C-ABI call is wrapped in an NVTX range named after the stage ("pm:project_scatter_fwd", ...), so a
+# timeline tool shows the path's stages inside the caller's own ranges (the reference has none)
+NVTX = __import__("os").environ.get("PM_NVTX", "0") not in ("", "0")
 
 
 def _instrument(name, n_launches):
@@ -32,6 +35,12 @@ def _instrument(name, n_launches):
             global LAUNCHES
             n = n_launches(*a, **k) if callable(n_launches) else n_launches
             LAUNCHES += n
+            if NVTX:
+                torch.cuda.nvtx.range_push("pm:" + (name(*a, **k) if callable(name) else name))
+                try:
+                    return fn(*a, **k)
+                finally:
+                    torch.cuda.nvtx.range_pop()
             if PROFILE is None:
                 return fn(*a, **k)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

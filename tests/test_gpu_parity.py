@@ -1485,3 +1485,19 @@ def test_peer_gather_on_two_gpus():
                         "127.0.0.1", "--master-port", "29577", os.path.join(root, "tools", "p2p_gather_check.py"), "64"],
                        capture_output=True, text=True, timeout=300)
     assert p.returncode == 0 and "p2p gather ok" in p.stdout, p.stdout[-1500:] + p.stderr[-1500:]
+
+
+def test_nvtx_ranges_do_not_change_results():
+    """PM_NVTX=1 wraps every C-ABI call in an NVTX range (ops.NVTX); same outputs, launches still counted."""
+    from prometheus_b200 import ops
+
+    cams = torch.from_numpy(np.load(os.path.join(os.path.dirname(__file__), "golden", "cameras.npz"))["cameras"]).to(DEV).float()
+    want = ops.camera_prep(cams, 96, 96)
+    before, ops.NVTX = ops.LAUNCHES, True
+    try:
+        got = ops.camera_prep(cams, 96, 96)
+    finally:
+        ops.NVTX = False
+    assert ops.LAUNCHES == before + 1
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
