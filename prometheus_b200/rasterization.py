@@ -26,6 +26,71 @@ _RENDER_MODES = ("RGB", "D", "ED", "RGB+D", "RGB+ED")
 
 # test/bench hook: route every call through the generic emit + onesweep path
 FORCE_GENERIC_SORT = False
+# `rasterization(...)` renders with the fused sort-as-you-go kernel (same bits) and computes the fully sorted
+# intersection arrays of `meta` only when one of them is read (_LazyMeta). "0": always run the full per-tile sort
+# + composite_fwd (developer knob for A/B runs; bench.py's `operator_path.full_sort` figure).
+OPERATOR_FUSED = __import__("os").environ.get("PM_OPERATOR_FUSED", "1") != "0"
+
+
+class _LazyMeta(dict):
+    """gsplat's `meta` dict. The reference reads `radii` and `means2d` from it (gaussians_renderer.py:428-445); the
+    sorted intersection arrays `tiles_per_gauss`, `isect_ids`, `flatten_ids` — which the fused renderer never needs as
+    a whole — are produced by the separate-stage kernels (projection with per-Gaussian tile counts, binning, full
+    per-tile sort) the first time any of them is read through the mapping interface, and are then ordinary entries.
+    Until then the keys exist (membership, len, keys() behave as usual)."""
+
+    LAZY = frozenset(("tiles_per_gauss", "isect_ids", "flatten_ids"))
+
+    def __init__(self, eager, thunk):
+        super().__init__(eager)
+        for k in self.LAZY:
+            dict.__setitem__(self, k, None)
+        self._thunk = thunk
+
+    @property
+    def materialized(self) -> bool:
+        return self._thunk is None
+
+    def materialize(self):
+        thunk, self._thunk = self._thunk, None
+        if thunk is not None:
+            dict.update(self, thunk())
+        return self
+
+    def __getitem__(self, k):
+        if k in self.LAZY:
+            self.materialize()
+        return dict.__getitem__(self, k)
+
+    def get(self, k, default=None):
+        if k in self.LAZY:
+            self.materialize()
+        return dict.get(self, k, default)
+
+    def pop(self, k, *default):
+        if k in self.LAZY:
+            self.materialize()
+        return dict.pop(self, k, *default)
+
+    def __setitem__(self, k, v):
+        if k in self.LAZY:
+            self.materialize()
+        dict.__setitem__(self, k, v)
+
+    def __iter__(self):  # (also makes dict(meta) / {**meta} go through keys() + __getitem__ instead of a raw copy)
+        return dict.__iter__(self)
+
+    def items(self):
+        return dict.items(self.materialize())
+
+    def values(self):
+        return dict.values(self.materialize())
+
+    def copy(self):
+        return dict(self.materialize())
+
+    def __repr__(self):
+        return dict.__repr__(self) if self.materialized else "_LazyMeta(sorted arrays pending; keys %s)" % sorted(self.keys())
 
 
 def _new_touched(link, means2d):
@@ -133,7 +198,8 @@ class _TileRender(torch.autograd.Function):
     """Fused sort-as-you-go forward (ops.tile_render_fwd) + the ordinary compositing backward."""
 
     @staticmethod
-    def forward(ctx, means2d, conics, opacities, colors, depths, backgrounds, records, offsets, width, height, link=None):
+    def forward(ctx, means2d, conics, opacities, colors, depths, backgrounds, records, offsets, width, height, link=None,
+                tile_order=None):
         ctx.set_materialize_grads(False)  # undefined cotangents arrive as None, not as zero tensors the size of the outputs
         ctx.link = link
         means2d, conics = means2d.contiguous(), conics.contiguous()
@@ -143,7 +209,7 @@ class _TileRender(torch.autograd.Function):
         backgrounds = None if backgrounds is None else backgrounds.contiguous().float()
         need_bwd = any(ctx.needs_input_grad[:6])
         out = ops.tile_render_fwd(records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height,
-                                  want_stream=need_bwd)
+                                  tile_order=tile_order, want_stream=need_bwd)
         render, alphas, last_ids, flat, sorted_counts, flag, trans = out[:7]
         ctx.save_for_backward(means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, alphas, last_ids,
                               trans, out[7] if need_bwd else None)
@@ -166,7 +232,7 @@ class _TileRender(torch.autograd.Function):
         if backgrounds is not None and ctx.needs_input_grad[5] and v_render is not None:
             D = backgrounds.shape[-1]
             v_bg = (v_render[..., :D] * trans.unsqueeze(-1)).sum(dim=(1, 2))
-        return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None, None
+        return v_means2d, v_conics, v_opac, v_colors, v_depths, v_bg, None, None, None, None, None, None
 
 
 class _TileRenderPacked(torch.autograd.Function):
@@ -345,20 +411,21 @@ def rasterization(
     return _rasterize_core(means, quats, scales, opacities, colors, viewmats, Ks, width, height, near_plane,
                            far_plane, radius_clip, eps2d, sh_degree, packed, tile_size, backgrounds, render_mode,
                            sparse_grad, absgrad, rasterize_mode, channel_chunk, distributed, camera_model,
-                           covars, per_view_means2d=False)
+                           covars, per_view_means2d=False, fused=OPERATOR_FUSED, lazy_meta=True)
 
 
 def _rasterize_core(means, quats, scales, opacities, colors, viewmats, Ks, width, height, near_plane=0.01,
                     far_plane=1e10, radius_clip=0.0, eps2d=0.3, sh_degree=None, packed=True, tile_size=16,
                     backgrounds=None, render_mode="RGB", sparse_grad=False, absgrad=False,
                     rasterize_mode="classic", channel_chunk=32, distributed=False, camera_model="pinhole",
-                    covars=None, per_view_means2d=False, fused=False):
+                    covars=None, per_view_means2d=False, fused=False, lazy_meta=False):
     """Body of `rasterization`. `per_view_means2d=True` (used by renderer.GaussianRenderer)
     additionally returns meta["means2d_views"]: one [1,N,2] graph tensor per camera with
     retain_grad() set, the batched equivalent of gaussians_renderer.py:428-445.
     `fused=True` (module-level fast path) renders with the sort-as-you-go kernel: images are
     bit-identical, but meta["isect_ids"] is None and meta["flatten_ids"] is sorted only up to
-    meta["sorted_counts"] entries per tile."""
+    meta["sorted_counts"] entries per tile — unless `lazy_meta=True` (what `rasterization` passes): then `meta` is a
+    _LazyMeta whose tiles_per_gauss / isect_ids / flatten_ids are gsplat's fully sorted arrays, computed on first read."""
     N = means.shape[0]
     C = viewmats.shape[0]
     assert means.shape == (N, 3), means.shape
@@ -417,15 +484,21 @@ def _rasterize_core(means, quats, scales, opacities, colors, viewmats, Ks, width
     sorted_counts = None
     if use_fused:
         m2d, dep = means2d.detach(), depths.detach()
-        isect_offsets, stats = ops.tile_scan(aux)  # aux = per-tile histogram, counted inside the projection
+        # aux = per-tile histogram, counted inside the projection; tiles are rendered heaviest first
+        isect_offsets, stats, tile_order = ops.tile_scan(aux, want_order=True)
         n_isects, max_count = stats.tolist()
         records = ops.bin_scatter(m2d, radii, dep, isect_offsets, width, height, n_isects)
-        render, alphas, flag, flatten_ids, sorted_counts = _TileRender.apply(*comp_args, records, isect_offsets, width, height, link)
+        render, alphas, flag, flatten_ids, sorted_counts = _TileRender.apply(*comp_args, records, isect_offsets, width, height, link,
+                                                                             tile_order)
         isect_ids = None
         # a depth sub-bucket larger than the group capacity can only exist if some tile is larger than it
         if max_count > FUSED_GROUP_CAP and int(flag.item()) != 0:
             render = None
     if render is None:
+        if tpg is None:  # the fused attempt overflowed a sort group: the separate stages need the per-Gaussian counts
+            with torch.no_grad():
+                tpg = ops.project_fwd(means.detach(), quats.detach(), scales.detach(), viewmats, Ks, width, height, eps2d,
+                                      near_plane, far_plane, radius_clip, count_tiles=True)[4]
         isect_ids, flatten_ids, isect_offsets = isect_tiles(means2d.detach(), radii, depths.detach(), tpg, width,
                                                             height, C, force_generic=FORCE_GENERIC_SORT)
         sorted_counts = None
@@ -443,6 +516,19 @@ def _rasterize_core(means, quats, scales, opacities, colors, viewmats, Ks, width
     }
     if means2d_views is not None:
         meta["means2d_views"] = means2d_views
+    if sorted_counts is not None and lazy_meta:
+        # the fused renderer produced the images; gsplat's sorted arrays follow on demand from the same projection
+        proj_args = (means.detach(), quats.detach(), scales.detach(), viewmats, Ks, width, height, eps2d, near_plane,
+                     far_plane, radius_clip)
+        m2d, rad, dep = means2d.detach(), radii, depths.detach()
+
+        def sorted_arrays():
+            with torch.no_grad():
+                tiles_per_gauss = ops.project_fwd(*proj_args, count_tiles=True)[4]
+                ids, flat, _ = isect_tiles(m2d, rad, dep, tiles_per_gauss, width, height, C, force_generic=FORCE_GENERIC_SORT)
+            return {"tiles_per_gauss": tiles_per_gauss, "isect_ids": ids, "flatten_ids": flat}
+
+        return render, alphas, _LazyMeta(meta, sorted_arrays)
     if sorted_counts is not None:
         meta["sorted_counts"] = sorted_counts
     return render, alphas, meta

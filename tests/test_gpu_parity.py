@@ -422,6 +422,47 @@ def test_generic_and_binned_paths_agree_through_the_operator(cases):
     assert torch.equal(r1, r2) and torch.equal(a1, a2)
 
 
+@pytest.mark.parametrize("mode", ["RGB+ED", "RGB", "D"])
+def test_operator_lazy_meta_equals_the_eager_one(cases, mode):
+    """`rasterization(...)` renders with the fused kernel and computes gsplat's sorted meta arrays when they are read:
+    no sort kernel runs before that, the arrays equal the separate-stage path's, the images are the same bits and so
+    are the gradients' inputs (same backward kernel on the same saved state)."""
+    import importlib
+
+    import prometheus_b200 as pb
+    from prometheus_b200 import ops
+
+    rz = importlib.import_module("prometheus_b200.rasterization")
+    s, bg, st = cases["blobs"]
+    args = [dev(s[k]) for k in ("means", "quats", "scales", "opacities", "colors")] + [dev(s["viewmats"]), dev(s["Ks"]), s["width"], s["height"]]
+    kw = dict(backgrounds=None if mode == "D" else dev(bg), render_mode=mode, packed=False)
+    prof, ops.PROFILE = ops.PROFILE, []
+    try:
+        r1, a1, m1 = pb.rasterization(*args, **kw)
+        names = [n for n, _, _ in ops.PROFILE]
+    finally:
+        ops.PROFILE = prof
+    assert isinstance(m1, rz._LazyMeta) and not m1.materialized
+    assert "tile_render_fwd" in names and "tile_sort" not in names and "composite_fwd" not in names
+    assert "isect_ids" in m1 and set(m1.keys()) >= {"radii", "means2d", "tiles_per_gauss", "isect_ids", "flatten_ids", "isect_offsets"}
+    r2, a2, m2 = rz._rasterize_core(*args, **kw)           # separate stages, eager meta
+    assert not isinstance(m2, rz._LazyMeta)
+    assert torch.equal(r1, r2) and torch.equal(a1, a2)
+    for k in ("radii", "means2d", "depths", "conics", "isect_offsets"):
+        assert torch.equal(m1[k], m2[k]), k
+    assert not m1.materialized
+    for k in ("tiles_per_gauss", "isect_ids", "flatten_ids"):
+        assert torch.equal(m1[k], m2[k]), k
+    assert m1.materialized and dict(m1).keys() == m1.keys()
+    old = rz.OPERATOR_FUSED
+    try:  # the knob: every call through the full sort
+        rz.OPERATOR_FUSED = False
+        r3, a3, m3 = pb.rasterization(*args, **kw)
+        assert not isinstance(m3, rz._LazyMeta) and torch.equal(r3, r1) and torch.equal(m3["flatten_ids"], m1["flatten_ids"])
+    finally:
+        rz.OPERATOR_FUSED = old
+
+
 # --------------------------------------------------------------------------- stage 4
 @pytest.mark.parametrize("name", CASE_NAMES)
 def test_composite_fwd(cases, name):
