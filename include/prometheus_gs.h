@@ -35,8 +35,9 @@ extern "C" {
 
 /* 2: exact final transmittance kept for the backward; 3: splat stream (TMA-replayed backward), touched-pair map;
  * 4: pm_project_scatter_fwd (single-pass binning), record_stride of pm_tile_render_packed_fwd;
- * 5: pm_project_scatter_fwd(opacities): bins only the tiles a splat can be seen in; histogram-only form */
-#define PM_ABI_VERSION 5
+ * 5: pm_project_scatter_fwd(opacities): bins only the tiles a splat can be seen in; histogram-only form;
+ * 6: hit map from pm_tile_render_packed_fwd to pm_composite_bwd_packed (pm_hit_words_stride) */
+#define PM_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define PM_API __attribute__((visibility("default")))
@@ -361,7 +362,15 @@ PM_API int pm_tile_render_packed_fwd(const uint64_t *records, int64_t record_str
                               float *images, float *depth_out, float *masks, int32_t *last_ids,
                               int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
                               const int32_t *tile_order, int views_per_scene, float *transmittance,
-                              float *splat_stream, pm_stream_t stream);
+                              float *splat_stream, uint32_t *hit_words, int64_t hit_stride, pm_stream_t stream);
+
+/* The HIT MAP (optional, only useful when a backward follows): hit_words [8, hit_stride] uint32, zero-filled by the
+ * caller, hit_stride >= pm_hit_words_stride(n_isects, ...). Row w belongs to warp footprint w of every tile (the 8 x 4
+ * pixel blocks of a 16 x 16 tile, row-major in steps of (8, 4)); tile (c, t)'s words start at
+ * (isect_offsets[c, t] >> 5) + (c * tiles + t) and bit p of them is set iff the forward evaluated list entry p of the
+ * tile for that footprint (it passed the footprint's culling). pm_composite_bwd_packed replays exactly those entries
+ * and skips its own culling; chunks of 32 entries without a set bit are not even copied. NULL: no map. */
+PM_API int64_t pm_hit_words_stride(int64_t n_isects, int C, int width, int height, int tile_size);
 
 /* Backward. Replays splat_stream (see above; colours [N,D] or [C,N,D] per colors_per_camera, has_depth = the forward
  * rendered a depth channel, CD = D + has_depth). v_render [C,H,W,CD], v_alphas [C,H,W] (either may be NULL).
@@ -381,7 +390,8 @@ PM_API int pm_composite_bwd(const float *splat_stream, int colors_per_camera, in
 
 /* Backward of pm_tile_render_packed_fwd: cotangents of the packed outputs (any may be NULL) in,
  * the same accumulated per-Gaussian gradients out. masks / depth_out are the forward's outputs.
- * tile_order (may be NULL): launch order of the tiles, e.g. pm_tile_scan over the forward's sorted_counts. */
+ * tile_order (may be NULL): launch order of the tiles, e.g. pm_tile_scan over the forward's sorted_counts.
+ * hit_words / hit_stride (may be NULL / 0): the forward's hit map, see pm_tile_render_packed_fwd. */
 PM_API int pm_composite_bwd_packed(const float *splat_stream, int colors_per_camera,
                      const float *backgrounds, const int32_t *isect_offsets,
                      int64_t n_isects, const int32_t *d_n,
@@ -391,7 +401,7 @@ PM_API int pm_composite_bwd_packed(const float *splat_stream, int colors_per_cam
                      const float *v_images, const float *v_depth_out, const float *v_masks,
                      float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
                      float *v_depths, const int32_t *tile_order, int views_per_scene, uint8_t *touched,
-                     pm_stream_t stream);
+                     const uint32_t *hit_words, int64_t hit_stride, pm_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
  * Trajectory rendering: pose sampling along a camera path and

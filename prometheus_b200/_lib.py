@@ -19,7 +19,7 @@ _CSRC = os.path.join(_PKG, "csrc")
 _lib = None
 
 PM_OK = 0
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # name -> (restype, argtypes); mirrors include/prometheus_gs.h one to one
 _F, _I, _L, _P, _S = c_float, c_int, c_int64, c_void_p, c_size_t
@@ -51,9 +51,10 @@ SIGNATURES = {
     "pm_composite_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "pm_splat_stream_build": (c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _L, _P, _I, _I, _I, _P, _P]),
     "pm_tile_render_fwd": (c_int, [_P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "pm_tile_render_packed_fwd": (c_int, [_P, _L, _P, _L, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
+    "pm_tile_render_packed_fwd": (c_int, [_P, _L, _P, _L, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _L, _P]),
+    "pm_hit_words_stride": (_L, [_L, _I, _I, _I, _I]),
     "pm_composite_bwd_packed": (c_int, [_P, _I, _P, _P, _L, _P, _I, _I, _I, _I, _I,
-                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
+                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _L, _P]),
     "pm_splat_keys": (c_int, [_P, _P, _L, _I, _P, _P, _P]),
     "pm_splat_pack": (c_int, [_P, _P, _P, _P, _P, _P, _L, _I, _P, _P]),
     "pm_loss_terms_fwd": (c_int, [_P, _P, _P, _P, _L, _I, _I, _P, _P, _P, _P]),

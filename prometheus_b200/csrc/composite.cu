@@ -136,6 +136,8 @@ struct BwdShared {
   BwdWarpShared w[kBwdWarps];
 };
 
+// MAP: the forward left a hit map (pm_tile_render_packed_fwd) — no culling code in that instantiation
+template <bool MAP>
 __global__ void __launch_bounds__(kBwdThreads, PM_BWD_MINBLOCKS)
 composite_bwd_kernel(const float *__restrict__ stream, int colors_per_camera, int D, int has_depth,
                      const float *__restrict__ backgrounds, const int32_t *__restrict__ offsets, int64_t n_host,
@@ -148,7 +150,8 @@ composite_bwd_kernel(const float *__restrict__ stream, int colors_per_camera, in
                      const float *__restrict__ v_images, const float *__restrict__ v_depth_out,
                      const float *__restrict__ v_masks, const float *__restrict__ depth_out, int packed,
                      const int32_t *__restrict__ tile_order, int views_per_scene,
-                     const float *__restrict__ transmittance, uint8_t *__restrict__ touched) {
+                     const float *__restrict__ transmittance, uint8_t *__restrict__ touched,
+                     const uint32_t *__restrict__ hit_words, int64_t hit_stride) {
   extern __shared__ __align__(16) unsigned char bwd_smem[];
   BwdWarpShared &sh = reinterpret_cast<BwdShared *>(bwd_smem)->w[threadIdx.x >> 5];
 
@@ -359,17 +362,25 @@ composite_bwd_kernel(const float *__restrict__ stream, int colors_per_camera, in
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(aS), "l"(src), "r"(bytes), "r"(aBar) : "memory");
   };
-  if (lane == 0) stage_chunk(first);
+  // The forward's hit map, when it wrote one (pm_tile_render_packed_fwd): bit p of this (warp footprint, tile)'s words
+  // = the forward evaluated list entry p for this footprint. Those are exactly the entries with anything to replay
+  // here (an entry the forward culled was blended on no pixel of the footprint), so the map replaces the culling
+  // below — and a chunk without a set bit is neither copied nor waited for.
+  const uint32_t *hw = MAP ? hit_words + (size_t)warp * (size_t)hit_stride + (size_t)(range_start >> 5) + (size_t)ct : nullptr;
+  uint32_t word_next = MAP ? __ldg(hw + (first >> 5)) : 0xffffffffu;
+  bool staged_next = word_next != 0u;
+  if (lane == 0 && staged_next) stage_chunk(first);
   uint32_t phase = 0;
   int queued = 0;  // hits in queue slots [0, queued), rearmost first
   for (int c0 = first; c0 >= -32; c0 -= 32) {  // (one extra pass with no entries flushes the queue)
     const int chunk_start = range_start + c0;
-    // cull this chunk against the rectangle of the warp's live pixels
-    const unsigned live = __ballot_sync(0xffffffffu, my_last >= chunk_start);
-    const LiveRect rect = live_rect(live, wcx, wcy);
+    const uint32_t word = word_next;
+    const bool staged = staged_next && c0 >= 0;
+    word_next = (MAP && c0 >= 32) ? __ldg(hw + ((c0 - 32) >> 5)) : 0xffffffffu;
+    staged_next = c0 >= 32 && word_next != 0u;
     bool hit = false;
     float4 ra4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rb4 = ra4;
-    if (c0 >= 0) {
+    if (staged) {
       // wait for this chunk's records (all lanes poll the mbarrier's phase bit)
       uint32_t done = 0;
       while (!done) {
@@ -377,11 +388,23 @@ composite_bwd_kernel(const float *__restrict__ stream, int colors_per_camera, in
                      : "=r"(done) : "r"(aBar), "r"(phase) : "memory");
       }
       phase ^= 1u;
-      if (c0 + lane < n_w) {
-        ra4 = lds128(aS + lane * 48);
-        rb4 = lds128(aS + lane * 48 + 16);
-        const float2 ext = unpack_extents(ra4.z);
-        hit = cull_hit_reg(make_float4(ra4.x, ra4.y, ext.x, ext.y), rb4, rect);  // (+inf extents = no culling)
+      if (MAP) {
+        hit = c0 + lane < n_w && ((word >> lane) & 1u) != 0u;
+        if (hit) {
+          ra4 = lds128(aS + lane * 48);
+          rb4 = lds128(aS + lane * 48 + 16);
+        }
+      } else {
+        // no map (operator path, streams built from a foreign forward state): cull this chunk against the rectangle of
+        // the warp's live pixels (`staged` is warp-uniform: every lane takes part in the ballot)
+        const unsigned live = __ballot_sync(0xffffffffu, my_last >= chunk_start);
+        const LiveRect rect = live_rect(live, wcx, wcy);
+        if (c0 + lane < n_w) {
+          ra4 = lds128(aS + lane * 48);
+          rb4 = lds128(aS + lane * 48 + 16);
+          const float2 ext = unpack_extents(ra4.z);
+          hit = cull_hit_reg(make_float4(ra4.x, ra4.y, ext.x, ext.y), rb4, rect);  // (+inf extents = no culling)
+        }
       }
     }
     const unsigned bal = __ballot_sync(0xffffffffu, hit);
@@ -396,7 +419,7 @@ composite_bwd_kernel(const float *__restrict__ stream, int colors_per_camera, in
     // the staged chunk is consumed (every lane's reads above have returned): order them before the async proxy's
     // next write into the same bytes, then start the copy of the next chunk — it runs during the replay below
     __syncwarp();
-    if (lane == 0) {
+    if (lane == 0 && staged_next) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       stage_chunk(c0 - 32);
     }
@@ -433,7 +456,9 @@ composite_bwd_kernel(const float *__restrict__ stream, int colors_per_camera, in
 
 static int bwd_set_attr() {
   // per device and cheap: set on every call (a process may drive several GPUs)
-  if (cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (cudaFuncSetAttribute(composite_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sizeof(BwdShared)) != cudaSuccess ||
+      cudaFuncSetAttribute(composite_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)sizeof(BwdShared)) != cudaSuccess) {
     set_last_cuda_error(cudaGetLastError());
     return PM_ERR_CUDA;
@@ -482,7 +507,8 @@ static int bwd_launch(const float *splat_stream, int colors_per_camera, int D, i
                       const float *v_render, const float *v_alphas, float *v_means2d, float *v_conics, float *v_colors,
                       float *v_opacities, float *v_depths, const float *v_images, const float *v_depth_out,
                       const float *v_masks, const float *depth_out, int packed, const int32_t *tile_order,
-                      int views_per_scene, uint8_t *touched, pm_stream_t stream) {
+                      int views_per_scene, uint8_t *touched, const uint32_t *hit_words, int64_t hit_stride,
+                      pm_stream_t stream) {
   if (N < 0 || C < 0 || width <= 0 || height <= 0 || n_isects < 0 || D < 0) return PM_ERR_BAD_ARG;
   if (tile_size != kTile) return PM_ERR_UNSUPPORTED;
   const int CD = D + (has_depth ? 1 : 0);
@@ -499,11 +525,14 @@ static int bwd_launch(const float *splat_stream, int colors_per_camera, int D, i
   const int tw = (width + kTile - 1) / kTile, th = (height + kTile - 1) / kTile;
   const int64_t blocks = (int64_t)C * tw * th;
   if (blocks * kBwdParts >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
+  if (hit_words && hit_stride < pm_hit_words_stride(n_isects, C, width, height, tile_size)) return PM_ERR_WORKSPACE;
   if (bwd_set_attr() != PM_OK) return PM_ERR_CUDA;
-  composite_bwd_kernel<<<(unsigned)(blocks * kBwdParts), kBwdThreads, sizeof(BwdShared), as_stream(stream)>>>(
+  auto kernel = hit_words ? composite_bwd_kernel<true> : composite_bwd_kernel<false>;
+  kernel<<<(unsigned)(blocks * kBwdParts), kBwdThreads, sizeof(BwdShared), as_stream(stream)>>>(
       splat_stream, colors_per_camera, D, has_depth ? 1 : 0, backgrounds, isect_offsets, n_isects, d_n, N, width, height,
       tw, th, alphas, last_ids, v_render, v_alphas, v_means2d, v_conics, v_colors, v_opacities, v_depths, v_images,
-      v_depth_out, v_masks, depth_out, packed, tile_order, views_per_scene > 0 ? views_per_scene : C, transmittance, touched);
+      v_depth_out, v_masks, depth_out, packed, tile_order, views_per_scene > 0 ? views_per_scene : C, transmittance, touched,
+      hit_words, hit_stride);
   return check_launch();
 }
 
@@ -559,7 +588,8 @@ int pm_composite_bwd(const float *splat_stream, int colors_per_camera, int D, in
                      float *v_depths, uint8_t *touched, pm_stream_t stream) {
   return pm::bwd_launch(splat_stream, colors_per_camera, D, has_depth, backgrounds, isect_offsets, n_isects, d_n, N, C,
                         width, height, tile_size, alphas, last_ids, transmittance, v_render, v_alphas, v_means2d, v_conics,
-                        v_colors, v_opacities, v_depths, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, touched, stream);
+                        v_colors, v_opacities, v_depths, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, touched, nullptr, 0,
+                        stream);
 }
 
 int pm_composite_bwd_packed(const float *splat_stream, int colors_per_camera, const float *backgrounds,
@@ -568,12 +598,13 @@ int pm_composite_bwd_packed(const float *splat_stream, int colors_per_camera, co
                             const int32_t *last_ids, const float *transmittance, const float *v_images,
                             const float *v_depth_out, const float *v_masks, float *v_means2d, float *v_conics,
                             float *v_colors, float *v_opacities, float *v_depths, const int32_t *tile_order,
-                            int views_per_scene, uint8_t *touched, pm_stream_t stream) {
+                            int views_per_scene, uint8_t *touched, const uint32_t *hit_words, int64_t hit_stride,
+                            pm_stream_t stream) {
   if (!masks || !depth_out || !v_colors || !v_depths) return PM_ERR_BAD_ARG;
   return pm::bwd_launch(splat_stream, colors_per_camera, 3, 1, backgrounds, isect_offsets, n_isects, d_n, N, C, width,
                         height, tile_size, masks, last_ids, transmittance, nullptr, nullptr, v_means2d, v_conics, v_colors,
                         v_opacities, v_depths, v_images, v_depth_out, v_masks, depth_out, 1, tile_order, views_per_scene,
-                        touched, stream);
+                        touched, hit_words, hit_stride, stream);
 }
 
 }  // extern "C"

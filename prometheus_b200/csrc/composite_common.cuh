@@ -393,7 +393,8 @@ __device__ __forceinline__ unsigned footprint_mask(float mx, float my, float hx,
 template <int CAP>
 __device__ __forceinline__ void composite_group_masked_fwd(uint32_t aS, uint32_t aQ, uint32_t aCQ, uint32_t aM,
                                                            int batch_size, int list_pos, const WarpFootprint &fp,
-                                                           PixelState &st) {
+                                                           PixelState &st, uint32_t *__restrict__ hit_words = nullptr,
+                                                           int rel0 = 0) {
   static_assert(CAP <= 1024, "one footprint word per lane");
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
@@ -432,7 +433,15 @@ __device__ __forceinline__ void composite_group_masked_fwd(uint32_t aS, uint32_t
 #ifdef PM_STATS
     if (lane == 0) { atomicAdd(&g_pm_stats[0], 1ull); atomicAdd(&g_pm_stats[1], (unsigned long long)n); }
 #endif
-    if (hit) sts32(aQ + __popc(bal & lt) * 4, ga);
+    if (hit) {
+      sts32(aQ + __popc(bal & lt) * 4, ga);
+      // hit map for the backward (one bit per (warp footprint, list entry), zero-filled by the caller): the entries this
+      // warp evaluates are exactly the ones its backward has to replay — it then skips its own culling
+      if (hit_words) {
+        const int p = rel0 + (int)((ga - aS) >> 4);  // position in the tile's list
+        atomicOr(hit_words + (p >> 5), 1u << (p & 31));
+      }
+    }
     if (lane == 0) sts32(aQ + n * 4, aS + CAP * 16);
     __syncwarp();
     for (int i = 0; i < n; i += 2) {

@@ -230,7 +230,8 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, int64_t record_stri
                        int32_t *__restrict__ overflow_flag, float *__restrict__ images,
                        float *__restrict__ depth_out, float *__restrict__ masks,
                        const int32_t *__restrict__ tile_order, int views_per_scene,
-                       float *__restrict__ transmittance, float *__restrict__ stream) {
+                       float *__restrict__ transmittance, float *__restrict__ stream,
+                       uint32_t *__restrict__ hit_words, int64_t hit_stride) {
   extern __shared__ __align__(16) unsigned char tr_smem[];
   TrShared &sh = *reinterpret_cast<TrShared *>(tr_smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -394,8 +395,13 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, int64_t record_stri
     __syncthreads();
     // @region tr_composite_call
     // composite the whole group; warps do not wait for each other — same arithmetic as composite_fwd_kernel
-    if (!__all_sync(0xffffffffu, pixel_done(st)))
-      composite_group_masked_fwd<kTrCap>(aS, aQ, aCQ, aM, m, start + list_base + gs, fp, st);
+    if (!__all_sync(0xffffffffu, pixel_done(st))) {
+      // hit map of this (warp footprint, tile): bit p of the words at (start >> 5) + ct = list entry p was evaluated
+      // (tiles never share a word: (start >> 5) + ct grows by at least ceil(count / 32) from tile to tile); formed
+      // here from values that are live anyway — held across the kernel the pointer cost two registers and a spill
+      uint32_t *hit_base = hit_words ? hit_words + (size_t)warp * (size_t)hit_stride + (size_t)(start >> 5) + (size_t)ct : nullptr;
+      composite_group_masked_fwd<kTrCap>(aS, aQ, aCQ, aM, m, start + list_base + gs, fp, st, hit_base, list_base + gs);
+    }
   };
 
   // @region tr_group_walk
@@ -519,6 +525,12 @@ tile_render_fwd_kernel(const uint64_t *__restrict__ records, int64_t record_stri
 
 extern "C" {
 
+int64_t pm_hit_words_stride(int64_t n_isects, int C, int width, int height, int tile_size) {
+  if (n_isects < 0 || C < 0 || width <= 0 || height <= 0 || tile_size <= 0) return 0;
+  const int64_t tw = (width + tile_size - 1) / tile_size, th = (height + tile_size - 1) / tile_size;
+  return (n_isects >> 5) + (int64_t)C * tw * th + 1;
+}
+
 static int tile_render_launch(const uint64_t *records, int64_t record_stride, const int32_t *isect_offsets, int64_t n_isects,
                               const int32_t *d_n, const float *means2d, const float *conics, const float *opacities,
                               const float *colors, int colors_per_camera, int D, const float *depths,
@@ -526,7 +538,7 @@ static int tile_render_launch(const uint64_t *records, int64_t record_stride, co
                               float *render, float *alphas, int32_t *last_ids, int32_t *flatten_ids,
                               int32_t *sorted_counts, int32_t *overflow_flag, float *images, float *depth_out,
                               float *masks, const int32_t *tile_order, int views_per_scene, float *transmittance,
-                              float *splat_stream, pm_stream_t stream) {
+                              float *splat_stream, uint32_t *hit_words, int64_t hit_stride, pm_stream_t stream) {
   if (N < 0 || C < 0 || width <= 0 || height <= 0 || n_isects < 0 || D < 0 || record_stride < 0) return PM_ERR_BAD_ARG;
   if (record_stride >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
   if (tile_size != pm::kTile) return PM_ERR_UNSUPPORTED;
@@ -551,6 +563,7 @@ static int tile_render_launch(const uint64_t *records, int64_t record_stride, co
   const int tw = (width + pm::kTile - 1) / pm::kTile, th = (height + pm::kTile - 1) / pm::kTile;
   const int64_t blocks = (int64_t)C * tw * th;
   if (blocks >= ((int64_t)1 << 31)) return PM_ERR_RANGE;
+  if (hit_words && hit_stride < pm_hit_words_stride(n_isects, C, width, height, tile_size)) return PM_ERR_WORKSPACE;
   // per device and cheap: set on every call (a process may drive several GPUs)
   if (cudaFuncSetAttribute(pm::tile_render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)pm::kTrSmemBytes) != cudaSuccess) {
@@ -560,7 +573,8 @@ static int tile_render_launch(const uint64_t *records, int64_t record_stride, co
   pm::tile_render_fwd_kernel<<<(unsigned)blocks, pm::kTrThreads, pm::kTrSmemBytes, pm::as_stream(stream)>>>(
       records, record_stride, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera, D, depths,
       backgrounds, N, width, height, tw, th, render, alphas, last_ids, flatten_ids, sorted_counts, overflow_flag,
-      images, depth_out, masks, tile_order, views_per_scene > 0 ? views_per_scene : C, transmittance, splat_stream);
+      images, depth_out, masks, tile_order, views_per_scene > 0 ? views_per_scene : C, transmittance, splat_stream,
+      hit_words, hit_stride);
   return pm::check_launch();
 }
 
@@ -586,7 +600,7 @@ int pm_tile_render_fwd(const uint64_t *records, const int32_t *isect_offsets, in
   return tile_render_launch(records, 0, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera,
                             D, depths, backgrounds, N, C, width, height, tile_size, render, alphas, last_ids,
                             flatten_ids, sorted_counts, overflow_flag, nullptr, nullptr, nullptr, tile_order, 0, transmittance,
-                            splat_stream, stream);
+                            splat_stream, nullptr, 0, stream);
 }
 
 int pm_tile_render_packed_fwd(const uint64_t *records, int64_t record_stride, const int32_t *isect_offsets, int64_t n_isects,
@@ -596,12 +610,12 @@ int pm_tile_render_packed_fwd(const uint64_t *records, int64_t record_stride, co
                               int tile_size, float *images, float *depth_out, float *masks, int32_t *last_ids,
                               int32_t *flatten_ids, int32_t *sorted_counts, int32_t *overflow_flag,
                               const int32_t *tile_order, int views_per_scene, float *transmittance,
-                              float *splat_stream, pm_stream_t stream) {
+                              float *splat_stream, uint32_t *hit_words, int64_t hit_stride, pm_stream_t stream) {
   if (!images) return PM_ERR_BAD_ARG;
   return tile_render_launch(records, record_stride, isect_offsets, n_isects, d_n, means2d, conics, opacities, colors, colors_per_camera,
                             3, depths, backgrounds, N, C, width, height, tile_size, nullptr, nullptr, last_ids,
                             flatten_ids, sorted_counts, overflow_flag, images, depth_out, masks, tile_order, views_per_scene,
-                            transmittance, splat_stream, stream);
+                            transmittance, splat_stream, hit_words, hit_stride, stream);
 }
 
 }  // extern "C"

@@ -411,6 +411,9 @@ def composite_fwd(means2d, conics, opacities, colors, depths, backgrounds, offse
 
 
 STREAM_FLOATS = 12  # floats per splat-stream record (include/prometheus_gs.h)
+# the fused forward leaves the backward a map of the list entries each warp footprint evaluated (1 bit per entry and
+# footprint), so that composite_bwd replays those and skips its own culling ("0": developer knob for A/B runs)
+HIT_MAP = __import__("os").environ.get("PM_HIT_MAP", "1") != "0"
 
 
 @_instrument("splat_stream_build", 1)
@@ -491,8 +494,9 @@ def tile_render_packed_fwd(records, offsets, means2d, conics, opacities, colors,
                            capacity=None):
     """Fused sort-as-you-go forward with the module epilogue: -> images [C,3,H,W] (2 rgb - 1),
     depth_out [C,1,H,W] (expected depth), masks [C,1,H,W], last_ids [C,H,W], flatten_ids (sorted prefix per
-    tile), sorted_counts [C,th,tw], overflow flag int32[1], transmittance [C,H,W] and splat_stream [n,12] (both None
-    unless for_backward: the backward's exact T_final and the records it replays). `records` may be a speculative
+    tile), sorted_counts [C,th,tw], overflow flag int32[1], transmittance [C,H,W], splat_stream [n,12] and hit_words
+    [8, W] int32 (all three None unless for_backward: the backward's exact T_final, the records it replays and the map of
+    the entries each warp footprint evaluated, which replaces the backward's culling). `records` may be a speculative
     capacity with the true count in d_n[0] (see pm_tile_render_packed_fwd). record_stride > 0: `records` is the
     fixed-capacity tile layout of project_fwd(tile_capacity=...) and `capacity` sizes flatten_ids / the stream."""
     L = _lib.load()
@@ -511,24 +515,30 @@ def tile_render_packed_fwd(records, offsets, means2d, conics, opacities, colors,
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
     trans = torch.empty(C, height, width, device=dev) if for_backward else None
     stream = torch.empty(n, STREAM_FLOATS, device=dev) if for_backward else None
+    hit_words = None
+    if for_backward and HIT_MAP:
+        hit_words = torch.zeros(8, int(L.pm_hit_words_stride(n, C, width, height, TILE)), dtype=torch.int32, device=dev)
     _lib.check(L.pm_tile_render_packed_fwd(_ptr(records), int(record_stride), _ptr(offsets), n, _ptr(d_n), _ptr(means2d), _ptr(conics),
                                            _ptr(opacities), _ptr(colors), per_cam, _ptr(depths), _ptr(backgrounds), N, C,
                                            width, height, TILE, _ptr(images), _ptr(depth_out), _ptr(masks),
                                            _ptr(last_ids), _ptr(flat), _ptr(sorted_counts), _ptr(flag), _ptr(tile_order),
-                                           int(views_per_scene), _ptr(trans), _ptr(stream), _stream()),
+                                           int(views_per_scene), _ptr(trans), _ptr(stream), _ptr(hit_words),
+                                           0 if hit_words is None else hit_words.shape[1], _stream()),
                "pm_tile_render_packed_fwd")
-    return images, depth_out, masks, last_ids, flat, sorted_counts, flag, trans, stream
+    return images, depth_out, masks, last_ids, flat, sorted_counts, flag, trans, stream, hit_words
 
 
 @_instrument("composite_bwd", 1)
 def composite_bwd_packed(means2d, conics, opacities, colors, depths, backgrounds, offsets, flatten_ids, width, height,
                          masks, depth_out, last_ids, v_images, v_depth_out, v_masks, d_n=None, tile_order=None,
-                         views_per_scene=0, transmittance=None, stream=None, touched=None):
+                         views_per_scene=0, transmittance=None, stream=None, touched=None, hit_words=None):
+    """hit_words: the forward's hit map (tile_render_packed_fwd), valid only together with ITS stream."""
     L = _lib.load()
     C, N = means2d.shape[:2]
     colors, per_cam, D = _colors_layout(colors, C, N * (C // views_per_scene if views_per_scene else 1))
     if stream is None:
         stream = splat_stream_build(means2d, conics, opacities, colors, depths, flatten_ids, d_n, views_per_scene)
+        hit_words = None
     v_images, v_depth_out, v_masks = (_opt(t, torch.float32, "grad") for t in (v_images, v_depth_out, v_masks))
     # the five accumulation targets as views of ONE zero-filled allocation (one fill kernel instead of five)
     shapes = [means2d.shape, conics.shape, colors.shape, opacities.shape, depths.shape]
@@ -543,7 +553,8 @@ def composite_bwd_packed(means2d, conics, opacities, colors, depths, backgrounds
                                          N, C, width, height, TILE, _ptr(masks), _ptr(depth_out), _ptr(last_ids),
                                          _ptr(transmittance), _ptr(v_images), _ptr(v_depth_out), _ptr(v_masks),
                                          _ptr(v_means2d), _ptr(v_conics), _ptr(v_colors), _ptr(v_opac), _ptr(v_depths),
-                                         _ptr(tile_order), int(views_per_scene), _ptr(touched), _stream()),
+                                         _ptr(tile_order), int(views_per_scene), _ptr(touched), _ptr(hit_words),
+                                         0 if hit_words is None else hit_words.shape[1], _stream()),
                "pm_composite_bwd_packed")
     return v_means2d, v_conics, v_colors, v_opac, v_depths
 

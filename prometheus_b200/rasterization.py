@@ -252,12 +252,12 @@ class _TileRenderPacked(torch.autograd.Function):
         # the exact final transmittance (4 B/pixel) and the splat stream the backward replays (48 B per staged
         # Gaussian) are written only when a backward will consume them
         need_bwd = any(ctx.needs_input_grad[:6])
-        images, depth_out, masks, last_ids, flat, sorted_counts, flag, trans, stream = ops.tile_render_packed_fwd(
+        images, depth_out, masks, last_ids, flat, sorted_counts, flag, trans, stream, hit_words = ops.tile_render_packed_fwd(
             records, offsets, means2d, conics, opacities, colors, depths, backgrounds, width, height, d_n=stats,
             tile_order=tile_order, views_per_scene=views_per_scene, for_backward=need_bwd, record_stride=record_stride,
             capacity=capacity)
         ctx.save_for_backward(means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, masks, depth_out,
-                              last_ids, stats, sorted_counts, trans, stream)
+                              last_ids, stats, sorted_counts, trans, stream, hit_words)
         ctx.dims = (width, height)
         ctx.mark_non_differentiable(flag, flat, sorted_counts)
         return images, depth_out, masks, flag, flat, sorted_counts
@@ -265,7 +265,7 @@ class _TileRenderPacked(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_images, v_depth_out, v_masks, _vf, _vflat, _vsc):
         (means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, masks, depth_out, last_ids,
-         stats, sorted_counts, trans, stream) = ctx.saved_tensors
+         stats, sorted_counts, trans, stream, hit_words) = ctx.saved_tensors
         width, height = ctx.dims
         # the backward replays what the forward sorted: tiles with the longest sorted prefix go first
         order = ops.tile_scan(sorted_counts, want_order=True)[2]
@@ -273,7 +273,7 @@ class _TileRenderPacked(torch.autograd.Function):
         v_means2d, v_conics, v_colors, v_opac, v_depths = ops.composite_bwd_packed(
             means2d, conics, opacities, colors, depths, backgrounds, offsets, flat, width, height, masks, depth_out,
             last_ids, v_images, v_depth_out, v_masks, d_n=stats, tile_order=order, views_per_scene=ctx.views_per_scene,
-            transmittance=trans, stream=stream, touched=touched)
+            transmittance=trans, stream=stream, touched=touched, hit_words=hit_words)
         _leave_touched(ctx.link, touched, v_means2d, v_conics, v_depths)
         if ctx.grad_sink is not None:
             ctx.grad_sink["v_means2d"] = v_means2d

@@ -32,7 +32,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert os.path.exists(_lib.library_path())
     for s in declared_symbols():
         assert hasattr(lib, s), s
-    assert lib.pm_abi_version() == 5
+    assert lib.pm_abi_version() == 6
     assert lib.pm_status_string(0) == b"ok"
     assert b"workspace" in lib.pm_status_string(-3)
 

@@ -924,6 +924,55 @@ def test_single_pass_binning_same_bits_and_overflow_recovery():
     torch.testing.assert_close(grads[0], grads[1], rtol=1e-4, atol=1e-7)
 
 
+def test_hit_map_backward_equals_the_culling_backward():
+    """The fused forward leaves a map of the list entries each warp footprint evaluated; composite_bwd replays exactly
+    those instead of culling every chunk itself. Same gradients as the culling form (up to the order of the atomics),
+    on the two-pass and the single-pass layouts, and the map is not empty."""
+    from prometheus_b200 import GaussianRenderer, ops
+
+    sc, conv = _module_scene()
+    cams = sc.cameras_out.to(DEV)
+    grads = {}
+    old = ops.HIT_MAP
+    try:
+        for use_map in (False, True):
+            ops.HIT_MAP = use_map
+            r = GaussianRenderer().to(DEV)
+            for call in range(2):  # first call: two binning passes; second: single pass, usable tiles
+                p = sc.params.to(DEV).clone().requires_grad_(True)
+                im, de, ma, _, _ = r(cams, conv(p, sc.cameras_in.to(DEV)), h=80, w=80)
+                (im.square().mean() + de.mean() + ma.mean()).backward()
+                grads[(use_map, call)] = p.grad.clone()
+    finally:
+        ops.HIT_MAP = old
+    for call in range(2):
+        share, worst = violations(grads[(True, call)].cpu().numpy(), grads[(False, call)].cpu().numpy())
+        assert share <= 1e-4, (call, share, worst)
+    # the map itself: bits only inside the tiles' lists, at least one per non-empty sorted tile
+    with torch.no_grad():
+        g = conv(sc.params.to(DEV), sc.cameras_in.to(DEV))
+        vm, K = ops.camera_prep(cams[0], 80, 80)
+        radii, m2, dep, con, _, counts = ops.project_fwd(g[0][0], g[4][0], g[3][0], vm, K, 80, 80, count_tiles=False, tile_histogram=True)
+        offs, stats, order = ops.tile_scan(counts, want_order=True)
+        n = int(stats[0].item())
+        rec = ops.bin_scatter(m2, radii, dep, offs, 80, 80, n)
+        out = ops.tile_render_packed_fwd(rec, offs, m2, con, g[2][0, :, 0].contiguous(), g[1][0, :, 0].contiguous(), dep,
+                                         torch.ones(vm.shape[0], 3, device=DEV), 80, 80, tile_order=order, for_backward=True)
+    hit = out[9]
+    assert hit is not None and hit.shape[0] == 8 and hit.shape[1] >= (n >> 5) + counts.numel() + 1
+    words = hit.cpu().numpy().view(np.uint32)
+    off = offs.reshape(-1).cpu().numpy().astype(np.int64)
+    cnt = counts.reshape(-1).cpu().numpy().astype(np.int64)
+    used = np.zeros(words.shape[1], dtype=bool)
+    for t in range(len(off)):
+        b = (off[t] >> 5) + t
+        nw = (cnt[t] + 31) // 32
+        used[b:b + nw] = True
+        if cnt[t] % 32 and nw:
+            assert not (words[:, b + nw - 1] >> np.uint32(cnt[t] % 32)).any()   # no bit beyond the tile's list
+    assert not words[:, ~used].any() and words.any()
+
+
 def test_single_pass_binning_fallback_paths():
     """Single-pass binning outside its comfort zone: unstructured Gaussians on a 66 x 66 tile grid (a CTA's bounding
     box exceeds the shared-memory window: records go to global memory one atomic each) with a few splats so large
