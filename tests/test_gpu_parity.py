@@ -1591,3 +1591,12 @@ def test_nvtx_ranges_do_not_change_results():
     assert ops.LAUNCHES == before + 1
     for a, b in zip(got, want):
         assert torch.equal(a, b)
+
+
+def test_randomised_stress_of_the_fused_paths():
+    """tools/stress_fused.py, 15 cases: random sizes (not multiples of 16), camera counts, anisotropic splats, thin depth
+    shells, exactly repeated depths, everything on a few tiles — fused renderer vs separate stages (same bits), usable-tile
+    single-pass binning (same pixels), the operator's lazy meta (same arrays), hit-map backward vs culling backward."""
+    from tools import stress_fused
+
+    assert stress_fused.run(15) == 0

@@ -2,7 +2,9 @@
 """Randomised stress test of the fused fast path against the separate-stage path (developer tool; GPU):
 random sizes, camera counts, splat sizes, opacities and depth distributions (incl. thin dense shells and
 exactly repeated depths that exercise the second-level buckets / radix fallback). Bit-for-bit equality of
-render / alpha is required; a raised overflow flag is reported, not an error."""
+render / alpha is required; a raised overflow flag is reported, not an error. Also per case: single-pass binning of the
+usable tiles (same pixels), the operator's lazy meta (same arrays), and — every third case — the backward with the
+forward's hit map against the backward with its own culling."""
 import sys
 import os
 
@@ -15,9 +17,9 @@ rz = importlib.import_module("prometheus_b200.rasterization")
 from prometheus_b200 import ops  # noqa: E402
 
 DEV = "cuda"
-n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
-bad = 0
-for case in range(n_cases):
+
+
+def run_case(case: int) -> bool:
     g = torch.Generator().manual_seed(1000 + case)
     r = lambda *s: torch.rand(*s, generator=g)
     W = int(16 + r(1) * 240)
@@ -59,8 +61,43 @@ for case in range(n_cases):
             torch.equal(de[:, 0], r2[..., 3])
     n_is = int(m2["flatten_ids"].numel())
     cnt_max = int(torch.diff(torch.cat([m2["isect_offsets"].flatten(), torch.tensor([n_is], device=DEV, dtype=torch.int32)])).max()) if n_is else 0
-    print("case %2d mode %d %3dx%3d C=%d n=%6d isects=%8d max tile=%6d fallback=%s  %s" % (
-        case, mode, W, H, C, n, n_is, cnt_max, fell_back, "ok" if ok and ok2 else "MISMATCH fused=%s packed=%s" % (ok, ok2)))
-    bad += not (ok and ok2)
-print("mismatches:", bad)
-sys.exit(1 if bad else 0)
+    # single-pass binning of the usable tiles only (the module's steady state): same pixels from fewer records
+    ok3, n_u = True, n_is
+    if n_is and int(info["overflow_flag"].item()) == 0:
+        im3, de3, ma3, info3 = rz.render_views_packed(*args[:7], bg, W, H, capacity=n_is + 5, tile_capacity=cnt_max + 1)
+        n_u = int(info3["stats"][0].item())
+        ok3 = info3["usable_tiles"] and n_u <= n_is and int(info3["overflow_flag"].item()) == 0 and \
+            torch.equal(im3, im) and torch.equal(de3, de) and torch.equal(ma3, ma)
+    # the operator with its lazy meta: fused render, gsplat's sorted arrays when read
+    r4, a4, m4 = rz.rasterization(*args, backgrounds=bg, render_mode="RGB+ED", packed=False)
+    ok4 = torch.equal(r4, r2) and torch.equal(a4, a2) and torch.equal(m4["flatten_ids"], m2["flatten_ids"]) and \
+        torch.equal(m4["isect_ids"], m2["isect_ids"]) and torch.equal(m4["tiles_per_gauss"], m2["tiles_per_gauss"])
+    # backward: the forward's hit map vs the backward's own culling (same gradients up to the order of the atomics)
+    ok5 = True
+    if n_is and int(info["overflow_flag"].item()) == 0 and case % 3 == 0:
+        grads = []
+        for use_map in (False, True):
+            ops.HIT_MAP = use_map
+            leaves = [t.clone().requires_grad_(True) for t in args[:5]]
+            im5, de5, ma5, _ = rz.render_views_packed(*leaves, *args[5:7], bg, W, H, capacity=n_is + 5, tile_capacity=cnt_max + 1)
+            (im5.square().mean() + de5.mean() + ma5.mean()).backward()
+            grads.append([t.grad for t in leaves])
+        ops.HIT_MAP = True
+        for ga, gb in zip(*grads):
+            tol = 1e-5 * float(gb.abs().max()) + 1e-7
+            ok5 = ok5 and bool(((ga - gb).abs() <= tol + 1e-3 * gb.abs()).all())
+    print("case %2d mode %d %3dx%3d C=%d n=%6d isects=%8d (usable %8d) max tile=%6d fallback=%s  %s" % (
+        case, mode, W, H, C, n, n_is, n_u, cnt_max, fell_back,
+        "ok" if ok and ok2 and ok3 and ok4 and ok5 else "MISMATCH fused=%s packed=%s usable=%s lazy=%s hitmap=%s" % (ok, ok2, ok3, ok4, ok5)))
+    return bool(ok and ok2 and ok3 and ok4 and ok5)
+
+
+def run(n_cases: int = 40, first: int = 0) -> int:
+    """-> number of mismatching cases among first .. first + n_cases - 1"""
+    return sum(not run_case(c) for c in range(first, first + n_cases))
+
+
+if __name__ == "__main__":
+    bad = run(int(sys.argv[1]) if len(sys.argv) > 1 else 40)
+    print("mismatches:", bad)
+    sys.exit(1 if bad else 0)
