@@ -1600,3 +1600,5 @@ def test_randomised_stress_of_the_fused_paths():
     from tools import stress_fused
 
     assert stress_fused.run(15) == 0
+    # adversarial splats: needles and discs with axis ratios up to 5000, image-sized splats, opacities around 1 / 255
+    assert stress_fused.run(8, first=1000) == 0

@@ -42,6 +42,17 @@ def run_case(case: int) -> bool:
     quats = torch.randn(n, 4, generator=g)
     scales = 0.002 + r(n, 3) * (0.03 if mode != 3 else 0.01)
     opac = r(n) ** (1 if case % 2 else 3) * (0.15 if mode in (2, 3) else 1.0)
+    if case >= 1000:
+        # adversarial splats for the usable-tile binning and the culling extents: needle- and disc-shaped Gaussians (axis
+        # ratios up to 5000), a few that cover the whole image, opacities on both sides of the 1 / 255 threshold and at 1
+        scales = torch.exp(torch.log(torch.tensor(1e-4)) + r(n, 3) * (torch.log(torch.tensor(0.5)) - torch.log(torch.tensor(1e-4))))
+        scales[: max(1, n // 500)] = 2.0
+        pick = r(n)
+        opac = torch.where(pick < 0.25, 1.0 / 255.0 + (r(n) - 0.5) * 2e-4, torch.where(pick < 0.35, torch.ones(n), r(n)))
+        if n > 20000:  # keep the lists of these image-sized splats bounded
+            keep = torch.arange(n) % (n // 20000 + 1) == 0
+            means, quats, scales, opac = means[keep], quats[keep], scales[keep], opac[keep]
+            n = means.shape[0]
     colors = r(n, 3)
     vm = torch.eye(4).repeat(C, 1, 1)
     vm[:, 0, 3] = torch.linspace(-0.2, 0.2, C) if C > 1 else 0.0
@@ -97,7 +108,7 @@ def run(n_cases: int = 40, first: int = 0) -> int:
     return sum(not run_case(c) for c in range(first, first + n_cases))
 
 
-if __name__ == "__main__":
-    bad = run(int(sys.argv[1]) if len(sys.argv) > 1 else 40)
+if __name__ == "__main__":  # stress_fused.py [n_cases [first_case]]   (first_case >= 1000: adversarial splats)
+    bad = run(int(sys.argv[1]) if len(sys.argv) > 1 else 40, int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     print("mismatches:", bad)
     sys.exit(1 if bad else 0)
