@@ -36,7 +36,8 @@ extern "C" {
 /* 2: exact final transmittance kept for the backward; 3: splat stream (TMA-replayed backward), touched-pair map;
  * 4: pm_project_scatter_fwd (single-pass binning), record_stride of pm_tile_render_packed_fwd;
  * 5: pm_project_scatter_fwd(opacities): bins only the tiles a splat can be seen in; histogram-only form;
- * 6: hit map from pm_tile_render_packed_fwd to pm_composite_bwd_packed (pm_hit_words_stride) */
+ * 6: hit map from pm_tile_render_packed_fwd to pm_composite_bwd_packed (pm_hit_words_stride); pm_bin_scatter(conics,
+ *    opacities): the usable-tile rule for the two-pass binning as well */
 #define PM_ABI_VERSION 6
 
 #if defined(__GNUC__)
@@ -254,11 +255,16 @@ PM_API int pm_tile_scan(const int32_t *tile_counts, int64_t T, int32_t *isect_of
 
 /* Scatter every (pair, tile) intersection into its tile segment as a packed
  * 8-byte record {depth bits (low 32), flatten id (high 32)}. cursors [T] must be
- * zero-filled by the caller. Order inside a segment is unspecified. */
+ * zero-filled by the caller. Order inside a segment is unspecified.
+ * conics [C,N,3] + opacities [S * N] (both or neither; views_per_scene as in pm_project_count_fwd): scatter only the
+ * tiles a splat can be seen in — the rule of pm_project_scatter_fwd(opacities), whose histogram-only form
+ * (records = NULL) then supplies the counts behind isect_offsets. NULL: gsplat's AABB (the counts of
+ * pm_project_count_fwd / pm_bin_count). */
 PM_API int pm_bin_scatter(const float *means2d, const int32_t *radii, const float *depths,
                           const int32_t *isect_offsets, int32_t *cursors, int N, int C,
                           int tile_size, int tile_width, int tile_height,
-                          uint64_t *records, int64_t capacity, pm_stream_t stream);
+                          uint64_t *records, int64_t capacity, const float *conics, const float *opacities,
+                          int views_per_scene, pm_stream_t stream);
 
 /* Segment size pm_tile_sort sorts in one shared-memory pass (entries). Larger
  * segments are first split by depth through `scratch` (see pm_tile_sort). */

@@ -38,7 +38,7 @@ SIGNATURES = {
     "pm_project_scatter_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "pm_bin_count": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "pm_tile_scan": (c_int, [_P, _L, _P, _P, _P, _P]),
-    "pm_bin_scatter": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _L, _P]),
+    "pm_bin_scatter": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _L, _P, _P, _I, _P]),
     "pm_tile_sort_capacity": (c_int, []),
     "pm_tile_sort": (c_int, [_P, _P, _P, _L, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "pm_project_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -80,40 +80,7 @@ constexpr int kProjCamChunk = 32;  // cameras per launch (shared-memory table); 
 #ifndef PM_PROJ_MINBLOCKS
 #define PM_PROJ_MINBLOCKS 5  // 48 registers: 0.320 -> 0.316 ms on C2 (6: 0.318)
 #endif
-// Fast-path binning bins the tiles a splat can actually be SEEN in: gsplat's tile AABB is the square of 3 sigma of the
-// LARGER axis, but the compositor skips a splat wherever alpha < 1/255, i.e. outside the ellipse sigma <= ln(255 o),
-// whose half extents along x / y are sqrt(2 ln(255 o) Sigma_xx / yy) — 19-20 % fewer (Gaussian, tile) pairs on the
-// anisotropic splats of C2 / C5 (tools/isect_stats.py). A tile is kept iff it lies in gsplat's AABB (never a tile more
-// than upstream) AND the span of its pixel centres meets that extent. The extent is the compositor's OWN culling
-// extent (alpha_extents, common.cuh: the value its footprint / live-rectangle tests use, already inflated against fp
-// rounding), widened once more, so a dropped tile is one where the compositor would have culled the splat on every
-// pixel anyway: images, depths, masks and gradients are unchanged bit for bit (checked at full size on C1 / C2 / C3 /
-// C5, tests/test_gpu_parity_full.py: check_usable_tiles); only the fast path's private intersection lists get shorter.
-__device__ __forceinline__ void usable_tiles(float mx, float my, float q0, float q1, float q2, float o, int &x0, int &x1,
-                                             int &y0, int &y1) {
-  // alpha_extents (common.cuh) with approximate division / square root (a few ulp; this kernel is issue-bound and
-  // the IEEE forms cost 0.04 ms on C2), widened by 1e-4 relative + 0.01 px + the rounding of the closed form below
-  const float o255 = o * 255.0f;
-  if (!(o255 > 1.0f)) { x1 = x0; y1 = y0; return; }   // alpha < 1/255 everywhere
-  const float w = q1 * q1;
-  const float det = fmaf(q0, q2, -w) + fmaf(-q1, q1, w);
-  if (!(det > 0.0f) || !(q0 > 0.0f) || !(q2 > 0.0f)) return;  // degenerate conic: keep gsplat's box
-  const float r = __fdividef(2.0f * __logf(o255) * 1.001f + 1e-3f, det);
-  const float ex = r * q2, ey = r * q0;
-  float hx = ex * rsqrtf(ex) * 1.005f + 0.05f, hy = ey * rsqrtf(ey) * 1.005f + 0.05f;
-  if (!(hx < 1e6f) || !(hy < 1e6f)) return;           // NaN / huge: keep gsplat's box
-  hx = hx * 1.0001f + 0.01f + 1e-6f * fabsf(mx);
-  hy = hy * 1.0001f + 0.01f + 1e-6f * fabsf(my);
-  // tile t holds the pixel centres 16 t + 0.5 .. 16 t + 15.5 (composite_common.cuh: footprint_mask keeps it iff
-  // 16 t + 0.5 - m <= h and 16 t + 15.5 - m >= -h)
-  const float inv_ts = 1.0f / (float)kTile;
-  const float lo_x = fmaxf((mx - hx - ((float)kTile - 0.5f)) * inv_ts, -1.0f), hi_x = fminf((mx + hx - 0.5f) * inv_ts, 1e6f);
-  const float lo_y = fmaxf((my - hy - ((float)kTile - 0.5f)) * inv_ts, -1.0f), hi_y = fminf((my + hy - 0.5f) * inv_ts, 1e6f);
-  x0 = max(x0, (int)ceilf(lo_x)); x1 = min(x1, (int)floorf(hi_x) + 1);
-  y0 = max(y0, (int)ceilf(lo_y)); y1 = min(y1, (int)floorf(hi_y) + 1);
-  if (x1 <= x0 || y1 <= y0) { x1 = x0; y1 = y0; }
-}
-
+// (usable_tiles: common.cuh — shared with the scatter pass of the two-pass binning, tile_sort.cu)
 // MODE 0: projection only; 1: + per-(camera, tile) histogram; 2: + single-pass binning (histogram and the
 // intersection records, each written into its tile's fixed-capacity region — binning_common.cuh)
 template <int MODE>

@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(256)
 bin_kernel(const float *__restrict__ means2d, const int32_t *__restrict__ radii,
            const float *__restrict__ depths, const int32_t *__restrict__ offsets,
            int32_t *__restrict__ global, int N, int tile_width, int tile_height, int chunk_stride,
-           uint64_t *__restrict__ records, int64_t capacity) {
+           uint64_t *__restrict__ records, int64_t capacity, const float *__restrict__ conics,
+           const float *__restrict__ opacities, int views_per_scene) {
   __shared__ TileHash h;
   __shared__ int win[kWinCells];
   __shared__ int win_base[SCATTER ? kWinCells : 1];
@@ -66,6 +67,10 @@ bin_kernel(const float *__restrict__ means2d, const int32_t *__restrict__ radii,
     if (r > 0) {
       const float2 m = reinterpret_cast<const float2 *>(means2d)[f];
       tile_aabb(m.x, m.y, r, tile_width, tile_height, x0, x1, y0, y1);
+      // only the tiles the splat can be seen in (common.cuh: usable_tiles) — the rule of the histogram this pass fills
+      if (opacities != nullptr)
+        usable_tiles(m.x, m.y, conics[f * 3 + 0], conics[f * 3 + 1], conics[f * 3 + 2],
+                     opacities[(size_t)(cid / views_per_scene) * N + g], x0, x1, y0, y1);
       if (SCATTER) rec = ((uint64_t)(uint32_t)f << 32) | (uint64_t)__float_as_uint(depths[f]);
     }
   }
@@ -519,7 +524,8 @@ int pm_bin_count(const float *means2d, const int32_t *radii, int N, int C, int t
   const int nb = (N + 255) / 256;
   dim3 grid(nb, C);
   pm::bin_kernel<false><<<grid, 256, 0, pm::as_stream(stream)>>>(
-      means2d, radii, nullptr, nullptr, tile_counts, N, tile_width, tile_height, pm::coprime_stride(nb), nullptr, 0);
+      means2d, radii, nullptr, nullptr, tile_counts, N, tile_width, tile_height, pm::coprime_stride(nb), nullptr, 0,
+      nullptr, nullptr, 1);
   return pm::check_launch();
 }
 
@@ -534,8 +540,10 @@ int pm_tile_scan(const int32_t *tile_counts, int64_t T, int32_t *isect_offsets, 
 int pm_bin_scatter(const float *means2d, const int32_t *radii, const float *depths,
                    const int32_t *isect_offsets, int32_t *cursors, int N, int C, int tile_size,
                    int tile_width, int tile_height, uint64_t *records, int64_t capacity,
-                   pm_stream_t stream) {
+                   const float *conics, const float *opacities, int views_per_scene, pm_stream_t stream) {
   if (N < 0 || C < 0 || tile_width <= 0 || tile_height <= 0 || capacity < 0) return PM_ERR_BAD_ARG;
+  if ((conics == nullptr) != (opacities == nullptr)) return PM_ERR_BAD_ARG;
+  if (views_per_scene < 0 || (views_per_scene > 0 && C % views_per_scene != 0)) return PM_ERR_BAD_ARG;
   if (tile_size != pm::kTile) return PM_ERR_UNSUPPORTED;
   if (N == 0 || C == 0 || capacity == 0) return PM_OK;
   if (!means2d || !radii || !depths || !isect_offsets || !cursors || !records) return PM_ERR_BAD_ARG;
@@ -545,7 +553,8 @@ int pm_bin_scatter(const float *means2d, const int32_t *radii, const float *dept
   const int nb = (N + 255) / 256;
   dim3 grid(nb, C);
   pm::bin_kernel<true><<<grid, 256, 0, pm::as_stream(stream)>>>(
-      means2d, radii, depths, isect_offsets, cursors, N, tile_width, tile_height, pm::coprime_stride(nb), records, capacity);
+      means2d, radii, depths, isect_offsets, cursors, N, tile_width, tile_height, pm::coprime_stride(nb), records, capacity,
+      conics, opacities, views_per_scene > 0 ? views_per_scene : (C > 0 ? C : 1));
   return pm::check_launch();
 }
 

@@ -308,15 +308,24 @@ def tile_scan(tile_counts, want_order=False):
 
 
 @_instrument("bin_scatter", 1)
-def bin_scatter(means2d, radii, depths, offsets, width, height, capacity: int):
-    """Scatter intersections into their tile segments as packed {depth bits, flatten id} records."""
+def bin_scatter(means2d, radii, depths, offsets, width, height, capacity: int, conics=None, opacities=None,
+                views_per_scene=0):
+    """Scatter intersections into their tile segments as packed {depth bits, flatten id} records.
+    conics + opacities: only the tiles a splat can be seen in (`offsets` must then come from the histogram of
+    project_fwd(tile_histogram=True, opacities=...))."""
     L = _lib.load()
     C, N = radii.shape
     tw, th = tile_grid(width, height)
     cursors = torch.zeros_like(offsets)
     records = torch.empty(capacity, dtype=torch.int64, device=radii.device)
+    if opacities is not None:
+        conics, opacities = _req(conics, torch.float32, "conics"), _req(opacities, torch.float32, "opacities")
+        assert opacities.numel() == N * (C // views_per_scene if views_per_scene else 1)
+    else:
+        conics = None
     _lib.check(L.pm_bin_scatter(_ptr(means2d), _ptr(radii), _ptr(depths), _ptr(offsets), _ptr(cursors), N, C, TILE,
-                                tw, th, _ptr(records), capacity, _stream()), "pm_bin_scatter")
+                                tw, th, _ptr(records), capacity, _ptr(conics), _ptr(opacities), int(views_per_scene),
+                                _stream()), "pm_bin_scatter")
     return records
 
 

@@ -132,7 +132,7 @@ class _Project(torch.autograd.Function):
         out = ops.project_fwd(means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
                               radius_clip, count_tiles=not fused_count, tile_histogram=fused_count,
                               views_per_scene=views_per_scene, tile_capacity=tile_capacity if fused_count else 0,
-                              opacities=bin_opacities if (fused_count and tile_capacity) else None)
+                              opacities=bin_opacities if fused_count else None)
         ctx.views_per_scene = views_per_scene
         radii, means2d, depths, conics, tpg = out[:5]
         aux = out[5] if fused_count else tpg
@@ -301,7 +301,7 @@ def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, b
     intersection record straight into its tile's region of T records (pm_project_scatter_fwd), so the second pass over
     the pairs (pm_bin_scatter) disappears. Speculative like `capacity`: the caller must also check
     info["stats"][1] (the largest tile) <= T afterwards and re-render without it otherwise.
-    `usable_tiles` (single-pass binning only): bin a splat only into the tiles of gsplat's AABB where it can reach
+    `usable_tiles`: bin a splat only into the tiles of gsplat's AABB where it can reach
     alpha >= 1/255 (project.cu: usable_tiles) — same images / gradients bit for bit; the private lists
     (info["stats"], "isect_offsets", "flatten_ids", "sorted_counts") then describe a SUBSET of gsplat's intersections,
     in the same order. False: gsplat's intersections exactly.
@@ -317,7 +317,7 @@ def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, b
     single_pass = bool(tile_capacity) and capacity is not None
     proj = _Project.apply(means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
                           True, views_per_scene, link, int(tile_capacity) if single_pass else 0,
-                          opacities.detach() if (single_pass and usable_tiles) else None)
+                          opacities.detach() if usable_tiles else None)
     means2d, depths, conics, radii, counts = proj[:5]
     # The reference keeps one [1,N,2] screen-space tensor per rendered view and reads its .grad after backward
     # (`viewspace_points`, gaussians_renderer.py:428-445). Routing autograd through per-view tensors costs a cat and a
@@ -336,14 +336,16 @@ def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, b
     if single_pass:
         records = proj[5]
     else:
-        records = ops.bin_scatter(means2d.detach(), radii, depths.detach(), isect_offsets, width, height, int(capacity))
+        records = ops.bin_scatter(means2d.detach(), radii, depths.detach(), isect_offsets, width, height, int(capacity),
+                                  conics=conics.detach() if usable_tiles else None,
+                                  opacities=opacities.detach() if usable_tiles else None, views_per_scene=views_per_scene)
     images, depth_out, masks, flag, flatten_ids, sorted_counts = _TileRenderPacked.apply(
         means2d, conics, opacities, colors, depths, backgrounds, records, isect_offsets, stats, width, height, grad_sink,
         tile_order, views_per_scene, link, int(tile_capacity) if single_pass else 0, int(capacity))
     info = {"radii": radii, "means2d": means2d, "means2d_views": means2d_views, "depths": depths, "conics": conics,
             "isect_offsets": isect_offsets, "flatten_ids": flatten_ids, "sorted_counts": sorted_counts,
             "stats": stats, "overflow_flag": flag, "capacity": int(capacity), "means2d_grad_sink": grad_sink,
-            "tile_capacity": int(tile_capacity) if single_pass else 0, "usable_tiles": bool(single_pass and usable_tiles)}
+            "tile_capacity": int(tile_capacity) if single_pass else 0, "usable_tiles": bool(usable_tiles)}
     return images, depth_out, masks, info
 
 

@@ -62,7 +62,8 @@ def test_argument_errors_are_reported_before_launch():
     assert lib.pm_composite_fwd(one, one, one, one, 0, 5, null, null, one, one, 10, null, 4, 1, 32, 32, 16, one, one, one, null, null, null) == -2
     assert lib.pm_tile_sort_capacity() == 8192
     assert lib.pm_tile_sort(one, null, one, 10, null, 1, 2, 2, -1, one, one, null, null) == -1  # overflow flag is mandatory
-    assert lib.pm_bin_scatter(one, one, one, one, one, 4, 1, 8, 2, 2, one, 10, null) == -2  # tile_size 8
+    assert lib.pm_bin_scatter(one, one, one, one, one, 4, 1, 8, 2, 2, one, 10, null, null, 0, null) == -2  # tile_size 8
+    assert lib.pm_bin_scatter(one, one, one, one, one, 4, 1, 16, 2, 2, one, 10, one, null, 0, null) == -1  # conics without opacities
     assert lib.pm_sort_workspace_bytes(1 << 20) >= (1 << 20) // 4096 * 1024 * 4
     assert lib.pm_scan_workspace_bytes(1 << 20) >= (1 << 20) // 2048 * 4
 

@@ -986,7 +986,7 @@ def test_single_pass_binning_fallback_paths():
     args = [dev(s[k]) for k in ("means", "quats", "scales", "opacities", "colors", "viewmats", "Ks")]
     bg = torch.ones(2, 3, device=DEV)
     with torch.no_grad():
-        im0, de0, ma0, info0 = render_views_packed(*args, bg, 1056, 1056)
+        im0, de0, ma0, info0 = render_views_packed(*args, bg, 1056, 1056, usable_tiles=False)
         n_isects, max_count = (int(v) for v in info0["stats"].tolist())
         assert max_count > 6 and int(info0["overflow_flag"].item()) == 0
         im1, de1, ma1, info1 = render_views_packed(*args, bg, 1056, 1056, capacity=n_isects + 100, tile_capacity=max_count + 3,
@@ -996,6 +996,11 @@ def test_single_pass_binning_fallback_paths():
         # the module's default: only the tiles a splat can be seen in — fewer records, same pixels
         im2, de2, ma2, info2 = render_views_packed(*args, bg, 1056, 1056, capacity=n_isects + 100, tile_capacity=max_count + 3)
         assert info2["usable_tiles"] and info2["stats"][0].item() < n_isects and info2["stats"][1].item() <= max_count
+        # ... and the two-pass form of the same rule (first call of a shape): same counts, same pixels
+        im3, de3, ma3, info3 = render_views_packed(*args, bg, 1056, 1056)
+        assert info3["usable_tiles"] and torch.equal(info3["stats"], info2["stats"])
+        assert torch.equal(info3["isect_offsets"], info2["isect_offsets"])
+        assert torch.equal(im3, im0) and torch.equal(de3, de0) and torch.equal(ma3, ma0)
     for a, b, c in ((im0, im1, im2), (de0, de1, de2), (ma0, ma1, ma2)):
         assert torch.equal(a, b) and torch.equal(a, c)
 
@@ -1010,7 +1015,7 @@ def test_single_pass_binning_many_cameras(C):
     args = [dev(s[k]) for k in ("means", "quats", "scales", "opacities", "colors", "viewmats", "Ks")]
     bg = torch.rand(C, 3, device=DEV)
     with torch.no_grad():
-        im0, de0, ma0, info0 = render_views_packed(*args, bg, 96, 64)
+        im0, de0, ma0, info0 = render_views_packed(*args, bg, 96, 64, usable_tiles=False)
         n_isects, max_count = (int(v) for v in info0["stats"].tolist())
         im1, de1, ma1, info1 = render_views_packed(*args, bg, 96, 64, capacity=n_isects + 7, tile_capacity=max_count,
                                                    usable_tiles=False)
@@ -1019,8 +1024,19 @@ def test_single_pass_binning_many_cameras(C):
         assert info2["stats"][0].item() <= n_isects and bool((info2["isect_offsets"] <= info0["isect_offsets"]).all())
         # histogram-only form of the same call (records = NULL): the counts the scatter call bins
         from prometheus_b200 import ops
-        counts = ops.project_fwd(*args[:3], *args[5:7], 96, 64, count_tiles=False, tile_histogram=True, opacities=args[3])[5]
-        assert torch.equal(ops.tile_scan(counts)[0], info2["isect_offsets"])
+        radii, m2, dep, con, _, counts = ops.project_fwd(*args[:3], *args[5:7], 96, 64, count_tiles=False, tile_histogram=True,
+                                                         opacities=args[3])
+        offs, stats = ops.tile_scan(counts)
+        assert torch.equal(offs, info2["isect_offsets"])
+        # the scatter pass of the two-pass form applies the same rule (tile_sort.cu vs project.cu: same tiles bit for
+        # bit): every slot of every segment holds a record of a visible pair with that pair's depth
+        n_u = int(stats[0].item())
+        rec = ops.bin_scatter(m2, radii, dep, offs, 96, 64, n_u, conics=con, opacities=args[3])
+        f = (rec >> 32) & 0xffffffff
+        assert bool((f < radii.numel()).all()) and bool((radii.reshape(-1)[f] > 0).all())
+        assert torch.equal((rec & 0xffffffff).to(torch.int32), dep.reshape(-1)[f].view(torch.int32))
+        im3, de3, ma3, info3 = render_views_packed(*args, bg, 96, 64)   # two passes, usable tiles
+        assert torch.equal(info3["stats"], info2["stats"]) and torch.equal(im3, im0) and torch.equal(de3, de0)
     for a, b, c in ((im0, im1, im2), (de0, de1, de2), (ma0, ma1, ma2)):
         assert torch.equal(a, b) and torch.equal(a, c)
 
