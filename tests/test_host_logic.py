@@ -104,3 +104,32 @@ def test_view_sharded_gather_world2_gloo():
     assert ret[0][0] and ret[1][0]
     assert ret[0][1] == (0, 3) and ret[1][1] == (3, 6)
     assert ret[0][2] == (3, 18)
+
+
+def test_lazy_meta_mapping_semantics():
+    """`rasterization`'s meta dict: the sorted arrays are computed once, by the first read of any of them through the
+    mapping interface; membership / keys / eager entries never trigger it."""
+    from prometheus_b200.rasterization import _LazyMeta
+
+    calls = []
+
+    def thunk():
+        calls.append(1)
+        return {"tiles_per_gauss": "tpg", "isect_ids": "ids", "flatten_ids": "flat"}
+
+    m = _LazyMeta({"radii": "r", "isect_offsets": "off"}, thunk)
+    assert "isect_ids" in m and len(m) == 5 and set(m.keys()) == {"radii", "isect_offsets", "tiles_per_gauss", "isect_ids", "flatten_ids"}
+    assert m["radii"] == "r" and m.get("isect_offsets") == "off" and not m.materialized and not calls
+    assert "pending" in repr(m) and not calls
+    assert m["flatten_ids"] == "flat" and m.materialized and calls == [1]
+    assert m["isect_ids"] == "ids" and m.get("tiles_per_gauss") == "tpg" and calls == [1]
+    for make in (dict, lambda d: {**d}, lambda d: d.copy(), lambda d: dict(d.items())):
+        m2 = _LazyMeta({"radii": "r"}, thunk)
+        assert make(m2)["isect_ids"] == "ids" and m2.materialized
+    m3 = _LazyMeta({"radii": "r"}, thunk)
+    assert list(m3.values()).count("ids") == 1
+    m4 = _LazyMeta({"radii": "r"}, thunk)
+    m4["isect_ids"] = "mine"                      # a caller's own value survives
+    assert m4["isect_ids"] == "mine" and m4["flatten_ids"] == "flat"
+    m5 = _LazyMeta({"radii": "r"}, thunk)
+    assert m5.pop("tiles_per_gauss") == "tpg" and "tiles_per_gauss" not in m5
