@@ -331,8 +331,12 @@ def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, b
     else:
         means2d_views = [v.unsqueeze(0) for v in means2d.unbind(0)]
     isect_offsets, stats, tile_order = ops.tile_scan(counts, want_order=True)
+    exact_counts = None
     if capacity is None:
-        capacity = int(stats[0].item())
+        # the one host read of the exact-size path brings both counts: the caller can size its NEXT call of this
+        # shape (e.g. the next chunk of a trajectory) at once instead of waiting for this call's deferred check
+        exact_counts = tuple(int(v) for v in stats.tolist())
+        capacity = exact_counts[0]
     if single_pass:
         records = proj[5]
     else:
@@ -345,7 +349,8 @@ def render_views_packed(means, quats, scales, opacities, colors, viewmats, Ks, b
     info = {"radii": radii, "means2d": means2d, "means2d_views": means2d_views, "depths": depths, "conics": conics,
             "isect_offsets": isect_offsets, "flatten_ids": flatten_ids, "sorted_counts": sorted_counts,
             "stats": stats, "overflow_flag": flag, "capacity": int(capacity), "means2d_grad_sink": grad_sink,
-            "tile_capacity": int(tile_capacity) if single_pass else 0, "usable_tiles": bool(usable_tiles)}
+            "tile_capacity": int(tile_capacity) if single_pass else 0, "usable_tiles": bool(usable_tiles),
+            "exact_counts": exact_counts}
     return images, depth_out, masks, info
 
 

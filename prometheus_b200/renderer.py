@@ -156,7 +156,15 @@ class GaussianRenderer(nn.Module):
         images, depths, masks, info = render_views_packed(xyz, rot, sc, opac, feat, viewmats, Ks, bgs, int(w), int(h),
                                                           capacity=cap, tile_capacity=self._tile_cap_for(key, cap, h, w),
                                                           usable_tiles=self.usable_tiles)
+        self._hint_from_exact(key, cap, info)
         return images, depths, masks, info, key
+
+    def _hint_from_exact(self, key, cap, info) -> None:
+        """A first call of a shape ran with exact sizes and read {n_isects, max tile count} on the way: set the hints
+        now, so that the following chunks of the same forward (a trajectory: 15 chunks of one shape) already run
+        speculatively — single-pass binning, no host read — instead of all taking the exact path."""
+        if cap is None and self.speculative_capacity and info.get("exact_counts") and key not in self._cap_hint:
+            self._update_hint(key, *info["exact_counts"])
 
     def _tile_cap_for(self, key, cap, h, w):
         """Region size for single-pass binning, or None (two passes): needs both hints of the shape."""
@@ -249,6 +257,7 @@ class GaussianRenderer(nn.Module):
         im, de, ma, info = render_views_packed(*args, int(w), int(h), capacity=cap, views_per_scene=N,
                                                tile_capacity=self._tile_cap_for(key, cap, h, w),
                                                usable_tiles=self.usable_tiles)
+        self._hint_from_exact(key, cap, info)
         job = self._job_for(args, (im, de, ma), info, key)
         if self.defer_checks:
             self._pending.append(dict(key=key, capacity=job["capacity"], stats_host=job["stats_host"], event=job["event"],
